@@ -1,0 +1,253 @@
+"""Trajectory metrics on the GPU (drop-in for
+/root/reference/analysis/metrics/trajectory_metrics.py:12-325, compute part only).
+
+The per-frame reductions (||T_i - S_i||, consecutive-frame velocities, direction dot
+products, start-to-end distances) and the per-frame Wasserstein distances come from two
+streaming CUDA kernels (``dtraj_metrics_pairs`` / ``dtraj_wasserstein``); the f64 scalar
+formulas (log1p / exp / ratios) are evaluated on the host exactly as the reference does, so
+1e-4 parity does not depend on the device's libm.
+
+Batched API (what the sweep drivers use): ``pair_reductions`` + ``wasserstein_frames`` +
+``scalar_metrics_batched`` over [N, L, D] device tensors.  ``compute_trajectory_metrics``
+keeps the reference's list-of-tensors signature and 25-key result.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from ... import _lib
+
+SCALAR_KEYS = (
+    "endpoint_distance", "mse", "trajectory_mse", "point_by_point_similarity", "log_mse_similarity",
+    "teacher_path_length", "student_path_length", "path_length_similarity", "teacher_efficiency",
+    "student_efficiency", "efficiency_similarity", "mean_velocity_similarity", "mean_position_difference",
+    "max_position_difference", "mean_directional_consistency", "weighted_directional_consistency",
+    "mean_wasserstein", "distribution_similarity",
+)   # the 18 keys compare_trajectories averages (np.float32 path_alignment and the lists are dropped there)
+
+
+# ----------------------------------------------------------------------------- kernels
+def _dev(t):
+    if t.device.type != "cuda":
+        raise _lib.DtrajError("trajectory metrics run on CUDA only (no CPU fallback)")
+    return t
+
+
+def pair_reductions(teacher, student):
+    """[N, L, D] x2 (CUDA fp32, contiguous) -> device tensor [N, L, 6] (see include/dtraj.h)."""
+    lib = _lib.load()
+    teacher, student = _dev(teacher).contiguous(), _dev(student).contiguous()
+    if teacher.shape != student.shape or teacher.dim() != 3:
+        raise ValueError("pair_reductions expects two [N, L, D] tensors of equal shape")
+    N, L, D = teacher.shape
+    out = torch.empty(N, L, _lib.METRIC_Q, dtype=torch.float32, device=teacher.device)
+    with torch.cuda.device(teacher.device):
+        _lib.check(lib.dtraj_metrics_pairs(_lib.ptr(teacher), _lib.ptr(student), N, L, D, _lib.ptr(out), _lib.stream_ptr()))
+    return out
+
+
+def wasserstein_frames(teacher, student, idx=None, idx_set=None):
+    """Per-frame W1 between gathered elements.  ``idx``: int32 [n_sets, L, K] (CUDA) or None for all
+    elements; ``idx_set``: int32 [N] choosing the set per pair.  Returns device [N, L] fp32."""
+    lib = _lib.load()
+    teacher, student = _dev(teacher).contiguous(), _dev(student).contiguous()
+    N, L, D = teacher.shape
+    K = D if idx is None else int(idx.shape[-1])
+    out = torch.empty(N, L, dtype=torch.float32, device=teacher.device)
+    if idx is not None:
+        idx = idx.to(teacher.device, torch.int32).contiguous()
+    if idx_set is not None:
+        idx_set = idx_set.to(teacher.device, torch.int32).contiguous()
+    with torch.cuda.device(teacher.device):
+        _lib.check(lib.dtraj_wasserstein(_lib.ptr(teacher), _lib.ptr(student), N, L, D, _lib.ptr(idx), _lib.ptr(idx_set),
+                                         K, _lib.ptr(out), _lib.stream_ptr()))
+    return out
+
+
+# ----------------------------------------------------------------------------- host formulas
+def _ratio(a, b):
+    hi = np.maximum(a, b)
+    lo = np.minimum(a, b)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        return np.where(hi > 0, lo / np.where(hi > 0, hi, 1.0), 1.0)
+
+
+def scalar_metrics_batched(red, w1, pixels, numel):
+    """Vectorised Q1 scalar formulas for N equal-length pairs.
+
+    red    np.float32 [N, L, 6] from ``pair_reductions`` (summed over the batch axis of a frame if any)
+    w1     np.float64/32 [N, L] per-frame Wasserstein distances
+    pixels H*W (the reference's path-length normaliser, trajectory_metrics.py:118-119)
+    numel  elements per frame tensor (torch.mean's denominator)
+    Returns dict key -> np.float64 [N] for the 18 scalar keys + 'path_alignment' (np.float32 [N])
+    and the per-frame arrays behind the 7 list keys.
+    """
+    red = np.asarray(red, np.float32)
+    N, L, _ = red.shape
+    f32 = np.float32
+    d = np.sqrt(red[:, :, 0]).astype(f32)                       # torch.norm -> fp32
+    m = (red[:, :, 0] / f32(numel)).astype(f32)                 # torch.mean -> fp32
+    vt = np.sqrt(red[:, : L - 1, 1]).astype(f32)
+    vs = np.sqrt(red[:, : L - 1, 2]).astype(f32)
+    dot = red[:, : L - 1, 3]
+    d64, m64, vt64, vs64 = d.astype(np.float64), m.astype(np.float64), vt.astype(np.float64), vs.astype(np.float64)
+    out = {}
+    out["endpoint_distance"] = d64[:, -1]                                             # :55
+    mse = m64[:, -1]                                                                  # :59
+    out["mse"] = mse
+    with np.errstate(invalid="ignore", divide="ignore"):
+        out["trajectory_mse"] = np.log1p(1.0 - m64.sum(axis=1) / L * 1000)            # :63-86
+        out["point_by_point_similarity"] = np.exp(-5.0 * d64.mean(axis=1))            # :90-101
+        out["log_mse_similarity"] = np.maximum(0, 1.0 - np.log1p(mse * 5000) / np.log1p(5000))   # :106-108
+        if L > 1:
+            tl = (vt64 / pixels).sum(axis=1) / (L - 1)                                # :111-131
+            sl = (vs64 / pixels).sum(axis=1) / (L - 1)
+        else:
+            tl = sl = np.full(N, np.nan)
+        out["teacher_path_length"], out["student_path_length"] = tl, sl
+        out["path_length_similarity"] = np.log1p(_ratio(tl, sl))                      # :134-137
+        te = np.sqrt(red[:, 0, 4]).astype(f32).astype(np.float64)                     # :140-153
+        se = np.sqrt(red[:, 0, 5]).astype(f32).astype(np.float64)
+        teff = np.where(tl > 0, te / np.where(tl > 0, tl, 1.0), 0.0)
+        seff = np.where(sl > 0, se / np.where(sl > 0, sl, 1.0), 0.0)
+        out["teacher_efficiency"], out["student_efficiency"] = teff, seff
+        out["efficiency_similarity"] = np.log1p(_ratio(teff, seff))
+        vsim = _ratio(vt64, vs64)                                                     # :156-177
+        out["mean_velocity_similarity"] = vsim.mean(axis=1) if L > 1 else np.zeros(N)
+        out["mean_position_difference"] = d64.mean(axis=1)                            # :180-187
+        out["max_position_difference"] = d64.max(axis=1)
+        ok = (vt > 0) & (vs > 0)                                                      # :190-231
+        cos = np.where(ok, dot / np.where(ok, vt * vs, f32(1)), f32(0)).astype(f32).astype(np.float64)
+        cnt = ok.sum(axis=1)
+        out["mean_directional_consistency"] = np.where(cnt > 0, cos.sum(axis=1) / np.maximum(cnt, 1), 0.0)
+        wgt = (vt64 + vs64) / 2
+        tw = wgt.sum(axis=1)
+        wm = np.where(tw > 0, (cos * wgt * ok).sum(axis=1) / np.where(tw > 0, tw, 1.0), 0.0)
+        out["weighted_directional_consistency"] = np.where(cnt > 0, wm ** 2, 0.0)
+        # :282-293 -- np.linalg.norm on float32 rows, float32 sum, float32 exp
+        area = d.sum(axis=1, dtype=f32)
+        out["path_alignment"] = np.exp(f32(-10.0) * area / f32(L)).astype(f32)
+        w1 = np.asarray(w1, np.float64)                                               # :296-323
+        out["mean_wasserstein"] = w1.mean(axis=1)
+        out["distribution_similarity"] = np.log1p(np.exp(-out["mean_wasserstein"]))
+    out["_position_differences"] = d64
+    out["_teacher_velocities"], out["_student_velocities"] = vt64, vs64
+    out["_velocity_similarities"] = vsim
+    out["_cos"], out["_cos_ok"] = cos, ok
+    out["_wasserstein"] = w1
+    return out
+
+
+def _images(traj):
+    # the third sampler stores (tensor, t) tuples (trajectory_metrics.py:29-37)
+    return [it[0] for it in traj] if isinstance(traj[0], tuple) else list(traj)
+
+
+def _stack_frames(images, device):
+    """list of L tensors [B, C, H, W] -> device tensor [L, B*C*H*W]."""
+    return torch.stack([im.detach().to(device, torch.float32).reshape(-1) for im in images])
+
+
+def _per_sample_layout(frames, B):
+    """[L, B*D] -> [B, L, D] so one kernel group owns one sample's trajectory."""
+    L = frames.shape[0]
+    return frames.reshape(L, B, -1).transpose(0, 1).contiguous()
+
+
+def _pick_device(images):
+    for im in images:
+        if im.device.type == "cuda":
+            return im.device
+    if not torch.cuda.is_available():
+        raise _lib.DtrajError("trajectory metrics need a CUDA device (no CPU fallback)")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def compute_trajectory_metrics(teacher_trajectory, student_trajectory, config=None):
+    """Metrics between one teacher and one student trajectory (lists of [B, C, H, W] tensors or
+    (tensor, t) tuples).  Same 25 keys, value types and numpy-global-RNG use as the reference."""
+    T = _images(teacher_trajectory)
+    S = _images(student_trajectory)
+    dev = _pick_device(T + S)
+    if T[-1].shape != S[-1].shape and T[-1].shape[2:] != S[-1].shape[2:]:
+        # trajectory_metrics.py:40-52: bilinear (align_corners) resize of every student frame
+        S = [torch.nn.functional.interpolate(s.to(dev), size=T[0].shape[2:], mode="bilinear", align_corners=True)
+             for s in S]
+    B = T[0].shape[0]
+    pixels = T[0].shape[2] * T[0].shape[3]
+    numel = T[0].numel()
+    LT, LS = len(T), len(S)
+    n = min(LT, LS)
+    ft, fs = _stack_frames(T, dev), _stack_frames(S, dev)          # [L, B*D]
+
+    def reduce_pair(a, b):
+        r = pair_reductions(_per_sample_layout(a, B), _per_sample_layout(b, B)).cpu().numpy()
+        return r.astype(np.float64).sum(axis=0, keepdims=True).astype(np.float32)       # sum over the batch axis
+
+    # Wasserstein subsample indices: global numpy RNG, one choice() per frame (trajectory_metrics.py:301-306)
+    K = min(1000, numel)
+    idx = np.stack([np.random.choice(numel, K, replace=False) for _ in range(n)]).astype(np.int32)
+    w1 = wasserstein_frames(ft[:n].unsqueeze(0), fs[:n].unsqueeze(0),
+                            None if K == numel else torch.from_numpy(idx).unsqueeze(0)).cpu().numpy()
+
+    if LT == LS:
+        sm = scalar_metrics_batched(reduce_pair(ft, fs), w1, pixels, numel)
+    else:
+        sm = _unequal_length_metrics(ft, fs, n, B, pixels, numel, w1, reduce_pair)
+
+    m = {}
+    for k in SCALAR_KEYS:
+        v = sm[k][0]
+        m[k] = float(v) if k in ("endpoint_distance", "mse", "teacher_path_length", "student_path_length",
+                                 "teacher_efficiency", "student_efficiency",
+                                 "weighted_directional_consistency") else np.float64(v)
+    m["path_alignment"] = sm["path_alignment"][0]
+    m["teacher_velocities"] = [float(v) for v in sm["_teacher_velocities"][0]]
+    m["student_velocities"] = [float(v) for v in sm["_student_velocities"][0]]
+    m["velocity_similarities"] = [float(v) for v in sm["_velocity_similarities"][0]]
+    m["position_differences"] = [float(v) for v in sm["_position_differences"][0]]
+    m["directional_consistency"] = [float(c) for c, ok in zip(sm["_cos"][0], sm["_cos_ok"][0]) if ok]
+    m["wasserstein_distances"] = [float(v) for v in sm["_wasserstein"][0]]
+    # keep the reference's key order (dict order is observable through .keys())
+    order = ["endpoint_distance", "mse", "trajectory_mse", "point_by_point_similarity", "log_mse_similarity",
+             "teacher_path_length", "student_path_length", "path_length_similarity", "teacher_efficiency",
+             "student_efficiency", "efficiency_similarity", "teacher_velocities", "student_velocities",
+             "velocity_similarities", "mean_velocity_similarity", "position_differences", "mean_position_difference",
+             "max_position_difference", "directional_consistency", "mean_directional_consistency",
+             "weighted_directional_consistency", "path_alignment", "wasserstein_distances", "mean_wasserstein",
+             "distribution_similarity"]
+    return {k: m[k] for k in order}
+
+
+def _unequal_length_metrics(ft, fs, n, B, pixels, numel, w1, reduce_pair):
+    """len(teacher) != len(student) (TrajectoryManager with teacher_steps != student_steps).
+    Prefix metrics use the first n = min(len) frames; endpoint / efficiency use each trajectory's own
+    last frame; velocity lists cover each full trajectory (trajectory_metrics.py:55-59,140-164)."""
+    sm = scalar_metrics_batched(reduce_pair(ft[:n], fs[:n]), w1, pixels, numel)
+    full_t = scalar_metrics_batched(reduce_pair(ft, ft), np.zeros((1, ft.shape[0])), pixels, numel)
+    full_s = scalar_metrics_batched(reduce_pair(fs, fs), np.zeros((1, fs.shape[0])), pixels, numel)
+    last = reduce_pair(ft[-1:], fs[-1:])
+    sm["endpoint_distance"] = np.sqrt(last[:, 0, 0]).astype(np.float32).astype(np.float64)
+    mse = (last[:, 0, 0] / np.float32(numel)).astype(np.float32).astype(np.float64)
+    sm["mse"] = mse
+    sm["log_mse_similarity"] = np.maximum(0, 1.0 - np.log1p(mse * 5000) / np.log1p(5000))
+    te = np.sqrt(reduce_pair(ft, ft)[:, 0, 4]).astype(np.float32).astype(np.float64)
+    se = np.sqrt(reduce_pair(fs, fs)[:, 0, 4]).astype(np.float32).astype(np.float64)
+    tl, sl = sm["teacher_path_length"], sm["student_path_length"]
+    sm["teacher_efficiency"] = np.where(tl > 0, te / np.where(tl > 0, tl, 1.0), 0.0)
+    sm["student_efficiency"] = np.where(sl > 0, se / np.where(sl > 0, sl, 1.0), 0.0)
+    sm["efficiency_similarity"] = np.log1p(_ratio(sm["teacher_efficiency"], sm["student_efficiency"]))
+    sm["_teacher_velocities"] = full_t["_teacher_velocities"]
+    sm["_student_velocities"] = full_s["_teacher_velocities"]
+    # path alignment: resample the longer trajectory on the shorter one's time axis (:239-279);
+    # host-side f64 linear interpolation of a corner case that no sweep on the hot path takes
+    a, b = ft.cpu().numpy().astype(np.float64), fs.cpu().numpy().astype(np.float64)
+    longer, shorter = (a, b) if a.shape[0] > b.shape[0] else (b, a)
+    lt, st = np.linspace(0, 1, longer.shape[0]), np.linspace(0, 1, shorter.shape[0])
+    pos = np.clip(np.searchsorted(lt, st, side="right") - 1, 0, longer.shape[0] - 2)
+    frac = ((st - lt[pos]) / (lt[pos + 1] - lt[pos]))[:, None]
+    res = longer[pos] * (1 - frac) + longer[pos + 1] * frac
+    dist = np.linalg.norm(res - shorter, axis=1)
+    sm["path_alignment"] = np.array([np.exp(-10.0 * dist.sum() / len(dist))])
+    return sm

@@ -1,0 +1,115 @@
+// Shared helpers for libdtraj (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+#include <string.h>
+
+#include "../../include/dtraj.h"
+
+namespace dtraj {
+
+// ---- error plumbing: C ABI never throws, it records a thread-local message -----------
+inline char* err_buf() {
+    static thread_local char buf[512] = {0};
+    return buf;
+}
+inline int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(err_buf(), 512, fmt, ap);
+    va_end(ap);
+    return code;
+}
+#define DTRAJ_CUDA(expr)                                                                   \
+    do {                                                                                   \
+        cudaError_t _e = (expr);                                                           \
+        if (_e != cudaSuccess)                                                             \
+            return ::dtraj::fail(DTRAJ_ECUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #expr,  \
+                                 cudaGetErrorString(_e));                                  \
+    } while (0)
+#define DTRAJ_LAUNCH_CHECK()                                                               \
+    do {                                                                                   \
+        cudaError_t _e = cudaGetLastError();                                               \
+        if (_e != cudaSuccess)                                                             \
+            return ::dtraj::fail(DTRAJ_ECUDA, "%s:%d launch -> %s", __FILE__, __LINE__,     \
+                                 cudaGetErrorString(_e));                                  \
+    } while (0)
+#define DTRAJ_TRY(expr)                                                                    \
+    do {                                                                                   \
+        int _r = (expr);                                                                   \
+        if (_r != 0) return _r;                                                            \
+    } while (0)
+
+constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs
+constexpr int kCPad = 32;     // channel padding unit of NHWC feature maps (= one 128-byte TMA/UMMA K block)
+
+inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
+inline int64_t round_up64(int64_t v, int64_t m) { return (v + m - 1) / m * m; }
+
+// activation post-processing chosen by the model's precision mode
+enum ActMode : int {
+    ACT_PLAIN = 0,   // store y
+    ACT_ROUND = 1,   // store rna_tf32(y): operands of the single-pass TF32 convs are exact tf32
+    ACT_SPLIT = 2    // store y and, lo_off floats further, y - trunc_tf32(y) for the 3xTF32 convs
+};
+
+// ---- tf32 helpers (device + host) --------------------------------------------------------
+__host__ __device__ inline float tf32_trunc(float v) {
+#ifdef __CUDA_ARCH__
+    return __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+#else
+    uint32_t u;
+    memcpy(&u, &v, 4);
+    u &= 0xffffe000u;
+    memcpy(&v, &u, 4);
+    return v;
+#endif
+}
+__device__ __forceinline__ float tf32_rna(float v) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+    return __uint_as_float(r);
+}
+inline float tf32_rna_host(float v) {  // round-to-nearest, ties away (matches cvt.rna)
+    uint32_t u;
+    memcpy(&u, &v, 4);
+    if ((u & 0x7f800000u) == 0x7f800000u) return v;
+    u += 0x00001000u;
+    u &= 0xffffe000u;
+    memcpy(&v, &u, 4);
+    return v;
+}
+
+// y -> what goes to memory under `mode`; writes the low plane when splitting
+__device__ __forceinline__ float act_store_value(float y, int mode) {
+    return mode == ACT_ROUND ? tf32_rna(y) : y;
+}
+__device__ __forceinline__ float4 act_round4(float4 v, int mode) {
+    if (mode == ACT_ROUND) {
+        v.x = tf32_rna(v.x); v.y = tf32_rna(v.y); v.z = tf32_rna(v.z); v.w = tf32_rna(v.w);
+    }
+    return v;
+}
+__device__ __forceinline__ float4 act_lo4(float4 v) {
+    return make_float4(v.x - tf32_trunc(v.x), v.y - tf32_trunc(v.y),
+                       v.z - tf32_trunc(v.z), v.w - tf32_trunc(v.w));
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// streaming 128-bit loads/stores that do not pollute L1
+__device__ __forceinline__ float4 ld_stream4(const float* p) {
+    float4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+    return r;
+}
+
+}  // namespace dtraj

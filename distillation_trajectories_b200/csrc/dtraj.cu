@@ -1,0 +1,732 @@
+// libdtraj.so -- C ABI (include/dtraj.h): model packing, forward plan, sampler loop with
+// CUDA-graph capture, metric entry points.  sm_100a only; no torch types anywhere.
+#include <map>
+#include <string>
+#include <vector>
+#include <cmath>
+
+#include "common.cuh"
+#include "elem.cuh"
+#include "conv_simt.cuh"
+#include "conv_umma.cuh"
+#include "metrics.cuh"
+
+using namespace dtraj;
+
+// ======================================================================================
+// model
+// ======================================================================================
+namespace {
+
+const char* kBlockNames[8] = {"enc1", "enc2", "enc3", "enc4", "bottleneck", "dec3", "dec2", "dec1"};
+
+struct PackedConv {          // one generic conv layer's parameters on the device
+    const float* w = nullptr;   // [npl][nkb][coutp][32], plane 0 = hi (or the only one), plane 1 = lo
+    const float* bias = nullptr;
+    int64_t rows = 0;           // npl * nkb * coutp
+    int c0p = 0, c1p = 0, coutp = 0, ntaps = 0;
+};
+
+struct BlockW {
+    int cin0 = 0, cin1 = 0, cout = 0, S = 0;   // real channels, spatial size
+    bool has_res = false;
+    PackedConv conv1, conv2, res;              // conv1/res unused for enc1 (first-conv kernel)
+};
+
+struct Arena {               // host staging of everything that goes to the device in one copy
+    std::vector<float> h;
+    size_t alloc(size_t n) {
+        size_t off = (h.size() + 63) / 64 * 64;
+        h.resize(off + n, 0.f);
+        return off;
+    }
+};
+
+}  // namespace
+
+struct dtraj_unet {
+    dtraj_unet_desc d;
+    int dp[4];                  // padded dims
+    int sizes[5];               // spatial size per level
+    int act_mode;               // ACT_* for GEMM operands
+    float* dev = nullptr;       // weight arena
+    size_t dev_floats = 0;
+    BlockW blk[8];
+    // first conv (enc1.conv1 + enc1.residual_conv)
+    const float *fw3 = nullptr, *fb3 = nullptr, *fw1 = nullptr, *fb1 = nullptr;
+    // final 1x1
+    const float *finw = nullptr, *finb = nullptr;
+    // time table
+    float* table = nullptr;     // [T][3][tb_stride]
+    int tb_stride = 0;
+    int tb_off[8];
+    // cached forward plan for dtraj_unet_forward
+    struct dtraj_plan* plan = nullptr;
+};
+
+namespace {
+
+struct TensorDict {
+    std::map<std::string, std::pair<const float*, int64_t>> m;
+    const float* get(const std::string& k, int64_t expect, int* err) const {
+        auto it = m.find(k);
+        if (it == m.end()) { *err = fail(DTRAJ_EMISSING, "state_dict entry '%s' missing", k.c_str()); return nullptr; }
+        if (expect >= 0 && it->second.second != expect) {
+            *err = fail(DTRAJ_EINVAL, "state_dict entry '%s' has %lld elements, expected %lld", k.c_str(),
+                        (long long)it->second.second, (long long)expect);
+            return nullptr;
+        }
+        return it->second.first;
+    }
+    bool has(const std::string& k) const { return m.count(k) != 0; }
+};
+
+// eval-mode BatchNorm folded into the preceding conv (models.py:48-51, eps = 1e-5):
+// y = (conv(x) + b - mean) * gamma / sqrt(var + eps) + beta
+int bn_fold(const TensorDict& sd, const std::string& conv, const std::string& norm, int cout,
+            std::vector<double>* scale, std::vector<double>* shift) {
+    int err = 0;
+    const float* b = sd.get(conv + ".bias", cout, &err);
+    const float* g = sd.get(norm + ".weight", cout, &err);
+    const float* be = sd.get(norm + ".bias", cout, &err);
+    const float* mu = sd.get(norm + ".running_mean", cout, &err);
+    const float* var = sd.get(norm + ".running_var", cout, &err);
+    if (err) return err;
+    scale->resize(cout); shift->resize(cout);
+    for (int n = 0; n < cout; ++n) {
+        double s = (double)g[n] / std::sqrt((double)var[n] + 1e-5);
+        (*scale)[n] = s;
+        (*shift)[n] = ((double)b[n] - (double)mu[n]) * s + (double)be[n];
+    }
+    return 0;
+}
+
+// Pack [cout][c0+c1][k][k] into K-major 32-channel blocks [tap][chunk][coutp][32] (+ low plane)
+void pack_conv(Arena* A, size_t* w_off, size_t* b_off, PackedConv* pc, const float* w, int cout, int c0, int c1,
+               int ksize, bool centre_only, const double* scale, const double* shift, int precision) {
+    const int c0p = round_up(c0, kCPad), c1p = c1 ? round_up(c1, kCPad) : 0, coutp = round_up(cout, kCPad);
+    const int ntaps = (ksize == 3 && !centre_only) ? 9 : 1;
+    const int nch0 = c0p / 32, nch = nch0 + c1p / 32, nkb = ntaps * nch;
+    const int npl = precision == DTRAJ_PREC_TF32X3 ? 2 : 1;
+    const size_t plane = (size_t)nkb * coutp * 32;
+    *w_off = A->alloc(plane * npl);
+    *b_off = A->alloc(coutp);
+    const int cin = c0 + c1;
+    for (int tap = 0; tap < ntaps; ++tap) {
+        int ky = 0, kx = 0;
+        if (ksize == 3) { ky = centre_only ? 1 : tap / 3; kx = centre_only ? 1 : tap % 3; }
+        for (int chunk = 0; chunk < nch; ++chunk)
+            for (int n = 0; n < cout; ++n)
+                for (int kk = 0; kk < 32; ++kk) {
+                    int c, ci;
+                    if (chunk < nch0) { c = chunk * 32 + kk; ci = c < c0 ? c : -1; }
+                    else { c = (chunk - nch0) * 32 + kk; ci = c < c1 ? c0 + c : -1; }
+                    if (ci < 0) continue;
+                    double v = (double)w[(((size_t)n * cin + ci) * ksize + ky) * ksize + kx] * (scale ? scale[n] : 1.0);
+                    float f = (float)v;
+                    size_t o = *w_off + (((size_t)(tap * nch + chunk) * coutp + n) * 32 + kk);
+                    if (precision == DTRAJ_PREC_FP32) A->h[o] = f;
+                    else {
+                        float hi = tf32_rna_host(f);
+                        A->h[o] = hi;
+                        if (npl == 2) A->h[o + plane] = f - hi;
+                    }
+                }
+    }
+    for (int n = 0; n < cout; ++n) A->h[*b_off + n] = (float)shift[n];
+    pc->rows = (int64_t)npl * nkb * coutp;
+    pc->c0p = c0p; pc->c1p = c1p; pc->coutp = coutp; pc->ntaps = ntaps;
+}
+
+}  // namespace
+
+extern "C" const char* dtraj_last_error(void) { return err_buf(); }
+extern "C" int dtraj_version(void) { return 100; }
+
+extern "C" int dtraj_unet_destroy(dtraj_unet* u);
+
+extern "C" int dtraj_unet_create(const dtraj_unet_desc* desc, const char* const* names, const float* const* tensors,
+                                 const int64_t* numel, int32_t n_tensors, dtraj_unet** out) {
+    if (!desc || !out || !names || !tensors || !numel) return fail(DTRAJ_EINVAL, "null argument");
+    const int C = desc->channels, H = desc->image_size, temb = desc->temb_dim, T = desc->n_timesteps;
+    if (C < 1 || C > 4) return fail(DTRAJ_EINVAL, "channels=%d unsupported (1..4)", C);
+    if (H < 16 || H > 32 || (H % 16) != 0) return fail(DTRAJ_EINVAL, "image_size=%d unsupported (16 or 32)", H);
+    if (temb < 2 || temb > 1024 || T < 1) return fail(DTRAJ_EINVAL, "bad temb_dim/n_timesteps");
+    if (desc->precision < 0 || desc->precision > 2) return fail(DTRAJ_EINVAL, "bad precision");
+    for (int i = 0; i < 4; ++i)
+        if (desc->dims[i] < 1 || desc->dims[i] > 256) return fail(DTRAJ_EINVAL, "dims[%d]=%d unsupported (1..256)", i, desc->dims[i]);
+    if (desc->dims[1] != desc->dims[2] || desc->dims[2] != desc->dims[3])
+        return fail(DTRAJ_EINVAL, "dims must be [b, m, m, m] (models.py:107-110)");
+
+    TensorDict sd;
+    for (int i = 0; i < n_tensors; ++i) sd.m[names[i]] = {tensors[i], numel[i]};
+
+    dtraj_unet* u = new dtraj_unet();
+    u->d = *desc;
+    for (int i = 0; i < 4; ++i) u->dp[i] = round_up(desc->dims[i], kCPad);
+    for (int l = 0; l < 5; ++l) u->sizes[l] = H >> l;
+    u->act_mode = desc->precision == DTRAJ_PREC_FP32 ? ACT_PLAIN : desc->precision == DTRAJ_PREC_TF32 ? ACT_ROUND : ACT_SPLIT;
+    const int* d = desc->dims;
+    // block geometry (models.py:137-154)
+    const int cin0[8] = {C, d[0], d[1], d[2], d[3], d[3], d[2], d[1]};
+    const int cin1[8] = {0, 0, 0, 0, 0, d[3], d[2], d[1]};
+    const int cout[8] = {d[0], d[1], d[2], d[3], d[3], d[2], d[1], d[0]};
+    const int lvl[8] = {0, 1, 2, 3, 4, 3, 2, 1};
+
+    Arena A;
+    int err = 0;
+    struct Off { size_t w1, b1, w2, b2, wr, br; } off[8] = {};
+    size_t o_fw3 = 0, o_fb3 = 0, o_fw1 = 0, o_fb1 = 0, o_finw = 0, o_finb = 0;
+    size_t o_tw1, o_tb1, o_cw0, o_cb0, o_cw2, o_cb2, o_bw[8], o_bb[8];
+
+    for (int b = 0; b < 8 && !err; ++b) {
+        BlockW& B = u->blk[b];
+        const std::string nm = kBlockNames[b];
+        B.cin0 = cin0[b]; B.cin1 = cin1[b]; B.cout = cout[b]; B.S = u->sizes[lvl[b]];
+        const int cin = B.cin0 + B.cin1;
+        B.has_res = sd.has(nm + ".residual_conv.weight");
+        if (!B.has_res && cin != B.cout) { err = fail(DTRAJ_EMISSING, "%s.residual_conv missing but in_ch != out_ch", nm.c_str()); break; }
+        const bool centre = B.S == 1;
+        std::vector<double> sc, sh;
+        // conv1
+        const float* w = sd.get(nm + ".conv1.weight", (int64_t)B.cout * cin * 9, &err);
+        if (err || (err = bn_fold(sd, nm + ".conv1", nm + ".norm1", B.cout, &sc, &sh))) break;
+        if (b == 0) {
+            // first conv: [9*C][coutp] tap-major (fp32 CUDA cores), residual [C][coutp]
+            const int cp = u->dp[0];
+            o_fw3 = A.alloc((size_t)9 * C * cp); o_fb3 = A.alloc(cp);
+            for (int n = 0; n < B.cout; ++n) {
+                for (int c = 0; c < C; ++c)
+                    for (int t9 = 0; t9 < 9; ++t9)
+                        A.h[o_fw3 + ((size_t)t9 * C + c) * cp + n] = (float)((double)w[((size_t)n * C + c) * 9 + t9] * sc[n]);
+                A.h[o_fb3 + n] = (float)sh[n];
+            }
+            if (!B.has_res) { err = fail(DTRAJ_EINVAL, "enc1 without residual_conv is unsupported"); break; }
+            const float* wr = sd.get(nm + ".residual_conv.weight", (int64_t)B.cout * C, &err);
+            const float* br = sd.get(nm + ".residual_conv.bias", B.cout, &err);
+            if (err) break;
+            o_fw1 = A.alloc((size_t)C * cp); o_fb1 = A.alloc(cp);
+            for (int n = 0; n < B.cout; ++n) {
+                for (int c = 0; c < C; ++c) A.h[o_fw1 + (size_t)c * cp + n] = wr[(size_t)n * C + c];
+                A.h[o_fb1 + n] = br[n];
+            }
+        } else {
+            pack_conv(&A, &off[b].w1, &off[b].b1, &B.conv1, w, B.cout, B.cin0, B.cin1, 3, centre, sc.data(), sh.data(), desc->precision);
+            if (B.has_res) {
+                const float* wr = sd.get(nm + ".residual_conv.weight", (int64_t)B.cout * cin, &err);
+                const float* br = sd.get(nm + ".residual_conv.bias", B.cout, &err);
+                if (err) break;
+                std::vector<double> rb(B.cout);
+                for (int n = 0; n < B.cout; ++n) rb[n] = br[n];
+                pack_conv(&A, &off[b].wr, &off[b].br, &B.res, wr, B.cout, B.cin0, B.cin1, 1, false, nullptr, rb.data(), desc->precision);
+            }
+        }
+        // conv2
+        const float* w2 = sd.get(nm + ".conv2.weight", (int64_t)B.cout * B.cout * 9, &err);
+        if (err || (err = bn_fold(sd, nm + ".conv2", nm + ".norm2", B.cout, &sc, &sh))) break;
+        pack_conv(&A, &off[b].w2, &off[b].b2, &B.conv2, w2, B.cout, B.cout, 0, 3, centre, sc.data(), sh.data(), desc->precision);
+        // block time MLP (raw)
+        const float* tw = sd.get(nm + ".time_mlp.weight", (int64_t)B.cout * temb, &err);
+        const float* tb = sd.get(nm + ".time_mlp.bias", B.cout, &err);
+        if (err) break;
+        o_bw[b] = A.alloc((size_t)B.cout * temb); memcpy(&A.h[o_bw[b]], tw, sizeof(float) * B.cout * temb);
+        o_bb[b] = A.alloc(B.cout); memcpy(&A.h[o_bb[b]], tb, sizeof(float) * B.cout);
+    }
+    auto copy_in = [&](const char* key, int64_t n, size_t* o) {
+        const float* p = sd.get(key, n, &err);
+        if (!p) return;
+        *o = A.alloc(n);
+        memcpy(&A.h[*o], p, sizeof(float) * n);
+    };
+    if (!err) {
+        copy_in("time_mlp.1.weight", (int64_t)temb * temb, &o_tw1); copy_in("time_mlp.1.bias", temb, &o_tb1);
+        copy_in("cond_emb.0.weight", temb, &o_cw0); copy_in("cond_emb.0.bias", temb, &o_cb0);
+        copy_in("cond_emb.2.weight", (int64_t)temb * temb, &o_cw2); copy_in("cond_emb.2.bias", temb, &o_cb2);
+    }
+    if (!err) {
+        const float* fw = sd.get("final.weight", (int64_t)C * d[0], &err);
+        const float* fb = sd.get("final.bias", C, &err);
+        if (!err) {
+            o_finw = A.alloc((size_t)C * u->dp[0]); o_finb = A.alloc(4);
+            for (int c = 0; c < C; ++c) {
+                for (int k = 0; k < d[0]; ++k) A.h[o_finw + (size_t)c * u->dp[0] + k] = fw[(size_t)c * d[0] + k];
+                A.h[o_finb + c] = fb[c];
+            }
+        }
+    }
+    if (err) { delete u; return err; }
+
+    // time table layout
+    int tbs = 0;
+    for (int b = 0; b < 8; ++b) { u->tb_off[b] = tbs; tbs += round_up(cout[b], kCPad); }
+    u->tb_stride = tbs;
+    const size_t o_table = A.alloc((size_t)T * 3 * tbs);
+
+    u->dev_floats = A.h.size();
+    cudaError_t ce = cudaMalloc(&u->dev, u->dev_floats * sizeof(float));
+    if (ce != cudaSuccess) { delete u; return fail(DTRAJ_ECUDA, "cudaMalloc(weights %zu B) -> %s", u->dev_floats * 4, cudaGetErrorString(ce)); }
+    ce = cudaMemcpy(u->dev, A.h.data(), u->dev_floats * sizeof(float), cudaMemcpyHostToDevice);
+    if (ce != cudaSuccess) { dtraj_unet_destroy(u); return fail(DTRAJ_ECUDA, "weight upload -> %s", cudaGetErrorString(ce)); }
+    float* D = u->dev;
+    for (int b = 1; b < 8; ++b) {
+        u->blk[b].conv1.w = D + off[b].w1; u->blk[b].conv1.bias = D + off[b].b1;
+        if (u->blk[b].has_res) { u->blk[b].res.w = D + off[b].wr; u->blk[b].res.bias = D + off[b].br; }
+    }
+    for (int b = 0; b < 8; ++b) { u->blk[b].conv2.w = D + off[b].w2; u->blk[b].conv2.bias = D + off[b].b2; }
+    u->fw3 = D + o_fw3; u->fb3 = D + o_fb3; u->fw1 = D + o_fw1; u->fb1 = D + o_fb1;
+    u->finw = D + o_finw; u->finb = D + o_finb;
+    u->table = D + o_table;
+
+    // time table on the device
+    TimeTableParams tp;
+    tp.temb = temb; tp.half = std::max(std::max(temb, 2) / 2, 1);
+    tp.freq_scale = (float)(-(std::log(10000.0) / ((double)tp.half - 1.0 + 1e-8)));
+    tp.w1 = D + o_tw1; tp.b1 = D + o_tb1; tp.cw0 = D + o_cw0; tp.cb0 = D + o_cb0; tp.cw2 = D + o_cw2; tp.cb2 = D + o_cb2;
+    for (int b = 0; b < 8; ++b) { tp.bw[b] = D + o_bw[b]; tp.bb[b] = D + o_bb[b]; tp.bcout[b] = cout[b]; tp.boff[b] = u->tb_off[b]; }
+    tp.tb_stride = tbs; tp.table = u->table;
+    k_time_table<<<dim3(T, 3), 256, 3 * temb * sizeof(float)>>>(tp);
+    ce = cudaGetLastError();
+    if (ce == cudaSuccess) ce = cudaDeviceSynchronize();
+    if (ce != cudaSuccess) { dtraj_unet_destroy(u); return fail(DTRAJ_ECUDA, "time table kernel -> %s", cudaGetErrorString(ce)); }
+    if (desc->precision != DTRAJ_PREC_FP32) {
+        ce = cudaFuncSetAttribute(k_conv_umma, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (ce != cudaSuccess) { dtraj_unet_destroy(u); return fail(DTRAJ_ECUDA, "smem attribute -> %s", cudaGetErrorString(ce)); }
+    }
+    *out = u;
+    return 0;
+}
+
+extern "C" int dtraj_unet_time_bias(const dtraj_unet* u, int32_t t, int32_t variant, int32_t block, float* out_host, int32_t n) {
+    if (!u || t < 0 || t >= u->d.n_timesteps || variant < 0 || variant > 2 || block < 0 || block > 7 || n > u->blk[block].cout)
+        return fail(DTRAJ_EINVAL, "time_bias: bad argument");
+    DTRAJ_CUDA(cudaMemcpy(out_host, u->table + (size_t)(t * 3 + variant) * u->tb_stride + u->tb_off[block], sizeof(float) * n,
+                          cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+// ======================================================================================
+// forward plan: workspace carving + one launch record per kernel
+// ======================================================================================
+struct dtraj_plan {
+    const dtraj_unet* u = nullptr;
+    int64_t R = 0;
+    float* ws = nullptr;
+    // buffers (float offsets into ws); lo planes follow at +size when act_mode == ACT_SPLIT
+    struct Buf { float* p = nullptr; int64_t n = 0; int64_t lo = 0; };
+    Buf tmp_h, tmp_r, tmp_x, p1, x2, p2, x3, p3, x4, p4, u3, u2, u1, y1, elow;
+    // generic conv launches in execution order
+    struct ConvOp { ConvLayer L; bool umma; UmmaLaunch U; int tb_block; };
+    std::vector<ConvOp> convs;   // 15 3x3 + residual 1x1s
+    int64_t launches_per_forward = 0;
+};
+
+namespace {
+
+int64_t plan_floats(const dtraj_unet* u, int64_t R, dtraj_plan* P) {
+    const int* dp = u->dp;
+    const int* S = u->sizes;
+    const int C = u->d.channels;
+    const bool split = u->act_mode == ACT_SPLIT;
+    int64_t off = 0;
+    auto take = [&](dtraj_plan::Buf* b, int64_t per_row, bool lo_plane) {
+        int64_t n = round_up64(R * per_row, 256);
+        if (P) { b->p = P->ws + off; b->n = n; b->lo = (split && lo_plane) ? n : 0; }
+        off += n * ((split && lo_plane) ? 2 : 1);
+    };
+    auto px = [&](int l) { return (int64_t)S[l] * S[l]; };
+    dtraj_plan dummy;
+    dtraj_plan* Q = P ? P : &dummy;
+    int64_t mh = 0;
+    for (int b = 0; b < 8; ++b) {
+        const int lv[8] = {0, 1, 2, 3, 4, 3, 2, 1};
+        const int co[8] = {dp[0], dp[1], dp[2], dp[3], dp[3], dp[2], dp[1], dp[0]};
+        mh = std::max(mh, px(lv[b]) * co[b]);
+    }
+    take(&Q->tmp_h, mh, true);
+    take(&Q->tmp_r, mh, false);
+    take(&Q->tmp_x, mh, true);
+    take(&Q->p1, px(1) * dp[0], true);
+    take(&Q->x2, px(1) * dp[1], true);
+    take(&Q->p2, px(2) * dp[1], true);
+    take(&Q->x3, px(2) * dp[2], true);
+    take(&Q->p3, px(3) * dp[2], true);
+    take(&Q->x4, px(3) * dp[3], true);
+    take(&Q->p4, px(4) * dp[3], true);
+    take(&Q->u3, px(3) * dp[3], true);
+    take(&Q->u2, px(2) * dp[2], true);
+    take(&Q->u1, px(1) * dp[1], true);
+    take(&Q->y1, px(1) * dp[0], false);
+    take(&Q->elow, px(1) * C, false);
+    return off;
+}
+
+int add_conv(dtraj_plan* P, const PackedConv& pc, const dtraj_plan::Buf& s0, const dtraj_plan::Buf* s1, int S,
+             const dtraj_plan::Buf& out, const float* resid, int flags, int tb_block, bool is_residual_conv) {
+    const dtraj_unet* u = P->u;
+    dtraj_plan::ConvOp op;
+    memset(&op.L, 0, sizeof(op.L));
+    ConvLayer& L = op.L;
+    L.src0 = s0.p; L.src0_lo = s0.p + s0.lo; L.c0p = pc.c0p;
+    if (s1) { L.src1 = s1->p; L.src1_lo = s1->p + s1->lo; L.c1p = pc.c1p; }
+    L.H = S; L.W = S; L.M = P->R * S * S; L.ntaps = pc.ntaps;
+    L.wpk = pc.w; L.bias = pc.bias; L.coutp = pc.coutp;
+    L.tb_var_stride = u->tb_stride;
+    L.resid = resid; L.out = out.p;
+    L.lo_off = out.lo;
+    L.act_mode = is_residual_conv ? ACT_PLAIN : (u->act_mode == ACT_SPLIT && out.lo == 0 ? ACT_PLAIN : u->act_mode);
+    L.flags = flags;
+    op.tb_block = tb_block;
+    op.umma = u->d.precision != DTRAJ_PREC_FP32;
+    if (op.umma) DTRAJ_TRY(build_umma_launch(&op.U, L, u->d.precision == DTRAJ_PREC_TF32X3 ? 3 : 1, pc.w, pc.rows));
+    P->convs.push_back(op);
+    return 0;
+}
+
+int plan_build(const dtraj_unet* u, int64_t R, void* ws, int64_t ws_bytes, dtraj_plan** out) {
+    if (R < 1) return fail(DTRAJ_EINVAL, "n_rows must be >= 1");
+    const int64_t need = plan_floats(u, R, nullptr) * 4;
+    if (ws_bytes < need) return fail(DTRAJ_ENOMEM, "workspace %lld B < required %lld B", (long long)ws_bytes, (long long)need);
+    if (((uintptr_t)ws & 255) != 0) return fail(DTRAJ_EINVAL, "workspace must be 256-byte aligned");
+    dtraj_plan* P = new dtraj_plan();
+    P->u = u; P->R = R; P->ws = (float*)ws;
+    plan_floats(u, R, P);
+    const int* S = u->sizes;
+    int rc = 0;
+    const int RT = CONV_RELU | CONV_TBIAS, RR = CONV_RELU | CONV_RESID;
+    auto blk = [&](int b) -> const BlockW& { return u->blk[b]; };
+#define ADD(...) if (!rc) rc = add_conv(P, __VA_ARGS__)
+    // enc1: conv1/res by k_conv_first; conv2 here
+    ADD(blk(0).conv2, P->tmp_h, nullptr, S[0], P->tmp_x, P->tmp_r.p, RR, -1, false);
+    // enc2 @ level 1
+    ADD(blk(1).res, P->p1, nullptr, S[1], P->tmp_r, nullptr, 0, -1, true);
+    ADD(blk(1).conv1, P->p1, nullptr, S[1], P->tmp_h, nullptr, RT, 1, false);
+    ADD(blk(1).conv2, P->tmp_h, nullptr, S[1], P->x2, P->tmp_r.p, RR, -1, false);
+    // enc3 @ level 2 (identity residual = pooled input)
+    const dtraj_plan::Buf* pin[3] = {&P->p2, &P->p3, &P->p4};
+    const dtraj_plan::Buf* xo[3] = {&P->x3, &P->x4, &P->tmp_x};
+    for (int k = 0; k < 3 && !rc; ++k) {
+        const int b = 2 + k, lv = 2 + k;
+        const float* resid = pin[k]->p;
+        if (blk(b).has_res) { ADD(blk(b).res, *pin[k], nullptr, S[lv], P->tmp_r, nullptr, 0, -1, true); resid = P->tmp_r.p; }
+        ADD(blk(b).conv1, *pin[k], nullptr, S[lv], P->tmp_h, nullptr, RT, b, false);
+        ADD(blk(b).conv2, P->tmp_h, nullptr, S[lv], *xo[k], resid, RR, -1, false);
+    }
+    // decoders: [upsampled | skip]
+    const dtraj_plan::Buf* up[3] = {&P->u3, &P->u2, &P->u1};
+    const dtraj_plan::Buf* skip[3] = {&P->x4, &P->x3, &P->x2};
+    const dtraj_plan::Buf* yo[3] = {&P->tmp_x, &P->tmp_x, &P->y1};
+    for (int k = 0; k < 3 && !rc; ++k) {
+        const int b = 5 + k, lv = 3 - k;
+        if (!blk(b).has_res) { rc = fail(DTRAJ_EINVAL, "%s without residual_conv unsupported", kBlockNames[b]); break; }
+        ADD(blk(b).res, *up[k], skip[k], S[lv], P->tmp_r, nullptr, 0, -1, true);
+        ADD(blk(b).conv1, *up[k], skip[k], S[lv], P->tmp_h, nullptr, RT, b, false);
+        ADD(blk(b).conv2, P->tmp_h, nullptr, S[lv], *yo[k], P->tmp_r.p, RR, -1, false);
+    }
+#undef ADD
+    if (rc) { delete P; return rc; }
+    *out = P;
+    return 0;
+}
+
+inline unsigned blocks_for(int64_t n, int per) { return (unsigned)((n + per - 1) / per); }
+
+// Enqueue one U-Net forward (models.py:159-224 up to the half-resolution eps map).
+int plan_forward(dtraj_plan* P, const float* x, int64_t x_stride, const int32_t* row_sample,
+                 const int32_t* row_variant, int t, cudaStream_t st, int64_t* launches) {
+    const dtraj_unet* u = P->u;
+    if (t < 0 || t >= u->d.n_timesteps) return fail(DTRAJ_EINVAL, "timestep %d outside the time table (0..%d)", t, u->d.n_timesteps - 1);
+    const int* S = u->sizes;
+    const int* dp = u->dp;
+    const int C = u->d.channels;
+    const int64_t R = P->R;
+    const float* trow = u->table + (size_t)t * 3 * u->tb_stride;
+    int64_t nl = 0;
+    {   // enc1.conv1 + residual
+        FirstConvParams f;
+        f.x = x; f.x_stride = x_stride; f.row_sample = row_sample; f.row_variant = row_variant;
+        f.C = C; f.H = S[0]; f.W = S[0]; f.coutp = dp[0];
+        f.w3 = u->fw3; f.b3 = u->fb3; f.w1 = u->fw1; f.b1 = u->fb1;
+        f.tbias = trow + u->tb_off[0]; f.tb_var_stride = u->tb_stride;
+        f.h = P->tmp_h.p; f.r = P->tmp_r.p; f.lo_off = P->tmp_h.lo; f.act_mode = u->act_mode;
+        const size_t smem = (round_up(C * (S[0] + 2) * (S[0] + 2), 4) + 10 * C * dp[0]) * sizeof(float);
+        k_conv_first<<<(unsigned)R, 256, smem, st>>>(f);
+        DTRAJ_LAUNCH_CHECK(); ++nl;
+    }
+    size_t ci = 0;
+    auto conv = [&]() -> int {
+        dtraj_plan::ConvOp& op = P->convs[ci++];
+        const float* tb = op.tb_block >= 0 ? trow + u->tb_off[op.tb_block] : nullptr;
+        ++nl;
+        if (op.umma) {
+            op.U.conv.L.tbias = tb; op.U.conv.L.row_variant = row_variant;
+            return launch_conv_umma(op.U, st);
+        }
+        op.L.tbias = tb; op.L.row_variant = row_variant;
+        return launch_conv_simt(op.L, st);
+    };
+    auto pool = [&](const dtraj_plan::Buf& in, const dtraj_plan::Buf& out, int So, int cp) -> int {
+        const int64_t n4 = R * So * So * (cp / 4);
+        k_pool2<<<blocks_for(n4, 256), 256, 0, st>>>(in.p, out.p, n4, So, So, cp / 4, out.lo, out.lo ? ACT_SPLIT : ACT_PLAIN);
+        DTRAJ_LAUNCH_CHECK(); ++nl;
+        return 0;
+    };
+    auto upsample = [&](const dtraj_plan::Buf& in, const dtraj_plan::Buf& out, int Si, int cp) -> int {
+        const int64_t n4 = R * (2 * Si) * (2 * Si) * (cp / 4);
+        k_upsample2<<<blocks_for(n4, 256), 256, 0, st>>>(in.p, out.p, n4, Si, Si, cp / 4, out.lo,
+                                                        (u->act_mode == ACT_SPLIT && !out.lo) ? ACT_PLAIN : u->act_mode);
+        DTRAJ_LAUNCH_CHECK(); ++nl;
+        return 0;
+    };
+    DTRAJ_TRY(conv());                                   // enc1.conv2 -> x1 (tmp_x)
+    DTRAJ_TRY(pool(P->tmp_x, P->p1, S[1], dp[0]));
+    DTRAJ_TRY(conv()); DTRAJ_TRY(conv()); DTRAJ_TRY(conv());   // enc2 -> x2
+    DTRAJ_TRY(pool(P->x2, P->p2, S[2], dp[1]));
+    const dtraj_plan::Buf* xo[3] = {&P->x3, &P->x4, &P->tmp_x};
+    const dtraj_plan::Buf* pn[2] = {&P->p3, &P->p4};
+    for (int k = 0; k < 3; ++k) {                        // enc3, enc4, bottleneck
+        if (u->blk[2 + k].has_res) DTRAJ_TRY(conv());
+        DTRAJ_TRY(conv()); DTRAJ_TRY(conv());
+        if (k < 2) DTRAJ_TRY(pool(*xo[k], *pn[k], S[3 + k], dp[2 + k]));
+    }
+    const dtraj_plan::Buf* up[3] = {&P->u3, &P->u2, &P->u1};
+    const int upc[3] = {dp[3], dp[2], dp[1]};
+    for (int k = 0; k < 3; ++k) {                        // dec3, dec2, dec1
+        DTRAJ_TRY(upsample(P->tmp_x, *up[k], S[4 - k], upc[k]));
+        DTRAJ_TRY(conv()); DTRAJ_TRY(conv()); DTRAJ_TRY(conv());
+    }
+    {   // final 1x1 at half resolution
+        const int64_t npix = R * S[1] * S[1];
+        k_final1x1<<<blocks_for(npix * 32, 256), 256, 0, st>>>(P->y1.p, u->finw, u->finb, P->elow.p, npix, dp[0], C);
+        DTRAJ_LAUNCH_CHECK(); ++nl;
+    }
+    if (launches) *launches += nl;
+    return 0;
+}
+
+}  // namespace
+
+extern "C" int64_t dtraj_unet_workspace_bytes(const dtraj_unet* u, int64_t n_rows) {
+    if (!u || n_rows < 1) return -1;
+    return plan_floats(u, n_rows, nullptr) * 4;
+}
+
+extern "C" int dtraj_unet_destroy(dtraj_unet* u) {
+    if (!u) return 0;
+    if (u->plan) delete u->plan;
+    if (u->dev) cudaFree(u->dev);
+    delete u;
+    return 0;
+}
+
+extern "C" int dtraj_unet_forward(dtraj_unet* u, const float* x, int64_t n_rows, int32_t t, const int32_t* row_variant,
+                                  float* eps, void* workspace, int64_t workspace_bytes, void* stream) {
+    if (!u || !x || !eps || !workspace) return fail(DTRAJ_EINVAL, "null argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!u->plan || u->plan->R != n_rows || u->plan->ws != (float*)workspace) {
+        if (u->plan) { delete u->plan; u->plan = nullptr; }
+        DTRAJ_TRY(plan_build(u, n_rows, workspace, workspace_bytes, &u->plan));
+    }
+    const int C = u->d.channels, H = u->d.image_size;
+    DTRAJ_TRY(plan_forward(u->plan, x, (int64_t)C * H * H, nullptr, row_variant, t, st, nullptr));
+    const int64_t n = n_rows * C * H * H;
+    k_eps_out<<<blocks_for(n, 256), 256, 0, st>>>(u->plan->elow.p, eps, n, C, H, H);
+    DTRAJ_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int dtraj_step_fused(int32_t rule, const float* k, const float* eps_u, const float* eps_c, const float* w,
+                                const float* x, int64_t x_stride, const float* z, int64_t z_stride, float* x_out,
+                                int64_t out_stride, int64_t n_samples, int64_t D, void* stream) {
+    if (rule < 1 || rule > 3 || !k || !eps_u || !x || !x_out) return fail(DTRAJ_EINVAL, "step: bad argument");
+    if (eps_c && !w) return fail(DTRAJ_EINVAL, "step: eps_c given without guidance weights");
+    if (n_samples * D == 0) return 0;
+    k_step_plain<<<blocks_for(n_samples * D, 256), 256, 0, (cudaStream_t)stream>>>(rule, k[0], k[1], k[2], eps_u, eps_c, w, x,
+                                                                                    x_stride, z, z_stride, x_out, out_stride,
+                                                                                    n_samples, D);
+    DTRAJ_LAUNCH_CHECK();
+    return 0;
+}
+
+// ======================================================================================
+// sampler: n_updates x { forward, fused step } (+ duplicate frame), optionally one CUDA graph
+// ======================================================================================
+struct dtraj_sampler {
+    dtraj_unet* u = nullptr;
+    dtraj_sampler_desc d;
+    std::vector<int32_t> ts;
+    std::vector<float> coef;
+    dtraj_plan* plan = nullptr;
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    int64_t launches = 0;
+};
+
+namespace {
+
+int sampler_enqueue(dtraj_sampler* s, cudaStream_t st, int64_t* launches) {
+    const dtraj_sampler_desc& d = s->d;
+    const int C = s->u->d.channels, H = s->u->d.image_size;
+    const int64_t D = (int64_t)C * H * H, fs = (int64_t)d.n_frames * D;
+    int64_t nl = 0;
+    for (int k = 0; k < d.n_updates; ++k) {
+        const float* xin = d.traj + (int64_t)k * D;
+        DTRAJ_TRY(plan_forward(s->plan, xin, fs, d.row_sample, d.row_variant, s->ts[k], st, &nl));
+        StepParams p;
+        p.rule = d.rule; p.k0 = s->coef[3 * k]; p.k1 = s->coef[3 * k + 1]; p.k2 = s->coef[3 * k + 2];
+        p.elow = s->plan->elow.p; p.sample_row_u = d.sample_row_u; p.sample_row_c = d.sample_row_c;
+        p.guidance = d.guidance; p.z_bank = d.z_bank;
+        p.z_index = d.z_index ? d.z_index + (int64_t)k * d.n_samples : nullptr;
+        p.x_in = xin; p.x_out = d.traj + (int64_t)(k + 1) * D; p.frame_stride = fs;
+        p.B = d.n_samples; p.C = C; p.H = H; p.W = H;
+        const int64_t nthr = (int64_t)d.n_samples * C * H * (H / 4);
+        k_step<<<blocks_for(nthr, 256), 256, 0, st>>>(p);
+        DTRAJ_LAUNCH_CHECK(); ++nl;
+    }
+    if (d.copy_last) {
+        const int64_t k = d.n_updates;
+        k_copy_frame<<<blocks_for((int64_t)d.n_samples * (D / 4), 256), 256, 0, st>>>(d.traj + k * D, d.traj + (k + 1) * D, fs,
+                                                                                      d.n_samples, (int)(D / 4));
+        DTRAJ_LAUNCH_CHECK(); ++nl;
+    }
+    if (launches) *launches = nl;
+    return 0;
+}
+
+}  // namespace
+
+extern "C" int dtraj_sampler_destroy(dtraj_sampler* s) {
+    if (!s) return 0;
+    if (s->exec) cudaGraphExecDestroy(s->exec);
+    if (s->graph) cudaGraphDestroy(s->graph);
+    if (s->plan) delete s->plan;
+    delete s;
+    return 0;
+}
+
+extern "C" int dtraj_sampler_create(dtraj_unet* u, const dtraj_sampler_desc* d, dtraj_sampler** out) {
+    if (!u || !d || !out) return fail(DTRAJ_EINVAL, "null argument");
+    if (d->rule < 1 || d->rule > 3) return fail(DTRAJ_EINVAL, "bad rule %d", d->rule);
+    if (d->n_samples < 1 || d->n_rows < d->n_samples || d->n_rows > 2 * d->n_samples) return fail(DTRAJ_EINVAL, "bad n_samples/n_rows");
+    if (d->n_updates < 0 || d->n_frames != 1 + d->n_updates + (d->copy_last ? 1 : 0)) return fail(DTRAJ_EINVAL, "n_frames != 1 + n_updates + copy_last");
+    if (!d->traj || !d->workspace || !d->row_sample || !d->row_variant || !d->sample_row_u) return fail(DTRAJ_EINVAL, "null device array");
+    if (d->n_updates && (!d->step_timestep || !d->step_coef)) return fail(DTRAJ_EINVAL, "null step tables");
+    if (d->sample_row_c && !d->guidance) return fail(DTRAJ_EINVAL, "sample_row_c given without guidance");
+    if (d->z_index && !d->z_bank) return fail(DTRAJ_EINVAL, "z_index given without z_bank");
+    dtraj_sampler* s = new dtraj_sampler();
+    s->u = u; s->d = *d;
+    s->ts.assign(d->step_timestep, d->step_timestep + d->n_updates);
+    s->coef.assign(d->step_coef, d->step_coef + 3 * (size_t)d->n_updates);
+    s->d.step_timestep = nullptr; s->d.step_coef = nullptr;
+    for (int k = 0; k < d->n_updates; ++k)
+        if (s->ts[k] < 0 || s->ts[k] >= u->d.n_timesteps) {
+            int t = s->ts[k];
+            delete s;
+            return fail(DTRAJ_EINVAL, "step %d: timestep %d outside the time table", k, t);
+        }
+    int rc = plan_build(u, d->n_rows, d->workspace, d->workspace_bytes, &s->plan);
+    if (rc) { delete s; return rc; }
+    if (d->use_graph) {
+        cudaStream_t cs;
+        cudaError_t ce = cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking);
+        if (ce != cudaSuccess) { dtraj_sampler_destroy(s); return fail(DTRAJ_ECUDA, "stream create -> %s", cudaGetErrorString(ce)); }
+        ce = cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal);
+        if (ce == cudaSuccess) {
+            rc = sampler_enqueue(s, cs, &s->launches);
+            cudaError_t ce2 = cudaStreamEndCapture(cs, &s->graph);
+            if (rc == 0 && ce2 != cudaSuccess) rc = fail(DTRAJ_ECUDA, "graph capture -> %s", cudaGetErrorString(ce2));
+            if (rc == 0) {
+                ce2 = cudaGraphInstantiate(&s->exec, s->graph, 0);
+                if (ce2 != cudaSuccess) rc = fail(DTRAJ_ECUDA, "graph instantiate -> %s", cudaGetErrorString(ce2));
+            }
+        } else rc = fail(DTRAJ_ECUDA, "begin capture -> %s", cudaGetErrorString(ce));
+        cudaStreamDestroy(cs);
+        if (rc) { dtraj_sampler_destroy(s); return rc; }
+    } else {
+        // dry count of launches
+        s->launches = (int64_t)d->n_updates * (2 + (int64_t)s->plan->convs.size() + 4 + 3 + 1) + (d->copy_last ? 1 : 0);
+    }
+    *out = s;
+    return 0;
+}
+
+extern "C" int dtraj_sampler_run(dtraj_sampler* s, void* stream) {
+    if (!s) return fail(DTRAJ_EINVAL, "null sampler");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (s->exec) { DTRAJ_CUDA(cudaGraphLaunch(s->exec, st)); return 0; }
+    return sampler_enqueue(s, st, nullptr);
+}
+
+extern "C" int64_t dtraj_sampler_launches(const dtraj_sampler* s) { return s ? s->launches : -1; }
+
+// ======================================================================================
+// metrics
+// ======================================================================================
+extern "C" int dtraj_metrics_pairs(const float* teacher, const float* student, int64_t N, int32_t L, int32_t D, float* out, void* stream) {
+    if (!teacher || !student || !out || N < 0) return fail(DTRAJ_EINVAL, "metrics: bad argument");
+    return launch_metrics_pairs(teacher, student, N, L, D, out, (cudaStream_t)stream);
+}
+
+extern "C" int dtraj_wasserstein(const float* teacher, const float* student, int64_t N, int32_t L, int32_t D, const int32_t* idx,
+                                 const int32_t* idx_set, int32_t K, float* out, void* stream) {
+    if (!teacher || !student || !out || N < 0 || L < 1) return fail(DTRAJ_EINVAL, "wasserstein: bad argument");
+    return launch_wasserstein(teacher, student, N, L, D, idx, idx_set, K, out, (cudaStream_t)stream);
+}
+
+// ======================================================================================
+// test hooks
+// ======================================================================================
+extern "C" unsigned int dtraj_debug_umma_error(void) {
+    unsigned int v = 0;
+    cudaMemcpyFromSymbol(&v, g_umma_error, sizeof(v));
+    return v;
+}
+
+extern "C" int dtraj_test_conv(int32_t precision, const float* x0, int32_t c0, const float* x1, int32_t c1, int64_t n, int32_t H,
+                               int32_t W, const float* w_host, const float* bias_host, int32_t cout, int32_t ksize, int32_t flags,
+                               const float* resid, float* out, void* stream) {
+    if (H != W) return fail(DTRAJ_EINVAL, "test_conv: H must equal W");
+    if (ksize != 1 && ksize != 3) return fail(DTRAJ_EINVAL, "test_conv: ksize must be 1 or 3");
+    cudaStream_t st = (cudaStream_t)stream;
+    Arena A;
+    PackedConv pc;
+    size_t wo, bo;
+    std::vector<double> shift(cout);
+    for (int i = 0; i < cout; ++i) shift[i] = bias_host[i];
+    pack_conv(&A, &wo, &bo, &pc, w_host, cout, c0, c1, ksize, ksize == 3 && H == 1, nullptr, shift.data(), precision);
+    float* dev = nullptr;
+    DTRAJ_CUDA(cudaMalloc(&dev, A.h.size() * sizeof(float)));
+    DTRAJ_CUDA(cudaMemcpy(dev, A.h.data(), A.h.size() * sizeof(float), cudaMemcpyHostToDevice));
+    ConvLayer L;
+    memset(&L, 0, sizeof(L));
+    const int64_t M = n * H * W;
+    L.src0 = x0; L.c0p = pc.c0p; L.src1 = x1; L.c1p = pc.c1p;
+    L.H = H; L.W = W; L.M = M; L.ntaps = pc.ntaps; L.wpk = dev + wo; L.bias = dev + bo; L.coutp = pc.coutp;
+    L.resid = resid; L.out = out; L.flags = (flags & 1 ? CONV_RELU : 0) | (resid ? CONV_RESID : 0);
+    L.act_mode = (flags & 2) ? ACT_ROUND : ACT_PLAIN;
+    int rc = 0;
+    float* lo = nullptr;
+    if (precision == DTRAJ_PREC_FP32) rc = launch_conv_simt(L, st);
+    else {
+        if (precision == DTRAJ_PREC_TF32X3) {
+            // low planes of the inputs, computed here for the test
+            const int64_t n0 = M * pc.c0p, n1 = M * pc.c1p;
+            std::vector<float> h(n0 + n1);
+            cudaMalloc(&lo, (n0 + n1) * sizeof(float));
+            cudaMemcpy(h.data(), x0, n0 * sizeof(float), cudaMemcpyDeviceToHost);
+            if (n1) cudaMemcpy(h.data() + n0, x1, n1 * sizeof(float), cudaMemcpyDeviceToHost);
+            for (auto& v : h) v = v - tf32_trunc(v);
+            cudaMemcpy(lo, h.data(), (n0 + n1) * sizeof(float), cudaMemcpyHostToDevice);
+            L.src0_lo = lo; L.src1_lo = lo + n0;
+        }
+        cudaFuncSetAttribute(k_conv_umma, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        UmmaLaunch U;
+        rc = build_umma_launch(&U, L, precision == DTRAJ_PREC_TF32X3 ? 3 : 1, dev + wo, pc.rows);
+        if (!rc) rc = launch_conv_umma(U, st);
+    }
+    cudaError_t ce = cudaStreamSynchronize(st);
+    cudaFree(dev);
+    if (lo) cudaFree(lo);
+    if (rc) return rc;
+    if (ce != cudaSuccess) return fail(DTRAJ_ECUDA, "test_conv -> %s", cudaGetErrorString(ce));
+    return 0;
+}

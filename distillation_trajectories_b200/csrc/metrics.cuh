@@ -1,0 +1,192 @@
+// Streaming trajectory-metric reductions (HBM-bound): every element of the teacher and the
+// student trajectory tensors [N, L, D] is read exactly once with 128-bit loads.
+//   reference per-frame reductions: analysis/metrics/trajectory_metrics.py:55-215
+//                                   analysis/metrics/time_dependent.py:57,78
+//   Wasserstein per frame:          analysis/metrics/trajectory_metrics.py:296-312
+#pragma once
+#include "common.cuh"
+
+namespace dtraj {
+
+constexpr int kMetricQ = 6;   // floats per (pair, frame) in the output
+
+// One group of G threads owns one trajectory pair and walks its L frames in order, keeping
+// the previous frame (and frame 0) in registers: no element is loaded twice.  Per-warp
+// partial sums of all frames are parked in shared memory, so there is a single barrier per
+// pair instead of one per frame.
+//   out[n][i][0] = sum (T_i - S_i)^2
+//   out[n][i][1] = sum (T_{i+1} - T_i)^2, [2] same for S, [3] = sum dT_i * dS_i     (i < L-1)
+//   out[n][0][4] = sum (T_{L-1} - T_0)^2, out[n][0][5] same for S
+template <int K>   // float4 per thread per frame
+__global__ void __launch_bounds__(256) k_metrics_pairs(const float* __restrict__ teacher,
+                                                       const float* __restrict__ student,
+                                                       int64_t N, int L, int D4, int G, float* __restrict__ out) {
+    extern __shared__ float part[];          // [pairs_per_block][L][warps_per_group][4]
+    const int ppb = 256 / G, wpg = G / 32 > 0 ? G / 32 : 1;
+    const int g = threadIdx.x / G, tg = threadIdx.x % G;
+    const int warp_in_group = tg >> 5, lane = threadIdx.x & 31;
+    const int64_t n = (int64_t)blockIdx.x * ppb + g;
+    const bool active = n < N;
+    float* mypart = part + (size_t)g * L * wpg * 4;
+    float4 firstT[K], firstS[K], prevT[K], prevS[K], nxtT[K], nxtS[K];
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4* Tb = reinterpret_cast<const float4*>(teacher) + (active ? n : 0) * (int64_t)L * D4;
+    const float4* Sb = reinterpret_cast<const float4*>(student) + (active ? n : 0) * (int64_t)L * D4;
+    auto load_frame = [&](int i, float4* t, float4* s) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const int e = tg + k * G;
+            if (active && e < D4) {
+                t[k] = ld_stream4(reinterpret_cast<const float*>(Tb + (int64_t)i * D4 + e));
+                s[k] = ld_stream4(reinterpret_cast<const float*>(Sb + (int64_t)i * D4 + e));
+            } else { t[k] = zero4; s[k] = zero4; }
+        }
+    };
+    auto sq4 = [](float4 a) { return a.x * a.x + a.y * a.y + a.z * a.z + a.w * a.w; };
+    auto sub4 = [](float4 a, float4 b) { return make_float4(a.x - b.x, a.y - b.y, a.z - b.z, a.w - b.w); };
+    auto dot4 = [](float4 a, float4 b) { return a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w; };
+
+    load_frame(0, nxtT, nxtS);
+    float endT = 0.f, endS = 0.f;
+    for (int i = 0; i < L; ++i) {
+        float4 curT[K], curS[K];
+#pragma unroll
+        for (int k = 0; k < K; ++k) { curT[k] = nxtT[k]; curS[k] = nxtS[k]; }
+        if (i + 1 < L) load_frame(i + 1, nxtT, nxtS);
+        float d2 = 0.f, vt2 = 0.f, vs2 = 0.f, dot = 0.f;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            d2 += sq4(sub4(curT[k], curS[k]));
+            if (i > 0) {
+                float4 dt = sub4(curT[k], prevT[k]), ds = sub4(curS[k], prevS[k]);
+                vt2 += sq4(dt); vs2 += sq4(ds); dot += dot4(dt, ds);
+            } else { firstT[k] = curT[k]; firstS[k] = curS[k]; }
+            prevT[k] = curT[k]; prevS[k] = curS[k];
+        }
+        if (i == L - 1) {
+#pragma unroll
+            for (int k = 0; k < K; ++k) { endT += sq4(sub4(curT[k], firstT[k])); endS += sq4(sub4(curS[k], firstS[k])); }
+        }
+        d2 = warp_sum(d2); vt2 = warp_sum(vt2); vs2 = warp_sum(vs2); dot = warp_sum(dot);
+        if (lane == 0) {
+            // velocity-type sums of step (i-1 -> i) belong to frame index i-1
+            mypart[(i * wpg + warp_in_group) * 4 + 0] = d2;
+            if (i > 0) {
+                float* q = mypart + ((i - 1) * wpg + warp_in_group) * 4;
+                q[1] = vt2; q[2] = vs2; q[3] = dot;
+            }
+            if (i == L - 1) { float* q = mypart + (i * wpg + warp_in_group) * 4; q[1] = 0.f; q[2] = 0.f; q[3] = 0.f; }
+        }
+    }
+    endT = warp_sum(endT); endS = warp_sum(endS);
+    __shared__ float endpart[8][2];
+    if (lane == 0) { endpart[threadIdx.x >> 5][0] = endT; endpart[threadIdx.x >> 5][1] = endS; }
+    __syncthreads();
+    if (!active) return;
+    float* o = out + n * (int64_t)L * kMetricQ;
+    for (int j = tg; j < L * 4; j += G) {
+        const int i = j >> 2, q = j & 3;
+        float s = 0.f;
+        for (int w = 0; w < wpg; ++w) s += mypart[(i * wpg + w) * 4 + q];
+        o[i * kMetricQ + q] = s;
+    }
+    for (int j = tg; j < L * 2; j += G) {
+        const int i = j >> 1, q = j & 1;
+        float s = 0.f;
+        if (i == 0) for (int w = 0; w < wpg; ++w) s += endpart[g * wpg + w][q];
+        o[i * kMetricQ + 4 + q] = s;
+    }
+}
+
+inline int launch_metrics_pairs(const float* T, const float* S, int64_t N, int L, int D, float* out, cudaStream_t st) {
+    if (D % 4 != 0 || D <= 0 || L < 1) return fail(DTRAJ_EINVAL, "metrics: D=%d must be a positive multiple of 4, L=%d >= 1", D, L);
+    const int D4 = D / 4;
+    int G = 32;
+    while (G < 256 && (D4 + G - 1) / G > 3) G *= 2;
+    const int K = (D4 + G - 1) / G;
+    if (K > 4) return fail(DTRAJ_EINVAL, "metrics: D=%d too large (max 4096)", D);
+    const int ppb = 256 / G, wpg = G / 32;
+    const size_t smem = (size_t)ppb * L * wpg * 4 * sizeof(float);
+    if (smem > 200 * 1024) return fail(DTRAJ_EINVAL, "metrics: L=%d too large", L);
+    const unsigned grid = (unsigned)((N + ppb - 1) / ppb);
+    if (N == 0) return 0;
+#define DTRAJ_MP(KK)                                                                              \
+    {                                                                                             \
+        if (smem > 48 * 1024)                                                                     \
+            DTRAJ_CUDA(cudaFuncSetAttribute(k_metrics_pairs<KK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        k_metrics_pairs<KK><<<grid, 256, smem, st>>>(T, S, N, L, D4, G, out);                     \
+    }
+    switch (K) {
+        case 1: DTRAJ_MP(1); break;
+        case 2: DTRAJ_MP(2); break;
+        case 3: DTRAJ_MP(3); break;
+        default: DTRAJ_MP(4); break;
+    }
+#undef DTRAJ_MP
+    DTRAJ_LAUNCH_CHECK();
+    return 0;
+}
+
+// 1-d Wasserstein distance between K gathered elements of T_i and S_i: for equal-size
+// samples W1 = mean |sort(u) - sort(v)| (scipy.stats.wasserstein_distance evaluates the
+// same quantity through the two CDFs).  One CTA per (pair, frame): gather -> bitonic sort
+// of both arrays in shared memory -> f64 sum of |a - b|.
+__global__ void __launch_bounds__(256) k_wasserstein(const float* __restrict__ teacher, const float* __restrict__ student,
+                                                     int L, int D, const int32_t* __restrict__ idx,
+                                                     const int32_t* __restrict__ idx_set, int K, int P,
+                                                     float* __restrict__ out) {
+    extern __shared__ float sv[];   // [2][P]
+    const int64_t pf = blockIdx.x;  // n*L + i
+    const int64_t n = pf / L;
+    const int i = (int)(pf % L);
+    const float* t = teacher + pf * D;
+    const float* s = student + pf * D;
+    const int32_t* ix = idx ? idx + ((int64_t)(idx_set ? idx_set[n] : 0) * L + i) * K : nullptr;
+    for (int k = threadIdx.x; k < P; k += blockDim.x) {
+        float a = INFINITY, b = INFINITY;
+        if (k < K) { const int e = ix ? ix[k] : k; a = t[e]; b = s[e]; }
+        sv[k] = a; sv[P + k] = b;
+    }
+    __syncthreads();
+    const int half = P >> 1;
+    for (int size = 2; size <= P; size <<= 1) {
+        for (int j = size >> 1; j > 0; j >>= 1) {
+            for (int ce = threadIdx.x; ce < P; ce += blockDim.x) {   // P/2 exchanges per array, two arrays
+                const int arr = ce / half, k = ce % half;
+                const int lo = ((k / j) * 2 * j) + (k % j), hi = lo + j;
+                float* v = sv + arr * P;
+                const float a = v[lo], b = v[hi];
+                const bool up = (lo & size) == 0;
+                if ((a > b) == up) { v[lo] = b; v[hi] = a; }
+            }
+            __syncthreads();
+        }
+    }
+    double acc = 0.0;
+    for (int k = threadIdx.x; k < K; k += blockDim.x) acc += (double)fabsf(sv[k] - sv[P + k]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    __shared__ double wsum[8];
+    if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double tot = 0.0;
+        for (int w = 0; w < 8; ++w) tot += wsum[w];
+        out[pf] = (float)(tot / (double)K);
+    }
+}
+
+inline int launch_wasserstein(const float* T, const float* S, int64_t N, int L, int D, const int32_t* idx,
+                              const int32_t* idx_set, int K, float* out, cudaStream_t st) {
+    if (K < 1 || K > D || K > 4096) return fail(DTRAJ_EINVAL, "wasserstein: K=%d out of range (D=%d)", K, D);
+    if (!idx && K != D) return fail(DTRAJ_EINVAL, "wasserstein: idx == NULL requires K == D");
+    if (N * L > 0x7fffffffLL) return fail(DTRAJ_EINVAL, "wasserstein: N*L too large for one launch");
+    if (N == 0) return 0;
+    int P = 2;
+    while (P < K) P *= 2;
+    k_wasserstein<<<(unsigned)(N * L), 256, 2 * P * sizeof(float), st>>>(T, S, L, D, idx, idx_set, K, P, out);
+    DTRAJ_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // namespace dtraj

@@ -1,0 +1,235 @@
+"""Host-side owners of the libdtraj handles: a packed U-Net and a captured sampling loop.
+
+PyTorch is used here only for device memory, streams and the RNG draws that must match
+the reference's noise; all arithmetic of the hot path runs inside libdtraj.so.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import (PREC_FP32, PREC_TF32, PREC_TF32X3, RULE_S1, RULE_S2, RULE_S3, VAR_COND0, VAR_COND1,
+                   VAR_NONE, DtrajError)
+
+_default_precision = {"S1": os.environ.get("DTRAJ_PRECISION_S1", os.environ.get("DTRAJ_PRECISION", "tf32x3")),
+                      "S2": os.environ.get("DTRAJ_PRECISION_S2", os.environ.get("DTRAJ_PRECISION", "tf32")),
+                      "S3": os.environ.get("DTRAJ_PRECISION_S3", os.environ.get("DTRAJ_PRECISION", "tf32")),
+                      "forward": os.environ.get("DTRAJ_PRECISION", "tf32x3")}
+
+
+def set_precision(mode, path=None):
+    """Choose the conv arithmetic: 'fp32' (CUDA cores), 'tf32' (tcgen05, one pass) or 'tf32x3'
+    (tcgen05, error-compensated).  ``path`` in {'S1','S2','S3','forward'} or None for all."""
+    if mode not in _lib.PRECISIONS:
+        raise ValueError(f"precision must be one of {sorted(_lib.PRECISIONS)}")
+    for k in ([path] if path else list(_default_precision)):
+        _default_precision[k] = mode
+
+
+def get_precision(path):
+    return _default_precision[path]
+
+
+def _require_cuda(device):
+    device = torch.device(device)
+    if device.type != "cuda":
+        raise DtrajError(f"distillation_trajectories_b200 runs on CUDA (sm_100a) only; got device '{device}'. "
+                         "There is no CPU fallback.")
+    return device
+
+
+def _model_geometry(model):
+    """Duck-typed read of a reference DiffusionUNet (models.py:95-110)."""
+    return dict(channels=int(model.channels), dims=[int(d) for d in model.dims],
+                temb_dim=int(model.time_emb_dim))
+
+
+def _weights_fingerprint(model):
+    return tuple((id(t), t._version) for t in list(model.parameters()) + list(model.buffers()))
+
+
+class UNetEngine:
+    """BN-folded, packed copy of one U-Net on one GPU + its time-embedding tables."""
+
+    def __init__(self, state_dict, channels, image_size, dims, temb_dim, n_timesteps, precision, device):
+        self.lib = _lib.load()
+        self.device = _require_cuda(device)
+        self.channels, self.image_size, self.dims, self.temb_dim = channels, image_size, list(dims), temb_dim
+        self.n_timesteps = int(n_timesteps)
+        self.precision = precision if isinstance(precision, int) else _lib.PRECISIONS[precision]
+        self.D = channels * image_size * image_size
+        desc = _lib.UNetDesc(channels, image_size, (C.c_int32 * 4)(*dims), temb_dim, self.n_timesteps, self.precision)
+        keep, names, ptrs, numel = [], [], [], []
+        for k, v in state_dict.items():
+            if not torch.is_floating_point(v):
+                continue                       # num_batches_tracked
+            a = v.detach().to("cpu", torch.float32).contiguous()
+            keep.append(a)
+            names.append(k.encode())
+            ptrs.append(a.data_ptr())
+            numel.append(a.numel())
+        n = len(names)
+        handle = C.c_void_p()
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.dtraj_unet_create(C.byref(desc), (C.c_char_p * n)(*names), (C.c_void_p * n)(*ptrs),
+                                                  (C.c_int64 * n)(*numel), n, C.byref(handle)))
+        self.handle = handle
+        self._ws = None
+        self._samplers = {}
+
+    @classmethod
+    def for_model(cls, model, image_size, n_timesteps, precision, device=None):
+        """Engine cached on the module; rebuilt when weights, precision or table size change."""
+        if getattr(model, "training", False):
+            raise DtrajError("model is in training mode; the hot path needs model.eval() "
+                             "(eval-mode BatchNorm/Dropout, as every reference caller does)")
+        if device is None:
+            device = next(model.parameters()).device
+        device = _require_cuda(device)
+        prec = precision if isinstance(precision, int) else _lib.PRECISIONS[precision]
+        cache = model.__dict__.setdefault("_dtraj_engines", {})
+        key = (prec, int(image_size), str(device))
+        fp = _weights_fingerprint(model)
+        ent = cache.get(key)
+        if ent is not None and ent[0] == fp and ent[1].n_timesteps >= n_timesteps:
+            return ent[1]
+        if ent is not None:
+            n_timesteps = max(n_timesteps, ent[1].n_timesteps)
+            ent[1].close()
+        g = _model_geometry(model)
+        eng = cls(model.state_dict(), g["channels"], int(image_size), g["dims"], g["temb_dim"], n_timesteps, prec, device)
+        cache[key] = (fp, eng)
+        return eng
+
+    def close(self):
+        for s in self._samplers.values():
+            s.close()
+        self._samplers = {}
+        if getattr(self, "handle", None):
+            self.lib.dtraj_unet_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def workspace_bytes(self, n_rows):
+        b = self.lib.dtraj_unet_workspace_bytes(self.handle, n_rows)
+        if b < 0:
+            raise DtrajError("workspace query failed")
+        return b
+
+    def workspace(self, n_rows):
+        need = self.workspace_bytes(n_rows)
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+        return self._ws
+
+    def time_bias(self, t, variant, block):
+        n = [self.dims[0], self.dims[1], self.dims[2], self.dims[3], self.dims[3], self.dims[2], self.dims[1], self.dims[0]][block]
+        out = np.empty(n, dtype=np.float32)
+        _lib.check(self.lib.dtraj_unet_time_bias(self.handle, t, variant, block, out.ctypes.data_as(C.c_void_p), n))
+        return out
+
+    def forward(self, x, t, variants=None):
+        """eps = U-Net(x, t, cond) for rows sharing timestep ``t`` (int).  ``variants``: int32 [R] of VAR_*."""
+        x = x.to(self.device, torch.float32).contiguous()
+        R = x.shape[0]
+        if tuple(x.shape[1:]) != (self.channels, self.image_size, self.image_size):
+            raise DtrajError(f"input shape {tuple(x.shape)} does not match engine "
+                             f"({self.channels},{self.image_size},{self.image_size})")
+        if variants is not None:
+            variants = variants.to(self.device, torch.int32).contiguous()
+        eps = torch.empty_like(x)
+        ws = self.workspace(R)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.dtraj_unet_forward(self.handle, _lib.ptr(x), R, int(t), _lib.ptr(variants), _lib.ptr(eps),
+                                                   _lib.ptr(ws), ws.numel(), _lib.stream_ptr()))
+        return eps
+
+
+class TrajectorySampler:
+    """One captured sampling loop: fixed (rule, batch layout, timestep list, coefficients).
+
+    Inputs are written into the device buffers it owns (``traj[:, 0]`` = x_T, ``z_bank``,
+    ``guidance``, ``z_index``) and ``run()`` replays the loop (one CUDA graph launch).
+    """
+
+    def __init__(self, engine, rule, n_samples, row_sample, row_variant, sample_row_u, sample_row_c,
+                 timesteps, coefs, copy_last, n_noise, use_graph=True):
+        self.engine = engine
+        self.lib = engine.lib
+        dev = engine.device
+        self.rule, self.B = rule, int(n_samples)
+        self.n_updates = len(timesteps)
+        self.n_frames = 1 + self.n_updates + (1 if copy_last else 0)
+        self.n_rows = len(row_sample)
+        i32 = dict(dtype=torch.int32, device=dev)
+        self.row_sample = torch.as_tensor(np.asarray(row_sample, np.int32), **i32)
+        self.row_variant = torch.as_tensor(np.asarray(row_variant, np.int32), **i32)
+        self.sample_row_u = torch.as_tensor(np.asarray(sample_row_u, np.int32), **i32)
+        self.sample_row_c = None if sample_row_c is None else torch.as_tensor(np.asarray(sample_row_c, np.int32), **i32)
+        self.guidance = torch.zeros(self.B, dtype=torch.float32, device=dev)
+        self.n_noise = int(n_noise)
+        self.z_bank = torch.zeros(max(self.n_noise, 1), engine.D, dtype=torch.float32, device=dev)
+        self.z_index = torch.full((max(self.n_updates, 1), self.B), -1, **i32)
+        self.traj = torch.zeros(self.B, self.n_frames, engine.channels, engine.image_size, engine.image_size,
+                                dtype=torch.float32, device=dev)
+        self.ws = torch.empty(engine.workspace_bytes(self.n_rows), dtype=torch.uint8, device=dev)
+        ts = np.asarray(timesteps, np.int32)
+        cf = np.ascontiguousarray(np.asarray(coefs, np.float32).reshape(-1))
+        if cf.size != 3 * self.n_updates:
+            raise ValueError("coefs must be [n_updates, 3]")
+        d = _lib.SamplerDesc()
+        d.rule, d.n_samples, d.n_rows, d.n_updates = rule, self.B, self.n_rows, self.n_updates
+        d.copy_last, d.n_frames, d.use_graph = int(bool(copy_last)), self.n_frames, int(bool(use_graph))
+        d.step_timestep = ts.ctypes.data if ts.size else None
+        d.step_coef = cf.ctypes.data if cf.size else None
+        d.row_sample, d.row_variant = self.row_sample.data_ptr(), self.row_variant.data_ptr()
+        d.sample_row_u = self.sample_row_u.data_ptr()
+        d.sample_row_c = None if self.sample_row_c is None else self.sample_row_c.data_ptr()
+        d.guidance = self.guidance.data_ptr()
+        d.z_bank, d.z_index = self.z_bank.data_ptr(), self.z_index.data_ptr()
+        d.traj, d.workspace, d.workspace_bytes = self.traj.data_ptr(), self.ws.data_ptr(), self.ws.numel()
+        h = C.c_void_p()
+        with torch.cuda.device(dev):
+            torch.cuda.synchronize(dev)
+            _lib.check(self.lib.dtraj_sampler_create(engine.handle, C.byref(d), C.byref(h)))
+        self.handle = h
+        self.launches = int(self.lib.dtraj_sampler_launches(h))
+
+    def run(self):
+        with torch.cuda.device(self.engine.device):
+            _lib.check(self.lib.dtraj_sampler_run(self.handle, _lib.stream_ptr()))
+        return self.traj
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self.lib.dtraj_sampler_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def cached_sampler(engine, key, factory):
+    s = engine._samplers.get(key)
+    if s is None:
+        if len(engine._samplers) >= 8:            # bound the device memory held by old layouts
+            old = next(iter(engine._samplers))
+            engine._samplers.pop(old).close()
+        s = factory()
+        engine._samplers[key] = s
+    return s
+
+
+def umma_error_flag():
+    """Non-zero if any tcgen05 kernel timed out on a barrier since the library was loaded."""
+    return int(_lib.load().dtraj_debug_umma_error())

@@ -1,0 +1,208 @@
+/*
+ * dtraj.h -- C ABI of libdtraj.so, the B200 (sm_100a) implementation of the trajectory
+ * hot path of henriChevreux/distillation_trajectories.
+ *
+ * The reference has no FFI layer (it is pure Python/PyTorch); its boundary for this path
+ * is a set of Python signatures.  The Python package
+ * `distillation_trajectories_b200` keeps those signatures and calls the entry points
+ * below through ctypes.  Each entry point names the reference code it replaces.
+ *
+ * Conventions
+ *   - every function returns 0 on success and a negative DTRAJ_E* code on failure;
+ *     dtraj_last_error() returns a thread-local message.  Nothing throws.
+ *   - pointers marked "dev" are CUDA device pointers owned by the caller (torch tensors'
+ *     data_ptr()); "host" pointers are ordinary memory.  `stream` is a cudaStream_t
+ *     passed as void* (0 = legacy default stream).
+ *   - activations are fp32.  Images and trajectories use the reference layout
+ *     [N, C, H, W] / [N, L, C, H, W]; internal feature maps are NHWC in the workspace.
+ *   - a handle is used by one host thread at a time; one process drives one GPU.
+ */
+#ifndef DTRAJ_H
+#define DTRAJ_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DTRAJ_OK            0
+#define DTRAJ_EINVAL      (-1)  /* bad argument / unsupported shape            */
+#define DTRAJ_ECUDA       (-2)  /* CUDA runtime or driver error                */
+#define DTRAJ_EMISSING    (-3)  /* a state_dict tensor the model needs is absent */
+#define DTRAJ_ENOMEM      (-4)  /* workspace too small                         */
+
+/* arithmetic used for the 3x3 / 1x1 convolutions of the U-Net */
+#define DTRAJ_PREC_FP32     0   /* CUDA-core fp32 implicit GEMM (exact mode)                 */
+#define DTRAJ_PREC_TF32     1   /* tcgen05.mma kind::tf32, one pass (fast mode)              */
+#define DTRAJ_PREC_TF32X3   2   /* tcgen05.mma kind::tf32, hi/lo split, 3 passes (~fp32)     */
+
+/* conditioning variant of one forward row (reference models.py:181-185) */
+#define DTRAJ_VAR_NONE      0   /* cond=None: time embedding only                            */
+#define DTRAJ_VAR_COND0     1   /* cond=[[0.]] through cond_emb (trajectory_engine.py:72)    */
+#define DTRAJ_VAR_COND1     2   /* cond=[[1.]] through cond_emb                              */
+
+/* update rules of the three reference samplers */
+#define DTRAJ_RULE_S1       1   /* utils/diffusion.py:149-158        x' = k0*(x - k1*eps) + k2*z      */
+#define DTRAJ_RULE_S2       2   /* analysis/trajectory_engine.py:98-110  x' = (k0*x - k1*eps) + k2*z  */
+#define DTRAJ_RULE_S3       3   /* utils/trajectory_manager.py:194-203   x' = (x - k0*eps)/k1 + k2*z  */
+
+const char* dtraj_last_error(void);
+int dtraj_version(void);
+
+/* ------------------------------------------------------------------ U-Net (models.py) */
+
+typedef struct dtraj_unet dtraj_unet;
+
+typedef struct {
+    int32_t channels;      /* config.channels                       models.py:99           */
+    int32_t image_size;    /* H == W; 16 or 32 (multiple of 16)                            */
+    int32_t dims[4];       /* DiffusionUNet.dims                    models.py:110          */
+    int32_t temb_dim;      /* DiffusionUNet.time_emb_dim            models.py:101          */
+    int32_t n_timesteps;   /* time tables cover t = 0 .. n_timesteps-1                     */
+    int32_t precision;     /* DTRAJ_PREC_*                                                 */
+} dtraj_unet_desc;
+
+/*
+ * Replaces DiffusionUNet.__init__/load_state_dict + .eval()  (models.py:95-157).
+ * `names[i]` are state_dict keys ("enc1.conv1.weight", "enc1.norm1.running_var", ...),
+ * `tensors[i]` host fp32 arrays in the reference's layouts ([Cout,Cin,kh,kw], [out,in]),
+ * `numel[i]` their element counts.  BatchNorm (eval, eps 1e-5) is folded into the conv
+ * weights here; weights are padded and packed K-major for the kernels, uploaded, and the
+ * per-(timestep, variant, block) time-embedding biases relu(time_mlp(temb)) are
+ * precomputed on the device (models.py:15-39,66-67,175-185).
+ */
+int dtraj_unet_create(const dtraj_unet_desc* desc,
+                      const char* const* names, const float* const* tensors,
+                      const int64_t* numel, int32_t n_tensors,
+                      dtraj_unet** out);
+int dtraj_unet_destroy(dtraj_unet* unet);
+
+/* bytes of workspace one forward over `n_rows` rows needs */
+int64_t dtraj_unet_workspace_bytes(const dtraj_unet* unet, int64_t n_rows);
+
+/* host copy of the time table row: relu(block.time_mlp(time_emb(t, variant))) for block
+ * index `block` (0..7 = enc1..enc4, bottleneck, dec3, dec2, dec1); `out` host [dims]. */
+int dtraj_unet_time_bias(const dtraj_unet* unet, int32_t t, int32_t variant, int32_t block,
+                         float* out_host, int32_t n);
+
+/*
+ * Replaces DiffusionUNet.forward(x, t, cond)  (models.py:159-224) for a batch that shares
+ * one timestep value `t` (every caller on the hot path does: utils/diffusion.py:204,
+ * analysis/trajectory_engine.py:62).
+ *   x            dev [n_rows, C, H, W]
+ *   row_variant  dev int32 [n_rows], DTRAJ_VAR_* per row (NULL = all DTRAJ_VAR_NONE)
+ *   eps          dev [n_rows, C, H, W]
+ */
+int dtraj_unet_forward(dtraj_unet* unet, const float* x, int64_t n_rows, int32_t t,
+                       const int32_t* row_variant, float* eps,
+                       void* workspace, int64_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------ fused sampler step */
+
+/*
+ * One reverse-process step for `n_samples` samples: classifier-free-guidance combine
+ * eps = eps_u + w*(eps_c - eps_u)  (utils/diffusion.py:126, trajectory_engine.py:80),
+ * the update rule `rule` with coefficients k[3], and the store of x' (the next trajectory
+ * frame).  All arrays dev fp32 [n_samples, D] with the given sample strides (in floats);
+ * eps_c / w may be NULL (no guidance), z may be NULL (no noise, e.g. t == 0).
+ * This is the stand-alone form; inside dtraj_sampler the same kernel also performs the
+ * final bilinear x2 upsample of the half-resolution eps.
+ */
+int dtraj_step_fused(int32_t rule, const float* k_host3,
+                     const float* eps_u, const float* eps_c, const float* w,
+                     const float* x, int64_t x_stride,
+                     const float* z, int64_t z_stride,
+                     float* x_out, int64_t out_stride,
+                     int64_t n_samples, int64_t D, void* stream);
+
+/* ------------------------------------------------------------------ whole sampling loop */
+
+typedef struct dtraj_sampler dtraj_sampler;
+
+typedef struct {
+    int32_t rule;              /* DTRAJ_RULE_*                                              */
+    int32_t n_samples;         /* B trajectories generated together                         */
+    int32_t n_rows;            /* forward rows per step (B, or up to 2B with guidance)       */
+    int32_t n_updates;         /* model-driven steps                                         */
+    int32_t copy_last;         /* 1: append a duplicate of the last frame (S2 at t == 0,
+                                  trajectory_engine.py:86,113)                               */
+    int32_t n_frames;          /* L = 1 + n_updates + copy_last                              */
+    int32_t use_graph;         /* capture the whole loop in one CUDA graph                   */
+    int32_t reserved;
+    const int32_t* step_timestep;  /* host [n_updates]  timestep value fed to the model      */
+    const float*   step_coef;      /* host [n_updates*3] k0,k1,k2 of the rule, per step      */
+    const int32_t* row_sample;     /* dev [n_rows]   sample whose x this row evaluates       */
+    const int32_t* row_variant;    /* dev [n_rows]   DTRAJ_VAR_*                             */
+    const int32_t* sample_row_u;   /* dev [n_samples] row holding eps_u (or the only eps)    */
+    const int32_t* sample_row_c;   /* dev [n_samples] row holding eps_c, -1 = no guidance    */
+    const float*   guidance;       /* dev [n_samples] w                                      */
+    const float*   z_bank;         /* dev [*, D] injected noise draws                        */
+    const int32_t* z_index;        /* dev [n_updates, n_samples] draw index, -1 = z = 0      */
+    float*         traj;           /* dev [n_samples, n_frames, C, H, W]; frame 0 = x_T in   */
+    void*          workspace;      /* dev, >= dtraj_unet_workspace_bytes(unet, n_rows)       */
+    int64_t        workspace_bytes;
+} dtraj_sampler_desc;
+
+/*
+ * Replaces the loops of p_sample_loop (utils/diffusion.py:199-208), generate_trajectory
+ * (analysis/trajectory_engine.py:61-113) and TrajectoryManager.generate_trajectory
+ * (utils/trajectory_manager.py:98-111): n_updates x { U-Net forward over n_rows rows,
+ * fused step } writing every frame into `traj` on the device.  The device arrays named in
+ * the descriptor are read at run time, so their CONTENTS (x_T in frame 0, noise bank,
+ * guidance, indices) may change between runs; their addresses may not.
+ */
+int dtraj_sampler_create(dtraj_unet* unet, const dtraj_sampler_desc* desc, dtraj_sampler** out);
+int dtraj_sampler_run(dtraj_sampler* s, void* stream);
+int dtraj_sampler_destroy(dtraj_sampler* s);
+/* number of kernel launches one dtraj_sampler_run performs (graph nodes) */
+int64_t dtraj_sampler_launches(const dtraj_sampler* s);
+
+/* ------------------------------------------------------------------ trajectory metrics */
+
+/*
+ * Streaming reductions behind compute_trajectory_metrics
+ * (analysis/metrics/trajectory_metrics.py:55-215) and analyze_time_dependent_distances
+ * (analysis/metrics/time_dependent.py:57,78) for N trajectory pairs at once.
+ *   teacher, student  dev [N, L, D] fp32 (D = C*H*W)
+ *   out               dev [N, L, 6] fp32:
+ *        [i][0] = sum (T_i - S_i)^2                 position difference / mse numerators
+ *        [i][1] = sum (T_{i+1} - T_i)^2   (i < L-1) teacher velocity^2
+ *        [i][2] = sum (S_{i+1} - S_i)^2   (i < L-1) student velocity^2
+ *        [i][3] = sum (T_{i+1}-T_i)(S_{i+1}-S_i)    direction dot product
+ *        [0][4] = sum (T_{L-1} - T_0)^2,  [0][5] = sum (S_{L-1} - S_0)^2   (other [i][4..5] = 0)
+ * Every element of both tensors is read exactly once.  The f64 scalar formulas
+ * (log1p / exp / ratios) stay on the host as in the reference.
+ */
+int dtraj_metrics_pairs(const float* teacher, const float* student,
+                        int64_t N, int32_t L, int32_t D, float* out, void* stream);
+
+/*
+ * 1-d Wasserstein distance per frame (trajectory_metrics.py:296-312; scipy's
+ * wasserstein_distance on K = min(1000, D) subsampled elements).
+ *   idx   dev int32 [n_idx_sets, L, K] element indices (np.random.choice on the host);
+ *         pair n uses set idx_set[n] (dev int32 [N], NULL = set 0 for all);
+ *         idx == NULL means K == D, all elements.
+ *   out   dev [N, L] fp32
+ */
+int dtraj_wasserstein(const float* teacher, const float* student,
+                      int64_t N, int32_t L, int32_t D,
+                      const int32_t* idx, const int32_t* idx_set, int32_t K,
+                      float* out, void* stream);
+
+/* ------------------------------------------------------------------ test hooks
+ * Single convolution layer through either implementation, for kernel-vs-kernel parity
+ * tests (tests/test_gpu_conv.py).  x0/x1 NHWC dev [n, H, W, c0p]/[.., c1p] (x1 may be
+ * NULL); w host [Cout, c0+c1, k, k] (k = 1 or 3), bias host [Cout]; out dev NHWC
+ * [n, H, W, coutp] with coutp = round_up(Cout, 32).  flags: bit0 relu, bit1 round
+ * outputs to tf32. */
+int dtraj_test_conv(int32_t precision, const float* x0, int32_t c0, const float* x1, int32_t c1,
+                    int64_t n, int32_t H, int32_t W, const float* w_host, const float* bias_host,
+                    int32_t cout, int32_t ksize, int32_t flags, const float* resid,
+                    float* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DTRAJ_H */

@@ -1,0 +1,37 @@
+"""CPU: libdtraj.so loads without a GPU and exports every symbol include/dtraj.h declares."""
+import ctypes
+import os
+import re
+
+from distillation_trajectories_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    src = open(os.path.join(ROOT, "include", "dtraj.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(dtraj_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_header_symbols():
+    lib = _lib.load()
+    names = _declared()
+    assert len(names) >= 15
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/dtraj.h but not exported"
+    assert sorted(_lib.SIGNATURES) == names, "ctypes signature table out of sync with the header"
+
+
+def test_version_and_error_string_without_gpu():
+    lib = _lib.load()
+    assert lib.dtraj_version() == 100
+    assert isinstance(lib.dtraj_last_error(), bytes)
+    # argument validation happens before any CUDA call
+    assert lib.dtraj_unet_create(None, None, None, None, 0, None) == -1
+    assert b"null" in lib.dtraj_last_error()
+
+
+def test_struct_sizes_match_header():
+    assert ctypes.sizeof(_lib.UNetDesc) == 9 * 4
+    assert ctypes.sizeof(_lib.SamplerDesc) == 8 * 4 + 11 * 8 + 8

@@ -1,0 +1,150 @@
+"""CPU: host-side logic of the product package (schedules, coefficients, row layouts, f64 metric
+formulas, sharding) checked against the oracle.  No CUDA call is made here."""
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import metrics as om
+from oracle import samplers as osmp
+from distillation_trajectories_b200 import sampling, grid
+from distillation_trajectories_b200.analysis.metrics import trajectory_metrics as tm
+from distillation_trajectories_b200.analysis import trajectory_engine as te
+from distillation_trajectories_b200.utils import diffusion, metric_transformations
+from distillation_trajectories_b200._lib import VAR_COND0, VAR_COND1, VAR_NONE
+from helpers import Cfg, load_golden
+
+
+@pytest.mark.parametrize("S,Tc", [(50, 50), (100, 50), (4000, 50), (10, 50), (7, 3), (1, 1)])
+def test_s1_indices_bit_exact(S, Tc):
+    assert sampling.s1_timestep_indices(S, Tc) == osmp.s1_timestep_indices(S, Tc)
+
+
+@pytest.mark.parametrize("S,steps", [(50, 50), (100, 50), (100, 30), (6, 3), (20, 5)])
+def test_s3_indices_bit_exact(S, steps):
+    assert sampling.s3_timestep_indices(S, steps) == osmp.s3_timestep_indices(S, steps)
+
+
+def test_schedule_tables_bit_exact():
+    cfg = Cfg(force_cpu=True)
+    for T in (1, 6, 50, 1000):
+        a = diffusion.get_diffusion_params(T, cfg)
+        b = osmp.diffusion_params(T)
+        assert sorted(a) == sorted(b)
+        for k in a:
+            assert torch.equal(a[k].cpu(), b[k]), k
+
+
+def test_s1_coefficients_bit_exact():
+    p = osmp.diffusion_params(50)
+    idx = [49, 7, 0, 75, -3]                       # includes out-of-range values: extract() clamps
+    got = sampling.s1_coefficients(p, idx)
+    for i, (k0, k1, k2) in zip(idx, got):
+        t = torch.tensor([i])
+        assert k0 == osmp.gather_coef(p["sqrt_recip_alphas"], t, 4).item()
+        assert k1 == (1.0 - osmp.gather_coef(p["sqrt_one_minus_alphas_cumprod"], t, 4)).item()
+        assert k2 == osmp.gather_coef(p["betas"], t, 4).item()
+
+
+def test_s2_s3_coefficients_bit_exact():
+    ours, ref = sampling.s2_coefficients(50), osmp.s2_coefficients(50)
+    for t in range(1, 50):
+        assert ours[t] == tuple(c.item() for c in ref[t])
+    x, e, z = torch.randn(4), torch.randn(4), torch.randn(4)
+    for t, (k0, k1, k2) in zip((49, 10, 1), sampling.s3_coefficients((49, 10, 1), 50)):
+        want = osmp.s3_update(x, e, t, z, 50)
+        got = (x - k0 * e) / k1 + k2 * z
+        assert torch.equal(want, got)
+
+
+def test_s2_layout():
+    rs, rv, ru, rc = sampling.s2_layout([None, 1.0, 3.0, 0.5, 7.5])
+    assert rs == [0, 1, 2, 3, 4, 2, 4]
+    assert rv == [VAR_NONE, VAR_NONE, VAR_COND0, VAR_NONE, VAR_COND0, VAR_COND1, VAR_COND1]
+    assert ru == [0, 1, 2, 3, 4] and rc == [-1, -1, 5, -1, 6]
+
+
+def _cpu_reductions(T, S):
+    """what dtraj_metrics_pairs computes, in numpy (test-side restatement of include/dtraj.h)."""
+    T, S = T.astype(np.float64), S.astype(np.float64)
+    N, L, D = T.shape
+    red = np.zeros((N, L, 6))
+    red[:, :, 0] = ((T - S) ** 2).sum(-1)
+    dT, dS = np.diff(T, axis=1), np.diff(S, axis=1)
+    red[:, :-1, 1], red[:, :-1, 2], red[:, :-1, 3] = (dT ** 2).sum(-1), (dS ** 2).sum(-1), (dT * dS).sum(-1)
+    red[:, 0, 4], red[:, 0, 5] = ((T[:, -1] - T[:, 0]) ** 2).sum(-1), ((S[:, -1] - S[:, 0]) ** 2).sum(-1)
+    return red.astype(np.float32)
+
+
+@pytest.mark.parametrize("C,H,L", [(1, 16, 51), (3, 32, 11), (1, 16, 2)])
+def test_scalar_metrics_match_oracle(C, H, L):
+    rng = np.random.RandomState(1)
+    N, D = 3, C * H * H
+    T = np.cumsum(rng.randn(N, L, D).astype(np.float32) * 0.1, axis=1)
+    S = T + rng.randn(N, L, D).astype(np.float32) * 0.01
+    S[1] = T[1]                              # identical pair: zero distances
+    T[2, 3:] = T[2, 2:3]                     # teacher stops moving: zero-norm steps are skipped
+    S[2, 3:] = S[2, 2:3]
+    w1 = np.zeros((N, L))
+    want = []
+    for n in range(N):
+        np.random.seed(10 + n)
+        m = om.trajectory_metrics([torch.from_numpy(T[n, i]).reshape(1, C, H, H) for i in range(L)],
+                                  [torch.from_numpy(S[n, i]).reshape(1, C, H, H) for i in range(L)])
+        want.append(m)
+        w1[n] = m["wasserstein_distances"]
+    got = tm.scalar_metrics_batched(_cpu_reductions(T, S), w1, H * H, D)
+    for n in range(N):
+        for k in tm.SCALAR_KEYS:
+            np.testing.assert_allclose(got[k][n], want[n][k], rtol=1e-4, atol=1e-9, equal_nan=True, err_msg=f"{k}[{n}]")
+        np.testing.assert_allclose(got["path_alignment"][n], want[n]["path_alignment"], rtol=1e-4, atol=1e-30)
+        assert got["path_alignment"].dtype == np.float32
+        dc = [c for c, ok in zip(got["_cos"][n], got["_cos_ok"][n]) if ok]
+        np.testing.assert_allclose(dc, want[n]["directional_consistency"], rtol=1e-4, atol=1e-6)
+    assert len(tm.SCALAR_KEYS) == 18 and set(tm.SCALAR_KEYS) == set(om.average_scalar_metrics(want))
+
+
+def test_wasserstein_index_sets_follow_numpy_global_rng():
+    idx = te.wasserstein_index_sets([42, 43], timesteps=5, n_frames=6, numel=3072)
+    np.random.seed(44)                       # seed + 1 of the second sample
+    for f in range(6):
+        assert np.array_equal(idx[1, f], np.random.choice(3072, 1000, replace=False))
+    assert te.wasserstein_index_sets([42], 5, 6, 256) is None     # all elements used, order irrelevant
+
+
+def test_transform_metrics_golden():
+    for r in load_golden("transform")["rows"]:
+        out = metric_transformations.transform_metrics(*r[:4])
+        got = [out["path_length_similarity"], out["trajectory_mse"], out["mean_directional_consistency"],
+               out["distribution_similarity"]]
+        np.testing.assert_allclose(got, r[4:], rtol=1e-15)
+    assert list(out) == ["path_length_similarity", "trajectory_mse", "mean_directional_consistency",
+                         "distribution_similarity"]
+
+
+def test_shard_samples_partition():
+    for n, w in ((10, 1), (10, 4), (3, 8), (65536, 8)):
+        parts = [grid.shard_samples(n, r, w) for r in range(w)]
+        assert sorted(sum(parts, [])) == list(range(n))
+
+
+def test_cpu_device_is_refused_loudly():
+    from distillation_trajectories_b200 import DtrajError
+    from helpers import make_model
+    cfg = Cfg()
+    m = make_model(cfg, 0.05, 1)
+    with pytest.raises(DtrajError):
+        m(torch.zeros(1, 1, 16, 16), torch.tensor([0]))
+    with pytest.raises(DtrajError):
+        diffusion.p_sample_loop(m, (1, 1, 16, 16), 4, diffusion.get_diffusion_params(4, Cfg(force_cpu=True)), device="cpu")
+
+
+def test_product_never_imports_oracle():
+    import os
+    root = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "distillation_trajectories_b200")
+    for dp, _, files in os.walk(root):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(dp, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), os.path.join(dp, f)
