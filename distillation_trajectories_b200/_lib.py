@@ -54,6 +54,7 @@ SIGNATURES = {
     "dtraj_sampler_run": (C.c_int, [_P, _P]),
     "dtraj_sampler_destroy": (C.c_int, [_P]),
     "dtraj_sampler_launches": (_I64, [_P]),
+    "dtraj_sampler_profile": (C.c_int, [_P, _P, C.POINTER(C.c_double), C.POINTER(_I64), C.POINTER(C.c_double)]),
     "dtraj_metrics_pairs": (C.c_int, [_P, _P, _I64, _I32, _I32, _P, _P]),
     "dtraj_wasserstein": (C.c_int, [_P, _P, _I64, _I32, _I32, _P, _P, _I32, _P, _P]),
     "dtraj_test_conv": (C.c_int, [_I32, _P, _I32, _P, _I32, _I64, _I32, _I32, _P, _P, _I32, _I32, _I32,

@@ -46,7 +46,7 @@ def generate_trajectory(model, noise, timesteps, device, seed=None, guidance_sca
         np.random.seed(seed)
     eng = UNetEngine.for_model(model, x.shape[2], timesteps, get_precision("S2"), device)
     B = x.shape[0]
-    zs = _draw_step_noise(tuple(x.shape), device, timesteps, seed)
+    zs = _draw_step_noise(tuple(x.shape), sampling.noise_device(device), timesteps, seed)
     n = len(zs)
     if n:
         bank = torch.stack(zs).reshape(n * B, -1)            # step-major, then sample
@@ -77,7 +77,7 @@ def generate_trajectories_batched(model, noises, seeds, guidance, timesteps, dev
     model.eval()
     device = torch.device(device)
     eng = UNetEngine.for_model(model, noises.shape[2], timesteps, precision or get_precision("S2"), device)
-    bank, first = _noise_bank(seeds, (1,) + tuple(noises.shape[1:]), device, timesteps)
+    bank, first = _noise_bank(seeds, (1,) + tuple(noises.shape[1:]), sampling.noise_device(device), timesteps)
     ts = np.arange(timesteps - 1, 0, -1)
     z_index = (np.asarray(seeds)[None, :] + ts[:, None] - first).astype(np.int32) if len(ts) else np.zeros((1, len(seeds)), np.int32)
     return sampling.s2_sample(eng, noises.to(device), timesteps, list(guidance), bank, z_index)

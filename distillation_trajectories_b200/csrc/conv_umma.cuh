@@ -30,7 +30,8 @@ struct UmmaConv {
     ConvLayer L;               // epilogue parameters + shapes (wpk unused here)
     int npass;                 // 1 (TF32) or 3 (TF32X3)
     int stages;
-    int tmem_cols;             // power of two >= coutp
+    int tmem_cols;             // power of two >= coutp (x2 for 3 passes: main + correction accumulator)
+    int corr_col;              // first TMEM column of the correction accumulator (3 passes), else 0
     int box_h, box_n;          // A box = {32, W, box_h, box_n}
     int tiles_per_img;         // >= 1
     int b_lo_row;              // row offset of the low-plane weights inside the B tensor map
@@ -193,9 +194,16 @@ k_conv_umma(const __grid_constant__ UmmaMaps maps, const UmmaConv p) {
                 ptx::tc_fence_after();
                 const uint32_t a_src = base + s * stage_bytes, b_src = a_src + kATileBytes;
                 const uint64_t adesc = umma_desc_sw128(a_src), bdesc = umma_desc_sw128(b_src);
+                // 3xTF32: the two small cross terms go to their own accumulator.  The tensor core adds
+                // into the accumulator with round-toward-zero; adding 2^-11-sized terms to a full-size
+                // accumulator for 2/3 of the K loop costs ~K/16 ulps of systematic shrink (measured 6e-5
+                // at K = 4608), a separate accumulator keeps that at the single-pass level.
+                const bool corr = it >= iters_per_pass;
+                const uint32_t d_tmem = tmem_base + (corr ? (uint32_t)p.corr_col : 0u);
+                const int first_it = corr ? iters_per_pass : 0;
 #pragma unroll
                 for (int k = 0; k < 4; ++k)   // 4 x (K = 8 tf32 = 32 bytes) inside the 128-byte swizzle atom
-                    ptx::mma_tf32(tmem_base, adesc + 2u * k, bdesc + 2u * k, idesc, (it | k) != 0);
+                    ptx::mma_tf32(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, (it != first_it) || (k != 0));
                 ptx::tc_commit(empty_bar(s));   // frees the smem slot when these MMAs retire
             }
             ptx::tc_commit(accum_bar);          // accumulator complete
@@ -216,7 +224,15 @@ k_conv_umma(const __grid_constant__ UmmaMaps maps, const UmmaConv p) {
         for (int c0 = 0; c0 < coutp; c0 += 32) {
             uint32_t raw[32];
             ptx::tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, raw);
-            ptx::tmem_ld_wait();
+            if (p.npass == 3) {
+                uint32_t raw2[32];
+                ptx::tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(p.corr_col + c0), raw2);
+                ptx::tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 32; ++j) raw[j] = __float_as_uint(__uint_as_float(raw[j]) + __uint_as_float(raw2[j]));
+            } else {
+                ptx::tmem_ld_wait();
+            }
             if (!valid) continue;
             float* dst = p.L.out + m * coutp + c0;
             const float* res = (p.L.flags & CONV_RESID) ? p.L.resid + m * coutp + c0 : nullptr;
@@ -318,6 +334,8 @@ inline int build_umma_launch(UmmaLaunch* U, const ConvLayer& L, int npass, const
     c.tiles_per_img = HW >= 128 ? HW / 128 : 1;
     c.tmem_cols = 32;
     while (c.tmem_cols < L.coutp) c.tmem_cols *= 2;
+    c.corr_col = 0;
+    if (npass == 3) { c.corr_col = c.tmem_cols; c.tmem_cols *= 2; }
     const int nkb = L.ntaps * (L.c0p + L.c1p) / 32;
     c.b_lo_row = nkb * L.coutp;
     const size_t stage = kATileBytes + (size_t)L.coutp * 128;

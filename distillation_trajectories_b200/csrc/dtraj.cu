@@ -25,6 +25,7 @@ struct PackedConv {          // one generic conv layer's parameters on the devic
     const float* bias = nullptr;
     int64_t rows = 0;           // npl * nkb * coutp
     int c0p = 0, c1p = 0, coutp = 0, ntaps = 0;
+    int c0 = 0, c1 = 0, cout = 0;   // real (unpadded) channels: algorithmic flop count
 };
 
 struct BlockW {
@@ -136,6 +137,7 @@ void pack_conv(Arena* A, size_t* w_off, size_t* b_off, PackedConv* pc, const flo
     for (int n = 0; n < cout; ++n) A->h[*b_off + n] = (float)shift[n];
     pc->rows = (int64_t)npl * nkb * coutp;
     pc->c0p = c0p; pc->c1p = c1p; pc->coutp = coutp; pc->ntaps = ntaps;
+    pc->c0 = c0; pc->c1 = c1; pc->cout = cout;
 }
 
 }  // namespace
@@ -307,6 +309,23 @@ extern "C" int dtraj_unet_time_bias(const dtraj_unet* u, int32_t t, int32_t vari
 // ======================================================================================
 // forward plan: workspace carving + one launch record per kernel
 // ======================================================================================
+// Optional per-launch timing (dtraj_sampler_profile): one event pair per launch, summed per class.
+enum KernelClass : int { KC_CONV = 0, KC_FIRST = 1, KC_RESAMPLE = 2, KC_STEP = 3, KC_COUNT = 4 };
+struct Profiler {
+    struct Rec { int cls; cudaEvent_t a, b; };
+    std::vector<Rec> recs;
+    cudaStream_t st = nullptr;
+    void begin(int cls) {
+        Rec r; r.cls = cls;
+        cudaEventCreate(&r.a); cudaEventCreate(&r.b);
+        cudaEventRecord(r.a, st);
+        recs.push_back(r);
+    }
+    void end() { cudaEventRecord(recs.back().b, st); }
+};
+#define PROF_BEGIN(prof, cls) do { if (prof) (prof)->begin(cls); } while (0)
+#define PROF_END(prof) do { if (prof) (prof)->end(); } while (0)
+
 struct dtraj_plan {
     const dtraj_unet* u = nullptr;
     int64_t R = 0;
@@ -315,7 +334,7 @@ struct dtraj_plan {
     struct Buf { float* p = nullptr; int64_t n = 0; int64_t lo = 0; };
     Buf tmp_h, tmp_r, tmp_x, p1, x2, p2, x3, p3, x4, p4, u3, u2, u1, y1, elow;
     // generic conv launches in execution order
-    struct ConvOp { ConvLayer L; bool umma; UmmaLaunch U; int tb_block; };
+    struct ConvOp { ConvLayer L; bool umma; UmmaLaunch U; int tb_block; double flops; };
     std::vector<ConvOp> convs;   // 15 3x3 + residual 1x1s
     int64_t launches_per_forward = 0;
 };
@@ -376,6 +395,7 @@ int add_conv(dtraj_plan* P, const PackedConv& pc, const dtraj_plan::Buf& s0, con
     L.act_mode = is_residual_conv ? ACT_PLAIN : (u->act_mode == ACT_SPLIT && out.lo == 0 ? ACT_PLAIN : u->act_mode);
     L.flags = flags;
     op.tb_block = tb_block;
+    op.flops = 2.0 * (double)L.M * pc.cout * (double)(pc.c0 + pc.c1) * pc.ntaps;   // executed taps, real channels
     op.umma = u->d.precision != DTRAJ_PREC_FP32;
     if (op.umma) DTRAJ_TRY(build_umma_launch(&op.U, L, u->d.precision == DTRAJ_PREC_TF32X3 ? 3 : 1, pc.w, pc.rows));
     P->convs.push_back(op);
@@ -432,7 +452,7 @@ inline unsigned blocks_for(int64_t n, int per) { return (unsigned)((n + per - 1)
 
 // Enqueue one U-Net forward (models.py:159-224 up to the half-resolution eps map).
 int plan_forward(dtraj_plan* P, const float* x, int64_t x_stride, const int32_t* row_sample,
-                 const int32_t* row_variant, int t, cudaStream_t st, int64_t* launches) {
+                 const int32_t* row_variant, int t, cudaStream_t st, int64_t* launches, Profiler* prof = nullptr) {
     const dtraj_unet* u = P->u;
     if (t < 0 || t >= u->d.n_timesteps) return fail(DTRAJ_EINVAL, "timestep %d outside the time table (0..%d)", t, u->d.n_timesteps - 1);
     const int* S = u->sizes;
@@ -449,7 +469,9 @@ int plan_forward(dtraj_plan* P, const float* x, int64_t x_stride, const int32_t*
         f.tbias = trow + u->tb_off[0]; f.tb_var_stride = u->tb_stride;
         f.h = P->tmp_h.p; f.r = P->tmp_r.p; f.lo_off = P->tmp_h.lo; f.act_mode = u->act_mode;
         const size_t smem = (round_up(C * (S[0] + 2) * (S[0] + 2), 4) + 10 * C * dp[0]) * sizeof(float);
+        PROF_BEGIN(prof, KC_FIRST);
         k_conv_first<<<(unsigned)R, 256, smem, st>>>(f);
+        PROF_END(prof);
         DTRAJ_LAUNCH_CHECK(); ++nl;
     }
     size_t ci = 0;
@@ -457,23 +479,32 @@ int plan_forward(dtraj_plan* P, const float* x, int64_t x_stride, const int32_t*
         dtraj_plan::ConvOp& op = P->convs[ci++];
         const float* tb = op.tb_block >= 0 ? trow + u->tb_off[op.tb_block] : nullptr;
         ++nl;
+        int rc;
+        PROF_BEGIN(prof, KC_CONV);
         if (op.umma) {
             op.U.conv.L.tbias = tb; op.U.conv.L.row_variant = row_variant;
-            return launch_conv_umma(op.U, st);
+            rc = launch_conv_umma(op.U, st);
+        } else {
+            op.L.tbias = tb; op.L.row_variant = row_variant;
+            rc = launch_conv_simt(op.L, st);
         }
-        op.L.tbias = tb; op.L.row_variant = row_variant;
-        return launch_conv_simt(op.L, st);
+        PROF_END(prof);
+        return rc;
     };
     auto pool = [&](const dtraj_plan::Buf& in, const dtraj_plan::Buf& out, int So, int cp) -> int {
         const int64_t n4 = R * So * So * (cp / 4);
+        PROF_BEGIN(prof, KC_RESAMPLE);
         k_pool2<<<blocks_for(n4, 256), 256, 0, st>>>(in.p, out.p, n4, So, So, cp / 4, out.lo, out.lo ? ACT_SPLIT : ACT_PLAIN);
+        PROF_END(prof);
         DTRAJ_LAUNCH_CHECK(); ++nl;
         return 0;
     };
     auto upsample = [&](const dtraj_plan::Buf& in, const dtraj_plan::Buf& out, int Si, int cp) -> int {
         const int64_t n4 = R * (2 * Si) * (2 * Si) * (cp / 4);
+        PROF_BEGIN(prof, KC_RESAMPLE);
         k_upsample2<<<blocks_for(n4, 256), 256, 0, st>>>(in.p, out.p, n4, Si, Si, cp / 4, out.lo,
                                                         (u->act_mode == ACT_SPLIT && !out.lo) ? ACT_PLAIN : u->act_mode);
+        PROF_END(prof);
         DTRAJ_LAUNCH_CHECK(); ++nl;
         return 0;
     };
@@ -496,7 +527,9 @@ int plan_forward(dtraj_plan* P, const float* x, int64_t x_stride, const int32_t*
     }
     {   // final 1x1 at half resolution
         const int64_t npix = R * S[1] * S[1];
+        PROF_BEGIN(prof, KC_RESAMPLE);
         k_final1x1<<<blocks_for(npix * 32, 256), 256, 0, st>>>(P->y1.p, u->finw, u->finb, P->elow.p, npix, dp[0], C);
+        PROF_END(prof);
         DTRAJ_LAUNCH_CHECK(); ++nl;
     }
     if (launches) *launches += nl;
@@ -563,14 +596,14 @@ struct dtraj_sampler {
 
 namespace {
 
-int sampler_enqueue(dtraj_sampler* s, cudaStream_t st, int64_t* launches) {
+int sampler_enqueue(dtraj_sampler* s, cudaStream_t st, int64_t* launches, Profiler* prof = nullptr) {
     const dtraj_sampler_desc& d = s->d;
     const int C = s->u->d.channels, H = s->u->d.image_size;
     const int64_t D = (int64_t)C * H * H, fs = (int64_t)d.n_frames * D;
     int64_t nl = 0;
     for (int k = 0; k < d.n_updates; ++k) {
         const float* xin = d.traj + (int64_t)k * D;
-        DTRAJ_TRY(plan_forward(s->plan, xin, fs, d.row_sample, d.row_variant, s->ts[k], st, &nl));
+        DTRAJ_TRY(plan_forward(s->plan, xin, fs, d.row_sample, d.row_variant, s->ts[k], st, &nl, prof));
         StepParams p;
         p.rule = d.rule; p.k0 = s->coef[3 * k]; p.k1 = s->coef[3 * k + 1]; p.k2 = s->coef[3 * k + 2];
         p.elow = s->plan->elow.p; p.sample_row_u = d.sample_row_u; p.sample_row_c = d.sample_row_c;
@@ -579,13 +612,17 @@ int sampler_enqueue(dtraj_sampler* s, cudaStream_t st, int64_t* launches) {
         p.x_in = xin; p.x_out = d.traj + (int64_t)(k + 1) * D; p.frame_stride = fs;
         p.B = d.n_samples; p.C = C; p.H = H; p.W = H;
         const int64_t nthr = (int64_t)d.n_samples * C * H * (H / 4);
+        PROF_BEGIN(prof, KC_STEP);
         k_step<<<blocks_for(nthr, 256), 256, 0, st>>>(p);
+        PROF_END(prof);
         DTRAJ_LAUNCH_CHECK(); ++nl;
     }
     if (d.copy_last) {
         const int64_t k = d.n_updates;
+        PROF_BEGIN(prof, KC_STEP);
         k_copy_frame<<<blocks_for((int64_t)d.n_samples * (D / 4), 256), 256, 0, st>>>(d.traj + k * D, d.traj + (k + 1) * D, fs,
                                                                                       d.n_samples, (int)(D / 4));
+        PROF_END(prof);
         DTRAJ_LAUNCH_CHECK(); ++nl;
     }
     if (launches) *launches = nl;
@@ -658,16 +695,41 @@ extern "C" int dtraj_sampler_run(dtraj_sampler* s, void* stream) {
 
 extern "C" int64_t dtraj_sampler_launches(const dtraj_sampler* s) { return s ? s->launches : -1; }
 
+extern "C" int dtraj_sampler_profile(dtraj_sampler* s, void* stream, double* class_ms, int64_t* class_launches, double* conv_flops) {
+    if (!s || !class_ms || !class_launches || !conv_flops) return fail(DTRAJ_EINVAL, "profile: null argument");
+    Profiler prof;
+    prof.st = (cudaStream_t)stream;
+    int rc = sampler_enqueue(s, prof.st, nullptr, &prof);
+    cudaError_t ce = cudaStreamSynchronize(prof.st);
+    for (int c = 0; c < KC_COUNT; ++c) { class_ms[c] = 0.0; class_launches[c] = 0; }
+    for (auto& r : prof.recs) {
+        float ms = 0.f;
+        if (rc == 0 && ce == cudaSuccess && cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) {
+            class_ms[r.cls] += ms;
+            class_launches[r.cls] += 1;
+        }
+        cudaEventDestroy(r.a); cudaEventDestroy(r.b);
+    }
+    double f = 0.0;
+    for (auto& op : s->plan->convs) f += op.flops;
+    *conv_flops = f * s->d.n_updates;
+    if (rc) return rc;
+    if (ce != cudaSuccess) return fail(DTRAJ_ECUDA, "profile -> %s", cudaGetErrorString(ce));
+    return 0;
+}
+
 // ======================================================================================
 // metrics
 // ======================================================================================
 extern "C" int dtraj_metrics_pairs(const float* teacher, const float* student, int64_t N, int32_t L, int32_t D, float* out, void* stream) {
+    if (N == 0) return 0;
     if (!teacher || !student || !out || N < 0) return fail(DTRAJ_EINVAL, "metrics: bad argument");
     return launch_metrics_pairs(teacher, student, N, L, D, out, (cudaStream_t)stream);
 }
 
 extern "C" int dtraj_wasserstein(const float* teacher, const float* student, int64_t N, int32_t L, int32_t D, const int32_t* idx,
                                  const int32_t* idx_set, int32_t K, float* out, void* stream) {
+    if (N == 0) return 0;
     if (!teacher || !student || !out || N < 0 || L < 1) return fail(DTRAJ_EINVAL, "wasserstein: bad argument");
     return launch_wasserstein(teacher, student, N, L, D, idx, idx_set, K, out, (cudaStream_t)stream);
 }

@@ -207,6 +207,14 @@ class TrajectorySampler:
             _lib.check(self.lib.dtraj_sampler_run(self.handle, _lib.stream_ptr()))
         return self.traj
 
+    def profile(self):
+        """One un-captured run with an event pair around every launch (see include/dtraj.h).
+        Returns dict(ms=[4], launches=[4], conv_flops=float)."""
+        ms, nl, fl = (C.c_double * 4)(), (C.c_int64 * 4)(), C.c_double()
+        with torch.cuda.device(self.engine.device):
+            _lib.check(self.lib.dtraj_sampler_profile(self.handle, _lib.stream_ptr(), ms, nl, C.byref(fl)))
+        return dict(ms=list(ms), launches=list(nl), conv_flops=fl.value)
+
     def close(self):
         if getattr(self, "handle", None):
             self.lib.dtraj_sampler_destroy(self.handle)

@@ -65,7 +65,7 @@ def p_sample(model, x, t, t_index, diffusion_params, guidance_scale=1.0):
     variants = torch.tensor([VAR_NONE] * B + [VAR_COND1] * B, dtype=torch.int32, device=eng.device)
     eps = eng.forward(torch.cat([xx, xx]), tv, variants)
     k0, k1, k2 = sampling.s1_coefficients(diffusion_params, [tv])[0]
-    z = torch.randn_like(xx) if t_index > 0 else None
+    z = torch.randn(xx.shape, device=sampling.noise_device(eng.device)).to(eng.device) if t_index > 0 else None
     out = torch.empty_like(xx)
     w = torch.full((B,), float(guidance_scale), dtype=torch.float32, device=eng.device)
     import ctypes as C
@@ -91,7 +91,8 @@ def p_sample_loop(model, shape, sample_steps, diffusion_params, device=None, con
         device = next(model.parameters()).device
     device = torch.device(device)
     shape = tuple(shape)
-    img = torch.randn(shape, device=device)
+    ndev = sampling.noise_device(device)
+    img = torch.randn(shape, device=ndev)
     num_timesteps = config.timesteps if config else sample_steps
     indices = sampling.s1_timestep_indices(sample_steps, num_timesteps)
     eng = UNetEngine.for_model(model, shape[2], max(indices) + 1, get_precision("S1"), device)
@@ -99,7 +100,7 @@ def p_sample_loop(model, shape, sample_steps, diffusion_params, device=None, con
     noise = torch.stack([torch.randn_like(img) for _ in range(noisy)]) if noisy else None
     coefs = sampling.s1_coefficients(diffusion_params, indices)
     traj = sampling.s1_sample(eng, img, noise, indices, coefs, guidance_scale)
-    final = traj[:, -1].clone()
+    final = traj[:, -1].clone().to(device)
     if track_trajectory:
         return final, sampling.frames_to_cpu_list(traj)
     return final

@@ -35,7 +35,8 @@ class TrajectoryManager:
         ts = list(reversed(idx))
         eng = UNetEngine.for_model(model, x.shape[2], max(ts) + 1, get_precision("S3"), self.device)
         n_upd = sum(1 for t in ts if t > 0)
-        noise = torch.stack([torch.randn_like(x) for _ in range(n_upd)]) if n_upd else None
+        ndev = sampling.noise_device(self.device)
+        noise = torch.stack([torch.randn(x.shape, device=ndev) for _ in range(n_upd)]) if n_upd else None
         traj = sampling.s3_sample(eng, x, ts, cfg.teacher_steps, noise)
         return [(traj[:, k].clone(), t) for k, t in enumerate(ts)]
 

@@ -1,0 +1,94 @@
+"""GPU: DiffusionUNet.forward through libdtraj against the committed reference outputs
+(tests/golden, made by the unmodified reference on CPU) and against the CPU oracle."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import unet as ounet
+from distillation_trajectories_b200 import set_precision, umma_error_flag, _lib
+from distillation_trajectories_b200.engine import UNetEngine
+from helpers import Cfg, assert_close, cpu_sd, golden_models, make_model
+
+pytestmark = pytest.mark.gpu
+
+# max |err| / max |ref| allowed for one forward.  fp32 / 3xTF32 differ from the reference only by
+# summation order and BatchNorm folding (3xTF32 also by the tensor core's round-toward-zero
+# accumulation, ~1e-5 per deep layer); single-pass TF32 carries 10-bit-mantissa operand rounding.
+FWD_TOL = {"fp32": 2e-5, "tf32x3": 6e-5, "tf32": 4e-3}
+
+
+@pytest.fixture(scope="module", params=["tiny16", "tiny32"])
+def case(request):
+    return golden_models(request.param, device="cuda")
+
+
+@pytest.mark.parametrize("prec", ["fp32", "tf32x3", "tf32"])
+def test_forward_matches_reference_fixture(case, prec):
+    g, cfg, teacher, student = case
+    set_precision(prec, "forward")
+    try:
+        x = torch.from_numpy(g["fwd_x"]).cuda()
+        for tval in (0, cfg.timesteps - 1):
+            t = torch.full((3,), tval, dtype=torch.long, device="cuda")
+            for name, model, cond in ((f"fwd_t{tval}_none", teacher, None),
+                                      (f"fwd_t{tval}_cond1", teacher, torch.ones(3, 1, device="cuda")),
+                                      (f"fwd_t{tval}_cond0", teacher, torch.zeros(3, 1, device="cuda")),
+                                      (f"fwd_student_t{tval}_cond1", student, torch.ones(3, 1, device="cuda"))):
+                out = model(x, t, cond)
+                assert out.shape == x.shape and out.device.type == "cuda"
+                assert_close(out.cpu().numpy(), g[name], 0.0, FWD_TOL[prec], f"{name} [{prec}]")
+        assert umma_error_flag() == 0
+    finally:
+        set_precision("tf32x3", "forward")
+
+
+def test_time_bias_table_matches_oracle(case):
+    """per-(t, variant, block) relu(time_mlp(temb)) table (models.py:15-39,66-67,175-185)."""
+    g, cfg, teacher, _ = case
+    sd = cpu_sd(teacher)
+    eng = UNetEngine.for_model(teacher, cfg.image_size, cfg.timesteps, "fp32")
+    for t in (0, 1, cfg.timesteps - 1):
+        tt = torch.tensor([t])
+        for variant, cond in ((_lib.VAR_NONE, None), (_lib.VAR_COND0, torch.zeros(1, 1)), (_lib.VAR_COND1, torch.ones(1, 1))):
+            temb = ounet.time_embedding(sd, tt, cond)
+            for b, name in enumerate(ounet.BLOCKS):
+                want = ounet.block_time_bias(sd, name, temb)[0].numpy()
+                got = eng.time_bias(t, variant, b)
+                np.testing.assert_allclose(got, want, rtol=2e-5, atol=2e-6, err_msg=f"t={t} v={variant} {name}")
+
+
+@pytest.mark.parametrize("sf,C,H", [(1.0, 1, 16), (0.5, 1, 16), (0.3, 3, 32), (1.0, 3, 32)])
+@pytest.mark.parametrize("prec", ["fp32", "tf32x3", "tf32"])
+def test_forward_matches_oracle_real_widths(sf, C, H, prec):
+    """teacher / student widths of the BASELINE configs, mixed conditioning variants in one batch."""
+    cfg = Cfg(C, H, 50)
+    model = make_model(cfg, sf, 7, device="cuda")
+    sd = cpu_sd(model)
+    torch.manual_seed(3)
+    B = 5
+    x = torch.randn(B, C, H, H)
+    eng = UNetEngine.for_model(model, H, 50, prec)
+    variants = torch.tensor([0, 1, 2, 2, 0], dtype=torch.int32)
+    for t in (49, 17):
+        got = eng.forward(x.cuda(), t, variants.cuda()).cpu().numpy()
+        tt = torch.full((1,), t, dtype=torch.long)
+        for r in range(B):
+            cond = None if variants[r] == 0 else torch.full((1, 1), float(variants[r] - 1))
+            want = ounet.unet_forward(sd, x[r:r + 1], tt, cond).numpy()
+            assert_close(got[r:r + 1], want, 0.0, FWD_TOL[prec], f"row {r} t={t} [{prec}]")
+    assert umma_error_flag() == 0
+
+
+def test_training_mode_and_bad_input_fail_loudly():
+    from distillation_trajectories_b200 import DtrajError
+    cfg = Cfg(1, 16, 4)
+    m = make_model(cfg, 0.05, 1, device="cuda")
+    m.train()
+    with pytest.raises(DtrajError):
+        m(torch.zeros(1, 1, 16, 16, device="cuda"), torch.tensor([0], device="cuda"))
+    m.eval()
+    with pytest.raises(DtrajError):
+        m(torch.zeros(2, 1, 16, 16, device="cuda"), torch.tensor([0, 1], device="cuda"))     # mixed timesteps
+    eng = UNetEngine.for_model(m, 16, 4, "fp32")
+    with pytest.raises(DtrajError):
+        eng.forward(torch.zeros(1, 1, 16, 16, device="cuda"), 9)                              # t outside the table
