@@ -78,6 +78,8 @@ def load():
         fn = getattr(lib, name)       # AttributeError if the .so is stale / incomplete
         fn.restype = res
         fn.argtypes = args
+    lib.dtraj_bench_conv.restype = C.c_int
+    lib.dtraj_bench_conv.argtypes = [_I32, _I32, _I32, _I32, _I64, _I32, _I32, _I32, _I32, _I32, C.POINTER(C.c_float)]
     lib.dtraj_debug_umma_error.restype = C.c_uint
     lib.dtraj_debug_umma_error.argtypes = []
     _lib = lib

@@ -35,11 +35,17 @@ struct UmmaConv {
     int box_h, box_n;          // A box = {32, W, box_h, box_n}
     int tiles_per_img;         // >= 1
     int b_lo_row;              // row offset of the low-plane weights inside the B tensor map
+    int cb;                    // epilogue column block: 128, 64 or 32 (largest that divides coutp)
+    int log2_hw;               // H*W is a power of two: image index of output row m is m >> log2_hw
+    int debug;                 // timing experiments only (dtraj_bench_conv): bit0 skip B loads after the ring is
+                               // primed, bit1 skip A loads likewise, bit2 skip the epilogue's global traffic
 };
 
 struct UmmaMaps {              // 64-byte aligned tensor maps, passed as __grid_constant__
     CUtensorMap a[4];          // [src0 hi, src1 hi, src0 lo, src1 lo]
     CUtensorMap b;
+    CUtensorMap out;           // [M, coutp] output, box {32 ch, 32 rows}   (epilogue TMA store)
+    CUtensorMap res;           // [M, coutp] residual, same box             (epilogue TMA load)
 };
 
 namespace ptx {
@@ -51,6 +57,9 @@ __device__ __forceinline__ bool elect_one() {
 }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
@@ -78,6 +87,14 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
                  "[%0], [%1, {%3, %4}], [%2];"
                  ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
 }
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                 ::"l"(map), "r"(src), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
@@ -116,6 +133,7 @@ __host__ __device__ inline uint32_t umma_idesc_tf32(int n) {
 }
 
 constexpr int kUmmaThreads = 192;
+constexpr int kEpiBufs = 4;              // per-warp ring of 4 KB (32 rows x 32 columns) epilogue buffers
 constexpr int kATileBytes = 128 * 128;   // 128 rows x 32 fp32
 
 __global__ void __launch_bounds__(kUmmaThreads, 1)
@@ -131,6 +149,7 @@ k_conv_umma(const __grid_constant__ UmmaMaps maps, const UmmaConv p) {
     auto empty_bar = [&](int s) { return bar_base + 8u * (p.stages + s); };
     const uint32_t accum_bar = bar_base + 16u * p.stages;
     const uint32_t tmem_slot = accum_bar + 8u;
+    const uint32_t res_bar0 = accum_bar + 16u;                 // [4 warps][kEpiBufs] residual-chunk barriers
     volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(
         smem_raw + (tmem_slot - ptx::smem_u32(smem_raw)));
 
@@ -146,6 +165,9 @@ k_conv_umma(const __grid_constant__ UmmaMaps maps, const UmmaConv p) {
             if (p.L.c1p) ptx::prefetch_tmap(&maps.a[1]);
             for (int s = 0; s < p.stages; ++s) { ptx::mbar_init(full_bar(s), 1); ptx::mbar_init(empty_bar(s), 1); }
             ptx::mbar_init(accum_bar, 1);
+            for (int i = 0; i < 4 * kEpiBufs; ++i) ptx::mbar_init(res_bar0 + 8u * i, 1);
+            ptx::prefetch_tmap(&maps.out);
+            if (p.L.flags & CONV_RESID) ptx::prefetch_tmap(&maps.res);
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
         __syncwarp();
@@ -161,35 +183,47 @@ k_conv_umma(const __grid_constant__ UmmaMaps maps, const UmmaConv p) {
     const int tile = blockIdx.x;
     if (warp == 0) {
         // ------------------------------------------------------------ TMA producer
+        // (one thread; every index is carried incrementally -- a division per iteration made this
+        // single thread, not the tensor pipe, the pace-setter of the first version)
         if (ptx::elect_one()) {
             int img0, y0;
             if (p.tiles_per_img > 1) { img0 = tile / p.tiles_per_img; y0 = (tile % p.tiles_per_img) * p.box_h; }
             else { img0 = tile * p.box_n; y0 = 0; }
-            for (int it = 0; it < n_iters; ++it) {
-                const int s = it % p.stages;
-                const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
-                if (!ptx::mbar_wait(empty_bar(s), ph ^ 1u)) break;
-                const int pass = it / iters_per_pass, kb = it % iters_per_pass;
-                const int tap = kb / nch, chunk = kb % nch;
-                int dy = 0, dx = 0;
-                if (p.L.ntaps == 9) { dy = tap / 3 - 1; dx = tap % 3 - 1; }
-                const int src = chunk < nch0 ? 0 : 1;
-                const int c0 = (src == 0 ? chunk : chunk - nch0) * 32;
-                const CUtensorMap* amap = &maps.a[src + (pass == 2 ? 2 : 0)];
-                const uint32_t a_dst = base + s * stage_bytes, b_dst = a_dst + kATileBytes;
-                ptx::mbar_expect_tx(full_bar(s), kATileBytes + b_bytes);
-                ptx::tma_load_4d(a_dst, amap, full_bar(s), c0, dx, y0 + dy, img0);
-                ptx::tma_load_2d(b_dst, &maps.b, full_bar(s), 0, (pass == 1 ? p.b_lo_row : 0) + kb * coutp);
+            int s = 0, n_issued = 0;
+            uint32_t ph = 0;
+            bool ok = true;
+            for (int pass = 0; pass < p.npass && ok; ++pass) {
+                const int asel = pass == 2 ? 2 : 0;
+                int b_row = pass == 1 ? p.b_lo_row : 0;
+                int dy = p.L.ntaps == 9 ? -1 : 0, dx = dy;
+                for (int tap = 0; tap < p.L.ntaps && ok; ++tap) {
+                    for (int chunk = 0; chunk < nch; ++chunk) {
+                        if (!ptx::mbar_wait(empty_bar(s), ph ^ 1u)) { ok = false; break; }
+                        const int src = chunk < nch0 ? 0 : 1;
+                        const int c0 = (src == 0 ? chunk : chunk - nch0) * 32;
+                        const uint32_t a_dst = base + s * stage_bytes, b_dst = a_dst + kATileBytes;
+                        const bool primed = n_issued >= p.stages;
+                        const bool do_a = !((p.debug & 2) && primed), do_b = !((p.debug & 1) && primed);
+                        ++n_issued;
+                        if (do_a || do_b) ptx::mbar_expect_tx(full_bar(s), (do_a ? kATileBytes : 0) + (do_b ? b_bytes : 0));
+                        else ptx::mbar_arrive(full_bar(s));
+                        if (do_a) ptx::tma_load_4d(a_dst, &maps.a[src + asel], full_bar(s), c0, dx, y0 + dy, img0);
+                        if (do_b) ptx::tma_load_2d(b_dst, &maps.b, full_bar(s), 0, b_row);
+                        b_row += coutp;
+                        if (++s == p.stages) { s = 0; ph ^= 1u; }
+                    }
+                    if (++dx == 2) { dx = -1; ++dy; }
+                }
             }
         }
     } else if (warp == 1) {
         // ------------------------------------------------------------ MMA issuer
         if (ptx::elect_one()) {
             const uint32_t idesc = umma_idesc_tf32(coutp);
+            int s = 0;
+            uint32_t ph = 0;
             bool ok = true;
             for (int it = 0; it < n_iters && ok; ++it) {
-                const int s = it % p.stages;
-                const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
                 ok = ptx::mbar_wait(full_bar(s), ph);
                 ptx::tc_fence_after();
                 const uint32_t a_src = base + s * stage_bytes, b_src = a_src + kATileBytes;
@@ -205,57 +239,159 @@ k_conv_umma(const __grid_constant__ UmmaMaps maps, const UmmaConv p) {
                 for (int k = 0; k < 4; ++k)   // 4 x (K = 8 tf32 = 32 bytes) inside the 128-byte swizzle atom
                     ptx::mma_tf32(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, (it != first_it) || (k != 0));
                 ptx::tc_commit(empty_bar(s));   // frees the smem slot when these MMAs retire
+                if (++s == p.stages) { s = 0; ph ^= 1u; }
             }
             ptx::tc_commit(accum_bar);          // accumulator complete
         }
     } else {
         // ------------------------------------------------------------ epilogue (warps 2..5)
+        // TMEM holds one output pixel per lane.  Reading it gives each THREAD a row, but global memory
+        // wants each WARP INSTRUCTION on one row: every warp transposes its 32 rows through shared
+        // memory (the pipeline stages are free once the accumulator barrier fires), after which bias,
+        // ReLU, time bias, residual add and the store run on 16-byte-per-lane coalesced rows.
         const int q = warp & 3;                 // TMEM lane quarter this warp may access
-        const int64_t m = (int64_t)tile * 128 + q * 32 + lane;
+        const int64_t m_warp = (int64_t)tile * 128 + q * 32;
         ptx::mbar_wait(accum_bar, 0);
         ptx::tc_fence_after();
-        const bool valid = m < p.L.M;
-        const int HW = p.L.H * p.L.W;
-        const float* tb = nullptr;
-        if ((p.L.flags & CONV_TBIAS) && valid) {
-            const int var = p.L.row_variant ? p.L.row_variant[m / HW] : 0;
-            tb = p.L.tbias + (size_t)var * p.L.tb_var_stride;
-        }
-        for (int c0 = 0; c0 < coutp; c0 += 32) {
-            uint32_t raw[32];
-            ptx::tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, raw);
-            if (p.npass == 3) {
-                uint32_t raw2[32];
-                ptx::tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(p.corr_col + c0), raw2);
-                ptx::tmem_ld_wait();
-#pragma unroll
-                for (int j = 0; j < 32; ++j) raw[j] = __float_as_uint(__uint_as_float(raw[j]) + __uint_as_float(raw2[j]));
-            } else {
-                ptx::tmem_ld_wait();
+        if (p.L.act_mode != ACT_SPLIT) {
+            // ---- bulk path: per warp a ring of 4 KB buffers [32 rows][32 columns], 128-byte swizzled.
+            // TMA loads the residual chunk into a buffer, the warp adds its accumulator chunk in place
+            // (thread = row, conflict-free thanks to the swizzle), TMA stores the buffer.  Bytes in
+            // flight no longer depend on registers: the first epilogue issued plain 16-byte loads/stores
+            // and was latency-bound at ~2 TB/s, which made every residual layer epilogue-paced.
+            const int nchunk = coutp >> 5;
+            const bool has_res = (p.L.flags & CONV_RESID) != 0 && !(p.debug & 4);
+            const uint32_t buf0 = base + (uint32_t)q * kEpiBufs * 4096u;
+            const uint32_t rbar = res_bar0 + 8u * (q * kEpiBufs);
+            const int row = (int)m_warp;            // TMA coordinates are 32-bit; M < 2^31 is checked on the host
+            if (has_res && lane == 0) {
+                for (int c = 0; c < nchunk && c < kEpiBufs; ++c) {
+                    ptx::mbar_expect_tx(rbar + 8u * c, 4096u);
+                    ptx::tma_load_2d(buf0 + 4096u * c, &maps.res, rbar + 8u * c, 32 * c, row);
+                }
             }
-            if (!valid) continue;
-            float* dst = p.L.out + m * coutp + c0;
-            const float* res = (p.L.flags & CONV_RESID) ? p.L.resid + m * coutp + c0 : nullptr;
+            const bool valid = m_warp + lane < p.L.M;
+            const float* tb = nullptr;
+            if (p.L.flags & CONV_TBIAS) {
+                const int var = (p.L.row_variant && valid) ? p.L.row_variant[(m_warp + lane) >> p.log2_hw] : 0;
+                tb = p.L.tbias + (size_t)var * p.L.tb_var_stride;
+            }
+            const uint32_t swz = (uint32_t)(lane & 7);
+            for (int c = 0; c < nchunk; ++c) {
+                const int b = c % kEpiBufs;
+                uint32_t raw[32];
+                ptx::tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(32 * c), raw);
+                if (p.npass == 3) {
+                    uint32_t raw2[32];
+                    ptx::tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(p.corr_col + 32 * c), raw2);
+                    ptx::tmem_ld_wait();
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-                float4 b4 = __ldg(reinterpret_cast<const float4*>(p.L.bias + c0 + j));
-                float4 v = make_float4(__uint_as_float(raw[j]) + b4.x, __uint_as_float(raw[j + 1]) + b4.y,
-                                       __uint_as_float(raw[j + 2]) + b4.z, __uint_as_float(raw[j + 3]) + b4.w);
+                    for (int j = 0; j < 32; ++j) raw[j] = __float_as_uint(__uint_as_float(raw[j]) + __uint_as_float(raw2[j]));
+                } else {
+                    ptx::tmem_ld_wait();
+                }
+                if (has_res) ptx::mbar_wait(rbar + 8u * b, (uint32_t)(c / kEpiBufs) & 1u);
+                uint8_t* rowp = smem_raw + (buf0 + 4096u * b - ptx::smem_u32(smem_raw)) + lane * 128;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.L.bias + 32 * c + 4 * j));
+                    float4 v = make_float4(__uint_as_float(raw[4 * j]) + b4.x, __uint_as_float(raw[4 * j + 1]) + b4.y,
+                                           __uint_as_float(raw[4 * j + 2]) + b4.z, __uint_as_float(raw[4 * j + 3]) + b4.w);
+                    if (p.L.flags & CONV_RELU) {
+                        v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+                    }
+                    if (tb) {
+                        const float4 t4 = __ldg(reinterpret_cast<const float4*>(tb + 32 * c + 4 * j));
+                        v.x += t4.x; v.y += t4.y; v.z += t4.z; v.w += t4.w;
+                    }
+                    float4* cell = reinterpret_cast<float4*>(rowp + (((uint32_t)j ^ swz) << 4));
+                    if (has_res) {
+                        const float4 r4 = *cell;
+                        v.x += r4.x; v.y += r4.y; v.z += r4.z; v.w += r4.w;
+                    }
+                    *cell = act_round4(v, p.L.act_mode);
+                }
+                ptx::fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) {
+                    if (!(p.debug & 4)) ptx::tma_store_2d(&maps.out, buf0 + 4096u * b, 32 * c, row);
+                    ptx::bulk_commit();
+                    // recycle the buffer of the PREVIOUS chunk (its store has had a chunk's time to drain)
+                    const int cn = c - 1 + kEpiBufs;
+                    if (c >= 1 && cn < nchunk) {
+                        ptx::bulk_wait_read<1>();
+                        if (has_res) {
+                            ptx::mbar_expect_tx(rbar + 8u * ((c - 1) % kEpiBufs), 4096u);
+                            ptx::tma_load_2d(buf0 + 4096u * ((c - 1) % kEpiBufs), &maps.res, rbar + 8u * ((c - 1) % kEpiBufs), 32 * cn, row);
+                        }
+                    }
+                }
+                // without a residual the next use of buffer (c + 1) % kEpiBufs is a plain write: it must not
+                // race the store that last read it (chunk c + 1 - kEpiBufs)
+                if (!has_res && c + 1 >= kEpiBufs && c + 1 < nchunk) {
+                    if (lane == 0) ptx::bulk_wait_read<kEpiBufs - 1>();
+                    __syncwarp();
+                }
+            }
+            if (lane == 0) ptx::bulk_wait_read<0>();    // smem must outlive the stores' reads
+            __syncwarp();
+        } else {
+        const int CB = p.cb;                    // columns per block: 128, 64 or 32 (divides coutp)
+        const int pitch = CB + 4;               // floats; +4 keeps the float4 row writes conflict-free
+        float* stg = reinterpret_cast<float*>(smem_raw + (base - ptx::smem_u32(smem_raw))) + (size_t)q * 32 * pitch;
+        const int lpr = CB >> 2;                // lanes per row
+        const int rpi = 32 / lpr;               // rows per warp instruction
+        const int c4 = lane % lpr, rsub = lane / lpr;
+        for (int cb0 = 0; cb0 < coutp; cb0 += CB) {
+            // phase 1: TMEM -> registers -> staging rows (raw accumulators)
+            for (int c0 = 0; c0 < CB; c0 += 32) {
+                uint32_t raw[32];
+                ptx::tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(cb0 + c0), raw);
+                if (p.npass == 3) {
+                    uint32_t raw2[32];
+                    ptx::tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(p.corr_col + cb0 + c0), raw2);
+                    ptx::tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) raw[j] = __float_as_uint(__uint_as_float(raw[j]) + __uint_as_float(raw2[j]));
+                } else {
+                    ptx::tmem_ld_wait();
+                }
+                float4* dst = reinterpret_cast<float4*>(stg + lane * pitch + c0);
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    dst[j] = make_float4(__uint_as_float(raw[4 * j]), __uint_as_float(raw[4 * j + 1]),
+                                         __uint_as_float(raw[4 * j + 2]), __uint_as_float(raw[4 * j + 3]));
+            }
+            __syncwarp();
+            // phase 2: row-wise epilogue, 16 bytes per lane
+            const int col = cb0 + 4 * c4;
+            const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.L.bias + col));
+#pragma unroll 4
+            for (int r0 = 0; r0 < 32; r0 += rpi) {
+                const int r = r0 + rsub;
+                const int64_t m = m_warp + r;
+                if (m >= p.L.M || (p.debug & 4)) continue;
+                float4 v = *reinterpret_cast<const float4*>(stg + r * pitch + 4 * c4);
+                v.x += b4.x; v.y += b4.y; v.z += b4.z; v.w += b4.w;
                 if (p.L.flags & CONV_RELU) {
                     v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
                 }
-                if (tb) {
-                    float4 t4 = __ldg(reinterpret_cast<const float4*>(tb + c0 + j));
+                if (p.L.flags & CONV_TBIAS) {
+                    const int var = p.L.row_variant ? p.L.row_variant[m >> p.log2_hw] : 0;
+                    const float4 t4 = __ldg(reinterpret_cast<const float4*>(p.L.tbias + (size_t)var * p.L.tb_var_stride + col));
                     v.x += t4.x; v.y += t4.y; v.z += t4.z; v.w += t4.w;
                 }
-                if (res) {
-                    float4 r4 = *reinterpret_cast<const float4*>(res + j);
+                if (p.L.flags & CONV_RESID) {
+                    const float4 r4 = ld_stream4(p.L.resid + m * coutp + col);
                     v.x += r4.x; v.y += r4.y; v.z += r4.z; v.w += r4.w;
                 }
                 v = act_round4(v, p.L.act_mode);
-                *reinterpret_cast<float4*>(dst + j) = v;
-                if (p.L.act_mode == ACT_SPLIT) *reinterpret_cast<float4*>(dst + p.L.lo_off + j) = act_lo4(v);
+                float* dst = p.L.out + m * coutp + col;
+                *reinterpret_cast<float4*>(dst) = v;
+                if (p.L.act_mode == ACT_SPLIT) *reinterpret_cast<float4*>(dst + p.L.lo_off) = act_lo4(v);
             }
+            __syncwarp();
+        }
         }
     }
     ptx::tc_fence_before();
@@ -312,6 +448,21 @@ inline int make_w_map(CUtensorMap* m, const float* base, int64_t rows, int coutp
     return 0;
 }
 
+// row-major [M, coutp] activation as a 2-d map {coutp, M} with box {32, 32} (epilogue chunks)
+inline int make_rows_map(CUtensorMap* m, const float* base, int64_t M, int coutp) {
+    PFN_encodeTiled enc = get_encode_tiled();
+    if (!enc) return fail(DTRAJ_ECUDA, "cuTensorMapEncodeTiled not available");
+    cuuint64_t dims[2] = {(cuuint64_t)coutp, (cuuint64_t)M};
+    cuuint64_t strides[1] = {(cuuint64_t)coutp * 4};
+    cuuint32_t box[2] = {32, 32};
+    cuuint32_t es[2] = {1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(DTRAJ_ECUDA, "cuTensorMapEncodeTiled(rows M=%lld cp=%d) -> %d", (long long)M, coutp, (int)r);
+    return 0;
+}
+
 struct UmmaLaunch {            // everything a launch needs, built once per (layer, batch)
     UmmaMaps maps;
     UmmaConv conv;
@@ -338,13 +489,21 @@ inline int build_umma_launch(UmmaLaunch* U, const ConvLayer& L, int npass, const
     if (npass == 3) { c.corr_col = c.tmem_cols; c.tmem_cols *= 2; }
     const int nkb = L.ntaps * (L.c0p + L.c1p) / 32;
     c.b_lo_row = nkb * L.coutp;
+    c.cb = L.coutp % 128 == 0 ? 128 : (L.coutp % 64 == 0 ? 64 : 32);
+    c.log2_hw = 0;
+    while ((1 << c.log2_hw) < HW) ++c.log2_hw;
+    if ((1 << c.log2_hw) != HW) return fail(DTRAJ_EINVAL, "umma conv: H*W=%d is not a power of two", HW);
     const size_t stage = kATileBytes + (size_t)L.coutp * 128;
     // <= ~100 KB so two CTAs share an SM: one runs its epilogue while the other's MMAs run
     int stages = (int)((100 * 1024) / stage);
     if (stages < 2) stages = 2;
     if (stages > 6) stages = 6;
     c.stages = stages;
-    U->smem = 1024 + stages * stage + 16 * stages + 16 + 16;
+    if ((size_t)stages * stage < (size_t)4 * 32 * (c.cb + 4) * sizeof(float))
+        return fail(DTRAJ_EINVAL, "umma conv: pipeline smem too small to stage the epilogue");
+    U->smem = 1024 + stages * stage + 16 * stages + 16 + 16 + 8 * 4 * kEpiBufs;
+    if ((size_t)stages * stage < (size_t)4 * kEpiBufs * 4096)
+        return fail(DTRAJ_EINVAL, "umma conv: pipeline smem too small for the epilogue ring");
     U->grid = (unsigned)((L.M + 127) / 128);
     const int64_t n_img = L.M / HW;
     DTRAJ_TRY(make_act_map(&U->maps.a[0], L.src0, L.c0p, L.W, L.H, n_img, c.box_h, c.box_n));
@@ -354,6 +513,9 @@ inline int build_umma_launch(UmmaLaunch* U, const ConvLayer& L, int npass, const
         if (L.c1p) DTRAJ_TRY(make_act_map(&U->maps.a[3], L.src1_lo, L.c1p, L.W, L.H, n_img, c.box_h, c.box_n));
     }
     DTRAJ_TRY(make_w_map(&U->maps.b, wpk, w_rows, L.coutp));
+    if (L.M >= (int64_t)1 << 31) return fail(DTRAJ_EINVAL, "umma conv: M too large for 32-bit TMA coordinates");
+    DTRAJ_TRY(make_rows_map(&U->maps.out, L.out, L.M, L.coutp));
+    if (L.flags & CONV_RESID) DTRAJ_TRY(make_rows_map(&U->maps.res, L.resid, L.M, L.coutp));
     return 0;
 }
 

@@ -743,6 +743,62 @@ extern "C" unsigned int dtraj_debug_umma_error(void) {
     return v;
 }
 
+// Kernel-only timing of one conv layer shape (tools/conv_bench.py): device buffers are allocated and
+// zero-filled here, `iters` launches are timed with one event pair.  debug: see g_umma_debug.
+extern "C" int dtraj_bench_conv(int32_t precision, int32_t c0, int32_t c1, int32_t cout, int64_t n, int32_t H, int32_t ksize,
+                                int32_t flags, int32_t iters, int32_t debug, float* ms_out) {
+    if (precision == DTRAJ_PREC_FP32 && debug) return fail(DTRAJ_EINVAL, "bench_conv: debug needs a tcgen05 mode");
+    const int c0p = round_up(c0, kCPad), c1p = c1 ? round_up(c1, kCPad) : 0, coutp = round_up(cout, kCPad);
+    const int64_t M = n * H * H;
+    std::vector<float> w((size_t)cout * (c0 + c1) * ksize * ksize, 0.01f);
+    std::vector<double> shift(cout, 0.0);
+    Arena A;
+    PackedConv pc;
+    size_t wo, bo;
+    pack_conv(&A, &wo, &bo, &pc, w.data(), cout, c0, c1, ksize, ksize == 3 && H == 1, nullptr, shift.data(), precision);
+    float *dev = nullptr, *x0 = nullptr, *x1 = nullptr, *res = nullptr, *out = nullptr;
+    const int planes = precision == DTRAJ_PREC_TF32X3 ? 2 : 1;
+    DTRAJ_CUDA(cudaMalloc(&dev, A.h.size() * sizeof(float)));
+    DTRAJ_CUDA(cudaMemcpy(dev, A.h.data(), A.h.size() * sizeof(float), cudaMemcpyHostToDevice));
+    DTRAJ_CUDA(cudaMalloc(&x0, (size_t)M * c0p * 4 * planes));
+    DTRAJ_CUDA(cudaMemset(x0, 0, (size_t)M * c0p * 4 * planes));
+    if (c1p) { DTRAJ_CUDA(cudaMalloc(&x1, (size_t)M * c1p * 4 * planes)); DTRAJ_CUDA(cudaMemset(x1, 0, (size_t)M * c1p * 4 * planes)); }
+    DTRAJ_CUDA(cudaMalloc(&res, (size_t)M * coutp * 4));
+    DTRAJ_CUDA(cudaMemset(res, 0, (size_t)M * coutp * 4));
+    DTRAJ_CUDA(cudaMalloc(&out, (size_t)M * coutp * 4 * planes));
+    ConvLayer L;
+    memset(&L, 0, sizeof(L));
+    L.src0 = x0; L.src0_lo = x0 + (size_t)M * c0p; L.c0p = c0p;
+    L.src1 = x1; L.src1_lo = x1 ? x1 + (size_t)M * c1p : nullptr; L.c1p = c1p;
+    L.H = H; L.W = H; L.M = M; L.ntaps = pc.ntaps; L.wpk = dev + wo; L.bias = dev + bo; L.coutp = coutp;
+    L.resid = (flags & 4) ? res : nullptr; L.out = out; L.lo_off = (int64_t)M * coutp;
+    L.flags = (flags & 1 ? CONV_RELU : 0) | (flags & 4 ? CONV_RESID : 0);
+    L.act_mode = precision == DTRAJ_PREC_TF32 ? ACT_ROUND : precision == DTRAJ_PREC_TF32X3 ? ACT_SPLIT : ACT_PLAIN;
+    int rc = 0;
+    UmmaLaunch U;
+    if (precision != DTRAJ_PREC_FP32) {
+        cudaFuncSetAttribute(k_conv_umma, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        rc = build_umma_launch(&U, L, precision == DTRAJ_PREC_TF32X3 ? 3 : 1, dev + wo, pc.rows);
+        U.conv.debug = debug;
+    }
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    for (int i = 0; i < iters + 2 && !rc; ++i) {
+        if (i == 2) cudaEventRecord(e0, 0);
+        rc = precision == DTRAJ_PREC_FP32 ? launch_conv_simt(L, 0) : launch_conv_umma(U, 0);
+    }
+    cudaEventRecord(e1, 0);
+    cudaError_t ce = cudaDeviceSynchronize();
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(dev); cudaFree(x0); if (x1) cudaFree(x1); cudaFree(res); cudaFree(out);
+    if (rc) return rc;
+    if (ce != cudaSuccess) return fail(DTRAJ_ECUDA, "bench_conv -> %s", cudaGetErrorString(ce));
+    *ms_out = ms / iters;
+    return 0;
+}
+
 extern "C" int dtraj_test_conv(int32_t precision, const float* x0, int32_t c0, const float* x1, int32_t c1, int64_t n, int32_t H,
                                int32_t W, const float* w_host, const float* bias_host, int32_t cout, int32_t ksize, int32_t flags,
                                const float* resid, float* out, void* stream) {
