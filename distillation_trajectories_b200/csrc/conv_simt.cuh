@@ -8,7 +8,11 @@
 
 namespace dtraj {
 
-enum ConvFlags : int { CONV_RELU = 1, CONV_TBIAS = 2, CONV_RESID = 4 };
+enum ConvFlags : int {
+    CONV_RELU = 1, CONV_TBIAS = 2, CONV_RESID = 4,
+    // fused tails, tcgen05 kernel only (conv_umma.cuh)
+    CONV_POOL = 8, CONV_NOSTORE = 16, CONV_RESX = 32, CONV_FINAL = 64
+};
 
 // One convolution layer over up to two NHWC sources (implicit channel concat,
 // models.py:206,211,216).  M = n_img*H*W output pixels, N = coutp, K = ntaps * (c0p + c1p).
@@ -30,6 +34,18 @@ struct ConvLayer {
     int64_t lo_off;            // ACT_SPLIT low plane offset (floats)
     int act_mode;
     int flags;
+    // fused tails (tcgen05 kernel only)
+    float* pool_out;           // CONV_POOL: [M/4, coutp] max-pooled output
+    const float* xraw;         // CONV_RESX: raw input frame base; sample s at xraw + s*x_stride, [xC,H,W]
+    int64_t x_stride;
+    const int32_t* row_sample; //            per image: sample index (null = identity)
+    const float* rw1;          //            residual 1x1 weights [xC][coutp]
+    const float* rb1;          //            residual 1x1 bias [coutp]
+    int xC;
+    int finC;                  // CONV_FINAL: output channels of the final 1x1
+    const float* finw;         //            [finC][coutp]
+    const float* finb;         //            [finC]
+    float* elow;               //            [M, finC]
 };
 
 template <int BN>

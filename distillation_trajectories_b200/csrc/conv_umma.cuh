@@ -18,6 +18,7 @@
 // into the same accumulator, where x_lo = x - trunc_tf32(x) is kept in a second plane by
 // every producer of an activation (ACT_SPLIT) and the weights are split on the host.
 #pragma once
+#include <cstdlib>
 #include "common.cuh"
 #include "conv_simt.cuh"
 
@@ -30,13 +31,20 @@ struct UmmaConv {
     ConvLayer L;               // epilogue parameters + shapes (wpk unused here)
     int npass;                 // 1 (TF32) or 3 (TF32X3)
     int stages;
-    int tmem_cols;             // power of two >= coutp (x2 for 3 passes: main + correction accumulator)
-    int corr_col;              // first TMEM column of the correction accumulator (3 passes), else 0
+    int tmem_cols;             // total TMEM columns allocated (power of two): acc_stages x acc_cols
+    int acc_cols;              // columns of one accumulator set (x2 for 3 passes: main + correction accumulator)
+    int acc_stages;            // 2 when two accumulator sets fit in 512 columns, else 1
+    int corr_col;              // offset of the correction accumulator inside a set (3 passes), else 0
+    int n_tiles;               // 128-row output tiles
+    int n_split;               // column split of a tile when there are fewer tiles than SMs (power of two)
+    int ncols;                 // coutp / n_split: columns per work item (multiple of 32)
+    int n_work;                // n_tiles * n_split work items; CTA b handles b, b + gridDim.x, ...
     int box_h, box_n;          // A box = {32, W, box_h, box_n}
     int tiles_per_img;         // >= 1
     int b_lo_row;              // row offset of the low-plane weights inside the B tensor map
     int cb;                    // epilogue column block: 128, 64 or 32 (largest that divides coutp)
     int log2_hw;               // H*W is a power of two: image index of output row m is m >> log2_hw
+    int log2_wh;               // log2(W / 2) (CONV_POOL)
     int debug;                 // timing experiments only (dtraj_bench_conv): bit0 skip B loads after the ring is
                                // primed, bit1 skip A loads likewise, bit2 skip the epilogue's global traffic
 };
@@ -45,6 +53,7 @@ struct UmmaMaps {              // 64-byte aligned tensor maps, passed as __grid_
     CUtensorMap a[4];          // [src0 hi, src1 hi, src0 lo, src1 lo]
     CUtensorMap b;
     CUtensorMap out;           // [M, coutp] output, box {32 ch, 32 rows}   (epilogue TMA store)
+    CUtensorMap out_lo;        // low plane of the output (3xTF32)
     CUtensorMap res;           // [M, coutp] residual, same box             (epilogue TMA load)
 };
 
@@ -132,24 +141,35 @@ __host__ __device__ inline uint32_t umma_idesc_tf32(int n) {
     return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 }
 
-constexpr int kUmmaThreads = 192;
-constexpr int kEpiBufs = 4;              // per-warp ring of 4 KB (32 rows x 32 columns) epilogue buffers
+constexpr int kEpiWarps = 8;             // two per TMEM lane quarter, each takes every other 32-column chunk
+constexpr int kUmmaThreads = 64 + 32 * kEpiWarps;
+constexpr int kEpiBufs = 2;              // per-warp ring of 4 KB (32 rows x 32 columns) epilogue buffers
+constexpr int kEpiRingBytes = kEpiWarps * kEpiBufs * 4096;
 constexpr int kATileBytes = 128 * 128;   // 128 rows x 32 fp32
 
+// Persistent kernel: one CTA per SM walks tiles blockIdx.x, blockIdx.x + gridDim.x, ...  The three roles
+// run decoupled: the producer streams operands for tile i+1 while the issuer is still on tile i, and the
+// epilogue warps drain accumulator buffer `acc` while the issuer fills the other one (TMEM holds two
+// accumulators whenever 2 x columns-per-tile <= 512), so neither the epilogue's latency nor its
+// instruction count sits on the tensor pipe's critical path.
 __global__ void __launch_bounds__(kUmmaThreads, 1)
 k_conv_umma(const __grid_constant__ UmmaMaps maps, const UmmaConv p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    // carve: [stages x (A 16 KB | B coutp*128 B)] then barriers
+    // carve: [stages x (A 16 KB | B coutp*128 B)] [epilogue ring 4 warps x kEpiBufs x 4 KB] [barriers]
     const uint32_t base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
     const int coutp = p.L.coutp;
-    const uint32_t b_bytes = (uint32_t)coutp * 128u;
-    const uint32_t stage_bytes = kATileBytes + b_bytes;        // multiple of 1024 (coutp % 32 == 0 -> b_bytes % 4096 == 0)
-    const uint32_t bar_base = base + p.stages * stage_bytes;   // full[stages], empty[stages], accum, tmem slot
+    const int ncols = p.ncols;                                 // columns this CTA computes per work item (coutp / n_split)
+    const uint32_t b_bytes = (uint32_t)ncols * 128u;
+    const uint32_t stage_bytes = kATileBytes + b_bytes;        // multiple of 1024 (ncols % 32 == 0 -> b_bytes % 4096 == 0)
+    const uint32_t ring_base = base + p.stages * stage_bytes;
+    const uint32_t bar_base = ring_base + kEpiRingBytes;
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
     auto empty_bar = [&](int s) { return bar_base + 8u * (p.stages + s); };
-    const uint32_t accum_bar = bar_base + 16u * p.stages;
-    const uint32_t tmem_slot = accum_bar + 8u;
-    const uint32_t res_bar0 = accum_bar + 16u;                 // [4 warps][kEpiBufs] residual-chunk barriers
+    const uint32_t acc_full0 = bar_base + 16u * p.stages;      // [2] accumulator ready   (issuer -> epilogue)
+    const uint32_t acc_empty0 = acc_full0 + 16u;               // [2] accumulator drained (epilogue -> issuer)
+    const uint32_t res_bar0 = acc_empty0 + 16u;                // [kEpiWarps][kEpiBufs] residual-chunk barriers
+    const uint32_t tmem_slot = res_bar0 + 8u * kEpiWarps * kEpiBufs;
+    const uint32_t fin_base = tmem_slot + 16u;                 // CONV_FINAL partial sums [4 quarters][32 lanes][4]
     volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(
         smem_raw + (tmem_slot - ptx::smem_u32(smem_raw)));
 
@@ -164,9 +184,9 @@ k_conv_umma(const __grid_constant__ UmmaMaps maps, const UmmaConv p) {
             ptx::prefetch_tmap(&maps.b);
             if (p.L.c1p) ptx::prefetch_tmap(&maps.a[1]);
             for (int s = 0; s < p.stages; ++s) { ptx::mbar_init(full_bar(s), 1); ptx::mbar_init(empty_bar(s), 1); }
-            ptx::mbar_init(accum_bar, 1);
-            for (int i = 0; i < 4 * kEpiBufs; ++i) ptx::mbar_init(res_bar0 + 8u * i, 1);
-            ptx::prefetch_tmap(&maps.out);
+            for (int i = 0; i < 2; ++i) { ptx::mbar_init(acc_full0 + 8u * i, 1); ptx::mbar_init(acc_empty0 + 8u * i, kEpiWarps); }
+            for (int i = 0; i < kEpiWarps * kEpiBufs; ++i) ptx::mbar_init(res_bar0 + 8u * i, 1);
+            if (!(p.L.flags & CONV_NOSTORE)) ptx::prefetch_tmap(&maps.out);
             if (p.L.flags & CONV_RESID) ptx::prefetch_tmap(&maps.res);
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
@@ -180,219 +200,270 @@ k_conv_umma(const __grid_constant__ UmmaMaps maps, const UmmaConv p) {
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
 
-    const int tile = blockIdx.x;
     if (warp == 0) {
         // ------------------------------------------------------------ TMA producer
         // (one thread; every index is carried incrementally -- a division per iteration made this
         // single thread, not the tensor pipe, the pace-setter of the first version)
         if (ptx::elect_one()) {
-            int img0, y0;
-            if (p.tiles_per_img > 1) { img0 = tile / p.tiles_per_img; y0 = (tile % p.tiles_per_img) * p.box_h; }
-            else { img0 = tile * p.box_n; y0 = 0; }
             int s = 0, n_issued = 0;
             uint32_t ph = 0;
             bool ok = true;
-            for (int pass = 0; pass < p.npass && ok; ++pass) {
-                const int asel = pass == 2 ? 2 : 0;
-                int b_row = pass == 1 ? p.b_lo_row : 0;
-                int dy = p.L.ntaps == 9 ? -1 : 0, dx = dy;
-                for (int tap = 0; tap < p.L.ntaps && ok; ++tap) {
-                    for (int chunk = 0; chunk < nch; ++chunk) {
-                        if (!ptx::mbar_wait(empty_bar(s), ph ^ 1u)) { ok = false; break; }
-                        const int src = chunk < nch0 ? 0 : 1;
-                        const int c0 = (src == 0 ? chunk : chunk - nch0) * 32;
-                        const uint32_t a_dst = base + s * stage_bytes, b_dst = a_dst + kATileBytes;
-                        const bool primed = n_issued >= p.stages;
-                        const bool do_a = !((p.debug & 2) && primed), do_b = !((p.debug & 1) && primed);
-                        ++n_issued;
-                        if (do_a || do_b) ptx::mbar_expect_tx(full_bar(s), (do_a ? kATileBytes : 0) + (do_b ? b_bytes : 0));
-                        else ptx::mbar_arrive(full_bar(s));
-                        if (do_a) ptx::tma_load_4d(a_dst, &maps.a[src + asel], full_bar(s), c0, dx, y0 + dy, img0);
-                        if (do_b) ptx::tma_load_2d(b_dst, &maps.b, full_bar(s), 0, b_row);
-                        b_row += coutp;
-                        if (++s == p.stages) { s = 0; ph ^= 1u; }
+            for (int work = blockIdx.x; work < p.n_work && ok; work += gridDim.x) {
+                const int tile = work / p.n_split, n0 = (work % p.n_split) * ncols;
+                int img0, y0;
+                if (p.tiles_per_img > 1) { img0 = tile / p.tiles_per_img; y0 = (tile % p.tiles_per_img) * p.box_h; }
+                else { img0 = tile * p.box_n; y0 = 0; }
+                for (int pass = 0; pass < p.npass && ok; ++pass) {
+                    const int asel = pass == 2 ? 2 : 0;
+                    int b_row = (pass == 1 ? p.b_lo_row : 0) + n0;
+                    int dy = p.L.ntaps == 9 ? -1 : 0, dx = dy;
+                    for (int tap = 0; tap < p.L.ntaps && ok; ++tap) {
+                        for (int chunk = 0; chunk < nch; ++chunk) {
+                            if (!ptx::mbar_wait(empty_bar(s), ph ^ 1u)) { ok = false; break; }
+                            const int src = chunk < nch0 ? 0 : 1;
+                            const int c0 = (src == 0 ? chunk : chunk - nch0) * 32;
+                            const uint32_t a_dst = base + s * stage_bytes, b_dst = a_dst + kATileBytes;
+                            const bool primed = n_issued >= p.stages;
+                            const bool do_a = !((p.debug & 2) && primed), do_b = !((p.debug & 1) && primed);
+                            ++n_issued;
+                            if (do_a || do_b) ptx::mbar_expect_tx(full_bar(s), (do_a ? kATileBytes : 0) + (do_b ? b_bytes : 0));
+                            else ptx::mbar_arrive(full_bar(s));
+                            if (do_a) ptx::tma_load_4d(a_dst, &maps.a[src + asel], full_bar(s), c0, dx, y0 + dy, img0);
+                            if (do_b) ptx::tma_load_2d(b_dst, &maps.b, full_bar(s), 0, b_row);
+                            b_row += coutp;
+                            if (++s == p.stages) { s = 0; ph ^= 1u; }
+                        }
+                        if (++dx == 2) { dx = -1; ++dy; }
                     }
-                    if (++dx == 2) { dx = -1; ++dy; }
                 }
             }
         }
     } else if (warp == 1) {
         // ------------------------------------------------------------ MMA issuer
         if (ptx::elect_one()) {
-            const uint32_t idesc = umma_idesc_tf32(coutp);
-            int s = 0;
-            uint32_t ph = 0;
+            const uint32_t idesc = umma_idesc_tf32(ncols);
+            int s = 0, acc = 0;
+            uint32_t ph = 0, acc_ph = 0;
             bool ok = true;
-            for (int it = 0; it < n_iters && ok; ++it) {
-                ok = ptx::mbar_wait(full_bar(s), ph);
+            for (int work = blockIdx.x; work < p.n_work && ok; work += gridDim.x) {
+                ok = ptx::mbar_wait(acc_empty0 + 8u * acc, acc_ph ^ 1u);      // epilogue has drained this buffer
                 ptx::tc_fence_after();
-                const uint32_t a_src = base + s * stage_bytes, b_src = a_src + kATileBytes;
-                const uint64_t adesc = umma_desc_sw128(a_src), bdesc = umma_desc_sw128(b_src);
-                // 3xTF32: the two small cross terms go to their own accumulator.  The tensor core adds
-                // into the accumulator with round-toward-zero; adding 2^-11-sized terms to a full-size
-                // accumulator for 2/3 of the K loop costs ~K/16 ulps of systematic shrink (measured 6e-5
-                // at K = 4608), a separate accumulator keeps that at the single-pass level.
-                const bool corr = it >= iters_per_pass;
-                const uint32_t d_tmem = tmem_base + (corr ? (uint32_t)p.corr_col : 0u);
-                const int first_it = corr ? iters_per_pass : 0;
+                const uint32_t d_main = tmem_base + (uint32_t)(acc * p.acc_cols);
+                for (int it = 0; it < n_iters && ok; ++it) {
+                    ok = ptx::mbar_wait(full_bar(s), ph);
+                    ptx::tc_fence_after();
+                    const uint32_t a_src = base + s * stage_bytes, b_src = a_src + kATileBytes;
+                    const uint64_t adesc = umma_desc_sw128(a_src), bdesc = umma_desc_sw128(b_src);
+                    // 3xTF32: the two small cross terms go to their own accumulator.  The tensor core adds
+                    // into the accumulator with round-toward-zero; adding 2^-11-sized terms to a full-size
+                    // accumulator for 2/3 of the K loop costs ~K/16 ulps of systematic shrink (measured 6e-5
+                    // at K = 4608), a separate accumulator keeps that at the single-pass level.
+                    const bool corr = it >= iters_per_pass;
+                    const uint32_t d_tmem = d_main + (corr ? (uint32_t)p.corr_col : 0u);
+                    const int first_it = corr ? iters_per_pass : 0;
 #pragma unroll
-                for (int k = 0; k < 4; ++k)   // 4 x (K = 8 tf32 = 32 bytes) inside the 128-byte swizzle atom
-                    ptx::mma_tf32(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, (it != first_it) || (k != 0));
-                ptx::tc_commit(empty_bar(s));   // frees the smem slot when these MMAs retire
-                if (++s == p.stages) { s = 0; ph ^= 1u; }
+                    for (int k = 0; k < 4; ++k)   // 4 x (K = 8 tf32 = 32 bytes) inside the 128-byte swizzle atom
+                        ptx::mma_tf32(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, (it != first_it) || (k != 0));
+                    ptx::tc_commit(empty_bar(s));   // frees the smem slot when these MMAs retire
+                    if (++s == p.stages) { s = 0; ph ^= 1u; }
+                }
+                ptx::tc_commit(acc_full0 + 8u * acc);   // accumulator complete
+                if (++acc == p.acc_stages) { acc = 0; acc_ph ^= 1u; }
             }
-            ptx::tc_commit(accum_bar);          // accumulator complete
         }
     } else {
         // ------------------------------------------------------------ epilogue (warps 2..5)
-        // TMEM holds one output pixel per lane.  Reading it gives each THREAD a row, but global memory
-        // wants each WARP INSTRUCTION on one row: every warp transposes its 32 rows through shared
-        // memory (the pipeline stages are free once the accumulator barrier fires), after which bias,
-        // ReLU, time bias, residual add and the store run on 16-byte-per-lane coalesced rows.
-        const int q = warp & 3;                 // TMEM lane quarter this warp may access
-        const int64_t m_warp = (int64_t)tile * 128 + q * 32;
-        ptx::mbar_wait(accum_bar, 0);
-        ptx::tc_fence_after();
-        if (p.L.act_mode != ACT_SPLIT) {
-            // ---- bulk path: per warp a ring of 4 KB buffers [32 rows][32 columns], 128-byte swizzled.
-            // TMA loads the residual chunk into a buffer, the warp adds its accumulator chunk in place
-            // (thread = row, conflict-free thanks to the swizzle), TMA stores the buffer.  Bytes in
-            // flight no longer depend on registers: the first epilogue issued plain 16-byte loads/stores
-            // and was latency-bound at ~2 TB/s, which made every residual layer epilogue-paced.
-            const int nchunk = coutp >> 5;
-            const bool has_res = (p.L.flags & CONV_RESID) != 0 && !(p.debug & 4);
-            const uint32_t buf0 = base + (uint32_t)q * kEpiBufs * 4096u;
-            const uint32_t rbar = res_bar0 + 8u * (q * kEpiBufs);
-            const int row = (int)m_warp;            // TMA coordinates are 32-bit; M < 2^31 is checked on the host
-            if (has_res && lane == 0) {
-                for (int c = 0; c < nchunk && c < kEpiBufs; ++c) {
-                    ptx::mbar_expect_tx(rbar + 8u * c, 4096u);
-                    ptx::tma_load_2d(buf0 + 4096u * c, &maps.res, rbar + 8u * c, 32 * c, row);
-                }
+        // TMEM holds one output pixel per lane; warp w may only touch lane quarter w % 4.
+        // Per warp a ring of 4 KB buffers [32 rows][32 columns], 128-byte swizzled: TMA loads the residual
+        // chunk into a buffer, the warp adds its accumulator chunk in place (thread = row, conflict-free
+        // thanks to the swizzle), TMA stores the buffer.  Bytes in flight do not depend on registers: the
+        // first epilogue issued plain 16-byte loads/stores and was latency-bound at ~2 TB/s.
+        // Optional fused tails (set by the forward plan in single-pass TF32 mode):
+        //   CONV_RESX    residual = 1x1 conv of the raw C-channel input, recomputed per element
+        //                (enc1.residual_conv, models.py:60) instead of a 128-channel tensor round trip
+        //   CONV_POOL    also emit MaxPool2d(2) of the tile (models.py:191-201): a warp's 32 rows
+        //                always hold 8 complete 2x2 windows when W <= 16
+        //   CONV_FINAL   final 1x1 conv (models.py:224, evaluated at half resolution) on the rows while
+        //                they are in registers; CONV_NOSTORE drops the main store when the full tensor
+        //                has no other consumer
+        // 3xTF32 (ACT_SPLIT) also writes the low plane y - trunc_tf32(y) through a second store.
+        const int q = warp & 3;
+        const int h = (warp - 2) >> 2;          // which of the quarter's two warps: takes chunks h, h + 2, ...
+        const int ew = warp - 2;
+        const int nchunk = ncols >> 5;
+        const int fl = p.L.flags;
+        const bool skip_io = (p.debug & 4) != 0;
+        const bool has_res = (fl & CONV_RESID) != 0 && !skip_io;
+        const bool do_store = !(fl & CONV_NOSTORE) && !skip_io;
+        const bool do_pool = (fl & CONV_POOL) != 0 && !skip_io;
+        const bool split = p.L.act_mode == ACT_SPLIT;
+        const uint32_t buf0 = ring_base + (uint32_t)ew * kEpiBufs * 4096u;
+        const uint32_t rbar = res_bar0 + 8u * (ew * kEpiBufs);
+        const uint32_t swz = (uint32_t)(lane & 7);
+        uint32_t res_par = 0;                   // bit b = parity the next wait on residual barrier b uses
+        int acc = 0;
+        uint32_t acc_ph = 0;
+        for (int work = blockIdx.x; work < p.n_work; work += gridDim.x) {
+            const int tile = work / p.n_split, n0 = (work % p.n_split) * ncols;
+            const int64_t m_warp = (int64_t)tile * 128 + q * 32;
+            const int row = (int)m_warp;        // TMA coordinates are 32-bit; M < 2^31 is checked on the host
+            if (lane == 0) {
+                ptx::bulk_wait_read<0>();       // the previous tile's stores have left the ring
+                if (has_res)
+                    for (int k = 0; k < kEpiBufs && h + 2 * k < nchunk; ++k) {
+                        ptx::mbar_expect_tx(rbar + 8u * k, 4096u);
+                        ptx::tma_load_2d(buf0 + 4096u * k, &maps.res, rbar + 8u * k, n0 + 32 * (h + 2 * k), row);
+                    }
             }
-            const bool valid = m_warp + lane < p.L.M;
+            __syncwarp();
+            const int64_t m = m_warp + lane;
+            const bool valid = m < p.L.M;
+            const int img = valid ? (int)(m >> p.log2_hw) : 0;
             const float* tb = nullptr;
-            if (p.L.flags & CONV_TBIAS) {
-                const int var = (p.L.row_variant && valid) ? p.L.row_variant[(m_warp + lane) >> p.log2_hw] : 0;
-                tb = p.L.tbias + (size_t)var * p.L.tb_var_stride;
+            if (fl & CONV_TBIAS) tb = p.L.tbias + (size_t)(p.L.row_variant ? p.L.row_variant[img] : 0) * p.L.tb_var_stride;
+            float xv[4] = {0.f, 0.f, 0.f, 0.f}, fe[4] = {0.f, 0.f, 0.f, 0.f};
+            if ((fl & CONV_RESX) && valid) {
+                const int HWm = (1 << p.log2_hw);
+                const float* xs = p.L.xraw + (size_t)(p.L.row_sample ? p.L.row_sample[img] : img) * p.L.x_stride + (m & (HWm - 1));
+#pragma unroll
+                for (int ch = 0; ch < 4; ++ch) if (ch < p.L.xC) xv[ch] = xs[(size_t)ch * HWm];
             }
-            const uint32_t swz = (uint32_t)(lane & 7);
-            for (int c = 0; c < nchunk; ++c) {
-                const int b = c % kEpiBufs;
+            ptx::mbar_wait(acc_full0 + 8u * acc, acc_ph);
+            ptx::tc_fence_after();
+            const uint32_t t_acc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.acc_cols);
+            const int c_last = nchunk - 1 - ((nchunk - 1 - h) & 1);   // this warp's last chunk (< h: it has none)
+            if (c_last < h) {                   // a single-chunk item leaves the quarter's second warp idle
+                ptx::tc_fence_before();
+                __syncwarp();
+                if (lane == 0) ptx::mbar_arrive(acc_empty0 + 8u * acc);
+            }
+            for (int c = h, k = 0; c < nchunk; c += 2, ++k) {
+                const int b = k % kEpiBufs;
                 uint32_t raw[32];
-                ptx::tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(32 * c), raw);
+                ptx::tmem_ld32(t_acc + (uint32_t)(32 * c), raw);
                 if (p.npass == 3) {
                     uint32_t raw2[32];
-                    ptx::tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(p.corr_col + 32 * c), raw2);
+                    ptx::tmem_ld32(t_acc + (uint32_t)(p.corr_col + 32 * c), raw2);
                     ptx::tmem_ld_wait();
 #pragma unroll
                     for (int j = 0; j < 32; ++j) raw[j] = __float_as_uint(__uint_as_float(raw[j]) + __uint_as_float(raw2[j]));
                 } else {
                     ptx::tmem_ld_wait();
                 }
-                if (has_res) ptx::mbar_wait(rbar + 8u * b, (uint32_t)(c / kEpiBufs) & 1u);
-                uint8_t* rowp = smem_raw + (buf0 + 4096u * b - ptx::smem_u32(smem_raw)) + lane * 128;
+                if (c == c_last) {
+                    // every TMEM read of this warp for this tile is done: hand the accumulator back to the issuer
+                    ptx::tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) ptx::mbar_arrive(acc_empty0 + 8u * acc);
+                }
+                if (has_res) { ptx::mbar_wait(rbar + 8u * b, (res_par >> b) & 1u); res_par ^= 1u << b; }
+                uint8_t* bufp = smem_raw + (buf0 + 4096u * b - ptx::smem_u32(smem_raw));
+                uint8_t* rowp = bufp + lane * 128;
+                float4 keep[8];                 // ACT_SPLIT: values for the low-plane store
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                    const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.L.bias + 32 * c + 4 * j));
+                    const int col = n0 + 32 * c + 4 * j;
+                    const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.L.bias + col));
                     float4 v = make_float4(__uint_as_float(raw[4 * j]) + b4.x, __uint_as_float(raw[4 * j + 1]) + b4.y,
                                            __uint_as_float(raw[4 * j + 2]) + b4.z, __uint_as_float(raw[4 * j + 3]) + b4.w);
-                    if (p.L.flags & CONV_RELU) {
+                    if (fl & CONV_RELU) {
                         v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
                     }
                     if (tb) {
-                        const float4 t4 = __ldg(reinterpret_cast<const float4*>(tb + 32 * c + 4 * j));
+                        const float4 t4 = __ldg(reinterpret_cast<const float4*>(tb + col));
                         v.x += t4.x; v.y += t4.y; v.z += t4.z; v.w += t4.w;
+                    }
+                    if (fl & CONV_RESX) {
+                        float4 r4 = __ldg(reinterpret_cast<const float4*>(p.L.rb1 + col));
+#pragma unroll
+                        for (int ch = 0; ch < 4; ++ch) {
+                            if (ch >= p.L.xC) break;
+                            const float4 w4 = __ldg(reinterpret_cast<const float4*>(p.L.rw1 + (size_t)ch * coutp + col));
+                            r4.x = fmaf(xv[ch], w4.x, r4.x); r4.y = fmaf(xv[ch], w4.y, r4.y);
+                            r4.z = fmaf(xv[ch], w4.z, r4.z); r4.w = fmaf(xv[ch], w4.w, r4.w);
+                        }
+                        v.x += r4.x; v.y += r4.y; v.z += r4.z; v.w += r4.w;
                     }
                     float4* cell = reinterpret_cast<float4*>(rowp + (((uint32_t)j ^ swz) << 4));
                     if (has_res) {
                         const float4 r4 = *cell;
                         v.x += r4.x; v.y += r4.y; v.z += r4.z; v.w += r4.w;
                     }
-                    *cell = act_round4(v, p.L.act_mode);
-                }
-                ptx::fence_proxy_async();
-                __syncwarp();
-                if (lane == 0) {
-                    if (!(p.debug & 4)) ptx::tma_store_2d(&maps.out, buf0 + 4096u * b, 32 * c, row);
-                    ptx::bulk_commit();
-                    // recycle the buffer of the PREVIOUS chunk (its store has had a chunk's time to drain)
-                    const int cn = c - 1 + kEpiBufs;
-                    if (c >= 1 && cn < nchunk) {
-                        ptx::bulk_wait_read<1>();
-                        if (has_res) {
-                            ptx::mbar_expect_tx(rbar + 8u * ((c - 1) % kEpiBufs), 4096u);
-                            ptx::tma_load_2d(buf0 + 4096u * ((c - 1) % kEpiBufs), &maps.res, rbar + 8u * ((c - 1) % kEpiBufs), 32 * cn, row);
+                    v = act_round4(v, p.L.act_mode);
+                    if (fl & CONV_FINAL) {
+#pragma unroll
+                        for (int o = 0; o < 4; ++o) {
+                            if (o >= p.L.finC) break;
+                            const float4 w4 = __ldg(reinterpret_cast<const float4*>(p.L.finw + (size_t)o * coutp + col));
+                            fe[o] = fmaf(v.x, w4.x, fmaf(v.y, w4.y, fmaf(v.z, w4.z, fmaf(v.w, w4.w, fe[o]))));
                         }
                     }
+                    if (do_store || do_pool) *cell = v;
+                    if (split) keep[j] = v;
                 }
-                // without a residual the next use of buffer (c + 1) % kEpiBufs is a plain write: it must not
-                // race the store that last read it (chunk c + 1 - kEpiBufs)
-                if (!has_res && c + 1 >= kEpiBufs && c + 1 < nchunk) {
+                if (do_store) ptx::fence_proxy_async();
+                __syncwarp();
+                if (do_pool) {
+                    // 8 pooled rows x 8 float4 per chunk: lane -> (pooled row, two float4 columns)
+                    const int W = p.L.W, pr = lane >> 2, x2 = pr & ((W >> 1) - 1), t = pr >> p.log2_wh;
+                    const int r00 = 2 * t * W + 2 * x2;
+                    if (m_warp + r00 < p.L.M) {
+                        float* dst = p.L.pool_out + ((m_warp >> 2) + pr) * coutp + n0 + 32 * c;
+#pragma unroll
+                        for (int jj = (lane & 3) * 2; jj < (lane & 3) * 2 + 2; ++jj) {
+                            auto at = [&](int r) { return *reinterpret_cast<const float4*>(bufp + r * 128 + (((uint32_t)jj ^ (uint32_t)(r & 7)) << 4)); };
+                            const float4 a = at(r00), bq = at(r00 + 1), cq = at(r00 + W), d = at(r00 + W + 1);
+                            *reinterpret_cast<float4*>(dst + 4 * jj) =
+                                make_float4(fmaxf(fmaxf(a.x, bq.x), fmaxf(cq.x, d.x)), fmaxf(fmaxf(a.y, bq.y), fmaxf(cq.y, d.y)),
+                                            fmaxf(fmaxf(a.z, bq.z), fmaxf(cq.z, d.z)), fmaxf(fmaxf(a.w, bq.w), fmaxf(cq.w, d.w)));
+                        }
+                    }
+                    __syncwarp();
+                }
+                if (lane == 0 && do_store) { ptx::tma_store_2d(&maps.out, buf0 + 4096u * b, n0 + 32 * c, row); ptx::bulk_commit(); }
+                if (split && do_store) {
+                    // low plane: reuse the same buffer once the high-plane store has read it
+                    if (lane == 0) ptx::bulk_wait_read<0>();
+                    __syncwarp();
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) *reinterpret_cast<float4*>(rowp + (((uint32_t)j ^ swz) << 4)) = act_lo4(keep[j]);
+                    ptx::fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0) { ptx::tma_store_2d(&maps.out_lo, buf0 + 4096u * b, n0 + 32 * c, row); ptx::bulk_commit(); }
+                }
+                if (lane == 0) {
+                    // recycle the buffer of this warp's PREVIOUS chunk (its store has had a chunk's time to drain)
+                    const int cn = c + 2 * (kEpiBufs - 1);
+                    if (has_res && k >= 1 && cn < nchunk) {
+                        if (do_store) ptx::bulk_wait_read<1>();
+                        ptx::mbar_expect_tx(rbar + 8u * ((k - 1) % kEpiBufs), 4096u);
+                        ptx::tma_load_2d(buf0 + 4096u * ((k - 1) % kEpiBufs), &maps.res, rbar + 8u * ((k - 1) % kEpiBufs), n0 + 32 * cn, row);
+                    }
+                }
+                // without a residual the next use of buffer (k + 1) % kEpiBufs is a plain write: it must not
+                // race the store that last read it (this warp's chunk k + 1 - kEpiBufs)
+                if (!has_res && do_store && k + 1 >= kEpiBufs && c + 2 < nchunk) {
                     if (lane == 0) ptx::bulk_wait_read<kEpiBufs - 1>();
                     __syncwarp();
                 }
             }
-            if (lane == 0) ptx::bulk_wait_read<0>();    // smem must outlive the stores' reads
-            __syncwarp();
-        } else {
-        const int CB = p.cb;                    // columns per block: 128, 64 or 32 (divides coutp)
-        const int pitch = CB + 4;               // floats; +4 keeps the float4 row writes conflict-free
-        float* stg = reinterpret_cast<float*>(smem_raw + (base - ptx::smem_u32(smem_raw))) + (size_t)q * 32 * pitch;
-        const int lpr = CB >> 2;                // lanes per row
-        const int rpi = 32 / lpr;               // rows per warp instruction
-        const int c4 = lane % lpr, rsub = lane / lpr;
-        for (int cb0 = 0; cb0 < coutp; cb0 += CB) {
-            // phase 1: TMEM -> registers -> staging rows (raw accumulators)
-            for (int c0 = 0; c0 < CB; c0 += 32) {
-                uint32_t raw[32];
-                ptx::tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(cb0 + c0), raw);
-                if (p.npass == 3) {
-                    uint32_t raw2[32];
-                    ptx::tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(p.corr_col + cb0 + c0), raw2);
-                    ptx::tmem_ld_wait();
+            if (fl & CONV_FINAL) {
+                // the quarter's two warps hold partial sums over alternate chunks of the same rows
+                float4* part = reinterpret_cast<float4*>(smem_raw + (fin_base - ptx::smem_u32(smem_raw))) + q * 32 + lane;
+                if (h == 1) *part = make_float4(fe[0], fe[1], fe[2], fe[3]);
+                asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
+                if (h == 0 && valid && !skip_io) {
+                    const float4 o4 = *part;
+                    const float other[4] = {o4.x, o4.y, o4.z, o4.w};
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) raw[j] = __float_as_uint(__uint_as_float(raw[j]) + __uint_as_float(raw2[j]));
-                } else {
-                    ptx::tmem_ld_wait();
+                    for (int o = 0; o < 4; ++o) if (o < p.L.finC) p.L.elow[m * p.L.finC + o] = (fe[o] + other[o]) + __ldg(p.L.finb + o);
                 }
-                float4* dst = reinterpret_cast<float4*>(stg + lane * pitch + c0);
-#pragma unroll
-                for (int j = 0; j < 8; ++j)
-                    dst[j] = make_float4(__uint_as_float(raw[4 * j]), __uint_as_float(raw[4 * j + 1]),
-                                         __uint_as_float(raw[4 * j + 2]), __uint_as_float(raw[4 * j + 3]));
+                asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
             }
-            __syncwarp();
-            // phase 2: row-wise epilogue, 16 bytes per lane
-            const int col = cb0 + 4 * c4;
-            const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.L.bias + col));
-#pragma unroll 4
-            for (int r0 = 0; r0 < 32; r0 += rpi) {
-                const int r = r0 + rsub;
-                const int64_t m = m_warp + r;
-                if (m >= p.L.M || (p.debug & 4)) continue;
-                float4 v = *reinterpret_cast<const float4*>(stg + r * pitch + 4 * c4);
-                v.x += b4.x; v.y += b4.y; v.z += b4.z; v.w += b4.w;
-                if (p.L.flags & CONV_RELU) {
-                    v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
-                }
-                if (p.L.flags & CONV_TBIAS) {
-                    const int var = p.L.row_variant ? p.L.row_variant[m >> p.log2_hw] : 0;
-                    const float4 t4 = __ldg(reinterpret_cast<const float4*>(p.L.tbias + (size_t)var * p.L.tb_var_stride + col));
-                    v.x += t4.x; v.y += t4.y; v.z += t4.z; v.w += t4.w;
-                }
-                if (p.L.flags & CONV_RESID) {
-                    const float4 r4 = ld_stream4(p.L.resid + m * coutp + col);
-                    v.x += r4.x; v.y += r4.y; v.z += r4.z; v.w += r4.w;
-                }
-                v = act_round4(v, p.L.act_mode);
-                float* dst = p.L.out + m * coutp + col;
-                *reinterpret_cast<float4*>(dst) = v;
-                if (p.L.act_mode == ACT_SPLIT) *reinterpret_cast<float4*>(dst + p.L.lo_off) = act_lo4(v);
-            }
-            __syncwarp();
+            if (++acc == p.acc_stages) { acc = 0; acc_ph ^= 1u; }
         }
-        }
+        if (lane == 0) ptx::bulk_wait_read<0>();    // smem must outlive the stores' reads
+        __syncwarp();
     }
     ptx::tc_fence_before();
     __syncthreads();
@@ -483,28 +554,40 @@ inline int build_umma_launch(UmmaLaunch* U, const ConvLayer& L, int npass, const
     c.box_h = HW >= 128 ? 128 / L.W : L.H;
     c.box_n = HW >= 128 ? 1 : 128 / HW;
     c.tiles_per_img = HW >= 128 ? HW / 128 : 1;
-    c.tmem_cols = 32;
-    while (c.tmem_cols < L.coutp) c.tmem_cols *= 2;
+    c.n_tiles = (int)((L.M + 127) / 128);
+    c.n_split = 1;
+    if (!(L.flags & CONV_FINAL))
+        while (c.n_tiles * c.n_split * 2 <= kNumSMs && (L.coutp / (c.n_split * 2)) % 32 == 0 && L.coutp / (c.n_split * 2) >= 64)
+            c.n_split *= 2;
+    if (getenv("DTRAJ_NO_NSPLIT")) c.n_split = 1;
+    c.ncols = L.coutp / c.n_split;
+    c.n_work = c.n_tiles * c.n_split;
+    c.acc_cols = 32;
+    while (c.acc_cols < c.ncols) c.acc_cols *= 2;
     c.corr_col = 0;
-    if (npass == 3) { c.corr_col = c.tmem_cols; c.tmem_cols *= 2; }
+    if (npass == 3) { c.corr_col = c.acc_cols; c.acc_cols *= 2; }
+    c.acc_stages = 2 * c.acc_cols <= 512 ? 2 : 1;
+    c.tmem_cols = c.acc_stages * c.acc_cols;
     const int nkb = L.ntaps * (L.c0p + L.c1p) / 32;
     c.b_lo_row = nkb * L.coutp;
-    c.cb = L.coutp % 128 == 0 ? 128 : (L.coutp % 64 == 0 ? 64 : 32);
+    c.cb = 0;
     c.log2_hw = 0;
     while ((1 << c.log2_hw) < HW) ++c.log2_hw;
     if ((1 << c.log2_hw) != HW) return fail(DTRAJ_EINVAL, "umma conv: H*W=%d is not a power of two", HW);
-    const size_t stage = kATileBytes + (size_t)L.coutp * 128;
-    // <= ~100 KB so two CTAs share an SM: one runs its epilogue while the other's MMAs run
-    int stages = (int)((100 * 1024) / stage);
-    if (stages < 2) stages = 2;
-    if (stages > 6) stages = 6;
+    c.log2_wh = 0;
+    while ((2 << c.log2_wh) < L.W) ++c.log2_wh;
+    if ((L.flags & CONV_POOL) && (L.W < 2 || L.W > 16 || L.H != L.W)) return fail(DTRAJ_EINVAL, "umma conv: fused pool needs 2 <= W <= 16");
+    if ((L.flags & (CONV_POOL | CONV_RESX | CONV_FINAL | CONV_NOSTORE)) && L.act_mode == ACT_SPLIT)
+        return fail(DTRAJ_EINVAL, "umma conv: fused tails are not available in 3xTF32 mode");
+    // one persistent CTA per SM: all shared memory that is not the epilogue ring goes to the operand ring
+    const size_t stage = kATileBytes + (size_t)c.ncols * 128;
+    const size_t fixed = 1024 + kEpiRingBytes + 512 + 2048;
+    int stages = (int)((227 * 1024 - fixed) / stage);
+    if (stages < 2) return fail(DTRAJ_EINVAL, "umma conv: operand ring does not fit");
+    if (stages > 8) stages = 8;
     c.stages = stages;
-    if ((size_t)stages * stage < (size_t)4 * 32 * (c.cb + 4) * sizeof(float))
-        return fail(DTRAJ_EINVAL, "umma conv: pipeline smem too small to stage the epilogue");
-    U->smem = 1024 + stages * stage + 16 * stages + 16 + 16 + 8 * 4 * kEpiBufs;
-    if ((size_t)stages * stage < (size_t)4 * kEpiBufs * 4096)
-        return fail(DTRAJ_EINVAL, "umma conv: pipeline smem too small for the epilogue ring");
-    U->grid = (unsigned)((L.M + 127) / 128);
+    U->smem = fixed + stages * stage;
+    U->grid = (unsigned)(c.n_work < kNumSMs ? c.n_work : kNumSMs);
     const int64_t n_img = L.M / HW;
     DTRAJ_TRY(make_act_map(&U->maps.a[0], L.src0, L.c0p, L.W, L.H, n_img, c.box_h, c.box_n));
     if (L.c1p) DTRAJ_TRY(make_act_map(&U->maps.a[1], L.src1, L.c1p, L.W, L.H, n_img, c.box_h, c.box_n));
@@ -512,9 +595,10 @@ inline int build_umma_launch(UmmaLaunch* U, const ConvLayer& L, int npass, const
         DTRAJ_TRY(make_act_map(&U->maps.a[2], L.src0_lo, L.c0p, L.W, L.H, n_img, c.box_h, c.box_n));
         if (L.c1p) DTRAJ_TRY(make_act_map(&U->maps.a[3], L.src1_lo, L.c1p, L.W, L.H, n_img, c.box_h, c.box_n));
     }
-    DTRAJ_TRY(make_w_map(&U->maps.b, wpk, w_rows, L.coutp));
+    DTRAJ_TRY(make_w_map(&U->maps.b, wpk, w_rows, c.ncols));
     if (L.M >= (int64_t)1 << 31) return fail(DTRAJ_EINVAL, "umma conv: M too large for 32-bit TMA coordinates");
-    DTRAJ_TRY(make_rows_map(&U->maps.out, L.out, L.M, L.coutp));
+    if (!(L.flags & CONV_NOSTORE)) DTRAJ_TRY(make_rows_map(&U->maps.out, L.out, L.M, L.coutp));
+    if (L.act_mode == ACT_SPLIT) DTRAJ_TRY(make_rows_map(&U->maps.out_lo, L.out + L.lo_off, L.M, L.coutp));
     if (L.flags & CONV_RESID) DTRAJ_TRY(make_rows_map(&U->maps.res, L.resid, L.M, L.coutp));
     return 0;
 }

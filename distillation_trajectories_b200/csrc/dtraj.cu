@@ -4,6 +4,7 @@
 #include <string>
 #include <vector>
 #include <cmath>
+#include <cstdlib>
 
 #include "common.cuh"
 #include "elem.cuh"
@@ -334,7 +335,10 @@ struct dtraj_plan {
     struct Buf { float* p = nullptr; int64_t n = 0; int64_t lo = 0; };
     Buf tmp_h, tmp_r, tmp_x, p1, x2, p2, x3, p3, x4, p4, u3, u2, u1, y1, elow;
     // generic conv launches in execution order
-    struct ConvOp { ConvLayer L; bool umma; UmmaLaunch U; int tb_block; double flops; };
+    struct ConvOp { ConvLayer L; bool umma; UmmaLaunch U; int tb_block; double flops; bool needs_x; };
+    // fused tails (single-pass TF32 mode): which stand-alone kernels the conv epilogues replace
+    bool fuse_resx = false, fuse_final = false;
+    bool fuse_pool[4] = {false, false, false, false};   // pool after enc1..enc4
     std::vector<ConvOp> convs;   // 15 3x3 + residual 1x1s
     int64_t launches_per_forward = 0;
 };
@@ -379,8 +383,14 @@ int64_t plan_floats(const dtraj_unet* u, int64_t R, dtraj_plan* P) {
     return off;
 }
 
+struct Tail {                // optional fused epilogue tails of one conv
+    float* pool_out = nullptr;
+    bool resx = false, final1x1 = false, nostore = false;
+};
+
 int add_conv(dtraj_plan* P, const PackedConv& pc, const dtraj_plan::Buf& s0, const dtraj_plan::Buf* s1, int S,
-             const dtraj_plan::Buf& out, const float* resid, int flags, int tb_block, bool is_residual_conv) {
+             const dtraj_plan::Buf& out, const float* resid, int flags, int tb_block, bool is_residual_conv,
+             const Tail& tail = Tail()) {
     const dtraj_unet* u = P->u;
     dtraj_plan::ConvOp op;
     memset(&op.L, 0, sizeof(op.L));
@@ -394,6 +404,18 @@ int add_conv(dtraj_plan* P, const PackedConv& pc, const dtraj_plan::Buf& s0, con
     L.lo_off = out.lo;
     L.act_mode = is_residual_conv ? ACT_PLAIN : (u->act_mode == ACT_SPLIT && out.lo == 0 ? ACT_PLAIN : u->act_mode);
     L.flags = flags;
+    op.needs_x = false;
+    if (tail.pool_out) { L.flags |= CONV_POOL; L.pool_out = tail.pool_out; }
+    if (tail.nostore) L.flags |= CONV_NOSTORE;
+    if (tail.resx) {
+        L.flags |= CONV_RESX;
+        L.rw1 = u->fw1; L.rb1 = u->fb1; L.xC = u->d.channels;
+        op.needs_x = true;
+    }
+    if (tail.final1x1) {
+        L.flags |= CONV_FINAL;
+        L.finw = u->finw; L.finb = u->finb; L.finC = u->d.channels; L.elow = P->elow.p;
+    }
     op.tb_block = tb_block;
     op.flops = 2.0 * (double)L.M * pc.cout * (double)(pc.c0 + pc.c1) * pc.ntaps;   // executed taps, real channels
     op.umma = u->d.precision != DTRAJ_PREC_FP32;
@@ -414,13 +436,31 @@ int plan_build(const dtraj_unet* u, int64_t R, void* ws, int64_t ws_bytes, dtraj
     int rc = 0;
     const int RT = CONV_RELU | CONV_TBIAS, RR = CONV_RELU | CONV_RESID;
     auto blk = [&](int b) -> const BlockW& { return u->blk[b]; };
+    // Fused epilogue tails exist in the tcgen05 kernel's bulk path only (single-pass TF32, the mode the
+    // sweeps run in); the exact modes keep the stand-alone pool / final / residual kernels.
+    const bool fused = u->d.precision == DTRAJ_PREC_TF32 && !getenv("DTRAJ_NO_FUSE");
+    P->fuse_resx = fused;
+    P->fuse_final = fused;
+    for (int l = 0; l < 4; ++l) P->fuse_pool[l] = fused && S[l] <= 16;
+    const dtraj_plan::Buf* pooled[4] = {&P->p1, &P->p2, &P->p3, &P->p4};
+    auto tail_for = [&](int enc) {   // conv2 of encoder block `enc` (0..3)
+        Tail t;
+        if (P->fuse_pool[enc]) t.pool_out = pooled[enc]->p;
+        return t;
+    };
 #define ADD(...) if (!rc) rc = add_conv(P, __VA_ARGS__)
-    // enc1: conv1/res by k_conv_first; conv2 here
-    ADD(blk(0).conv2, P->tmp_h, nullptr, S[0], P->tmp_x, P->tmp_r.p, RR, -1, false);
+    // enc1: conv1/res by k_conv_first; conv2 here.  x1 itself is never a skip input (models.py:206-216):
+    // with the pool fused, only the pooled tile is written.
+    {
+        Tail t = tail_for(0);
+        t.resx = P->fuse_resx;
+        t.nostore = P->fuse_pool[0];
+        ADD(blk(0).conv2, P->tmp_h, nullptr, S[0], P->tmp_x, t.resx ? nullptr : P->tmp_r.p, t.resx ? CONV_RELU : RR, -1, false, t);
+    }
     // enc2 @ level 1
     ADD(blk(1).res, P->p1, nullptr, S[1], P->tmp_r, nullptr, 0, -1, true);
     ADD(blk(1).conv1, P->p1, nullptr, S[1], P->tmp_h, nullptr, RT, 1, false);
-    ADD(blk(1).conv2, P->tmp_h, nullptr, S[1], P->x2, P->tmp_r.p, RR, -1, false);
+    ADD(blk(1).conv2, P->tmp_h, nullptr, S[1], P->x2, P->tmp_r.p, RR, -1, false, tail_for(1));
     // enc3 @ level 2 (identity residual = pooled input)
     const dtraj_plan::Buf* pin[3] = {&P->p2, &P->p3, &P->p4};
     const dtraj_plan::Buf* xo[3] = {&P->x3, &P->x4, &P->tmp_x};
@@ -429,7 +469,7 @@ int plan_build(const dtraj_unet* u, int64_t R, void* ws, int64_t ws_bytes, dtraj
         const float* resid = pin[k]->p;
         if (blk(b).has_res) { ADD(blk(b).res, *pin[k], nullptr, S[lv], P->tmp_r, nullptr, 0, -1, true); resid = P->tmp_r.p; }
         ADD(blk(b).conv1, *pin[k], nullptr, S[lv], P->tmp_h, nullptr, RT, b, false);
-        ADD(blk(b).conv2, P->tmp_h, nullptr, S[lv], *xo[k], resid, RR, -1, false);
+        ADD(blk(b).conv2, P->tmp_h, nullptr, S[lv], *xo[k], resid, RR, -1, false, k < 2 ? tail_for(2 + k) : Tail());
     }
     // decoders: [upsampled | skip]
     const dtraj_plan::Buf* up[3] = {&P->u3, &P->u2, &P->u1};
@@ -440,7 +480,9 @@ int plan_build(const dtraj_unet* u, int64_t R, void* ws, int64_t ws_bytes, dtraj
         if (!blk(b).has_res) { rc = fail(DTRAJ_EINVAL, "%s without residual_conv unsupported", kBlockNames[b]); break; }
         ADD(blk(b).res, *up[k], skip[k], S[lv], P->tmp_r, nullptr, 0, -1, true);
         ADD(blk(b).conv1, *up[k], skip[k], S[lv], P->tmp_h, nullptr, RT, b, false);
-        ADD(blk(b).conv2, P->tmp_h, nullptr, S[lv], *yo[k], P->tmp_r.p, RR, -1, false);
+        Tail t;
+        if (k == 2 && P->fuse_final) { t.final1x1 = true; t.nostore = true; }   // y1 only feeds the final 1x1
+        ADD(blk(b).conv2, P->tmp_h, nullptr, S[lv], *yo[k], P->tmp_r.p, RR, -1, false, t);
     }
 #undef ADD
     if (rc) { delete P; return rc; }
@@ -467,7 +509,7 @@ int plan_forward(dtraj_plan* P, const float* x, int64_t x_stride, const int32_t*
         f.C = C; f.H = S[0]; f.W = S[0]; f.coutp = dp[0];
         f.w3 = u->fw3; f.b3 = u->fb3; f.w1 = u->fw1; f.b1 = u->fb1;
         f.tbias = trow + u->tb_off[0]; f.tb_var_stride = u->tb_stride;
-        f.h = P->tmp_h.p; f.r = P->tmp_r.p; f.lo_off = P->tmp_h.lo; f.act_mode = u->act_mode;
+        f.h = P->tmp_h.p; f.r = P->fuse_resx ? nullptr : P->tmp_r.p; f.lo_off = P->tmp_h.lo; f.act_mode = u->act_mode;
         const size_t smem = (round_up(C * (S[0] + 2) * (S[0] + 2), 4) + 10 * C * dp[0]) * sizeof(float);
         PROF_BEGIN(prof, KC_FIRST);
         k_conv_first<<<(unsigned)R, 256, smem, st>>>(f);
@@ -483,6 +525,7 @@ int plan_forward(dtraj_plan* P, const float* x, int64_t x_stride, const int32_t*
         PROF_BEGIN(prof, KC_CONV);
         if (op.umma) {
             op.U.conv.L.tbias = tb; op.U.conv.L.row_variant = row_variant;
+            if (op.needs_x) { op.U.conv.L.xraw = x; op.U.conv.L.x_stride = x_stride; op.U.conv.L.row_sample = row_sample; }
             rc = launch_conv_umma(op.U, st);
         } else {
             op.L.tbias = tb; op.L.row_variant = row_variant;
@@ -491,7 +534,8 @@ int plan_forward(dtraj_plan* P, const float* x, int64_t x_stride, const int32_t*
         PROF_END(prof);
         return rc;
     };
-    auto pool = [&](const dtraj_plan::Buf& in, const dtraj_plan::Buf& out, int So, int cp) -> int {
+    auto pool = [&](const dtraj_plan::Buf& in, const dtraj_plan::Buf& out, int So, int cp, int level) -> int {
+        if (P->fuse_pool[level]) return 0;      // emitted by the producing conv's epilogue
         const int64_t n4 = R * So * So * (cp / 4);
         PROF_BEGIN(prof, KC_RESAMPLE);
         k_pool2<<<blocks_for(n4, 256), 256, 0, st>>>(in.p, out.p, n4, So, So, cp / 4, out.lo, out.lo ? ACT_SPLIT : ACT_PLAIN);
@@ -509,15 +553,15 @@ int plan_forward(dtraj_plan* P, const float* x, int64_t x_stride, const int32_t*
         return 0;
     };
     DTRAJ_TRY(conv());                                   // enc1.conv2 -> x1 (tmp_x)
-    DTRAJ_TRY(pool(P->tmp_x, P->p1, S[1], dp[0]));
+    DTRAJ_TRY(pool(P->tmp_x, P->p1, S[1], dp[0], 0));
     DTRAJ_TRY(conv()); DTRAJ_TRY(conv()); DTRAJ_TRY(conv());   // enc2 -> x2
-    DTRAJ_TRY(pool(P->x2, P->p2, S[2], dp[1]));
+    DTRAJ_TRY(pool(P->x2, P->p2, S[2], dp[1], 1));
     const dtraj_plan::Buf* xo[3] = {&P->x3, &P->x4, &P->tmp_x};
     const dtraj_plan::Buf* pn[2] = {&P->p3, &P->p4};
     for (int k = 0; k < 3; ++k) {                        // enc3, enc4, bottleneck
         if (u->blk[2 + k].has_res) DTRAJ_TRY(conv());
         DTRAJ_TRY(conv()); DTRAJ_TRY(conv());
-        if (k < 2) DTRAJ_TRY(pool(*xo[k], *pn[k], S[3 + k], dp[2 + k]));
+        if (k < 2) DTRAJ_TRY(pool(*xo[k], *pn[k], S[3 + k], dp[2 + k], 2 + k));
     }
     const dtraj_plan::Buf* up[3] = {&P->u3, &P->u2, &P->u1};
     const int upc[3] = {dp[3], dp[2], dp[1]};
@@ -525,7 +569,7 @@ int plan_forward(dtraj_plan* P, const float* x, int64_t x_stride, const int32_t*
         DTRAJ_TRY(upsample(P->tmp_x, *up[k], S[4 - k], upc[k]));
         DTRAJ_TRY(conv()); DTRAJ_TRY(conv()); DTRAJ_TRY(conv());
     }
-    {   // final 1x1 at half resolution
+    if (!P->fuse_final) {   // final 1x1 at half resolution (else: dec1.conv2's epilogue)
         const int64_t npix = R * S[1] * S[1];
         PROF_BEGIN(prof, KC_RESAMPLE);
         k_final1x1<<<blocks_for(npix * 32, 256), 256, 0, st>>>(P->y1.p, u->finw, u->finb, P->elow.p, npix, dp[0], C);
@@ -680,7 +724,9 @@ extern "C" int dtraj_sampler_create(dtraj_unet* u, const dtraj_sampler_desc* d, 
         if (rc) { dtraj_sampler_destroy(s); return rc; }
     } else {
         // dry count of launches
-        s->launches = (int64_t)d->n_updates * (2 + (int64_t)s->plan->convs.size() + 4 + 3 + 1) + (d->copy_last ? 1 : 0);
+        int extra = 3 + (s->plan->fuse_final ? 0 : 1);     // upsamples + final
+        for (int l = 0; l < 4; ++l) extra += s->plan->fuse_pool[l] ? 0 : 1;
+        s->launches = (int64_t)d->n_updates * (2 + (int64_t)s->plan->convs.size() + extra) + (d->copy_last ? 1 : 0);
     }
     *out = s;
     return 0;
@@ -772,8 +818,16 @@ extern "C" int dtraj_bench_conv(int32_t precision, int32_t c0, int32_t c1, int32
     L.src1 = x1; L.src1_lo = x1 ? x1 + (size_t)M * c1p : nullptr; L.c1p = c1p;
     L.H = H; L.W = H; L.M = M; L.ntaps = pc.ntaps; L.wpk = dev + wo; L.bias = dev + bo; L.coutp = coutp;
     L.resid = (flags & 4) ? res : nullptr; L.out = out; L.lo_off = (int64_t)M * coutp;
-    L.flags = (flags & 1 ? CONV_RELU : 0) | (flags & 4 ? CONV_RESID : 0);
+    L.flags = (flags & 1 ? CONV_RELU : 0) | (flags & 4 ? CONV_RESID : 0) | (flags & (CONV_POOL | CONV_NOSTORE | CONV_RESX | CONV_FINAL));
     L.act_mode = precision == DTRAJ_PREC_TF32 ? ACT_ROUND : precision == DTRAJ_PREC_TF32X3 ? ACT_SPLIT : ACT_PLAIN;
+    float* aux = nullptr;      // pooled output | raw input | 1x1 weights | final weights | eps, all zero
+    DTRAJ_CUDA(cudaMalloc(&aux, ((size_t)M / 4 * coutp + (size_t)n * 4 * H * H + 16 * coutp + (size_t)M * 4) * 4));
+    DTRAJ_CUDA(cudaMemset(aux, 0, ((size_t)M / 4 * coutp + (size_t)n * 4 * H * H + 16 * coutp + (size_t)M * 4) * 4));
+    L.pool_out = aux;
+    L.xraw = aux + (size_t)M / 4 * coutp; L.x_stride = 4 * H * H; L.xC = 1;
+    L.rw1 = L.xraw + (size_t)n * 4 * H * H; L.rb1 = L.rw1 + 4 * coutp;
+    L.finw = L.rb1 + 4 * coutp; L.finb = L.finw + 4 * coutp; L.finC = 1;
+    L.elow = aux + (size_t)M / 4 * coutp + (size_t)n * 4 * H * H + 16 * coutp;
     int rc = 0;
     UmmaLaunch U;
     if (precision != DTRAJ_PREC_FP32) {
@@ -792,7 +846,7 @@ extern "C" int dtraj_bench_conv(int32_t precision, int32_t c0, int32_t c1, int32
     float ms = 0.f;
     cudaEventElapsedTime(&ms, e0, e1);
     cudaEventDestroy(e0); cudaEventDestroy(e1);
-    cudaFree(dev); cudaFree(x0); if (x1) cudaFree(x1); cudaFree(res); cudaFree(out);
+    cudaFree(dev); cudaFree(x0); if (x1) cudaFree(x1); cudaFree(res); cudaFree(out); cudaFree(aux);
     if (rc) return rc;
     if (ce != cudaSuccess) return fail(DTRAJ_ECUDA, "bench_conv -> %s", cudaGetErrorString(ce));
     *ms_out = ms / iters;

@@ -89,7 +89,7 @@ struct FirstConvParams {
     const float* tbias;      // table row base for this t: + variant*tb_var_stride + block_off
     int tb_var_stride;
     float* h;                // [R,H,W,coutp]   relu(bn(conv1 x)) + tbias
-    float* r;                // [R,H,W,coutp]   residual_conv(x)
+    float* r;                // [R,H,W,coutp]   residual_conv(x); null when the consumer recomputes it (CONV_RESX)
     int64_t lo_off;          // ACT_SPLIT: h low plane offset
     int act_mode;
 };
@@ -142,7 +142,7 @@ __global__ void __launch_bounds__(256) k_conv_first(FirstConvParams p) {
         float* dst = hout + (size_t)pix * cp + g * 4;
         *reinterpret_cast<float4*>(dst) = o;
         if (p.act_mode == ACT_SPLIT) *reinterpret_cast<float4*>(dst + p.lo_off) = act_lo4(o);
-        *reinterpret_cast<float4*>(rout + (size_t)pix * cp + g * 4) = racc;
+        if (p.r) *reinterpret_cast<float4*>(rout + (size_t)pix * cp + g * 4) = racc;
     }
 }
 
