@@ -240,19 +240,21 @@ def run_ours(args):
 
     # ---- end-to-end leg: the public sweep API with host-side inputs, copies inside the timed region
     stats = {}
+    e2e_pairs = max(G, (S // max(1, args.e2e_chunks)) * G)
     for i in range(max(1, W // 2)):
-        grid.sweep(teacher, {"student": student}, Cfg, GUIDANCE, S * world, dev, rank, world, max_pairs=S * G,
+        grid.sweep(teacher, {"student": student}, Cfg, GUIDANCE, S * world, dev, rank, world, max_pairs=e2e_pairs,
                    precision=args.precision)
     barrier()
     t0 = time.perf_counter()
     for i in range(K):
-        res = grid.sweep(teacher, {"student": student}, Cfg, GUIDANCE, S * world, dev, rank, world, max_pairs=S * G,
+        res = grid.sweep(teacher, {"student": student}, Cfg, GUIDANCE, S * world, dev, rank, world, max_pairs=e2e_pairs,
                          precision=args.precision, stats=stats)
     barrier()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     e2e = {"value": traj_per_step * K / e2e_s, "unit": UNIT, "h2d_bytes_per_step": stats["h2d_bytes"] // K,
            "d2h_bytes_per_step": stats["d2h_bytes"] // K, "ms_per_step": e2e_s / K * 1e3,
            "api": "distillation_trajectories_b200.grid.sweep (batched compare_trajectories)",
+           "chunks_per_step": args.e2e_chunks,
            "check": {"trajectory_mse@w=7.5": res["student"][7.5]["trajectory_mse"],
                      "distribution_similarity@w=7.5": res["student"][7.5]["distribution_similarity"]}}
 
@@ -284,7 +286,6 @@ def run_ours(args):
     D, L, N = Cfg.channels * Cfg.image_size ** 2, Cfg.timesteps + 1, S * G
     step_ms = sum(p["ms"][3] for p in prof)
     step_bytes = sum(((16 if w <= 1.0 else 20) * D) for w in GUIDANCE) * S * (Cfg.timesteps - 1) * 2 + 2 * N * D * 8
-    tflat = keep[0]
     from distillation_trajectories_b200.analysis.metrics import trajectory_metrics as tm
     ta = samplers[0].traj.reshape(N, L, D)
     sa = samplers[1].traj.reshape(N, L, D)
@@ -336,6 +337,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--seeds", type=int, default=256, help="seeds per GPU per step (x 8 guidance scales x 2 models)")
     ap.add_argument("--precision", default="tf32", choices=["tf32", "tf32x3", "fp32"])
+    ap.add_argument("--e2e-chunks", type=int, default=1,
+                    help="chunks a sweep is cut into in the end-to-end leg (host staging of chunk i+1 overlaps chunk i on the GPU)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -57,14 +57,28 @@ def generate_trajectory(model, noise, timesteps, device, seed=None, guidance_sca
     return sampling.frames_to_cpu_list(traj)
 
 
+_generators = {}
+
+
+def _generator(device):
+    """A private generator per device.  ``g.manual_seed(k); torch.randn(..., generator=g)`` yields exactly the
+    stream of ``torch.manual_seed(k); torch.randn(...)`` on that device (same engine, same seeding) without
+    re-seeding every CUDA device's global generator for each of the hundreds of keys a batch needs."""
+    key = str(device)
+    if key not in _generators:
+        _generators[key] = torch.Generator(device=device)
+    return _generators[key]
+
+
 def _noise_bank(base_seeds, shape, device, timesteps):
     """z(sample, t) depends on seed + t only: draw each distinct key once.
     Returns (bank [n_keys, D], first_key)."""
     lo, hi = min(base_seeds) + 1, max(base_seeds) + timesteps - 1
+    g = _generator(device)
     rows = []
     for key in range(lo, hi + 1):
-        torch.manual_seed(key)
-        rows.append(torch.randn(shape, device=device).reshape(-1))
+        g.manual_seed(key)
+        rows.append(torch.randn(shape, device=device, generator=g).reshape(-1))
     if not rows:
         return torch.zeros(1, int(np.prod(shape)), device=device), lo
     return torch.stack(rows), lo

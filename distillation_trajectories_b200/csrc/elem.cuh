@@ -116,6 +116,43 @@ __global__ void __launch_bounds__(256) k_conv_first(FirstConvParams p) {
     const float* tb = p.tbias + (size_t)variant * p.tb_var_stride;
     float* hout = p.h + (size_t)row * H * W * cp;
     float* rout = p.r + (size_t)row * H * W * cp;
+    // 256 threads and cp/4 <= 64 channel groups: a thread's group is the same for every item it owns when
+    // 256 % groups == 0 (all padded widths except 96/160/192/224-style ones), so its 9*C weight vectors,
+    // bias and time bias live in registers and the pixel loop is 9*C broadcast loads + 36*C FMAs.
+    if (256 % groups == 0 && C == 1) {
+        const int g = threadIdx.x % groups;
+        float4 w[9];
+#pragma unroll
+        for (int t9 = 0; t9 < 9; ++t9) w[t9] = *reinterpret_cast<const float4*>(w3 + t9 * cp + g * 4);
+        const float4 wr = *reinterpret_cast<const float4*>(w1 + g * 4);
+        const float4 b3 = *reinterpret_cast<const float4*>(p.b3 + g * 4), b1 = *reinterpret_cast<const float4*>(p.b1 + g * 4);
+        const float4 t4 = *reinterpret_cast<const float4*>(tb + g * 4);
+        for (int pix = threadIdx.x / groups; pix < H * W; pix += 256 / groups) {
+            const int y = pix / W, xq = pix % W;
+            float4 acc = b3;
+#pragma unroll
+            for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+                for (int kx = 0; kx < 3; ++kx) {
+                    const float v = img[(y + ky) * PW + xq + kx];
+                    const float4 ww = w[ky * 3 + kx];
+                    acc.x = fmaf(v, ww.x, acc.x); acc.y = fmaf(v, ww.y, acc.y);
+                    acc.z = fmaf(v, ww.z, acc.z); acc.w = fmaf(v, ww.w, acc.w);
+                }
+            float4 o = make_float4(fmaxf(acc.x, 0.f) + t4.x, fmaxf(acc.y, 0.f) + t4.y,
+                                   fmaxf(acc.z, 0.f) + t4.z, fmaxf(acc.w, 0.f) + t4.w);
+            o = act_round4(o, p.act_mode);
+            float* dst = hout + (size_t)pix * cp + g * 4;
+            *reinterpret_cast<float4*>(dst) = o;
+            if (p.act_mode == ACT_SPLIT) *reinterpret_cast<float4*>(dst + p.lo_off) = act_lo4(o);
+            if (p.r) {
+                const float v = img[(y + 1) * PW + xq + 1];
+                *reinterpret_cast<float4*>(rout + (size_t)pix * cp + g * 4) =
+                    make_float4(fmaf(v, wr.x, b1.x), fmaf(v, wr.y, b1.y), fmaf(v, wr.z, b1.z), fmaf(v, wr.w, b1.w));
+            }
+        }
+        return;
+    }
     for (int item = threadIdx.x; item < H * W * groups; item += blockDim.x) {
         const int pix = item / groups, g = item % groups, y = pix / W, xq = pix % W;
         float4 acc = *reinterpret_cast<const float4*>(p.b3 + g * 4);

@@ -52,7 +52,7 @@ def averages_from_sums(sums, student_keys, guidance_scales):
 
 class Chunk:
     """Device-resident inputs of one batch of (seed, guidance) pairs; pair p = seed-major, guidance-minor."""
-    __slots__ = ("samples", "G", "x", "seeds", "ws", "bank", "z_index", "idx", "idx_set", "T", "h2d_bytes")
+    __slots__ = ("samples", "G", "x", "seeds", "ws", "ws_dev", "bank", "z_index", "idx", "idx_set", "T", "h2d_bytes")
 
 
 def stage_chunk(samples, config, guidance_scales, device):
@@ -66,10 +66,10 @@ def stage_chunk(samples, config, guidance_scales, device):
     ck = Chunk()
     ck.samples, ck.G, ck.T = list(samples), G, T
     noises = []
+    gen = te._generator(torch.device("cpu"))       # same stream as torch.manual_seed(42 + s); torch.randn(...)
     for s in ck.samples:
-        torch.manual_seed(42 + s)
-        np.random.seed(42 + s)
-        noises.append(torch.randn(1, C, H, H))
+        gen.manual_seed(42 + s)
+        noises.append(torch.randn(1, C, H, H, generator=gen))
     x = torch.cat(noises).repeat_interleave(G, dim=0)
     ck.seeds = [42 + s for s in ck.samples for _ in range(G)]
     ck.ws = [gs for _ in ck.samples for gs in guidance_scales]
@@ -89,6 +89,7 @@ def stage_chunk(samples, config, guidance_scales, device):
         return t.pin_memory().to(device, non_blocking=True)
 
     ck.x = up(x)
+    ck.ws_dev = up(torch.tensor([float(w) if w is not None else 0.0 for w in ck.ws], dtype=torch.float32))
     ck.bank = up(bank)
     ck.z_index = up(torch.from_numpy(zi))
     ck.idx = None if idx is None else up(torch.from_numpy(idx))
@@ -107,7 +108,7 @@ def run_chunk(teacher_model, student_models, ck, device, precision=None):
     def gen(model):
         model.eval()
         eng = te.UNetEngine.for_model(model, ck.x.shape[2], ck.T, prec, device)
-        return sampling.s2_sample(eng, ck.x, ck.T, ck.ws, ck.bank, ck.z_index)
+        return sampling.s2_sample(eng, ck.x, ck.T, ck.ws, ck.bank, ck.z_index, guidance_dev=ck.ws_dev)
 
     tt = gen(teacher_model)
     t_flat = tt.reshape(tt.shape[0], tt.shape[1], -1)
@@ -125,11 +126,46 @@ def run_chunk(teacher_model, student_models, ck, device, precision=None):
     return torch.stack(reds), torch.stack(w1s), n_traj
 
 
+class _Readback:
+    """Device-to-host copy of a chunk's reductions on a side stream, so that waiting for chunk i's numbers
+    does not wait for chunk i+1's kernels (already queued on the compute stream)."""
+
+    def __init__(self, red, w1, device):
+        self.stream = _copy_stream(device)
+        ready = torch.cuda.Event()
+        ready.record(torch.cuda.current_stream(device))
+        self.red_h = torch.empty(red.shape, dtype=red.dtype, pin_memory=True)
+        self.w1_h = torch.empty(w1.shape, dtype=w1.dtype, pin_memory=True)
+        self.keep = (red, w1)                       # keep the device tensors alive until the copy is done
+        with torch.cuda.stream(self.stream):
+            self.stream.wait_event(ready)
+            self.red_h.copy_(red, non_blocking=True)
+            self.w1_h.copy_(w1, non_blocking=True)
+            self.done = torch.cuda.Event()
+            self.done.record(self.stream)
+
+    def wait(self):
+        self.done.synchronize()
+        self.keep = None
+        return self.red_h.numpy(), self.w1_h.numpy()
+
+
+_copy_streams = {}
+
+
+def _copy_stream(device):
+    key = str(device)
+    if key not in _copy_streams:
+        _copy_streams[key] = torch.cuda.Stream(device)
+    return _copy_streams[key]
+
+
 def finish_chunk(red, w1, ck, config, sums):
     """Device-to-host copy of the reductions and the f64 scalar formulas; accumulates into ``sums``.
-    Returns the bytes copied."""
+    ``red`` / ``w1`` are device tensors or the numpy arrays of a finished ``_Readback``.  Returns the bytes copied."""
     H, D = config.image_size, config.channels * config.image_size ** 2
-    red_h, w1_h = red.cpu().numpy(), w1.cpu().numpy()
+    red_h = red if isinstance(red, np.ndarray) else red.cpu().numpy()
+    w1_h = w1 if isinstance(w1, np.ndarray) else w1.cpu().numpy()
     for i in range(red_h.shape[0]):
         sm = tm.scalar_metrics_batched(red_h[i], w1_h[i], H * H, D)
         for j, k in enumerate(tm.SCALAR_KEYS):
@@ -146,6 +182,10 @@ def sweep(teacher_model, students, config, guidance_scales, num_samples, device=
     Returns {name: {gs: {18 scalar metrics averaged over all ``num_samples`` seeds}}}; with
     ``reduce=True`` every rank returns the global averages.  ``stats`` (dict) receives counters:
     trajectories generated, pairs measured, bytes moved each way.
+
+    Chunks are software-pipelined: while the GPU runs chunk i (kernel launches are asynchronous), the
+    host draws and uploads chunk i+1's noise and evaluates chunk i-1's scalar formulas from a side-stream
+    read-back, so host work hides behind device work whenever a sweep has more than one chunk.
     """
     if device is None:
         device = next(teacher_model.parameters()).device
@@ -153,17 +193,27 @@ def sweep(teacher_model, students, config, guidance_scales, num_samples, device=
     guidance_scales = list(guidance_scales)
     G = len(guidance_scales)
     names = list(students)
+    models = [students[n] for n in names]
     sums = np.zeros((len(names), G, len(tm.SCALAR_KEYS) + 1), np.float64)
     mine = shard_samples(num_samples, rank, world_size)
     per_chunk = max(1, max_pairs // G)
+    pieces = [mine[c0:c0 + per_chunk] for c0 in range(0, len(mine), per_chunk)]
     n_traj = n_pairs = h2d = d2h = 0
-    for c0 in range(0, len(mine), per_chunk):
-        ck = stage_chunk(mine[c0:c0 + per_chunk], config, guidance_scales, device)
-        red, w1, nt = run_chunk(teacher_model, [students[n] for n in names], ck, device, precision)
-        d2h += finish_chunk(red, w1, ck, config, sums)
+    pending = None                                  # (readback, chunk) of the previous chunk
+    nxt = stage_chunk(pieces[0], config, guidance_scales, device) if pieces else None
+    for i in range(len(pieces)):
+        ck = nxt
+        red, w1, nt = run_chunk(teacher_model, models, ck, device, precision)      # queued, not waited for
+        rb = _Readback(red, w1, device)
+        nxt = stage_chunk(pieces[i + 1], config, guidance_scales, device) if i + 1 < len(pieces) else None
+        if pending is not None:
+            d2h += finish_chunk(*pending[0].wait(), pending[1], config, sums)
+        pending = (rb, ck)
         h2d += ck.h2d_bytes
         n_traj += nt
         n_pairs += len(ck.seeds) * len(names)
+    if pending is not None:
+        d2h += finish_chunk(*pending[0].wait(), pending[1], config, sums)
     if stats is not None:
         for k, v in (("trajectories", n_traj), ("pairs", n_pairs), ("h2d_bytes", h2d), ("d2h_bytes", d2h)):
             stats[k] = stats.get(k, 0) + v

@@ -164,3 +164,16 @@ def test_graph_and_eager_loops_agree():
     a = sampling.s2_sample(eng, x, 6, [2.0, None, 7.5], bank, zi, use_graph=True).cpu().numpy().copy()
     b = sampling.s2_sample(eng, x, 6, [2.0, None, 7.5], bank, zi, use_graph=False).cpu().numpy()
     np.testing.assert_array_equal(a, b)
+
+
+def test_private_generators_reproduce_global_seeding():
+    """the batched sweep draws with per-device private generators; the streams must equal what
+    torch.manual_seed(k); torch.randn(...) gives on that device (analysis/trajectory_engine.py:88-95)"""
+    for dev in ("cpu", "cuda"):
+        g = te._generator(torch.device(dev))
+        for k in (0, 43, 91, 12345):
+            g.manual_seed(k)
+            a = torch.randn(1, 3, 32, 32, device=dev, generator=g)
+            torch.manual_seed(k)
+            b = torch.randn(1, 3, 32, 32, device=dev)
+            assert torch.equal(a, b), (dev, k)
