@@ -39,6 +39,9 @@ struct UmmaConv {
     int n_split;               // column split of a tile when there are fewer tiles than SMs (power of two)
     int ncols;                 // coutp / n_split: columns per work item (multiple of 32)
     int n_work;                // n_tiles * n_split work items; CTA b handles b, b + gridDim.x, ...
+    int swap;                  // 1: operands swapped (coutp <= 128): the WEIGHTS are the 128-row M operand and
+                               //    `tn` output pixels the N operand, D^T[cout, pixel] accumulates in TMEM
+    int tn;                    // pixels per tile in swap mode (256, 128 or 64); 128 otherwise
     int box_h, box_n;          // A box = {32, W, box_h, box_n}
     int tiles_per_img;         // >= 1
     int b_lo_row;              // row offset of the low-plane weights inside the B tensor map
@@ -159,7 +162,8 @@ k_conv_umma(const __grid_constant__ UmmaMaps maps, const UmmaConv p) {
     const uint32_t base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
     const int coutp = p.L.coutp;
     const int ncols = p.ncols;                                 // columns this CTA computes per work item (coutp / n_split)
-    const uint32_t b_bytes = (uint32_t)ncols * 128u;
+    const int n_rows = p.swap ? p.tn : ncols;                  // rows of the N operand tile (UMMA N)
+    const uint32_t b_bytes = (uint32_t)n_rows * 128u;
     const uint32_t stage_bytes = kATileBytes + b_bytes;        // multiple of 1024 (ncols % 32 == 0 -> b_bytes % 4096 == 0)
     const uint32_t ring_base = base + p.stages * stage_bytes;
     const uint32_t bar_base = ring_base + kEpiRingBytes;
@@ -228,8 +232,13 @@ k_conv_umma(const __grid_constant__ UmmaMaps maps, const UmmaConv p) {
                             ++n_issued;
                             if (do_a || do_b) ptx::mbar_expect_tx(full_bar(s), (do_a ? kATileBytes : 0) + (do_b ? b_bytes : 0));
                             else ptx::mbar_arrive(full_bar(s));
-                            if (do_a) ptx::tma_load_4d(a_dst, &maps.a[src + asel], full_bar(s), c0, dx, y0 + dy, img0);
-                            if (do_b) ptx::tma_load_2d(b_dst, &maps.b, full_bar(s), 0, b_row);
+                            if (!p.swap) {
+                                if (do_a) ptx::tma_load_4d(a_dst, &maps.a[src + asel], full_bar(s), c0, dx, y0 + dy, img0);
+                                if (do_b) ptx::tma_load_2d(b_dst, &maps.b, full_bar(s), 0, b_row);
+                            } else {            // M operand <- 128 weight rows, N operand <- tn shifted pixels
+                                if (do_a) ptx::tma_load_2d(a_dst, &maps.b, full_bar(s), 0, b_row);
+                                if (do_b) ptx::tma_load_4d(b_dst, &maps.a[src + asel], full_bar(s), c0, dx, y0 + dy, img0);
+                            }
                             b_row += coutp;
                             if (++s == p.stages) { s = 0; ph ^= 1u; }
                         }
@@ -241,7 +250,7 @@ k_conv_umma(const __grid_constant__ UmmaMaps maps, const UmmaConv p) {
     } else if (warp == 1) {
         // ------------------------------------------------------------ MMA issuer
         if (ptx::elect_one()) {
-            const uint32_t idesc = umma_idesc_tf32(ncols);
+            const uint32_t idesc = umma_idesc_tf32(n_rows);
             int s = 0, acc = 0;
             uint32_t ph = 0, acc_ph = 0;
             bool ok = true;
@@ -287,6 +296,166 @@ k_conv_umma(const __grid_constant__ UmmaMaps maps, const UmmaConv p) {
         //                they are in registers; CONV_NOSTORE drops the main store when the full tensor
         //                has no other consumer
         // 3xTF32 (ACT_SPLIT) also writes the low plane y - trunc_tf32(y) through a second store.
+        if (p.swap) {
+            // ---- swapped operands: TMEM lane = output channel, TMEM column = pixel of the tile.  Warp (q, h)
+            // owns channels [32q, 32q+32) and the pixel blocks h, h+2, ... of 32 pixels; a ring buffer is the
+            // same [32 pixels][32 channels] swizzled box as in the other branch, accessed transposed (lane =
+            // channel: 32 consecutive words per pixel row, conflict-free).  Bias, time bias and the enc1
+            // residual weights are per-thread constants here.
+            const int q = warp & 3, h = (warp - 2) >> 2, ew = warp - 2;
+            const int fl = p.L.flags;
+            const bool skip_io = (p.debug & 4) != 0;
+            const bool has_res = (fl & CONV_RESID) != 0 && !skip_io;
+            const bool do_store = !(fl & CONV_NOSTORE) && !skip_io;
+            const bool do_pool = (fl & CONV_POOL) != 0 && !skip_io;
+            const bool split = p.L.act_mode == ACT_SPLIT;
+            const bool live = 32 * q < coutp;       // quarters beyond the real width only keep the barriers going
+            const int npb = p.tn >> 5;
+            const uint32_t buf0 = ring_base + (uint32_t)ew * kEpiBufs * 4096u;
+            const uint32_t rbar = res_bar0 + 8u * (ew * kEpiBufs);
+            const int ch = 32 * q + lane;
+            float bias_r = 0.f, tbr[3] = {0.f, 0.f, 0.f}, rw[4] = {0.f, 0.f, 0.f, 0.f}, rb = 0.f;
+            if (live) {
+                bias_r = __ldg(p.L.bias + ch);
+                if (fl & CONV_TBIAS)
+                    for (int v = 0; v < 3; ++v) tbr[v] = __ldg(p.L.tbias + (size_t)v * p.L.tb_var_stride + ch);
+                if (fl & CONV_RESX) {
+                    rb = __ldg(p.L.rb1 + ch);
+                    for (int c = 0; c < 4; ++c) if (c < p.L.xC) rw[c] = __ldg(p.L.rw1 + (size_t)c * coutp + ch);
+                }
+            }
+            // byte offset of this lane's word inside pixel row r of a ring buffer: r*128 + cell[r & 7]
+            uint32_t cell[8];
+#pragma unroll
+            for (int r = 0; r < 8; ++r) cell[r] = ((((uint32_t)lane >> 2) ^ (uint32_t)r) << 4) + ((uint32_t)lane & 3u) * 4u;
+            uint32_t res_par = 0;
+            int acc = 0;
+            uint32_t acc_ph = 0;
+            const int HWm = 1 << p.log2_hw;
+            for (int work = blockIdx.x; work < p.n_work; work += gridDim.x) {
+                const int64_t m_tile = (int64_t)work * p.tn;
+                if (lane == 0 && live) {
+                    ptx::bulk_wait_read<0>();
+                    if (has_res)
+                        for (int k = 0; k < kEpiBufs && h + 2 * k < npb; ++k) {
+                            ptx::mbar_expect_tx(rbar + 8u * k, 4096u);
+                            ptx::tma_load_2d(buf0 + 4096u * k, &maps.res, rbar + 8u * k, 32 * q, (int)m_tile + 32 * (h + 2 * k));
+                        }
+                }
+                __syncwarp();
+                ptx::mbar_wait(acc_full0 + 8u * acc, acc_ph);
+                ptx::tc_fence_after();
+                const uint32_t t_acc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.acc_cols);
+                const int pb_last = npb - 1 - ((npb - 1 - h) & 1);
+                if (!live || pb_last < h) {
+                    ptx::tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) ptx::mbar_arrive(acc_empty0 + 8u * acc);
+                }
+                if (live)
+                for (int pb = h, k = 0; pb < npb; pb += 2, ++k) {
+                    const int b = k % kEpiBufs;
+                    const int64_t m_chunk = m_tile + 32 * pb;
+                    uint32_t raw[32];
+                    ptx::tmem_ld32(t_acc + (uint32_t)(32 * pb), raw);
+                    if (p.npass == 3) {
+                        uint32_t raw2[32];
+                        ptx::tmem_ld32(t_acc + (uint32_t)(p.corr_col + 32 * pb), raw2);
+                        ptx::tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) raw[j] = __float_as_uint(__uint_as_float(raw[j]) + __uint_as_float(raw2[j]));
+                    } else {
+                        ptx::tmem_ld_wait();
+                    }
+                    if (pb == pb_last) {
+                        ptx::tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) ptx::mbar_arrive(acc_empty0 + 8u * acc);
+                    }
+                    // per-pixel side inputs, one pixel per lane, broadcast by shuffle in the loop below
+                    const int64_t m_l = m_chunk + lane;
+                    const bool valid_l = m_l < p.L.M;
+                    const int img_l = valid_l ? (int)(m_l >> p.log2_hw) : 0;
+                    int var_l = 0;
+                    if ((fl & CONV_TBIAS) && p.L.row_variant) var_l = p.L.row_variant[img_l];
+                    float xl[4] = {0.f, 0.f, 0.f, 0.f};
+                    if ((fl & CONV_RESX) && valid_l) {
+                        const float* xs = p.L.xraw + (size_t)(p.L.row_sample ? p.L.row_sample[img_l] : img_l) * p.L.x_stride + (m_l & (HWm - 1));
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) if (c < p.L.xC) xl[c] = xs[(size_t)c * HWm];
+                    }
+                    if (has_res) { ptx::mbar_wait(rbar + 8u * b, (res_par >> b) & 1u); res_par ^= 1u << b; }
+                    uint8_t* bufp = smem_raw + (buf0 + 4096u * b - ptx::smem_u32(smem_raw));
+                    float keep[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        float v = __uint_as_float(raw[j]) + bias_r;
+                        if (fl & CONV_RELU) v = fmaxf(v, 0.f);
+                        if (fl & CONV_TBIAS) {
+                            const int var = __shfl_sync(0xffffffffu, var_l, j);
+                            v += var == 0 ? tbr[0] : (var == 1 ? tbr[1] : tbr[2]);
+                        }
+                        if (fl & CONV_RESX) {
+                            float r = rb;
+#pragma unroll
+                            for (int c = 0; c < 4; ++c) {
+                                if (c >= p.L.xC) break;
+                                r = fmaf(__shfl_sync(0xffffffffu, xl[c], j), rw[c], r);
+                            }
+                            v += r;
+                        }
+                        float* wp = reinterpret_cast<float*>(bufp + j * 128 + cell[j & 7]);
+                        if (has_res) v += *wp;
+                        v = act_store_value(v, p.L.act_mode);
+                        if (do_store || do_pool) *wp = v;
+                        if (split) keep[j] = v;
+                    }
+                    if (do_store) ptx::fence_proxy_async();
+                    __syncwarp();
+                    if (do_pool) {
+                        const int W = p.L.W, pr = lane >> 2, x2 = pr & ((W >> 1) - 1), t = pr >> p.log2_wh;
+                        const int r00 = 2 * t * W + 2 * x2;
+                        if (m_chunk + r00 < p.L.M) {
+                            float* dst = p.L.pool_out + ((m_chunk >> 2) + pr) * coutp + 32 * q;
+#pragma unroll
+                            for (int jj = (lane & 3) * 2; jj < (lane & 3) * 2 + 2; ++jj) {
+                                auto at = [&](int r) { return *reinterpret_cast<const float4*>(bufp + r * 128 + (((uint32_t)jj ^ (uint32_t)(r & 7)) << 4)); };
+                                const float4 a = at(r00), bq = at(r00 + 1), cq = at(r00 + W), d = at(r00 + W + 1);
+                                *reinterpret_cast<float4*>(dst + 4 * jj) =
+                                    make_float4(fmaxf(fmaxf(a.x, bq.x), fmaxf(cq.x, d.x)), fmaxf(fmaxf(a.y, bq.y), fmaxf(cq.y, d.y)),
+                                                fmaxf(fmaxf(a.z, bq.z), fmaxf(cq.z, d.z)), fmaxf(fmaxf(a.w, bq.w), fmaxf(cq.w, d.w)));
+                            }
+                        }
+                        __syncwarp();
+                    }
+                    if (lane == 0 && do_store) { ptx::tma_store_2d(&maps.out, buf0 + 4096u * b, 32 * q, (int)m_chunk); ptx::bulk_commit(); }
+                    if (split && do_store) {
+                        if (lane == 0) ptx::bulk_wait_read<0>();
+                        __syncwarp();
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) *reinterpret_cast<float*>(bufp + j * 128 + cell[j & 7]) = keep[j] - tf32_trunc(keep[j]);
+                        ptx::fence_proxy_async();
+                        __syncwarp();
+                        if (lane == 0) { ptx::tma_store_2d(&maps.out_lo, buf0 + 4096u * b, 32 * q, (int)m_chunk); ptx::bulk_commit(); }
+                    }
+                    if (lane == 0) {
+                        const int pn = pb + 2 * (kEpiBufs - 1);
+                        if (has_res && k >= 1 && pn < npb) {
+                            if (do_store) ptx::bulk_wait_read<1>();
+                            ptx::mbar_expect_tx(rbar + 8u * ((k - 1) % kEpiBufs), 4096u);
+                            ptx::tma_load_2d(buf0 + 4096u * ((k - 1) % kEpiBufs), &maps.res, rbar + 8u * ((k - 1) % kEpiBufs), 32 * q, (int)m_tile + 32 * pn);
+                        }
+                    }
+                    if (!has_res && do_store && k + 1 >= kEpiBufs && pb + 2 < npb) {
+                        if (lane == 0) ptx::bulk_wait_read<kEpiBufs - 1>();
+                        __syncwarp();
+                    }
+                }
+                if (++acc == p.acc_stages) { acc = 0; acc_ph ^= 1u; }
+            }
+            if (lane == 0) ptx::bulk_wait_read<0>();
+            __syncwarp();
+        } else {
         const int q = warp & 3;
         const int h = (warp - 2) >> 2;          // which of the quarter's two warps: takes chunks h, h + 2, ...
         const int ew = warp - 2;
@@ -464,6 +633,7 @@ k_conv_umma(const __grid_constant__ UmmaMaps maps, const UmmaConv p) {
         }
         if (lane == 0) ptx::bulk_wait_read<0>();    // smem must outlive the stores' reads
         __syncwarp();
+        }
     }
     ptx::tc_fence_before();
     __syncthreads();
@@ -545,25 +715,36 @@ struct UmmaLaunch {            // everything a launch needs, built once per (lay
 inline int build_umma_launch(UmmaLaunch* U, const ConvLayer& L, int npass, const float* wpk, int64_t w_rows) {
     memset(U, 0, sizeof(*U));
     const int HW = L.H * L.W;
-    if (L.W > 32 || (HW < 128 && 128 % HW != 0) || (HW >= 128 && (128 % L.W != 0 || HW % 128 != 0)))
+    if (L.W > 32 || L.H != L.W || (HW & (HW - 1)) != 0)
         return fail(DTRAJ_EINVAL, "umma conv: unsupported spatial size %dx%d", L.H, L.W);
     if (L.coutp % 32 || L.coutp > 256 || L.c0p % 32 || L.c1p % 32) return fail(DTRAJ_EINVAL, "umma conv: bad channel padding");
     UmmaConv& c = U->conv;
     c.L = L;
     c.npass = npass;
-    c.box_h = HW >= 128 ? 128 / L.W : L.H;
-    c.box_n = HW >= 128 ? 1 : 128 / HW;
-    c.tiles_per_img = HW >= 128 ? HW / 128 : 1;
-    c.n_tiles = (int)((L.M + 127) / 128);
+    // operand swap: with <= 128 output channels an M=128 x N=cout MMA reads (128 + cout) x 32 B of shared
+    // memory for 128 x cout x 8 MACs and is shared-memory bound (measured 59 % of the tf32 peak at cout = 128
+    // with no loads at all); M = 128 weight rows x N = 256 pixels reads 1.5x the bytes for 2x the MACs.
+    // Measured (tools/conv_bench.py): a win only for exactly 128 channels, K >= 1024 and enough 256-pixel tiles
+    // to fill the GPU; narrower layers waste half of the 128 weight rows, short-K layers are epilogue-paced
+    // and the transposed epilogue moves single words through shared memory.
+    const int nkb_all = L.ntaps * (L.c0p + L.c1p) / 32;
+    c.swap = (L.coutp == 128 && nkb_all >= 32 && (L.M + 255) / 256 >= kNumSMs && !(L.flags & CONV_FINAL) &&
+              !getenv("DTRAJ_NO_SWAP")) ? 1 : 0;
+    c.tn = c.swap ? 256 : 128;
+    c.box_h = HW >= c.tn ? c.tn / L.W : L.H;
+    c.box_n = HW >= c.tn ? 1 : c.tn / HW;
+    c.tiles_per_img = HW >= c.tn ? HW / c.tn : 1;
+    c.n_tiles = (int)((L.M + c.tn - 1) / c.tn);
     c.n_split = 1;
-    if (!(L.flags & CONV_FINAL))
+    if (!c.swap && !(L.flags & CONV_FINAL))
         while (c.n_tiles * c.n_split * 2 <= kNumSMs && (L.coutp / (c.n_split * 2)) % 32 == 0 && L.coutp / (c.n_split * 2) >= 64)
             c.n_split *= 2;
     if (getenv("DTRAJ_NO_NSPLIT")) c.n_split = 1;
     c.ncols = L.coutp / c.n_split;
     c.n_work = c.n_tiles * c.n_split;
+    const int n_rows = c.swap ? c.tn : c.ncols;
     c.acc_cols = 32;
-    while (c.acc_cols < c.ncols) c.acc_cols *= 2;
+    while (c.acc_cols < n_rows) c.acc_cols *= 2;
     c.corr_col = 0;
     if (npass == 3) { c.corr_col = c.acc_cols; c.acc_cols *= 2; }
     c.acc_stages = 2 * c.acc_cols <= 512 ? 2 : 1;
@@ -580,7 +761,7 @@ inline int build_umma_launch(UmmaLaunch* U, const ConvLayer& L, int npass, const
     if ((L.flags & (CONV_POOL | CONV_RESX | CONV_FINAL | CONV_NOSTORE)) && L.act_mode == ACT_SPLIT)
         return fail(DTRAJ_EINVAL, "umma conv: fused tails are not available in 3xTF32 mode");
     // one persistent CTA per SM: all shared memory that is not the epilogue ring goes to the operand ring
-    const size_t stage = kATileBytes + (size_t)c.ncols * 128;
+    const size_t stage = kATileBytes + (size_t)n_rows * 128;
     const size_t fixed = 1024 + kEpiRingBytes + 512 + 2048;
     int stages = (int)((227 * 1024 - fixed) / stage);
     if (stages < 2) return fail(DTRAJ_EINVAL, "umma conv: operand ring does not fit");
@@ -595,7 +776,7 @@ inline int build_umma_launch(UmmaLaunch* U, const ConvLayer& L, int npass, const
         DTRAJ_TRY(make_act_map(&U->maps.a[2], L.src0_lo, L.c0p, L.W, L.H, n_img, c.box_h, c.box_n));
         if (L.c1p) DTRAJ_TRY(make_act_map(&U->maps.a[3], L.src1_lo, L.c1p, L.W, L.H, n_img, c.box_h, c.box_n));
     }
-    DTRAJ_TRY(make_w_map(&U->maps.b, wpk, w_rows, c.ncols));
+    DTRAJ_TRY(make_w_map(&U->maps.b, wpk, w_rows, c.swap ? 128 : c.ncols));
     if (L.M >= (int64_t)1 << 31) return fail(DTRAJ_EINVAL, "umma conv: M too large for 32-bit TMA coordinates");
     if (!(L.flags & CONV_NOSTORE)) DTRAJ_TRY(make_rows_map(&U->maps.out, L.out, L.M, L.coutp));
     if (L.act_mode == ACT_SPLIT) DTRAJ_TRY(make_rows_map(&U->maps.out_lo, L.out + L.lo_off, L.M, L.coutp));
