@@ -42,6 +42,8 @@ struct UmmaConv {
     int swap;                  // 1: operands swapped (coutp <= 128): the WEIGHTS are the 128-row M operand and
                                //    `tn` output pixels the N operand, D^T[cout, pixel] accumulates in TMEM
     int tn;                    // pixels per tile in swap mode (256, 128 or 64); 128 otherwise
+    int cluster;               // 1, or 2: CTA pairs (thread-block clusters) share the weight tile -- each CTA loads half
+                               // of it and TMA-multicasts that half into both CTAs' shared memory
     int box_h, box_n;          // A box = {32, W, box_h, box_n}
     int tiles_per_img;         // >= 1
     int b_lo_row;              // row offset of the low-plane weights inside the B tensor map
@@ -107,6 +109,23 @@ __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.comm
 template <int N>
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, uint16_t mask) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster "
+                 "[%0], [%1, {%3, %4}], [%2], %5;"
+                 ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void tc_commit_mc(uint32_t bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"(mask) : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
@@ -178,6 +197,9 @@ k_conv_umma(const __grid_constant__ UmmaMaps maps, const UmmaConv p) {
         smem_raw + (tmem_slot - ptx::smem_u32(smem_raw)));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int crank = p.cluster > 1 ? (int)ptx::cluster_ctarank() : 0;
+    const uint16_t cmask = (uint16_t)((1u << p.cluster) - 1u);
+    const int work0 = (int)blockIdx.x - crank;   // first work item of this CTA's cluster; all its CTAs loop alike
     const int nch0 = p.L.c0p / 32, nch = nch0 + p.L.c1p / 32;
     const int iters_per_pass = p.L.ntaps * nch;
     const int n_iters = p.npass * iters_per_pass;
@@ -187,7 +209,7 @@ k_conv_umma(const __grid_constant__ UmmaMaps maps, const UmmaConv p) {
             ptx::prefetch_tmap(&maps.a[0]);
             ptx::prefetch_tmap(&maps.b);
             if (p.L.c1p) ptx::prefetch_tmap(&maps.a[1]);
-            for (int s = 0; s < p.stages; ++s) { ptx::mbar_init(full_bar(s), 1); ptx::mbar_init(empty_bar(s), 1); }
+            for (int s = 0; s < p.stages; ++s) { ptx::mbar_init(full_bar(s), 1); ptx::mbar_init(empty_bar(s), p.cluster); }
             for (int i = 0; i < 2; ++i) { ptx::mbar_init(acc_full0 + 8u * i, 1); ptx::mbar_init(acc_empty0 + 8u * i, kEpiWarps); }
             for (int i = 0; i < kEpiWarps * kEpiBufs; ++i) ptx::mbar_init(res_bar0 + 8u * i, 1);
             if (!(p.L.flags & CONV_NOSTORE)) ptx::prefetch_tmap(&maps.out);
@@ -201,6 +223,7 @@ k_conv_umma(const __grid_constant__ UmmaMaps maps, const UmmaConv p) {
     }
     ptx::tc_fence_before();
     __syncthreads();
+    if (p.cluster > 1) ptx::cluster_sync_all();   // peers' barriers exist before anything is multicast at them
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
 
@@ -212,7 +235,10 @@ k_conv_umma(const __grid_constant__ UmmaMaps maps, const UmmaConv p) {
             int s = 0, n_issued = 0;
             uint32_t ph = 0;
             bool ok = true;
-            for (int work = blockIdx.x; work < p.n_work && ok; work += gridDim.x) {
+            const int w_rows = p.swap ? 128 : ncols;           // rows of the weight tile
+            const int w_half = w_rows / p.cluster;             // rows this CTA fetches (and multicasts)
+            for (int wk = work0; wk < p.n_work && ok; wk += gridDim.x) {
+                const int work = wk + crank;                   // may be a padding item past n_work: loads hit OOB zeros
                 const int tile = work / p.n_split, n0 = (work % p.n_split) * ncols;
                 int img0, y0;
                 if (p.tiles_per_img > 1) { img0 = tile / p.tiles_per_img; y0 = (tile % p.tiles_per_img) * p.box_h; }
@@ -232,12 +258,14 @@ k_conv_umma(const __grid_constant__ UmmaMaps maps, const UmmaConv p) {
                             ++n_issued;
                             if (do_a || do_b) ptx::mbar_expect_tx(full_bar(s), (do_a ? kATileBytes : 0) + (do_b ? b_bytes : 0));
                             else ptx::mbar_arrive(full_bar(s));
-                            if (!p.swap) {
-                                if (do_a) ptx::tma_load_4d(a_dst, &maps.a[src + asel], full_bar(s), c0, dx, y0 + dy, img0);
-                                if (do_b) ptx::tma_load_2d(b_dst, &maps.b, full_bar(s), 0, b_row);
-                            } else {            // M operand <- 128 weight rows, N operand <- tn shifted pixels
-                                if (do_a) ptx::tma_load_2d(a_dst, &maps.b, full_bar(s), 0, b_row);
-                                if (do_b) ptx::tma_load_4d(b_dst, &maps.a[src + asel], full_bar(s), c0, dx, y0 + dy, img0);
+                            // swap: M operand <- 128 weight rows, N operand <- tn shifted pixels
+                            const uint32_t act_dst = p.swap ? b_dst : a_dst, w_dst = p.swap ? a_dst : b_dst;
+                            const bool do_act = p.swap ? do_b : do_a, do_w = p.swap ? do_a : do_b;
+                            if (do_act) ptx::tma_load_4d(act_dst, &maps.a[src + asel], full_bar(s), c0, dx, y0 + dy, img0);
+                            if (do_w) {
+                                if (p.cluster == 1) ptx::tma_load_2d(w_dst, &maps.b, full_bar(s), 0, b_row);
+                                else ptx::tma_load_2d_mc(w_dst + (uint32_t)(crank * w_half) * 128u, &maps.b, full_bar(s), 0,
+                                                         b_row + crank * w_half, cmask);
                             }
                             b_row += coutp;
                             if (++s == p.stages) { s = 0; ph ^= 1u; }
@@ -254,7 +282,7 @@ k_conv_umma(const __grid_constant__ UmmaMaps maps, const UmmaConv p) {
             int s = 0, acc = 0;
             uint32_t ph = 0, acc_ph = 0;
             bool ok = true;
-            for (int work = blockIdx.x; work < p.n_work && ok; work += gridDim.x) {
+            for (int wk = work0; wk < p.n_work && ok; wk += gridDim.x) {
                 ok = ptx::mbar_wait(acc_empty0 + 8u * acc, acc_ph ^ 1u);      // epilogue has drained this buffer
                 ptx::tc_fence_after();
                 const uint32_t d_main = tmem_base + (uint32_t)(acc * p.acc_cols);
@@ -273,7 +301,9 @@ k_conv_umma(const __grid_constant__ UmmaMaps maps, const UmmaConv p) {
 #pragma unroll
                     for (int k = 0; k < 4; ++k)   // 4 x (K = 8 tf32 = 32 bytes) inside the 128-byte swizzle atom
                         ptx::mma_tf32(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, (it != first_it) || (k != 0));
-                    ptx::tc_commit(empty_bar(s));   // frees the smem slot when these MMAs retire
+                    // frees the smem slot when these MMAs retire -- in every CTA that multicasts into it
+                    if (p.cluster == 1) ptx::tc_commit(empty_bar(s));
+                    else ptx::tc_commit_mc(empty_bar(s), cmask);
                     if (++s == p.stages) { s = 0; ph ^= 1u; }
                 }
                 ptx::tc_commit(acc_full0 + 8u * acc);   // accumulator complete
@@ -332,7 +362,8 @@ k_conv_umma(const __grid_constant__ UmmaMaps maps, const UmmaConv p) {
             int acc = 0;
             uint32_t acc_ph = 0;
             const int HWm = 1 << p.log2_hw;
-            for (int work = blockIdx.x; work < p.n_work; work += gridDim.x) {
+            for (int wk = work0; wk < p.n_work; wk += gridDim.x) {
+                const int work = wk + crank;
                 const int64_t m_tile = (int64_t)work * p.tn;
                 if (lane == 0 && live) {
                     ptx::bulk_wait_read<0>();
@@ -472,7 +503,8 @@ k_conv_umma(const __grid_constant__ UmmaMaps maps, const UmmaConv p) {
         uint32_t res_par = 0;                   // bit b = parity the next wait on residual barrier b uses
         int acc = 0;
         uint32_t acc_ph = 0;
-        for (int work = blockIdx.x; work < p.n_work; work += gridDim.x) {
+        for (int wk = work0; wk < p.n_work; wk += gridDim.x) {
+            const int work = wk + crank;
             const int tile = work / p.n_split, n0 = (work % p.n_split) * ncols;
             const int64_t m_warp = (int64_t)tile * 128 + q * 32;
             const int row = (int)m_warp;        // TMA coordinates are 32-bit; M < 2^31 is checked on the host
@@ -637,6 +669,7 @@ k_conv_umma(const __grid_constant__ UmmaMaps maps, const UmmaConv p) {
     }
     ptx::tc_fence_before();
     __syncthreads();
+    if (p.cluster > 1) ptx::cluster_sync_all();   // no CTA leaves while a peer can still write its smem / barriers
     if (warp == 0) {
         ptx::tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols) : "memory");
@@ -743,6 +776,7 @@ inline int build_umma_launch(UmmaLaunch* U, const ConvLayer& L, int npass, const
     c.ncols = L.coutp / c.n_split;
     c.n_work = c.n_tiles * c.n_split;
     const int n_rows = c.swap ? c.tn : c.ncols;
+    c.cluster = (c.n_split == 1 && c.n_work >= 2 * kNumSMs && !getenv("DTRAJ_NO_CLUSTER")) ? 2 : 1;
     c.acc_cols = 32;
     while (c.acc_cols < n_rows) c.acc_cols *= 2;
     c.corr_col = 0;
@@ -769,6 +803,7 @@ inline int build_umma_launch(UmmaLaunch* U, const ConvLayer& L, int npass, const
     c.stages = stages;
     U->smem = fixed + stages * stage;
     U->grid = (unsigned)(c.n_work < kNumSMs ? c.n_work : kNumSMs);
+    if (c.cluster > 1) U->grid = (U->grid + c.cluster - 1) / c.cluster * c.cluster;
     const int64_t n_img = L.M / HW;
     DTRAJ_TRY(make_act_map(&U->maps.a[0], L.src0, L.c0p, L.W, L.H, n_img, c.box_h, c.box_n));
     if (L.c1p) DTRAJ_TRY(make_act_map(&U->maps.a[1], L.src1, L.c1p, L.W, L.H, n_img, c.box_h, c.box_n));
@@ -776,7 +811,7 @@ inline int build_umma_launch(UmmaLaunch* U, const ConvLayer& L, int npass, const
         DTRAJ_TRY(make_act_map(&U->maps.a[2], L.src0_lo, L.c0p, L.W, L.H, n_img, c.box_h, c.box_n));
         if (L.c1p) DTRAJ_TRY(make_act_map(&U->maps.a[3], L.src1_lo, L.c1p, L.W, L.H, n_img, c.box_h, c.box_n));
     }
-    DTRAJ_TRY(make_w_map(&U->maps.b, wpk, w_rows, c.swap ? 128 : c.ncols));
+    DTRAJ_TRY(make_w_map(&U->maps.b, wpk, w_rows, (c.swap ? 128 : c.ncols) / c.cluster));
     if (L.M >= (int64_t)1 << 31) return fail(DTRAJ_EINVAL, "umma conv: M too large for 32-bit TMA coordinates");
     if (!(L.flags & CONV_NOSTORE)) DTRAJ_TRY(make_rows_map(&U->maps.out, L.out, L.M, L.coutp));
     if (L.act_mode == ACT_SPLIT) DTRAJ_TRY(make_rows_map(&U->maps.out_lo, L.out + L.lo_off, L.M, L.coutp));
@@ -785,8 +820,25 @@ inline int build_umma_launch(UmmaLaunch* U, const ConvLayer& L, int npass, const
 }
 
 inline int launch_conv_umma(const UmmaLaunch& U, cudaStream_t st) {
-    k_conv_umma<<<U.grid, kUmmaThreads, U.smem, st>>>(U.maps, U.conv);
-    DTRAJ_LAUNCH_CHECK();
+    if (U.conv.cluster <= 1) {
+        k_conv_umma<<<U.grid, kUmmaThreads, U.smem, st>>>(U.maps, U.conv);
+        DTRAJ_LAUNCH_CHECK();
+        return 0;
+    }
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(U.grid);
+    cfg.blockDim = dim3(kUmmaThreads);
+    cfg.dynamicSmemBytes = U.smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)U.conv.cluster;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    DTRAJ_CUDA(cudaLaunchKernelEx(&cfg, k_conv_umma, U.maps, U.conv));
     return 0;
 }
 
