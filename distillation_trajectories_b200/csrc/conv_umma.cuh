@@ -42,6 +42,7 @@ struct UmmaConv {
     int swap;                  // 1: operands swapped (coutp <= 128): the WEIGHTS are the 128-row M operand and
                                //    `tn` output pixels the N operand, D^T[cout, pixel] accumulates in TMEM
     int tn;                    // pixels per tile in swap mode (256, 128 or 64); 128 otherwise
+    int epi_bufs;              // epilogue ring depth per warp (1 when the freed 32 KB buy another operand stage)
     int cluster;               // 1, or 2: CTA pairs (thread-block clusters) share the weight tile -- each CTA loads half
                                // of it and TMA-multicasts that half into both CTAs' shared memory
     int box_h, box_n;          // A box = {32, W, box_h, box_n}
@@ -165,8 +166,7 @@ __host__ __device__ inline uint32_t umma_idesc_tf32(int n) {
 
 constexpr int kEpiWarps = 8;             // two per TMEM lane quarter, each takes every other 32-column chunk
 constexpr int kUmmaThreads = 64 + 32 * kEpiWarps;
-constexpr int kEpiBufs = 2;              // per-warp ring of 4 KB (32 rows x 32 columns) epilogue buffers
-constexpr int kEpiRingBytes = kEpiWarps * kEpiBufs * 4096;
+constexpr int kEpiBufsMax = 2;           // per-warp ring of 4 KB (32 rows x 32 columns) epilogue buffers: 1 or 2
 constexpr int kATileBytes = 128 * 128;   // 128 rows x 32 fp32
 
 // Persistent kernel: one CTA per SM walks tiles blockIdx.x, blockIdx.x + gridDim.x, ...  The three roles
@@ -185,13 +185,14 @@ k_conv_umma(const __grid_constant__ UmmaMaps maps, const UmmaConv p) {
     const uint32_t b_bytes = (uint32_t)n_rows * 128u;
     const uint32_t stage_bytes = kATileBytes + b_bytes;        // multiple of 1024 (ncols % 32 == 0 -> b_bytes % 4096 == 0)
     const uint32_t ring_base = base + p.stages * stage_bytes;
-    const uint32_t bar_base = ring_base + kEpiRingBytes;
+    const int kEpiBufs = p.epi_bufs;
+    const uint32_t bar_base = ring_base + (uint32_t)(kEpiWarps * kEpiBufs * 4096);
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
     auto empty_bar = [&](int s) { return bar_base + 8u * (p.stages + s); };
     const uint32_t acc_full0 = bar_base + 16u * p.stages;      // [2] accumulator ready   (issuer -> epilogue)
     const uint32_t acc_empty0 = acc_full0 + 16u;               // [2] accumulator drained (epilogue -> issuer)
     const uint32_t res_bar0 = acc_empty0 + 16u;                // [kEpiWarps][kEpiBufs] residual-chunk barriers
-    const uint32_t tmem_slot = res_bar0 + 8u * kEpiWarps * kEpiBufs;
+    const uint32_t tmem_slot = res_bar0 + 8u * kEpiWarps * kEpiBufsMax;
     const uint32_t fin_base = tmem_slot + 16u;                 // CONV_FINAL partial sums [4 quarters][32 lanes][4]
     volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(
         smem_raw + (tmem_slot - ptx::smem_u32(smem_raw)));
@@ -211,7 +212,7 @@ k_conv_umma(const __grid_constant__ UmmaMaps maps, const UmmaConv p) {
             if (p.L.c1p) ptx::prefetch_tmap(&maps.a[1]);
             for (int s = 0; s < p.stages; ++s) { ptx::mbar_init(full_bar(s), 1); ptx::mbar_init(empty_bar(s), p.cluster); }
             for (int i = 0; i < 2; ++i) { ptx::mbar_init(acc_full0 + 8u * i, 1); ptx::mbar_init(acc_empty0 + 8u * i, kEpiWarps); }
-            for (int i = 0; i < kEpiWarps * kEpiBufs; ++i) ptx::mbar_init(res_bar0 + 8u * i, 1);
+            for (int i = 0; i < kEpiWarps * kEpiBufsMax; ++i) ptx::mbar_init(res_bar0 + 8u * i, 1);
             if (!(p.L.flags & CONV_NOSTORE)) ptx::prefetch_tmap(&maps.out);
             if (p.L.flags & CONV_RESID) ptx::prefetch_tmap(&maps.res);
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -342,7 +343,7 @@ k_conv_umma(const __grid_constant__ UmmaMaps maps, const UmmaConv p) {
             const bool live = 32 * q < coutp;       // quarters beyond the real width only keep the barriers going
             const int npb = p.tn >> 5;
             const uint32_t buf0 = ring_base + (uint32_t)ew * kEpiBufs * 4096u;
-            const uint32_t rbar = res_bar0 + 8u * (ew * kEpiBufs);
+            const uint32_t rbar = res_bar0 + 8u * (ew * kEpiBufsMax);
             const int ch = 32 * q + lane;
             float bias_r = 0.f, tbr[3] = {0.f, 0.f, 0.f}, rw[4] = {0.f, 0.f, 0.f, 0.f}, rb = 0.f;
             if (live) {
@@ -469,16 +470,17 @@ k_conv_umma(const __grid_constant__ UmmaMaps maps, const UmmaConv p) {
                         __syncwarp();
                         if (lane == 0) { ptx::tma_store_2d(&maps.out_lo, buf0 + 4096u * b, 32 * q, (int)m_chunk); ptx::bulk_commit(); }
                     }
-                    if (lane == 0) {
-                        const int pn = pb + 2 * (kEpiBufs - 1);
-                        if (has_res && k >= 1 && pn < npb) {
-                            if (do_store) ptx::bulk_wait_read<1>();
-                            ptx::mbar_expect_tx(rbar + 8u * ((k - 1) % kEpiBufs), 4096u);
-                            ptx::tma_load_2d(buf0 + 4096u * ((k - 1) % kEpiBufs), &maps.res, rbar + 8u * ((k - 1) % kEpiBufs), 32 * q, (int)m_tile + 32 * pn);
+                    // ring upkeep (depth B = kEpiBufs): my next chunk reuses buffer (k + 1) % B, last read by the store
+                    // of my chunk k + 1 - B -- allow B - 1 younger stores to stay in flight, then refill / rewrite it
+                    if (pb + 2 < npb && k + 1 >= kEpiBufs && (has_res || do_store)) {
+                        if (lane == 0) {
+                            if (do_store) { if (kEpiBufs == 2) ptx::bulk_wait_read<1>(); else ptx::bulk_wait_read<0>(); }
+                            if (has_res) {
+                                const int nb = (k + 1) % kEpiBufs;
+                                ptx::mbar_expect_tx(rbar + 8u * nb, 4096u);
+                                ptx::tma_load_2d(buf0 + 4096u * nb, &maps.res, rbar + 8u * nb, 32 * q, (int)m_tile + 32 * (pb + 2));
+                            }
                         }
-                    }
-                    if (!has_res && do_store && k + 1 >= kEpiBufs && pb + 2 < npb) {
-                        if (lane == 0) ptx::bulk_wait_read<kEpiBufs - 1>();
                         __syncwarp();
                     }
                 }
@@ -498,7 +500,7 @@ k_conv_umma(const __grid_constant__ UmmaMaps maps, const UmmaConv p) {
         const bool do_pool = (fl & CONV_POOL) != 0 && !skip_io;
         const bool split = p.L.act_mode == ACT_SPLIT;
         const uint32_t buf0 = ring_base + (uint32_t)ew * kEpiBufs * 4096u;
-        const uint32_t rbar = res_bar0 + 8u * (ew * kEpiBufs);
+        const uint32_t rbar = res_bar0 + 8u * (ew * kEpiBufsMax);
         const uint32_t swz = (uint32_t)(lane & 7);
         uint32_t res_par = 0;                   // bit b = parity the next wait on residual barrier b uses
         int acc = 0;
@@ -632,19 +634,17 @@ k_conv_umma(const __grid_constant__ UmmaMaps maps, const UmmaConv p) {
                     __syncwarp();
                     if (lane == 0) { ptx::tma_store_2d(&maps.out_lo, buf0 + 4096u * b, n0 + 32 * c, row); ptx::bulk_commit(); }
                 }
-                if (lane == 0) {
-                    // recycle the buffer of this warp's PREVIOUS chunk (its store has had a chunk's time to drain)
-                    const int cn = c + 2 * (kEpiBufs - 1);
-                    if (has_res && k >= 1 && cn < nchunk) {
-                        if (do_store) ptx::bulk_wait_read<1>();
-                        ptx::mbar_expect_tx(rbar + 8u * ((k - 1) % kEpiBufs), 4096u);
-                        ptx::tma_load_2d(buf0 + 4096u * ((k - 1) % kEpiBufs), &maps.res, rbar + 8u * ((k - 1) % kEpiBufs), n0 + 32 * cn, row);
+                // ring upkeep (depth B = kEpiBufs): my next chunk reuses buffer (k + 1) % B, last read by the store of
+                // my chunk k + 1 - B -- allow B - 1 younger stores to stay in flight, then refill / rewrite it
+                if (c + 2 < nchunk && k + 1 >= kEpiBufs && (has_res || do_store)) {
+                    if (lane == 0) {
+                        if (do_store) { if (kEpiBufs == 2) ptx::bulk_wait_read<1>(); else ptx::bulk_wait_read<0>(); }
+                        if (has_res) {
+                            const int nb = (k + 1) % kEpiBufs;
+                            ptx::mbar_expect_tx(rbar + 8u * nb, 4096u);
+                            ptx::tma_load_2d(buf0 + 4096u * nb, &maps.res, rbar + 8u * nb, n0 + 32 * (c + 2), row);
+                        }
                     }
-                }
-                // without a residual the next use of buffer (k + 1) % kEpiBufs is a plain write: it must not
-                // race the store that last read it (this warp's chunk k + 1 - kEpiBufs)
-                if (!has_res && do_store && k + 1 >= kEpiBufs && c + 2 < nchunk) {
-                    if (lane == 0) ptx::bulk_wait_read<kEpiBufs - 1>();
                     __syncwarp();
                 }
             }
@@ -794,14 +794,20 @@ inline int build_umma_launch(UmmaLaunch* U, const ConvLayer& L, int npass, const
     if ((L.flags & CONV_POOL) && (L.W < 2 || L.W > 16 || L.H != L.W)) return fail(DTRAJ_EINVAL, "umma conv: fused pool needs 2 <= W <= 16");
     if ((L.flags & (CONV_POOL | CONV_RESX | CONV_FINAL | CONV_NOSTORE)) && L.act_mode == ACT_SPLIT)
         return fail(DTRAJ_EINVAL, "umma conv: fused tails are not available in 3xTF32 mode");
-    // one persistent CTA per SM: all shared memory that is not the epilogue ring goes to the operand ring
+    // one persistent CTA per SM: all shared memory that is not the epilogue ring goes to the operand ring.  The
+    // ring is latency-bound (bytes in flight / ~1.3 us TMA latency): a deeper operand ring is worth more than a
+    // deeper epilogue ring whenever halving the latter buys a whole stage and the K loop is long enough to hide a
+    // single-buffered epilogue.
     const size_t stage = kATileBytes + (size_t)n_rows * 128;
-    const size_t fixed = 1024 + kEpiRingBytes + 512 + 2048;
-    int stages = (int)((227 * 1024 - fixed) / stage);
+    const size_t misc = 1024 + 512 + ((L.flags & CONV_FINAL) ? 2048 : 0);
+    auto stages_for = [&](int bufs) { return (int)((227 * 1024 - misc - (size_t)kEpiWarps * bufs * 4096) / stage); };
+    c.epi_bufs = 2;
+    if (nkb_all >= 16 && stages_for(1) > stages_for(2) && stages_for(2) < 8 && !getenv("DTRAJ_EPI2")) c.epi_bufs = 1;
+    int stages = stages_for(c.epi_bufs);
     if (stages < 2) return fail(DTRAJ_EINVAL, "umma conv: operand ring does not fit");
     if (stages > 8) stages = 8;
     c.stages = stages;
-    U->smem = fixed + stages * stage;
+    U->smem = misc + (size_t)kEpiWarps * c.epi_bufs * 4096 + stages * stage;
     U->grid = (unsigned)(c.n_work < kNumSMs ? c.n_work : kNumSMs);
     if (c.cluster > 1) U->grid = (U->grid + c.cluster - 1) / c.cluster * c.cluster;
     const int64_t n_img = L.M / HW;

@@ -15,7 +15,10 @@ KEEP = ["Kernel Name", "Grid Size", "Block Size", "gpu__time_duration.sum", "dra
         "sm__throughput.avg.pct_of_peak_sustained_elapsed", "launch__occupancy_limit_shared_mem",
         "launch__shared_mem_per_block_dynamic", "launch__waves_per_multiprocessor", "lts__t_bytes.sum", "lts__t_sectors_srcunit_tex.sum",
         "lts__throughput.avg.pct_of_peak_sustained_elapsed", "l1tex__throughput.avg.pct_of_peak_sustained_elapsed",
-        "sm__cycles_active.avg", "launch__cluster_dim_x"]
+        "sm__cycles_active.avg", "launch__cluster_dim_x", "l1tex__m_xbar2l1tex_read_bytes.sum",
+        "l1tex__m_xbar2l1tex_read_bytes.sum.per_second", "sm__inst_executed_pipe_uniform.sum", "smsp__inst_executed.sum",
+        "lts__t_sectors_srcunit_tex_op_read.sum", "lts__t_sector_hit_rate.pct",
+        "sm__ops_path_tensor_op_utchmma_src_tf32_dst_fp32_sparsity_off.avg.pct_of_peak_sustained_elapsed"]
 
 
 def launches(path):
