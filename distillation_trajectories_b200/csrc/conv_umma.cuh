@@ -42,6 +42,7 @@ struct UmmaConv {
     int swap;                  // 1: operands swapped (coutp <= 128): the WEIGHTS are the 128-row M operand and
                                //    `tn` output pixels the N operand, D^T[cout, pixel] accumulates in TMEM
     int tn;                    // pixels per tile in swap mode (256, 128 or 64); 128 otherwise
+    int kbs;                   // 32-channel K blocks per pipeline stage (2 when both sources have an even number of them)
     int epi_bufs;              // epilogue ring depth per warp (1 when the freed 32 KB buy another operand stage)
     int cluster;               // 1, or 2: CTA pairs (thread-block clusters) share the weight tile -- each CTA loads half
                                // of it and TMA-multicasts that half into both CTAs' shared memory
@@ -51,8 +52,7 @@ struct UmmaConv {
     int cb;                    // epilogue column block: 128, 64 or 32 (largest that divides coutp)
     int log2_hw;               // H*W is a power of two: image index of output row m is m >> log2_hw
     int log2_wh;               // log2(W / 2) (CONV_POOL)
-    int debug;                 // timing experiments only (dtraj_bench_conv): bit0 skip B loads after the ring is
-                               // primed, bit1 skip A loads likewise, bit2 skip the epilogue's global traffic
+    int debug;                 // timing experiments only (dtraj_bench_conv): bit2 skips the epilogue's global traffic
 };
 
 struct UmmaMaps {              // 64-byte aligned tensor maps, passed as __grid_constant__
@@ -80,16 +80,23 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
 // bounded wait: a protocol bug must surface as an error flag, never as a hung GPU
-__device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity) {
-    for (uint32_t i = 0; i < (1u << 22); ++i) {
-        uint32_t ok;
-        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-                     "selp.u32 %0, 1, 0, p;\n\t}"
-                     : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-        if (ok) return true;
-    }
+__device__ __forceinline__ uint32_t mbar_try(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                 "selp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok;
+}
+__device__ __noinline__ bool mbar_wait_slow(uint32_t bar, uint32_t parity) {
+#pragma unroll 1
+    for (uint32_t i = 0; i < (1u << 22); ++i)
+        if (mbar_try(bar, parity)) return true;
     atomicOr(&g_umma_error, 1u);
     return false;
+}
+__device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity) {
+    if (mbar_try(bar, parity)) return true;
+    return mbar_wait_slow(bar, parity);
 }
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar,
                                             int c0, int c1, int c2, int c3) {
@@ -183,7 +190,7 @@ k_conv_umma(const __grid_constant__ UmmaMaps maps, const UmmaConv p) {
     const int ncols = p.ncols;                                 // columns this CTA computes per work item (coutp / n_split)
     const int n_rows = p.swap ? p.tn : ncols;                  // rows of the N operand tile (UMMA N)
     const uint32_t b_bytes = (uint32_t)n_rows * 128u;
-    const uint32_t stage_bytes = kATileBytes + b_bytes;        // multiple of 1024 (ncols % 32 == 0 -> b_bytes % 4096 == 0)
+    const uint32_t stage_bytes = (uint32_t)p.kbs * (kATileBytes + b_bytes);   // kbs x [M tile 16 KB] then kbs x [N tile]
     const uint32_t ring_base = base + p.stages * stage_bytes;
     const int kEpiBufs = p.epi_bufs;
     const uint32_t bar_base = ring_base + (uint32_t)(kEpiWarps * kEpiBufs * 4096);
@@ -230,14 +237,21 @@ k_conv_umma(const __grid_constant__ UmmaMaps maps, const UmmaConv p) {
 
     if (warp == 0) {
         // ------------------------------------------------------------ TMA producer
-        // (one thread; every index is carried incrementally -- a division per iteration made this
-        // single thread, not the tensor pipe, the pace-setter of the first version)
+        // One thread.  Its instruction stream, not the memory system, paces short MMAs (ncu: ~750 cycles per
+        // iteration of the first persistent version against 128 cycles of MMA work at N = 64), so every index
+        // is carried incrementally and a stage holds `kbs` (1 or 2) 32-channel K blocks per barrier round trip.
         if (ptx::elect_one()) {
-            int s = 0, n_issued = 0;
-            uint32_t ph = 0;
-            bool ok = true;
             const int w_rows = p.swap ? 128 : ncols;           // rows of the weight tile
             const int w_half = w_rows / p.cluster;             // rows this CTA fetches (and multicasts)
+            const uint32_t w_off = (uint32_t)(crank * w_half) * 128u;
+            const uint32_t tx_bytes = (uint32_t)p.kbs * (kATileBytes + b_bytes);
+            const uint32_t act_off = p.swap ? (uint32_t)p.kbs * kATileBytes : 0u;   // N slots follow the M slots
+            const uint32_t w_base_off = p.swap ? 0u : (uint32_t)p.kbs * kATileBytes;
+            const uint32_t act_step = p.swap ? b_bytes : (uint32_t)kATileBytes;
+            const uint32_t w_step = p.swap ? (uint32_t)kATileBytes : b_bytes;
+            int s = 0;
+            uint32_t ph = 0;
+            bool ok = true;
             for (int wk = work0; wk < p.n_work && ok; wk += gridDim.x) {
                 const int work = wk + crank;                   // may be a padding item past n_work: loads hit OOB zeros
                 const int tile = work / p.n_split, n0 = (work % p.n_split) * ncols;
@@ -245,33 +259,24 @@ k_conv_umma(const __grid_constant__ UmmaMaps maps, const UmmaConv p) {
                 if (p.tiles_per_img > 1) { img0 = tile / p.tiles_per_img; y0 = (tile % p.tiles_per_img) * p.box_h; }
                 else { img0 = tile * p.box_n; y0 = 0; }
                 for (int pass = 0; pass < p.npass && ok; ++pass) {
-                    const int asel = pass == 2 ? 2 : 0;
-                    int b_row = (pass == 1 ? p.b_lo_row : 0) + n0;
-                    int dy = p.L.ntaps == 9 ? -1 : 0, dx = dy;
-                    for (int tap = 0; tap < p.L.ntaps && ok; ++tap) {
-                        for (int chunk = 0; chunk < nch; ++chunk) {
-                            if (!ptx::mbar_wait(empty_bar(s), ph ^ 1u)) { ok = false; break; }
-                            const int src = chunk < nch0 ? 0 : 1;
-                            const int c0 = (src == 0 ? chunk : chunk - nch0) * 32;
-                            const uint32_t a_dst = base + s * stage_bytes, b_dst = a_dst + kATileBytes;
-                            const bool primed = n_issued >= p.stages;
-                            const bool do_a = !((p.debug & 2) && primed), do_b = !((p.debug & 1) && primed);
-                            ++n_issued;
-                            if (do_a || do_b) ptx::mbar_expect_tx(full_bar(s), (do_a ? kATileBytes : 0) + (do_b ? b_bytes : 0));
-                            else ptx::mbar_arrive(full_bar(s));
-                            // swap: M operand <- 128 weight rows, N operand <- tn shifted pixels
-                            const uint32_t act_dst = p.swap ? b_dst : a_dst, w_dst = p.swap ? a_dst : b_dst;
-                            const bool do_act = p.swap ? do_b : do_a, do_w = p.swap ? do_a : do_b;
-                            if (do_act) ptx::tma_load_4d(act_dst, &maps.a[src + asel], full_bar(s), c0, dx, y0 + dy, img0);
-                            if (do_w) {
-                                if (p.cluster == 1) ptx::tma_load_2d(w_dst, &maps.b, full_bar(s), 0, b_row);
-                                else ptx::tma_load_2d_mc(w_dst + (uint32_t)(crank * w_half) * 128u, &maps.b, full_bar(s), 0,
-                                                         b_row + crank * w_half, cmask);
-                            }
+                    const CUtensorMap* am0 = &maps.a[pass == 2 ? 2 : 0];
+                    const CUtensorMap* am1 = &maps.a[pass == 2 ? 3 : 1];
+                    int b_row = (pass == 1 ? p.b_lo_row : 0) + n0 + crank * w_half;
+                    int dy = p.L.ntaps == 9 ? -1 : 0, dx = dy, chunk = 0;
+                    for (int it = 0; it < iters_per_pass; it += p.kbs) {
+                        if (!ptx::mbar_wait(empty_bar(s), ph ^ 1u)) { ok = false; break; }
+                        const uint32_t st0 = base + s * stage_bytes, fb = full_bar(s);
+                        ptx::mbar_expect_tx(fb, tx_bytes);
+                        for (int j = 0; j < p.kbs; ++j) {
+                            const bool second = chunk >= nch0;
+                            ptx::tma_load_4d(st0 + act_off + j * act_step, second ? am1 : am0, fb,
+                                             (second ? chunk - nch0 : chunk) * 32, dx, y0 + dy, img0);
+                            if (p.cluster == 1) ptx::tma_load_2d(st0 + w_base_off + j * w_step, &maps.b, fb, 0, b_row);
+                            else ptx::tma_load_2d_mc(st0 + w_base_off + j * w_step + w_off, &maps.b, fb, 0, b_row, cmask);
                             b_row += coutp;
-                            if (++s == p.stages) { s = 0; ph ^= 1u; }
+                            if (++chunk == nch) { chunk = 0; if (++dx == 2) { dx = -1; ++dy; } }
                         }
-                        if (++dx == 2) { dx = -1; ++dy; }
+                        if (++s == p.stages) { s = 0; ph ^= 1u; }
                     }
                 }
             }
@@ -280,32 +285,39 @@ k_conv_umma(const __grid_constant__ UmmaMaps maps, const UmmaConv p) {
         // ------------------------------------------------------------ MMA issuer
         if (ptx::elect_one()) {
             const uint32_t idesc = umma_idesc_tf32(n_rows);
+            // descriptors differ between stages / K blocks only in their 14-bit start-address field
+            const uint64_t desc0 = umma_desc_sw128(base);
+            const uint32_t stage16 = stage_bytes >> 4;
+            const uint32_t m_step16 = kATileBytes >> 4, n_step16 = b_bytes >> 4, n_off16 = ((uint32_t)p.kbs * kATileBytes) >> 4;
             int s = 0, acc = 0;
             uint32_t ph = 0, acc_ph = 0;
             bool ok = true;
             for (int wk = work0; wk < p.n_work && ok; wk += gridDim.x) {
                 ok = ptx::mbar_wait(acc_empty0 + 8u * acc, acc_ph ^ 1u);      // epilogue has drained this buffer
                 ptx::tc_fence_after();
-                const uint32_t d_main = tmem_base + (uint32_t)(acc * p.acc_cols);
-                for (int it = 0; it < n_iters && ok; ++it) {
-                    ok = ptx::mbar_wait(full_bar(s), ph);
-                    ptx::tc_fence_after();
-                    const uint32_t a_src = base + s * stage_bytes, b_src = a_src + kATileBytes;
-                    const uint64_t adesc = umma_desc_sw128(a_src), bdesc = umma_desc_sw128(b_src);
-                    // 3xTF32: the two small cross terms go to their own accumulator.  The tensor core adds
-                    // into the accumulator with round-toward-zero; adding 2^-11-sized terms to a full-size
-                    // accumulator for 2/3 of the K loop costs ~K/16 ulps of systematic shrink (measured 6e-5
-                    // at K = 4608), a separate accumulator keeps that at the single-pass level.
-                    const bool corr = it >= iters_per_pass;
-                    const uint32_t d_tmem = d_main + (corr ? (uint32_t)p.corr_col : 0u);
-                    const int first_it = corr ? iters_per_pass : 0;
+                // 3xTF32: the two small cross terms go to their own accumulator.  The tensor core adds into the
+                // accumulator with round-toward-zero; adding 2^-11-sized terms to a full-size accumulator for 2/3 of
+                // the K loop costs ~K/16 ulps of systematic shrink (measured 6e-5 at K = 4608), a separate
+                // accumulator keeps that at the single-pass level.
+                for (int pass = 0; pass < p.npass && ok; ++pass) {
+                    const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.acc_cols) + (pass ? (uint32_t)p.corr_col : 0u);
+                    uint32_t accum = pass == 2 ? 1u : 0u;                      // passes 1 and 2 share the correction accumulator
+                    for (int it = 0; it < iters_per_pass && ok; it += p.kbs) {
+                        ok = ptx::mbar_wait(full_bar(s), ph);
+                        ptx::tc_fence_after();
+                        const uint64_t md = desc0 + (uint64_t)(s * stage16), nd = md + n_off16;
+                        for (int j = 0; j < p.kbs; ++j) {
 #pragma unroll
-                    for (int k = 0; k < 4; ++k)   // 4 x (K = 8 tf32 = 32 bytes) inside the 128-byte swizzle atom
-                        ptx::mma_tf32(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, (it != first_it) || (k != 0));
-                    // frees the smem slot when these MMAs retire -- in every CTA that multicasts into it
-                    if (p.cluster == 1) ptx::tc_commit(empty_bar(s));
-                    else ptx::tc_commit_mc(empty_bar(s), cmask);
-                    if (++s == p.stages) { s = 0; ph ^= 1u; }
+                            for (int k = 0; k < 4; ++k) {   // 4 x (K = 8 tf32 = 32 bytes) inside the 128-byte swizzle atom
+                                ptx::mma_tf32(d_tmem, md + (uint64_t)(j * m_step16 + 2 * k), nd + (uint64_t)(j * n_step16 + 2 * k), idesc, accum);
+                                accum = 1u;
+                            }
+                        }
+                        // frees the smem slot when these MMAs retire -- in every CTA that multicasts into it
+                        if (p.cluster == 1) ptx::tc_commit(empty_bar(s));
+                        else ptx::tc_commit_mc(empty_bar(s), cmask);
+                        if (++s == p.stages) { s = 0; ph ^= 1u; }
+                    }
                 }
                 ptx::tc_commit(acc_full0 + 8u * acc);   // accumulator complete
                 if (++acc == p.acc_stages) { acc = 0; acc_ph ^= 1u; }
@@ -798,7 +810,10 @@ inline int build_umma_launch(UmmaLaunch* U, const ConvLayer& L, int npass, const
     // ring is latency-bound (bytes in flight / ~1.3 us TMA latency): a deeper operand ring is worth more than a
     // deeper epilogue ring whenever halving the latter buys a whole stage and the K loop is long enough to hide a
     // single-buffered epilogue.
-    const size_t stage = kATileBytes + (size_t)n_rows * 128;
+    // two K blocks per stage halve the single-thread loop overhead per MMA; worth it where an MMA is short
+    // (N <= 128: <= 256 cycles per K block) and the stage stays small enough to keep >= 3 stages in flight
+    c.kbs = (n_rows <= 128 && (L.c0p / 32) % 2 == 0 && (L.c1p / 32) % 2 == 0 && !getenv("DTRAJ_KBS1")) ? 2 : 1;
+    const size_t stage = (size_t)c.kbs * (kATileBytes + (size_t)n_rows * 128);
     const size_t misc = 1024 + 512 + ((L.flags & CONV_FINAL) ? 2048 : 0);
     auto stages_for = [&](int bufs) { return (int)((227 * 1024 - misc - (size_t)kEpiWarps * bufs * 4096) / stage); };
     c.epi_bufs = 2;
