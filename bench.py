@@ -147,7 +147,7 @@ def cpu_state():
     return fns
 
 
-def run_reference(args):
+def run_reference(args, emit=print):
     """--impl reference: the reference's CPU implementation of the path (oracle port: the Python reference
     cannot travel to the GPU box), all host threads, bounded sample per step."""
     rank = int(os.environ.get("RANK", "0"))
@@ -166,7 +166,7 @@ def run_reference(args):
     dt = time.perf_counter() - t0
     v = n / dt
     sample = f"{seeds} seed x {len(GUIDANCE)} guidance scales x (teacher, student) = {2 * seeds * len(GUIDANCE)} trajectories + {seeds * len(GUIDANCE)} metric pairs per step"
-    print(json.dumps({
+    emit(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / max(args.steps, 1) * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic (random-init weights, seeded N(0,1) noise)",
@@ -178,7 +178,7 @@ def run_reference(args):
 
 
 # --------------------------------------------------------------------------------------- GPU arm
-def run_ours(args):
+def run_ours(args, emit=print):
     import numpy as np
     import torch
     import torch.distributed as dist
@@ -195,6 +195,7 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        os.environ["NCCL_DEBUG"] = os.environ.get("DTRAJ_NCCL_DEBUG", "WARN")   # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
 
     def barrier():
@@ -341,7 +342,7 @@ def run_ours(args):
                                "sample": f"{n_seeds} seeds x {G} guidance scales x (teacher, student) = {n} trajectories "
                                          f"+ {n_seeds * G} metric pairs, {dt:.1f} s",
                                "torch": torch.__version__}
-    print(json.dumps(out))
+    emit(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
 
@@ -358,10 +359,24 @@ def main():
                     help="chunks a sweep is cut into in the end-to-end leg (host staging of chunk i+1 overlaps chunk i on the GPU)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
-    if args.impl == "reference":
-        run_reference(args)
-    else:
-        run_ours(args)
+    # stdout carries exactly one JSON line: anything libraries print there meanwhile (NCCL's version banner,
+    # model constructors) is sent to stderr
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    lines = []
+    emit = lines.append
+    try:
+        if args.impl == "reference":
+            run_reference(args, emit)
+        else:
+            run_ours(args, emit)
+    finally:
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        os.close(real_stdout)
+    for ln in lines:
+        print(ln, flush=True)
 
 
 if __name__ == "__main__":
