@@ -42,6 +42,8 @@ struct UmmaConv {
     int swap;                  // 1: operands swapped (coutp <= 128): the WEIGHTS are the 128-row M operand and
                                //    `tn` output pixels the N operand, D^T[cout, pixel] accumulates in TMEM
     int tn;                    // pixels per tile in swap mode (256, 128 or 64); 128 otherwise
+    int pair;                  // 1: CTA pairs run tcgen05.mma.cta_group::2 -- M = 256 (two 128-row tiles, one per CTA), each CTA
+                               //    stages only ITS half of the weight tile, the leader CTA issues for both
     int kbs;                   // 32-channel K blocks per pipeline stage (2 when both sources have an even number of them)
     int epi_bufs;              // epilogue ring depth per warp (1 when the freed 32 KB buy another operand stage)
     int cluster;               // 1, or 2: CTA pairs (thread-block clusters) share the weight tile -- each CTA loads half
@@ -126,6 +128,35 @@ __device__ __forceinline__ void tc_commit_mc(uint32_t bar, uint16_t mask) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
                  ::"r"(bar), "h"(mask) : "memory");
 }
+// ---- CTA-pair (cta_group::2) forms
+__device__ __forceinline__ void tma_load_4d_2sm(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes "
+                 "[%0], [%1, {%3, %4, %5, %6}], [%2];"
+                 ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes "
+                 "[%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void mma_tf32_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void tc_commit_2sm(uint32_t bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"(mask) : "memory");
+}
+// shared::cluster address of `addr` (a shared::cta address of this CTA) in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
 __device__ __forceinline__ uint32_t cluster_ctarank() {
     uint32_t r;
     asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
@@ -181,15 +212,16 @@ constexpr int kATileBytes = 128 * 128;   // 128 rows x 32 fp32
 // epilogue warps drain accumulator buffer `acc` while the issuer fills the other one (TMEM holds two
 // accumulators whenever 2 x columns-per-tile <= 512), so neither the epilogue's latency nor its
 // instruction count sits on the tensor pipe's critical path.
+template <bool kPair>
 __global__ void __launch_bounds__(kUmmaThreads, 1)
-k_conv_umma(const __grid_constant__ UmmaMaps maps, const UmmaConv p) {
+k_conv_umma_t(const __grid_constant__ UmmaMaps maps, const UmmaConv p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // carve: [stages x (A 16 KB | B coutp*128 B)] [epilogue ring 4 warps x kEpiBufs x 4 KB] [barriers]
     const uint32_t base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
     const int coutp = p.L.coutp;
     const int ncols = p.ncols;                                 // columns this CTA computes per work item (coutp / n_split)
     const int n_rows = p.swap ? p.tn : ncols;                  // rows of the N operand tile (UMMA N)
-    const uint32_t b_bytes = (uint32_t)n_rows * 128u;
+    const uint32_t b_bytes = (uint32_t)(kPair ? n_rows / 2 : n_rows) * 128u;   // N-operand bytes staged in THIS CTA
     const uint32_t stage_bytes = (uint32_t)p.kbs * (kATileBytes + b_bytes);   // kbs x [M tile 16 KB] then kbs x [N tile]
     const uint32_t ring_base = base + p.stages * stage_bytes;
     const int kEpiBufs = p.epi_bufs;
@@ -217,23 +249,36 @@ k_conv_umma(const __grid_constant__ UmmaMaps maps, const UmmaConv p) {
             ptx::prefetch_tmap(&maps.a[0]);
             ptx::prefetch_tmap(&maps.b);
             if (p.L.c1p) ptx::prefetch_tmap(&maps.a[1]);
-            for (int s = 0; s < p.stages; ++s) { ptx::mbar_init(full_bar(s), 1); ptx::mbar_init(empty_bar(s), p.cluster); }
-            for (int i = 0; i < 2; ++i) { ptx::mbar_init(acc_full0 + 8u * i, 1); ptx::mbar_init(acc_empty0 + 8u * i, kEpiWarps); }
+            for (int s = 0; s < p.stages; ++s) { ptx::mbar_init(full_bar(s), 1); ptx::mbar_init(empty_bar(s), kPair ? 1 : p.cluster); }
+            for (int i = 0; i < 2; ++i) {
+                ptx::mbar_init(acc_full0 + 8u * i, 1);
+                ptx::mbar_init(acc_empty0 + 8u * i, kEpiWarps * (kPair ? 2 : 1));   // pair: both CTAs' epilogues report to the leader
+            }
             for (int i = 0; i < kEpiWarps * kEpiBufsMax; ++i) ptx::mbar_init(res_bar0 + 8u * i, 1);
             if (!(p.L.flags & CONV_NOSTORE)) ptx::prefetch_tmap(&maps.out);
             if (p.L.flags & CONV_RESID) ptx::prefetch_tmap(&maps.res);
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
         __syncwarp();
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
-                     ::"r"(tmem_slot), "r"((uint32_t)p.tmem_cols) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if constexpr (!kPair) {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                         ::"r"(tmem_slot), "r"((uint32_t)p.tmem_cols) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;"
+                         ::"r"(tmem_slot), "r"((uint32_t)p.tmem_cols) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        }
     }
     ptx::tc_fence_before();
     __syncthreads();
     if (p.cluster > 1) ptx::cluster_sync_all();   // peers' barriers exist before anything is multicast at them
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
+    auto arrive_acc_empty = [&](int acc) {     // "accumulator drained": to this CTA's issuer, or to the pair leader's
+        if constexpr (!kPair) ptx::mbar_arrive(acc_empty0 + 8u * acc);
+        else ptx::mbar_arrive_cluster(ptx::map_to_cta(acc_empty0 + 8u * acc, 0));
+    };
 
     if (warp == 0) {
         // ------------------------------------------------------------ TMA producer
@@ -242,9 +287,10 @@ k_conv_umma(const __grid_constant__ UmmaMaps maps, const UmmaConv p) {
         // is carried incrementally and a stage holds `kbs` (1 or 2) 32-channel K blocks per barrier round trip.
         if (ptx::elect_one()) {
             const int w_rows = p.swap ? 128 : ncols;           // rows of the weight tile
-            const int w_half = w_rows / p.cluster;             // rows this CTA fetches (and multicasts)
-            const uint32_t w_off = (uint32_t)(crank * w_half) * 128u;
-            const uint32_t tx_bytes = (uint32_t)p.kbs * (kATileBytes + b_bytes);
+            const int w_half = w_rows / p.cluster;             // rows this CTA fetches (and multicasts, unless paired)
+            const uint32_t w_off = kPair ? 0u : (uint32_t)(crank * w_half) * 128u;
+            // pair: the LEADER's barrier collects the bytes of both CTAs' loads
+            const uint32_t tx_bytes = (uint32_t)p.kbs * (kATileBytes + b_bytes) * (kPair ? 2u : 1u);
             const uint32_t act_off = p.swap ? (uint32_t)p.kbs * kATileBytes : 0u;   // N slots follow the M slots
             const uint32_t w_base_off = p.swap ? 0u : (uint32_t)p.kbs * kATileBytes;
             const uint32_t act_step = p.swap ? b_bytes : (uint32_t)kATileBytes;
@@ -265,13 +311,19 @@ k_conv_umma(const __grid_constant__ UmmaMaps maps, const UmmaConv p) {
                     int dy = p.L.ntaps == 9 ? -1 : 0, dx = dy, chunk = 0;
                     for (int it = 0; it < iters_per_pass; it += p.kbs) {
                         if (!ptx::mbar_wait(empty_bar(s), ph ^ 1u)) { ok = false; break; }
-                        const uint32_t st0 = base + s * stage_bytes, fb = full_bar(s);
-                        ptx::mbar_expect_tx(fb, tx_bytes);
+                        const uint32_t st0 = base + s * stage_bytes;
+                        // pair: complete_tx goes to the leader's barrier (same offset, CTA 0 of the cluster)
+                        uint32_t fb = full_bar(s);
+                        if constexpr (kPair) fb = ptx::map_to_cta(fb, 0);
+                        if (!kPair || crank == 0) ptx::mbar_expect_tx(full_bar(s), tx_bytes);
                         for (int j = 0; j < p.kbs; ++j) {
                             const bool second = chunk >= nch0;
-                            ptx::tma_load_4d(st0 + act_off + j * act_step, second ? am1 : am0, fb,
-                                             (second ? chunk - nch0 : chunk) * 32, dx, y0 + dy, img0);
-                            if (p.cluster == 1) ptx::tma_load_2d(st0 + w_base_off + j * w_step, &maps.b, fb, 0, b_row);
+                            if constexpr (!kPair) ptx::tma_load_4d(st0 + act_off + j * act_step, second ? am1 : am0, fb,
+                                                                    (second ? chunk - nch0 : chunk) * 32, dx, y0 + dy, img0);
+                            else ptx::tma_load_4d_2sm(st0 + act_off + j * act_step, second ? am1 : am0, fb,
+                                                      (second ? chunk - nch0 : chunk) * 32, dx, y0 + dy, img0);
+                            if constexpr (kPair) ptx::tma_load_2d_2sm(st0 + w_base_off + j * w_step, &maps.b, fb, 0, b_row);
+                            else if (p.cluster == 1) ptx::tma_load_2d(st0 + w_base_off + j * w_step, &maps.b, fb, 0, b_row);
                             else ptx::tma_load_2d_mc(st0 + w_base_off + j * w_step + w_off, &maps.b, fb, 0, b_row, cmask);
                             b_row += coutp;
                             if (++chunk == nch) { chunk = 0; if (++dx == 2) { dx = -1; ++dy; } }
@@ -283,8 +335,8 @@ k_conv_umma(const __grid_constant__ UmmaMaps maps, const UmmaConv p) {
         }
     } else if (warp == 1) {
         // ------------------------------------------------------------ MMA issuer
-        if (ptx::elect_one()) {
-            const uint32_t idesc = umma_idesc_tf32(n_rows);
+        if (ptx::elect_one() && (!kPair || crank == 0)) {
+            const uint32_t idesc = umma_idesc_tf32(n_rows) + (kPair ? ((uint32_t)(128 >> 4) << 24) : 0u);   // pair: M = 256
             // descriptors differ between stages / K blocks only in their 14-bit start-address field
             const uint64_t desc0 = umma_desc_sw128(base);
             const uint32_t stage16 = stage_bytes >> 4;
@@ -309,17 +361,20 @@ k_conv_umma(const __grid_constant__ UmmaMaps maps, const UmmaConv p) {
                         for (int j = 0; j < p.kbs; ++j) {
 #pragma unroll
                             for (int k = 0; k < 4; ++k) {   // 4 x (K = 8 tf32 = 32 bytes) inside the 128-byte swizzle atom
-                                ptx::mma_tf32(d_tmem, md + (uint64_t)(j * m_step16 + 2 * k), nd + (uint64_t)(j * n_step16 + 2 * k), idesc, accum);
+                                if constexpr (!kPair) ptx::mma_tf32(d_tmem, md + (uint64_t)(j * m_step16 + 2 * k), nd + (uint64_t)(j * n_step16 + 2 * k), idesc, accum);
+                                else ptx::mma_tf32_2sm(d_tmem, md + (uint64_t)(j * m_step16 + 2 * k), nd + (uint64_t)(j * n_step16 + 2 * k), idesc, accum);
                                 accum = 1u;
                             }
                         }
                         // frees the smem slot when these MMAs retire -- in every CTA that multicasts into it
-                        if (p.cluster == 1) ptx::tc_commit(empty_bar(s));
+                        if constexpr (kPair) ptx::tc_commit_2sm(empty_bar(s), cmask);
+                        else if (p.cluster == 1) ptx::tc_commit(empty_bar(s));
                         else ptx::tc_commit_mc(empty_bar(s), cmask);
                         if (++s == p.stages) { s = 0; ph ^= 1u; }
                     }
                 }
-                ptx::tc_commit(acc_full0 + 8u * acc);   // accumulator complete
+                if constexpr (kPair) ptx::tc_commit_2sm(acc_full0 + 8u * acc, cmask);   // accumulator complete, in both CTAs
+                else ptx::tc_commit(acc_full0 + 8u * acc);
                 if (++acc == p.acc_stages) { acc = 0; acc_ph ^= 1u; }
             }
         }
@@ -394,7 +449,7 @@ k_conv_umma(const __grid_constant__ UmmaMaps maps, const UmmaConv p) {
                 if (!live || pb_last < h) {
                     ptx::tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) ptx::mbar_arrive(acc_empty0 + 8u * acc);
+                    if (lane == 0) arrive_acc_empty(acc);
                 }
                 if (live)
                 for (int pb = h, k = 0; pb < npb; pb += 2, ++k) {
@@ -414,7 +469,7 @@ k_conv_umma(const __grid_constant__ UmmaMaps maps, const UmmaConv p) {
                     if (pb == pb_last) {
                         ptx::tc_fence_before();
                         __syncwarp();
-                        if (lane == 0) ptx::mbar_arrive(acc_empty0 + 8u * acc);
+                        if (lane == 0) arrive_acc_empty(acc);
                     }
                     // per-pixel side inputs, one pixel per lane, broadcast by shuffle in the loop below
                     const int64_t m_l = m_chunk + lane;
@@ -550,7 +605,7 @@ k_conv_umma(const __grid_constant__ UmmaMaps maps, const UmmaConv p) {
             if (c_last < h) {                   // a single-chunk item leaves the quarter's second warp idle
                 ptx::tc_fence_before();
                 __syncwarp();
-                if (lane == 0) ptx::mbar_arrive(acc_empty0 + 8u * acc);
+                if (lane == 0) arrive_acc_empty(acc);
             }
             for (int c = h, k = 0; c < nchunk; c += 2, ++k) {
                 const int b = k % kEpiBufs;
@@ -569,7 +624,7 @@ k_conv_umma(const __grid_constant__ UmmaMaps maps, const UmmaConv p) {
                     // every TMEM read of this warp for this tile is done: hand the accumulator back to the issuer
                     ptx::tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) ptx::mbar_arrive(acc_empty0 + 8u * acc);
+                    if (lane == 0) arrive_acc_empty(acc);
                 }
                 if (has_res) { ptx::mbar_wait(rbar + 8u * b, (res_par >> b) & 1u); res_par ^= 1u << b; }
                 uint8_t* bufp = smem_raw + (buf0 + 4096u * b - ptx::smem_u32(smem_raw));
@@ -684,7 +739,8 @@ k_conv_umma(const __grid_constant__ UmmaMaps maps, const UmmaConv p) {
     if (p.cluster > 1) ptx::cluster_sync_all();   // no CTA leaves while a peer can still write its smem / barriers
     if (warp == 0) {
         ptx::tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols) : "memory");
+        if constexpr (!kPair) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols) : "memory");
+        else asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols) : "memory");
     }
 }
 
@@ -749,6 +805,12 @@ inline int make_rows_map(CUtensorMap* m, const float* base, int64_t M, int coutp
     return 0;
 }
 
+inline cudaError_t umma_set_smem_attr() {
+    cudaError_t e = cudaFuncSetAttribute(k_conv_umma_t<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(k_conv_umma_t<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+}
+
 struct UmmaLaunch {            // everything a launch needs, built once per (layer, batch)
     UmmaMaps maps;
     UmmaConv conv;
@@ -788,7 +850,12 @@ inline int build_umma_launch(UmmaLaunch* U, const ConvLayer& L, int npass, const
     c.ncols = L.coutp / c.n_split;
     c.n_work = c.n_tiles * c.n_split;
     const int n_rows = c.swap ? c.tn : c.ncols;
-    c.cluster = (c.n_split == 1 && c.n_work >= 2 * kNumSMs && !getenv("DTRAJ_NO_CLUSTER")) ? 2 : 1;
+    // CTA pairs (tcgen05.mma.cta_group::2): each CTA stages its own 128 pixels and HALF of the weight tile, so a K
+    // block costs 16 + N/4 KB of its shared memory instead of 16 + N/2 KB -- more K blocks in flight in the
+    // latency-bound operand ring.  Wide, long layers with plenty of tiles only.
+    c.pair = (!c.swap && c.n_split == 1 && L.coutp >= 128 && nkb_all >= 16 && c.n_work >= 2 * kNumSMs &&
+              !(L.flags & CONV_FINAL) && !getenv("DTRAJ_NO_PAIR")) ? 1 : 0;
+    c.cluster = (c.pair || (c.n_split == 1 && c.n_work >= 2 * kNumSMs && getenv("DTRAJ_CLUSTER"))) ? 2 : 1;
     c.acc_cols = 32;
     while (c.acc_cols < n_rows) c.acc_cols *= 2;
     c.corr_col = 0;
@@ -812,8 +879,9 @@ inline int build_umma_launch(UmmaLaunch* U, const ConvLayer& L, int npass, const
     // single-buffered epilogue.
     // two K blocks per stage halve the single-thread loop overhead per MMA; worth it where an MMA is short
     // (N <= 128: <= 256 cycles per K block) and the stage stays small enough to keep >= 3 stages in flight
-    c.kbs = (n_rows <= 128 && (L.c0p / 32) % 2 == 0 && (L.c1p / 32) % 2 == 0 && !getenv("DTRAJ_KBS1")) ? 2 : 1;
-    const size_t stage = (size_t)c.kbs * (kATileBytes + (size_t)n_rows * 128);
+    const int n_stage_rows = c.pair ? n_rows / 2 : n_rows;
+    c.kbs = (n_stage_rows <= 128 && !c.pair && (L.c0p / 32) % 2 == 0 && (L.c1p / 32) % 2 == 0 && !getenv("DTRAJ_KBS1")) ? 2 : 1;
+    const size_t stage = (size_t)c.kbs * (kATileBytes + (size_t)n_stage_rows * 128);
     const size_t misc = 1024 + 512 + ((L.flags & CONV_FINAL) ? 2048 : 0);
     auto stages_for = [&](int bufs) { return (int)((227 * 1024 - misc - (size_t)kEpiWarps * bufs * 4096) / stage); };
     c.epi_bufs = 2;
@@ -842,7 +910,7 @@ inline int build_umma_launch(UmmaLaunch* U, const ConvLayer& L, int npass, const
 
 inline int launch_conv_umma(const UmmaLaunch& U, cudaStream_t st) {
     if (U.conv.cluster <= 1) {
-        k_conv_umma<<<U.grid, kUmmaThreads, U.smem, st>>>(U.maps, U.conv);
+        k_conv_umma_t<false><<<U.grid, kUmmaThreads, U.smem, st>>>(U.maps, U.conv);
         DTRAJ_LAUNCH_CHECK();
         return 0;
     }
@@ -859,7 +927,8 @@ inline int launch_conv_umma(const UmmaLaunch& U, cudaStream_t st) {
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    DTRAJ_CUDA(cudaLaunchKernelEx(&cfg, k_conv_umma, U.maps, U.conv));
+    if (U.conv.pair) DTRAJ_CUDA(cudaLaunchKernelEx(&cfg, k_conv_umma_t<true>, U.maps, U.conv));
+    else DTRAJ_CUDA(cudaLaunchKernelEx(&cfg, k_conv_umma_t<false>, U.maps, U.conv));
     return 0;
 }
 

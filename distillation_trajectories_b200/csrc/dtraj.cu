@@ -292,7 +292,7 @@ extern "C" int dtraj_unet_create(const dtraj_unet_desc* desc, const char* const*
     if (ce == cudaSuccess) ce = cudaDeviceSynchronize();
     if (ce != cudaSuccess) { dtraj_unet_destroy(u); return fail(DTRAJ_ECUDA, "time table kernel -> %s", cudaGetErrorString(ce)); }
     if (desc->precision != DTRAJ_PREC_FP32) {
-        ce = cudaFuncSetAttribute(k_conv_umma, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        ce = umma_set_smem_attr();
         if (ce != cudaSuccess) { dtraj_unet_destroy(u); return fail(DTRAJ_ECUDA, "smem attribute -> %s", cudaGetErrorString(ce)); }
     }
     *out = u;
@@ -831,7 +831,7 @@ extern "C" int dtraj_bench_conv(int32_t precision, int32_t c0, int32_t c1, int32
     int rc = 0;
     UmmaLaunch U;
     if (precision != DTRAJ_PREC_FP32) {
-        cudaFuncSetAttribute(k_conv_umma, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        umma_set_smem_attr();
         rc = build_umma_launch(&U, L, precision == DTRAJ_PREC_TF32X3 ? 3 : 1, dev + wo, pc.rows);
         U.conv.debug = debug;
     }
@@ -890,7 +890,7 @@ extern "C" int dtraj_test_conv(int32_t precision, const float* x0, int32_t c0, c
             cudaMemcpy(lo, h.data(), (n0 + n1) * sizeof(float), cudaMemcpyHostToDevice);
             L.src0_lo = lo; L.src1_lo = lo + n0;
         }
-        cudaFuncSetAttribute(k_conv_umma, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        umma_set_smem_attr();
         UmmaLaunch U;
         rc = build_umma_launch(&U, L, precision == DTRAJ_PREC_TF32X3 ? 3 : 1, dev + wo, pc.rows);
         if (!rc) rc = launch_conv_umma(U, st);

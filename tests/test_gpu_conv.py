@@ -78,6 +78,9 @@ SHAPES = [
     (2, 128, 0, 256, 8, 3),      # teacher widths
     (1, 256, 256, 128, 16, 3),
     (2, 32, 0, 32, 32, 3),       # 32x32 level 0: 4-row boxes
+    (592, 128, 0, 256, 8, 3),    # 296 tiles: CTA pairs (tcgen05.mma.cta_group::2), persistent loop with 2 tiles per pair
+    (300, 64, 64, 128, 8, 3),    # 150 tiles of 128 rows: swapped operands off (K < 1024), single-CTA persistent path
+    (160, 128, 0, 128, 16, 3),   # 160 tiles of 256 pixels: swapped operands (weights as the M operand)
     (3, 64, 0, 32, 16, 1),       # 1x1 residual
     (4, 38, 38, 76, 4, 1),
 ]
