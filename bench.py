@@ -47,7 +47,7 @@ def workload_config(seeds, world):
             "seeds_per_gpu_per_step": seeds, "guidance_scales": GUIDANCE,
             "trajectories_per_step": 2 * seeds * len(GUIDANCE) * world,
             "parallelism": f"seed-sharded x{world}, one all-reduce of metric sums",
-            "l2": "per-step working set (2 x 107 MB trajectory buffers at 256 seeds + GBs of activations) "
+            "l2": "per-step working set (2 x 124 MB trajectory buffers at 296 seeds + GBs of activations) "
                   "exceeds the 126 MB L2; no explicit flush"}
 
 
@@ -353,7 +353,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--seeds", type=int, default=256, help="seeds per GPU per step (x 8 guidance scales x 2 models)")
+    ap.add_argument("--seeds", type=int, default=296, help="seeds per GPU per step (x 8 guidance scales x 2 models)")
     ap.add_argument("--precision", default="tf32", choices=["tf32", "tf32x3", "fp32"])
     ap.add_argument("--e2e-chunks", type=int, default=1,
                     help="chunks a sweep is cut into in the end-to-end leg (host staging of chunk i+1 overlaps chunk i on the GPU)")

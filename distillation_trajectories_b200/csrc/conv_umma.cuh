@@ -835,8 +835,10 @@ inline int build_umma_launch(UmmaLaunch* U, const ConvLayer& L, int npass, const
     // to fill the GPU; narrower layers waste half of the 128 weight rows, short-K layers are epilogue-paced
     // and the transposed epilogue moves single words through shared memory.
     const int nkb_all = L.ntaps * (L.c0p + L.c1p) / 32;
+    // ... and since CTA pairs exist (below) the pair form of the plain orientation beats it on every layer of
+    // the bench workload (enc1.conv2 424 vs 497 us, dec1.conv1 370 vs 408 us), so it is opt-in.
     c.swap = (L.coutp == 128 && nkb_all >= 32 && (L.M + 255) / 256 >= kNumSMs && !(L.flags & CONV_FINAL) &&
-              !getenv("DTRAJ_NO_SWAP")) ? 1 : 0;
+              getenv("DTRAJ_SWAP")) ? 1 : 0;
     c.tn = c.swap ? 256 : 128;
     c.box_h = HW >= c.tn ? c.tn / L.W : L.H;
     c.box_n = HW >= c.tn ? 1 : c.tn / HW;
@@ -854,7 +856,7 @@ inline int build_umma_launch(UmmaLaunch* U, const ConvLayer& L, int npass, const
     // block costs 16 + N/4 KB of its shared memory instead of 16 + N/2 KB -- more K blocks in flight in the
     // latency-bound operand ring.  Wide, long layers with plenty of tiles only.
     c.pair = (!c.swap && c.n_split == 1 && L.coutp >= 128 && nkb_all >= 16 && c.n_work >= 2 * kNumSMs &&
-              !(L.flags & CONV_FINAL) && !getenv("DTRAJ_NO_PAIR")) ? 1 : 0;
+              !getenv("DTRAJ_NO_PAIR")) ? 1 : 0;
     c.cluster = (c.pair || (c.n_split == 1 && c.n_work >= 2 * kNumSMs && getenv("DTRAJ_CLUSTER"))) ? 2 : 1;
     c.acc_cols = 32;
     while (c.acc_cols < n_rows) c.acc_cols *= 2;
@@ -880,7 +882,7 @@ inline int build_umma_launch(UmmaLaunch* U, const ConvLayer& L, int npass, const
     // two K blocks per stage halve the single-thread loop overhead per MMA; worth it where an MMA is short
     // (N <= 128: <= 256 cycles per K block) and the stage stays small enough to keep >= 3 stages in flight
     const int n_stage_rows = c.pair ? n_rows / 2 : n_rows;
-    c.kbs = (n_stage_rows <= 128 && !c.pair && (L.c0p / 32) % 2 == 0 && (L.c1p / 32) % 2 == 0 && !getenv("DTRAJ_KBS1")) ? 2 : 1;
+    c.kbs = (n_stage_rows <= (c.pair ? 64 : 128) && (L.c0p / 32) % 2 == 0 && (L.c1p / 32) % 2 == 0 && !getenv("DTRAJ_KBS1")) ? 2 : 1;
     const size_t stage = (size_t)c.kbs * (kATileBytes + (size_t)n_stage_rows * 128);
     const size_t misc = 1024 + 512 + ((L.flags & CONV_FINAL) ? 2048 : 0);
     auto stages_for = [&](int bufs) { return (int)((227 * 1024 - misc - (size_t)kEpiWarps * bufs * 4096) / stage); };
