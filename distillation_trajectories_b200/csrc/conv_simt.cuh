@@ -11,7 +11,8 @@ namespace dtraj {
 enum ConvFlags : int {
     CONV_RELU = 1, CONV_TBIAS = 2, CONV_RESID = 4,
     // fused tails, tcgen05 kernel only (conv_umma.cuh)
-    CONV_POOL = 8, CONV_NOSTORE = 16, CONV_RESX = 32, CONV_FINAL = 64
+    CONV_POOL = 8, CONV_NOSTORE = 16, CONV_RESX = 32, CONV_FINAL = 64,
+    CONV_RESACC = 128   // the block's 1x1 residual conv runs as extra MMAs of THIS kernel into a second accumulator
 };
 
 // One convolution layer over up to two NHWC sources (implicit channel concat,
@@ -46,6 +47,10 @@ struct ConvLayer {
     const float* finw;         //            [finC][coutp]
     const float* finb;         //            [finC]
     float* elow;               //            [M, finC]
+    const float* rsrc0;        // CONV_RESACC: the block's input maps (sources of residual_conv, models.py:54-60)
+    const float* rsrc1;
+    int rc0p, rc1p;
+    const float* rbias;        //            residual_conv bias [coutp]
 };
 
 template <int BN>

@@ -35,6 +35,8 @@ struct UmmaConv {
     int acc_cols;              // columns of one accumulator set (x2 for 3 passes: main + correction accumulator)
     int acc_stages;            // 2 when two accumulator sets fit in 512 columns, else 1
     int corr_col;              // offset of the correction accumulator inside a set (3 passes), else 0
+    int res_col;               // offset of the residual-conv accumulator inside a set (CONV_RESACC), else 0
+    int r_nch0, r_nch;         // 32-channel chunks of the residual conv's first source / of both sources
     int n_tiles;               // 128-row output tiles
     int n_split;               // column split of a tile when there are fewer tiles than SMs (power of two)
     int ncols;                 // coutp / n_split: columns per work item (multiple of 32)
@@ -63,6 +65,8 @@ struct UmmaMaps {              // 64-byte aligned tensor maps, passed as __grid_
     CUtensorMap out;           // [M, coutp] output, box {32 ch, 32 rows}   (epilogue TMA store)
     CUtensorMap out_lo;        // low plane of the output (3xTF32)
     CUtensorMap res;           // [M, coutp] residual, same box             (epilogue TMA load)
+    CUtensorMap ra[2];         // CONV_RESACC: the block's input maps (A operand of the fused 1x1 residual conv)
+    CUtensorMap rb;            //              its packed weights
 };
 
 namespace ptx {
@@ -304,31 +308,41 @@ k_conv_umma_t(const __grid_constant__ UmmaMaps maps, const UmmaConv p) {
                 int img0, y0;
                 if (p.tiles_per_img > 1) { img0 = tile / p.tiles_per_img; y0 = (tile % p.tiles_per_img) * p.box_h; }
                 else { img0 = tile * p.box_n; y0 = 0; }
+                // one pipeline stage: kbs K blocks = (activation box at tap (dx, dy), weight rows) pairs
+                auto fill_stage = [&](const CUtensorMap* am0, const CUtensorMap* am1, const CUtensorMap* wm, int n_first,
+                                      int& chunk, int n_chunks, int& dx, int& dy, int& b_row) -> bool {
+                    if (!ptx::mbar_wait(empty_bar(s), ph ^ 1u)) return false;
+                    const uint32_t st0 = base + s * stage_bytes;
+                    // pair: complete_tx goes to the leader's barrier (same offset, CTA 0 of the cluster)
+                    uint32_t fb = full_bar(s);
+                    if constexpr (kPair) fb = ptx::map_to_cta(fb, 0);
+                    if (!kPair || crank == 0) ptx::mbar_expect_tx(full_bar(s), tx_bytes);
+                    for (int j = 0; j < p.kbs; ++j) {
+                        const bool second = chunk >= n_first;
+                        const int c0 = (second ? chunk - n_first : chunk) * 32;
+                        if constexpr (!kPair) ptx::tma_load_4d(st0 + act_off + j * act_step, second ? am1 : am0, fb, c0, dx, y0 + dy, img0);
+                        else ptx::tma_load_4d_2sm(st0 + act_off + j * act_step, second ? am1 : am0, fb, c0, dx, y0 + dy, img0);
+                        if constexpr (kPair) ptx::tma_load_2d_2sm(st0 + w_base_off + j * w_step, wm, fb, 0, b_row);
+                        else if (p.cluster == 1) ptx::tma_load_2d(st0 + w_base_off + j * w_step, wm, fb, 0, b_row);
+                        else ptx::tma_load_2d_mc(st0 + w_base_off + j * w_step + w_off, wm, fb, 0, b_row, cmask);
+                        b_row += coutp;
+                        if (++chunk == n_chunks) { chunk = 0; if (++dx == 2) { dx = -1; ++dy; } }
+                    }
+                    if (++s == p.stages) { s = 0; ph ^= 1u; }
+                    return true;
+                };
                 for (int pass = 0; pass < p.npass && ok; ++pass) {
                     const CUtensorMap* am0 = &maps.a[pass == 2 ? 2 : 0];
                     const CUtensorMap* am1 = &maps.a[pass == 2 ? 3 : 1];
                     int b_row = (pass == 1 ? p.b_lo_row : 0) + n0 + crank * w_half;
                     int dy = p.L.ntaps == 9 ? -1 : 0, dx = dy, chunk = 0;
-                    for (int it = 0; it < iters_per_pass; it += p.kbs) {
-                        if (!ptx::mbar_wait(empty_bar(s), ph ^ 1u)) { ok = false; break; }
-                        const uint32_t st0 = base + s * stage_bytes;
-                        // pair: complete_tx goes to the leader's barrier (same offset, CTA 0 of the cluster)
-                        uint32_t fb = full_bar(s);
-                        if constexpr (kPair) fb = ptx::map_to_cta(fb, 0);
-                        if (!kPair || crank == 0) ptx::mbar_expect_tx(full_bar(s), tx_bytes);
-                        for (int j = 0; j < p.kbs; ++j) {
-                            const bool second = chunk >= nch0;
-                            if constexpr (!kPair) ptx::tma_load_4d(st0 + act_off + j * act_step, second ? am1 : am0, fb,
-                                                                    (second ? chunk - nch0 : chunk) * 32, dx, y0 + dy, img0);
-                            else ptx::tma_load_4d_2sm(st0 + act_off + j * act_step, second ? am1 : am0, fb,
-                                                      (second ? chunk - nch0 : chunk) * 32, dx, y0 + dy, img0);
-                            if constexpr (kPair) ptx::tma_load_2d_2sm(st0 + w_base_off + j * w_step, &maps.b, fb, 0, b_row);
-                            else if (p.cluster == 1) ptx::tma_load_2d(st0 + w_base_off + j * w_step, &maps.b, fb, 0, b_row);
-                            else ptx::tma_load_2d_mc(st0 + w_base_off + j * w_step + w_off, &maps.b, fb, 0, b_row, cmask);
-                            b_row += coutp;
-                            if (++chunk == nch) { chunk = 0; if (++dx == 2) { dx = -1; ++dy; } }
-                        }
-                        if (++s == p.stages) { s = 0; ph ^= 1u; }
+                    for (int it = 0; it < iters_per_pass && ok; it += p.kbs) ok = fill_stage(am0, am1, &maps.b, nch0, chunk, nch, dx, dy, b_row);
+                }
+                if (p.L.flags & CONV_RESACC) {     // the block's 1x1 residual conv: centre tap of the block INPUT maps
+                    int b_row = n0 + crank * w_half, dy = 0, dx = 0, chunk = 0;
+                    for (int it = 0; it < p.r_nch && ok; it += p.kbs) {
+                        dx = dy = 0;
+                        ok = fill_stage(&maps.ra[0], &maps.ra[1], &maps.rb, p.r_nch0, chunk, p.r_nch + 1, dx, dy, b_row);
                     }
                 }
             }
@@ -351,10 +365,8 @@ k_conv_umma_t(const __grid_constant__ UmmaMaps maps, const UmmaConv p) {
                 // accumulator with round-toward-zero; adding 2^-11-sized terms to a full-size accumulator for 2/3 of
                 // the K loop costs ~K/16 ulps of systematic shrink (measured 6e-5 at K = 4608), a separate
                 // accumulator keeps that at the single-pass level.
-                for (int pass = 0; pass < p.npass && ok; ++pass) {
-                    const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.acc_cols) + (pass ? (uint32_t)p.corr_col : 0u);
-                    uint32_t accum = pass == 2 ? 1u : 0u;                      // passes 1 and 2 share the correction accumulator
-                    for (int it = 0; it < iters_per_pass && ok; it += p.kbs) {
+                auto run_stages = [&](uint32_t d_tmem, uint32_t accum, int n_kblocks) {
+                    for (int it = 0; it < n_kblocks && ok; it += p.kbs) {
                         ok = ptx::mbar_wait(full_bar(s), ph);
                         ptx::tc_fence_after();
                         const uint64_t md = desc0 + (uint64_t)(s * stage16), nd = md + n_off16;
@@ -372,7 +384,12 @@ k_conv_umma_t(const __grid_constant__ UmmaMaps maps, const UmmaConv p) {
                         else ptx::tc_commit_mc(empty_bar(s), cmask);
                         if (++s == p.stages) { s = 0; ph ^= 1u; }
                     }
-                }
+                };
+                const uint32_t d_set = tmem_base + (uint32_t)(acc * p.acc_cols);
+                // passes 1 and 2 of 3xTF32 share the correction accumulator
+                for (int pass = 0; pass < p.npass && ok; ++pass)
+                    run_stages(d_set + (pass ? (uint32_t)p.corr_col : 0u), pass == 2 ? 1u : 0u, iters_per_pass);
+                if (p.L.flags & CONV_RESACC) run_stages(d_set + (uint32_t)p.res_col, 0u, p.r_nch);
                 if constexpr (kPair) ptx::tc_commit_2sm(acc_full0 + 8u * acc, cmask);   // accumulator complete, in both CTAs
                 else ptx::tc_commit(acc_full0 + 8u * acc);
                 if (++acc == p.acc_stages) { acc = 0; acc_ph ^= 1u; }
@@ -620,6 +637,11 @@ k_conv_umma_t(const __grid_constant__ UmmaMaps maps, const UmmaConv p) {
                 } else {
                     ptx::tmem_ld_wait();
                 }
+                uint32_t rres[32];
+                if (fl & CONV_RESACC) {
+                    ptx::tmem_ld32(t_acc + (uint32_t)(p.res_col + 32 * c), rres);
+                    ptx::tmem_ld_wait();
+                }
                 if (c == c_last) {
                     // every TMEM read of this warp for this tile is done: hand the accumulator back to the issuer
                     ptx::tc_fence_before();
@@ -653,6 +675,11 @@ k_conv_umma_t(const __grid_constant__ UmmaMaps maps, const UmmaConv p) {
                             r4.z = fmaf(xv[ch], w4.z, r4.z); r4.w = fmaf(xv[ch], w4.w, r4.w);
                         }
                         v.x += r4.x; v.y += r4.y; v.z += r4.z; v.w += r4.w;
+                    }
+                    if (fl & CONV_RESACC) {   // residual_conv(x) + its bias, accumulated by this kernel's extra MMAs
+                        const float4 rb4 = __ldg(reinterpret_cast<const float4*>(p.L.rbias + col));
+                        v.x += __uint_as_float(rres[4 * j]) + rb4.x; v.y += __uint_as_float(rres[4 * j + 1]) + rb4.y;
+                        v.z += __uint_as_float(rres[4 * j + 2]) + rb4.z; v.w += __uint_as_float(rres[4 * j + 3]) + rb4.w;
                     }
                     float4* cell = reinterpret_cast<float4*>(rowp + (((uint32_t)j ^ swz) << 4));
                     if (has_res) {
@@ -819,7 +846,8 @@ struct UmmaLaunch {            // everything a launch needs, built once per (lay
 };
 
 // `w_rows` = rows of the packed weight matrix (hi planes then, for 3 passes, lo planes)
-inline int build_umma_launch(UmmaLaunch* U, const ConvLayer& L, int npass, const float* wpk, int64_t w_rows) {
+inline int build_umma_launch(UmmaLaunch* U, const ConvLayer& L, int npass, const float* wpk, int64_t w_rows,
+                             const float* rwpk = nullptr, int64_t rw_rows = 0) {
     memset(U, 0, sizeof(*U));
     const int HW = L.H * L.W;
     if (L.W > 32 || L.H != L.W || (HW & (HW - 1)) != 0)
@@ -862,6 +890,15 @@ inline int build_umma_launch(UmmaLaunch* U, const ConvLayer& L, int npass, const
     while (c.acc_cols < n_rows) c.acc_cols *= 2;
     c.corr_col = 0;
     if (npass == 3) { c.corr_col = c.acc_cols; c.acc_cols *= 2; }
+    c.res_col = 0;
+    c.r_nch0 = L.rc0p / 32;
+    c.r_nch = (L.rc0p + L.rc1p) / 32;
+    if (L.flags & CONV_RESACC) {
+        if (npass != 1 || c.swap || !rwpk || L.rc0p % 32 || L.rc1p % 32 || !L.rsrc0 || (L.rc1p && !L.rsrc1))
+            return fail(DTRAJ_EINVAL, "umma conv: fused residual conv needs single-pass TF32 and packed residual weights");
+        c.res_col = c.acc_cols;
+        c.acc_cols *= 2;
+    }
     c.acc_stages = 2 * c.acc_cols <= 512 ? 2 : 1;
     c.tmem_cols = c.acc_stages * c.acc_cols;
     const int nkb = L.ntaps * (L.c0p + L.c1p) / 32;
@@ -882,7 +919,7 @@ inline int build_umma_launch(UmmaLaunch* U, const ConvLayer& L, int npass, const
     // two K blocks per stage halve the single-thread loop overhead per MMA; worth it where an MMA is short
     // (N <= 128: <= 256 cycles per K block) and the stage stays small enough to keep >= 3 stages in flight
     const int n_stage_rows = c.pair ? n_rows / 2 : n_rows;
-    c.kbs = (n_stage_rows <= (c.pair ? 64 : 128) && (L.c0p / 32) % 2 == 0 && (L.c1p / 32) % 2 == 0 && !getenv("DTRAJ_KBS1")) ? 2 : 1;
+    c.kbs = (n_stage_rows <= (c.pair ? 64 : 128) && c.r_nch0 % 2 == 0 && (c.r_nch - c.r_nch0) % 2 == 0 && (L.c0p / 32) % 2 == 0 && (L.c1p / 32) % 2 == 0 && !getenv("DTRAJ_KBS1")) ? 2 : 1;
     const size_t stage = (size_t)c.kbs * (kATileBytes + (size_t)n_stage_rows * 128);
     const size_t misc = 1024 + 512 + ((L.flags & CONV_FINAL) ? 2048 : 0);
     auto stages_for = [&](int bufs) { return (int)((227 * 1024 - misc - (size_t)kEpiWarps * bufs * 4096) / stage); };
@@ -903,6 +940,11 @@ inline int build_umma_launch(UmmaLaunch* U, const ConvLayer& L, int npass, const
         if (L.c1p) DTRAJ_TRY(make_act_map(&U->maps.a[3], L.src1_lo, L.c1p, L.W, L.H, n_img, c.box_h, c.box_n));
     }
     DTRAJ_TRY(make_w_map(&U->maps.b, wpk, w_rows, (c.swap ? 128 : c.ncols) / c.cluster));
+    if (L.flags & CONV_RESACC) {
+        DTRAJ_TRY(make_act_map(&U->maps.ra[0], L.rsrc0, L.rc0p, L.W, L.H, n_img, c.box_h, c.box_n));
+        if (L.rc1p) DTRAJ_TRY(make_act_map(&U->maps.ra[1], L.rsrc1, L.rc1p, L.W, L.H, n_img, c.box_h, c.box_n));
+        DTRAJ_TRY(make_w_map(&U->maps.rb, rwpk, rw_rows, c.ncols / c.cluster));
+    }
     if (L.M >= (int64_t)1 << 31) return fail(DTRAJ_EINVAL, "umma conv: M too large for 32-bit TMA coordinates");
     if (!(L.flags & CONV_NOSTORE)) DTRAJ_TRY(make_rows_map(&U->maps.out, L.out, L.M, L.coutp));
     if (L.act_mode == ACT_SPLIT) DTRAJ_TRY(make_rows_map(&U->maps.out_lo, L.out + L.lo_off, L.M, L.coutp));

@@ -337,7 +337,7 @@ struct dtraj_plan {
     // generic conv launches in execution order
     struct ConvOp { ConvLayer L; bool umma; UmmaLaunch U; int tb_block; double flops; bool needs_x; };
     // fused tails (single-pass TF32 mode): which stand-alone kernels the conv epilogues replace
-    bool fuse_resx = false, fuse_final = false;
+    bool fuse_resx = false, fuse_final = false, fuse_res = false;
     bool fuse_pool[4] = {false, false, false, false};   // pool after enc1..enc4
     std::vector<ConvOp> convs;   // 15 3x3 + residual 1x1s
     int64_t launches_per_forward = 0;
@@ -386,6 +386,10 @@ int64_t plan_floats(const dtraj_unet* u, int64_t R, dtraj_plan* P) {
 struct Tail {                // optional fused epilogue tails of one conv
     float* pool_out = nullptr;
     bool resx = false, final1x1 = false, nostore = false;
+    // fused residual conv (CONV_RESACC): the block's packed 1x1 weights and its input maps
+    const PackedConv* res = nullptr;
+    const dtraj_plan::Buf* rs0 = nullptr;
+    const dtraj_plan::Buf* rs1 = nullptr;
 };
 
 int add_conv(dtraj_plan* P, const PackedConv& pc, const dtraj_plan::Buf& s0, const dtraj_plan::Buf* s1, int S,
@@ -418,8 +422,16 @@ int add_conv(dtraj_plan* P, const PackedConv& pc, const dtraj_plan::Buf& s0, con
     }
     op.tb_block = tb_block;
     op.flops = 2.0 * (double)L.M * pc.cout * (double)(pc.c0 + pc.c1) * pc.ntaps;   // executed taps, real channels
+    if (tail.res) {
+        L.flags |= CONV_RESACC;
+        L.rsrc0 = tail.rs0->p; L.rc0p = tail.res->c0p;
+        if (tail.rs1) { L.rsrc1 = tail.rs1->p; L.rc1p = tail.res->c1p; }
+        L.rbias = tail.res->bias;
+        op.flops += 2.0 * (double)L.M * tail.res->cout * (double)(tail.res->c0 + tail.res->c1);
+    }
     op.umma = u->d.precision != DTRAJ_PREC_FP32;
-    if (op.umma) DTRAJ_TRY(build_umma_launch(&op.U, L, u->d.precision == DTRAJ_PREC_TF32X3 ? 3 : 1, pc.w, pc.rows));
+    if (op.umma) DTRAJ_TRY(build_umma_launch(&op.U, L, u->d.precision == DTRAJ_PREC_TF32X3 ? 3 : 1, pc.w, pc.rows,
+                                             tail.res ? tail.res->w : nullptr, tail.res ? tail.res->rows : 0));
     P->convs.push_back(op);
     return 0;
 }
@@ -442,6 +454,13 @@ int plan_build(const dtraj_unet* u, int64_t R, void* ws, int64_t ws_bytes, dtraj
     P->fuse_resx = fused;
     P->fuse_final = fused;
     for (int l = 0; l < 4; ++l) P->fuse_pool[l] = fused && S[l] <= 16;
+    // residual 1x1 convs as extra MMAs of the block's conv2 (CONV_RESACC): no r tensor, no extra launch
+    P->fuse_res = fused && !getenv("DTRAJ_NO_RESACC");
+    const bool fr = P->fuse_res;
+    auto with_res = [&](Tail t, int b, const dtraj_plan::Buf* s0, const dtraj_plan::Buf* s1) {
+        if (fr && blk(b).has_res) { t.res = &u->blk[b].res; t.rs0 = s0; t.rs1 = s1; }
+        return t;
+    };
     const dtraj_plan::Buf* pooled[4] = {&P->p1, &P->p2, &P->p3, &P->p4};
     auto tail_for = [&](int enc) {   // conv2 of encoder block `enc` (0..3)
         Tail t;
@@ -458,18 +477,22 @@ int plan_build(const dtraj_unet* u, int64_t R, void* ws, int64_t ws_bytes, dtraj
         ADD(blk(0).conv2, P->tmp_h, nullptr, S[0], P->tmp_x, t.resx ? nullptr : P->tmp_r.p, t.resx ? CONV_RELU : RR, -1, false, t);
     }
     // enc2 @ level 1
-    ADD(blk(1).res, P->p1, nullptr, S[1], P->tmp_r, nullptr, 0, -1, true);
+    if (!blk(1).has_res) rc = fail(DTRAJ_EINVAL, "enc2 without residual_conv unsupported");
+    if (!fr) ADD(blk(1).res, P->p1, nullptr, S[1], P->tmp_r, nullptr, 0, -1, true);
     ADD(blk(1).conv1, P->p1, nullptr, S[1], P->tmp_h, nullptr, RT, 1, false);
-    ADD(blk(1).conv2, P->tmp_h, nullptr, S[1], P->x2, P->tmp_r.p, RR, -1, false, tail_for(1));
+    ADD(blk(1).conv2, P->tmp_h, nullptr, S[1], P->x2, fr ? nullptr : P->tmp_r.p, fr ? CONV_RELU : RR, -1, false,
+        with_res(tail_for(1), 1, &P->p1, nullptr));
     // enc3 @ level 2 (identity residual = pooled input)
     const dtraj_plan::Buf* pin[3] = {&P->p2, &P->p3, &P->p4};
     const dtraj_plan::Buf* xo[3] = {&P->x3, &P->x4, &P->tmp_x};
     for (int k = 0; k < 3 && !rc; ++k) {
         const int b = 2 + k, lv = 2 + k;
         const float* resid = pin[k]->p;
-        if (blk(b).has_res) { ADD(blk(b).res, *pin[k], nullptr, S[lv], P->tmp_r, nullptr, 0, -1, true); resid = P->tmp_r.p; }
+        const bool fused_here = fr && blk(b).has_res;
+        if (blk(b).has_res && !fr) { ADD(blk(b).res, *pin[k], nullptr, S[lv], P->tmp_r, nullptr, 0, -1, true); resid = P->tmp_r.p; }
         ADD(blk(b).conv1, *pin[k], nullptr, S[lv], P->tmp_h, nullptr, RT, b, false);
-        ADD(blk(b).conv2, P->tmp_h, nullptr, S[lv], *xo[k], resid, RR, -1, false, k < 2 ? tail_for(2 + k) : Tail());
+        ADD(blk(b).conv2, P->tmp_h, nullptr, S[lv], *xo[k], fused_here ? nullptr : resid, fused_here ? CONV_RELU : RR, -1, false,
+            with_res(k < 2 ? tail_for(2 + k) : Tail(), b, pin[k], nullptr));
     }
     // decoders: [upsampled | skip]
     const dtraj_plan::Buf* up[3] = {&P->u3, &P->u2, &P->u1};
@@ -478,11 +501,12 @@ int plan_build(const dtraj_unet* u, int64_t R, void* ws, int64_t ws_bytes, dtraj
     for (int k = 0; k < 3 && !rc; ++k) {
         const int b = 5 + k, lv = 3 - k;
         if (!blk(b).has_res) { rc = fail(DTRAJ_EINVAL, "%s without residual_conv unsupported", kBlockNames[b]); break; }
-        ADD(blk(b).res, *up[k], skip[k], S[lv], P->tmp_r, nullptr, 0, -1, true);
+        if (!fr) ADD(blk(b).res, *up[k], skip[k], S[lv], P->tmp_r, nullptr, 0, -1, true);
         ADD(blk(b).conv1, *up[k], skip[k], S[lv], P->tmp_h, nullptr, RT, b, false);
         Tail t;
         if (k == 2 && P->fuse_final) { t.final1x1 = true; t.nostore = true; }   // y1 only feeds the final 1x1
-        ADD(blk(b).conv2, P->tmp_h, nullptr, S[lv], *yo[k], P->tmp_r.p, RR, -1, false, t);
+        ADD(blk(b).conv2, P->tmp_h, nullptr, S[lv], *yo[k], fr ? nullptr : P->tmp_r.p, fr ? CONV_RELU : RR, -1, false,
+            with_res(t, b, up[k], skip[k]));
     }
 #undef ADD
     if (rc) { delete P; return rc; }
@@ -545,6 +569,7 @@ int plan_forward(dtraj_plan* P, const float* x, int64_t x_stride, const int32_t*
     };
     auto upsample = [&](const dtraj_plan::Buf& in, const dtraj_plan::Buf& out, int Si, int cp) -> int {
         const int64_t n4 = R * (2 * Si) * (2 * Si) * (cp / 4);
+        if (n4 >= ((int64_t)1 << 31)) return fail(DTRAJ_EINVAL, "upsample: batch too large for 32-bit indexing");
         PROF_BEGIN(prof, KC_RESAMPLE);
         k_upsample2<<<blocks_for(n4, 256), 256, 0, st>>>(in.p, out.p, n4, Si, Si, cp / 4, out.lo,
                                                         (u->act_mode == ACT_SPLIT && !out.lo) ? ACT_PLAIN : u->act_mode);
@@ -554,12 +579,13 @@ int plan_forward(dtraj_plan* P, const float* x, int64_t x_stride, const int32_t*
     };
     DTRAJ_TRY(conv());                                   // enc1.conv2 -> x1 (tmp_x)
     DTRAJ_TRY(pool(P->tmp_x, P->p1, S[1], dp[0], 0));
-    DTRAJ_TRY(conv()); DTRAJ_TRY(conv()); DTRAJ_TRY(conv());   // enc2 -> x2
+    if (!P->fuse_res) DTRAJ_TRY(conv());                  // enc2.residual_conv (else inside conv2)
+    DTRAJ_TRY(conv()); DTRAJ_TRY(conv());                 // enc2 -> x2
     DTRAJ_TRY(pool(P->x2, P->p2, S[2], dp[1], 1));
     const dtraj_plan::Buf* xo[3] = {&P->x3, &P->x4, &P->tmp_x};
     const dtraj_plan::Buf* pn[2] = {&P->p3, &P->p4};
     for (int k = 0; k < 3; ++k) {                        // enc3, enc4, bottleneck
-        if (u->blk[2 + k].has_res) DTRAJ_TRY(conv());
+        if (u->blk[2 + k].has_res && !P->fuse_res) DTRAJ_TRY(conv());
         DTRAJ_TRY(conv()); DTRAJ_TRY(conv());
         if (k < 2) DTRAJ_TRY(pool(*xo[k], *pn[k], S[3 + k], dp[2 + k], 2 + k));
     }
@@ -567,7 +593,8 @@ int plan_forward(dtraj_plan* P, const float* x, int64_t x_stride, const int32_t*
     const int upc[3] = {dp[3], dp[2], dp[1]};
     for (int k = 0; k < 3; ++k) {                        // dec3, dec2, dec1
         DTRAJ_TRY(upsample(P->tmp_x, *up[k], S[4 - k], upc[k]));
-        DTRAJ_TRY(conv()); DTRAJ_TRY(conv()); DTRAJ_TRY(conv());
+        if (!P->fuse_res) DTRAJ_TRY(conv());
+        DTRAJ_TRY(conv()); DTRAJ_TRY(conv());
     }
     if (!P->fuse_final) {   // final 1x1 at half resolution (else: dec1.conv2's epilogue)
         const int64_t npix = R * S[1] * S[1];

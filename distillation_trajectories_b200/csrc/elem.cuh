@@ -223,24 +223,24 @@ __device__ __forceinline__ void up2_coord(int dst, int in, float scale, int& i0,
 __global__ void __launch_bounds__(256) k_upsample2(const float* __restrict__ in, float* __restrict__ out,
                                                    int64_t n_out4, int Hi, int Wi, int cp4,
                                                    int64_t lo_off, int act_mode) {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_out4) return;
+    // one thread = 4 channels of one output pixel; 32-bit index arithmetic (the host checks n_out4 < 2^31),
+    // Ho and Wo are powers of two
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (uint32_t)n_out4) return;
     const int Ho = Hi * 2, Wo = Wi * 2;
-    int c4 = (int)(i % cp4);
-    int64_t pix = i / cp4;
-    int xo = (int)(pix % Wo);
-    int64_t t = pix / Wo;
-    int yo = (int)(t % Ho);
-    int64_t n = t / Ho;
+    const uint32_t pix = i / (uint32_t)cp4, c4 = i - pix * (uint32_t)cp4;
+    const int lw = 31 - __clz(Wo), lh = 31 - __clz(Ho);
+    const int xo = (int)(pix & (uint32_t)(Wo - 1)), yo = (int)((pix >> lw) & (uint32_t)(Ho - 1));
+    const uint32_t n = pix >> (lw + lh);
     const float sh = Ho > 1 ? (float)(Hi - 1) / (float)(Ho - 1) : 0.f;
     const float sw = Wo > 1 ? (float)(Wi - 1) / (float)(Wo - 1) : 0.f;
     int y0, y1, x0, x1; float ly, lx;
     up2_coord(yo, Hi, sh, y0, y1, ly);
     up2_coord(xo, Wi, sw, x0, x1, lx);
     const float hy = 1.f - ly, hx = 1.f - lx;
-    const float4* base = reinterpret_cast<const float4*>(in) + n * Hi * Wi * cp4 + c4;
-    float4 v00 = base[((int64_t)y0 * Wi + x0) * cp4], v01 = base[((int64_t)y0 * Wi + x1) * cp4];
-    float4 v10 = base[((int64_t)y1 * Wi + x0) * cp4], v11 = base[((int64_t)y1 * Wi + x1) * cp4];
+    const float4* base = reinterpret_cast<const float4*>(in) + (size_t)n * Hi * Wi * cp4 + c4;
+    const float4 v00 = __ldg(base + (y0 * Wi + x0) * cp4), v01 = __ldg(base + (y0 * Wi + x1) * cp4);
+    const float4 v10 = __ldg(base + (y1 * Wi + x0) * cp4), v11 = __ldg(base + (y1 * Wi + x1) * cp4);
     float4 o;
     o.x = hy * (hx * v00.x + lx * v01.x) + ly * (hx * v10.x + lx * v11.x);
     o.y = hy * (hx * v00.y + lx * v01.y) + ly * (hx * v10.y + lx * v11.y);
