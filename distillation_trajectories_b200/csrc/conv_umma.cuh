@@ -883,7 +883,8 @@ inline int build_umma_launch(UmmaLaunch* U, const ConvLayer& L, int npass, const
     // CTA pairs (tcgen05.mma.cta_group::2): each CTA stages its own 128 pixels and HALF of the weight tile, so a K
     // block costs 16 + N/4 KB of its shared memory instead of 16 + N/2 KB -- more K blocks in flight in the
     // latency-bound operand ring.  Wide, long layers with plenty of tiles only.
-    c.pair = (!c.swap && c.n_split == 1 && L.coutp >= 128 && nkb_all >= 16 && c.n_work >= 2 * kNumSMs &&
+    const int pair_min = getenv("DTRAJ_PAIR_MIN") ? atoi(getenv("DTRAJ_PAIR_MIN")) : 64;
+    c.pair = (!c.swap && c.n_split == 1 && L.coutp >= pair_min && nkb_all >= 16 && c.n_work >= 2 * kNumSMs &&
               !getenv("DTRAJ_NO_PAIR")) ? 1 : 0;
     c.cluster = (c.pair || (c.n_split == 1 && c.n_work >= 2 * kNumSMs && getenv("DTRAJ_CLUSTER"))) ? 2 : 1;
     c.acc_cols = 32;
