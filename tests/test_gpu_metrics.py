@@ -157,3 +157,41 @@ def test_properties_full_size():
     # (f) W1 is invariant under a common permutation of elements and W1(x, x + c) = |c|
     w_all = tm.wasserstein_frames(T[:8, :, :1024].contiguous(), (T[:8, :, :1024] + 0.25).contiguous())
     torch.testing.assert_close(w_all, torch.full_like(w_all, 0.25), rtol=1e-4, atol=1e-6)
+
+
+def test_packed_store_matches_per_sample_pickles(tmp_path):
+    """the packed format (one batched loop, one file) holds exactly the frames the per-sample
+    path generates, its reader yields the reference structure, and the batched metrics agree with the per-pair ones."""
+    from distillation_trajectories_b200.utils import trajectory_store as store
+    g, cfg, teacher, student = golden_models("tiny16", device="cuda")
+    sampling.set_noise_device("cpu")
+    try:
+        for ss in (cfg.timesteps, max(2, cfg.timesteps // 2)):          # equal and unequal step counts
+            cfg.student_steps = ss
+            cfg.trajectory_dir = str(tmp_path / f"pk_{ss}")
+            a = TrajectoryManager(teacher, student, cfg, size_factor=0.05)
+            a.generate_and_save_trajectories(4)
+            cfg.trajectory_dir = str(tmp_path / f"pack_{ss}")
+            b = generate_trajectories_with_disk_storage(teacher, student, cfg, size_factor=0.05, num_samples=4, packed=True)
+            assert len(store.list_packs(cfg.trajectory_dir, 0.05)) == 1 and store.stored_samples(cfg.trajectory_dir, 0.05) == {0, 1, 2, 3}
+            cfg.trajectory_dir = str(tmp_path / f"pk_{ss}")
+            ta, sa = a.load_trajectories()
+            cfg.trajectory_dir = str(tmp_path / f"pack_{ss}")
+            tb, sb = b.load_trajectories()
+            assert len(ta) == len(tb) == 4
+            for la, lb in zip(ta + sa, tb + sb):
+                assert [t for _, t in la] == [t for _, t in lb]
+                for (xa, _), (xb, _) in zip(la, lb):
+                    assert torch.equal(xa.cpu(), xb.cpu())
+            np.random.seed(0)
+            mb = b.compute_trajectory_metrics_batch()
+            cfg.trajectory_dir = str(tmp_path / f"pk_{ss}")
+            np.random.seed(0)
+            ma = a.compute_trajectory_metrics_batch()
+            for k in ("endpoint_distances", "teacher_path_lengths", "wasserstein_distances", "distribution_similarity",
+                      "mean_directional_consistency", "wasserstein_distances_per_timestep"):
+                np.testing.assert_allclose(np.asarray(mb[k], np.float64), np.asarray(ma[k], np.float64), rtol=1e-5, atol=1e-8, err_msg=k)
+            assert abs(mb["endpoint_distances_avg"] - ma["endpoint_distances_avg"]) < 1e-6
+    finally:
+        sampling.set_noise_device(None)
+        cfg.student_steps = cfg.timesteps
