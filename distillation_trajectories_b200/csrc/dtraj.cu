@@ -11,6 +11,7 @@
 #include "conv_simt.cuh"
 #include "conv_umma.cuh"
 #include "metrics.cuh"
+#include "probe.cuh"
 
 using namespace dtraj;
 
@@ -810,6 +811,19 @@ extern "C" int dtraj_wasserstein(const float* teacher, const float* student, int
 // ======================================================================================
 // test hooks
 // ======================================================================================
+// hardware probe, see probe.cuh; out_host[128] = row id fetched for each of the 128 output rows
+extern "C" int dtraj_probe_umma_view(int32_t rows, int32_t start_row, int32_t sbo_bytes, int32_t base_off_mode, float* out_host) {
+    float* d = nullptr;
+    DTRAJ_CUDA(cudaMalloc(&d, 128 * sizeof(float)));
+    cudaFuncSetAttribute(k_probe_view, cudaFuncAttributeMaxDynamicSharedMemorySize, 40 * 1024);
+    k_probe_view<<<1, 128, 36 * 1024>>>(rows, start_row, sbo_bytes, base_off_mode, d);
+    cudaError_t ce = cudaDeviceSynchronize();
+    if (ce == cudaSuccess) ce = cudaMemcpy(out_host, d, 128 * sizeof(float), cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    if (ce != cudaSuccess) return fail(DTRAJ_ECUDA, "probe -> %s", cudaGetErrorString(ce));
+    return 0;
+}
+
 extern "C" unsigned int dtraj_debug_umma_error(void) {
     unsigned int v = 0;
     cudaMemcpyFromSymbol(&v, g_umma_error, sizeof(v));
