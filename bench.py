@@ -282,7 +282,13 @@ def run_ours(args, emit=print):
                 "launches_timed": conv_n, "avg_launch_us": conv_ms / max(conv_n, 1) * 1e3,
                 "flops_per_launch": conv_fl / max(conv_n, 1), "share_of_loop_time": conv_ms / all_ms,
                 "class_ms": {"conv": conv_ms, "first_conv": sum(p["ms"][1] for p in prof),
-                             "pool_upsample_final": sum(p["ms"][2] for p in prof), "step": sum(p["ms"][3] for p in prof)}}
+                             "pool_upsample_final": sum(p["ms"][2] for p in prof), "step": sum(p["ms"][3] for p in prof),
+                             "enc1_fused": sum(p["ms"][4] for p in prof)}}
+    e1_ms, e1_fl = sum(p["ms"][4] for p in prof), sum(p["enc1_flops"] for p in prof)
+    if e1_ms > 0:
+        roofline["enc1_kernel"] = {"kernel": "k_enc1_umma (conv1 on CUDA cores into smem + conv2 by tcgen05 tap views + pool)",
+                                   "achieved": e1_fl / (e1_ms / 1e3) / 1e12, "unit": "TFLOP/s (conv2 flops only)",
+                                   "frac": e1_fl / (e1_ms / 1e3) / 1e12 / tc_sust}
     # HBM-bound side kernels (algorithmic bytes: SURVEY.md 8d)
     D, L, N = Cfg.channels * Cfg.image_size ** 2, Cfg.timesteps + 1, S * G
     step_ms = sum(p["ms"][3] for p in prof)

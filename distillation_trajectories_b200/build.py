@@ -15,7 +15,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(CSRC, "libdtraj.so")
 STAMP = os.path.join(CSRC, ".libdtraj.stamp")
 SOURCES = ["dtraj.cu"]
-HEADERS = ["common.cuh", "elem.cuh", "conv_simt.cuh", "conv_umma.cuh", "metrics.cuh", "probe.cuh", "../../include/dtraj.h"]
+HEADERS = sorted(f for f in os.listdir(CSRC) if f.endswith(".cuh")) + ["../../include/dtraj.h"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17", "--shared", "-Xcompiler", "-fPIC",

@@ -12,6 +12,7 @@
 #include "conv_umma.cuh"
 #include "metrics.cuh"
 #include "probe.cuh"
+#include "enc1_umma.cuh"
 
 using namespace dtraj;
 
@@ -294,6 +295,7 @@ extern "C" int dtraj_unet_create(const dtraj_unet_desc* desc, const char* const*
     if (ce != cudaSuccess) { dtraj_unet_destroy(u); return fail(DTRAJ_ECUDA, "time table kernel -> %s", cudaGetErrorString(ce)); }
     if (desc->precision != DTRAJ_PREC_FP32) {
         ce = umma_set_smem_attr();
+        if (ce == cudaSuccess) ce = enc1_set_smem_attr();
         if (ce != cudaSuccess) { dtraj_unet_destroy(u); return fail(DTRAJ_ECUDA, "smem attribute -> %s", cudaGetErrorString(ce)); }
     }
     *out = u;
@@ -312,7 +314,7 @@ extern "C" int dtraj_unet_time_bias(const dtraj_unet* u, int32_t t, int32_t vari
 // forward plan: workspace carving + one launch record per kernel
 // ======================================================================================
 // Optional per-launch timing (dtraj_sampler_profile): one event pair per launch, summed per class.
-enum KernelClass : int { KC_CONV = 0, KC_FIRST = 1, KC_RESAMPLE = 2, KC_STEP = 3, KC_COUNT = 4 };
+enum KernelClass : int { KC_CONV = 0, KC_FIRST = 1, KC_RESAMPLE = 2, KC_STEP = 3, KC_ENC1 = 4, KC_COUNT = 5 };
 struct Profiler {
     struct Rec { int cls; cudaEvent_t a, b; };
     std::vector<Rec> recs;
@@ -339,6 +341,8 @@ struct dtraj_plan {
     struct ConvOp { ConvLayer L; bool umma; UmmaLaunch U; int tb_block; double flops; bool needs_x; };
     // fused tails (single-pass TF32 mode): which stand-alone kernels the conv epilogues replace
     bool fuse_resx = false, fuse_final = false, fuse_res = false;
+    bool fuse_enc1 = false;      // k_enc1_umma replaces k_conv_first + the enc1.conv2 launch
+    Enc1Launch enc1;
     bool fuse_pool[4] = {false, false, false, false};   // pool after enc1..enc4
     std::vector<ConvOp> convs;   // 15 3x3 + residual 1x1s
     int64_t launches_per_forward = 0;
@@ -471,7 +475,13 @@ int plan_build(const dtraj_unet* u, int64_t R, void* ws, int64_t ws_bytes, dtraj
 #define ADD(...) if (!rc) rc = add_conv(P, __VA_ARGS__)
     // enc1: conv1/res by k_conv_first; conv2 here.  x1 itself is never a skip input (models.py:206-216):
     // with the pool fused, only the pooled tile is written.
-    {
+    P->fuse_enc1 = fused && S[0] % 16 == 0 && u->d.channels <= 4 && !getenv("DTRAJ_NO_ENC1");
+    if (P->fuse_enc1) {
+        rc = build_enc1_launch(&P->enc1, u->d.channels, S[0], u->dp[0], blk(0).cout, P->R, blk(0).conv2.w, blk(0).conv2.rows);
+        Enc1Params& e = P->enc1.p;
+        e.w3 = u->fw3; e.b3 = u->fb3; e.rw1 = u->fw1; e.rb1 = u->fb1; e.bias2 = blk(0).conv2.bias;
+        e.tb_var_stride = u->tb_stride; e.pool_out = P->p1.p; e.act_mode = u->act_mode;
+    } else {
         Tail t = tail_for(0);
         t.resx = P->fuse_resx;
         t.nostore = P->fuse_pool[0];
@@ -528,7 +538,16 @@ int plan_forward(dtraj_plan* P, const float* x, int64_t x_stride, const int32_t*
     const int64_t R = P->R;
     const float* trow = u->table + (size_t)t * 3 * u->tb_stride;
     int64_t nl = 0;
-    {   // enc1.conv1 + residual
+    if (P->fuse_enc1) {   // whole enc1 block + pool in one kernel
+        Enc1Params& e = P->enc1.p;
+        e.x = x; e.x_stride = x_stride; e.row_sample = row_sample; e.row_variant = row_variant;
+        e.tbias = trow + u->tb_off[0];
+        PROF_BEGIN(prof, KC_ENC1);
+        int rc1 = launch_enc1(P->enc1, st);
+        PROF_END(prof);
+        DTRAJ_TRY(rc1);
+        ++nl;
+    } else {   // enc1.conv1 + residual
         FirstConvParams f;
         f.x = x; f.x_stride = x_stride; f.row_sample = row_sample; f.row_variant = row_variant;
         f.C = C; f.H = S[0]; f.W = S[0]; f.coutp = dp[0];
@@ -578,8 +597,10 @@ int plan_forward(dtraj_plan* P, const float* x, int64_t x_stride, const int32_t*
         DTRAJ_LAUNCH_CHECK(); ++nl;
         return 0;
     };
-    DTRAJ_TRY(conv());                                   // enc1.conv2 -> x1 (tmp_x)
-    DTRAJ_TRY(pool(P->tmp_x, P->p1, S[1], dp[0], 0));
+    if (!P->fuse_enc1) {
+        DTRAJ_TRY(conv());                               // enc1.conv2 -> x1 (tmp_x)
+        DTRAJ_TRY(pool(P->tmp_x, P->p1, S[1], dp[0], 0));
+    }
     if (!P->fuse_res) DTRAJ_TRY(conv());                  // enc2.residual_conv (else inside conv2)
     DTRAJ_TRY(conv()); DTRAJ_TRY(conv());                 // enc2 -> x2
     DTRAJ_TRY(pool(P->x2, P->p2, S[2], dp[1], 1));
@@ -752,7 +773,7 @@ extern "C" int dtraj_sampler_create(dtraj_unet* u, const dtraj_sampler_desc* d, 
         if (rc) { dtraj_sampler_destroy(s); return rc; }
     } else {
         // dry count of launches
-        int extra = 3 + (s->plan->fuse_final ? 0 : 1);     // upsamples + final
+        int extra = 3 + (s->plan->fuse_final ? 0 : 1) + (s->plan->fuse_enc1 ? -1 : 0);     // upsamples + final
         for (int l = 0; l < 4; ++l) extra += s->plan->fuse_pool[l] ? 0 : 1;
         s->launches = (int64_t)d->n_updates * (2 + (int64_t)s->plan->convs.size() + extra) + (d->copy_last ? 1 : 0);
     }
@@ -786,7 +807,8 @@ extern "C" int dtraj_sampler_profile(dtraj_sampler* s, void* stream, double* cla
     }
     double f = 0.0;
     for (auto& op : s->plan->convs) f += op.flops;
-    *conv_flops = f * s->d.n_updates;
+    conv_flops[0] = f * s->d.n_updates;
+    conv_flops[1] = s->plan->fuse_enc1 ? s->plan->enc1.flops * s->d.n_updates : 0.0;
     if (rc) return rc;
     if (ce != cudaSuccess) return fail(DTRAJ_ECUDA, "profile -> %s", cudaGetErrorString(ce));
     return 0;

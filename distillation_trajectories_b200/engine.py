@@ -209,11 +209,11 @@ class TrajectorySampler:
 
     def profile(self):
         """One un-captured run with an event pair around every launch (see include/dtraj.h).
-        Returns dict(ms=[4], launches=[4], conv_flops=float)."""
-        ms, nl, fl = (C.c_double * 4)(), (C.c_int64 * 4)(), C.c_double()
+        Returns dict(ms=[5], launches=[5], conv_flops=float, enc1_flops=float)."""
+        ms, nl, fl = (C.c_double * 5)(), (C.c_int64 * 5)(), (C.c_double * 2)()
         with torch.cuda.device(self.engine.device):
-            _lib.check(self.lib.dtraj_sampler_profile(self.handle, _lib.stream_ptr(), ms, nl, C.byref(fl)))
-        return dict(ms=list(ms), launches=list(nl), conv_flops=fl.value)
+            _lib.check(self.lib.dtraj_sampler_profile(self.handle, _lib.stream_ptr(), ms, nl, fl))
+        return dict(ms=list(ms), launches=list(nl), conv_flops=fl[0], enc1_flops=fl[1])
 
     def close(self):
         if getattr(self, "handle", None):

@@ -164,11 +164,13 @@ int64_t dtraj_sampler_launches(const dtraj_sampler* s);
  * every launch on `stream`, and returns the summed device time (ms) and launch count per kernel class
  *   [0] generic convolutions (tcgen05 implicit GEMM, or the CUDA-core kernel in DTRAJ_PREC_FP32)
  *   [1] first convolution (Cin <= 4)   [2] max-pool / upsample / final 1x1   [3] fused step / frame copy
- * plus the algorithmic flops of class 0: sum over layers and steps of 2 * M * Cout * Cin * taps with
- * REAL (unpadded) channel counts and the taps actually evaluated.  Synchronises the stream.
+ *   [4] fused enc1 block (conv1 on CUDA cores into shared memory + conv2 by tap views + pool)
+ * plus the algorithmic tensor-core flops of class 0 (conv_flops2[0]) and of class 4 (conv_flops2[1]): sum over
+ * layers and steps of 2 * M * Cout * Cin * taps with REAL (unpadded) channel counts and the taps actually
+ * evaluated.  Synchronises the stream.
  */
-int dtraj_sampler_profile(dtraj_sampler* s, void* stream, double* class_ms4, int64_t* class_launches4,
-                          double* conv_flops);
+int dtraj_sampler_profile(dtraj_sampler* s, void* stream, double* class_ms5, int64_t* class_launches5,
+                          double* conv_flops2);
 
 /* ------------------------------------------------------------------ trajectory metrics */
 
