@@ -22,8 +22,12 @@
 
 namespace dtraj {
 
-constexpr int kE1Gen = 4;                        // generator warps
-constexpr int kE1Threads = 64 + 32 * kEpiWarps + 32 * kE1Gen;
+// ncu on the first version (4 generator + 8 epilogue warps): the generators paced the kernel (311 cycles per
+// pixel-iteration of one warp per scheduler, tensor pipe 43 % active) while the epilogue warps idled on the
+// accumulator barrier -- hence 8 generator warps, two pixels per thread in flight, and 4 epilogue warps.
+constexpr int kE1Gen = 8;                        // generator warps
+constexpr int kE1Epi = 4;                        // epilogue warps (one per TMEM lane quarter); 8 + 8 warps measured slower (786 vs 690 us)
+constexpr int kE1Threads = 64 + 32 * kE1Epi + 32 * kE1Gen;
 constexpr int kE1HaloRows = 180;                 // 18 x 10 pixels
 constexpr int kE1HaloBytes = 23552;              // 180 x 128 B rounded up to 1024
 
@@ -43,6 +47,8 @@ struct Enc1Params {
     const float* rw1; const float* rb1;        // residual 1x1: [C][coutp], [coutp]
     float* pool_out;                           // [R, H/2, W/2, coutp]
     int act_mode;
+    int debug;                   // timing experiments (DTRAJ_E1_DEBUG): 1 generators store zeros without conv1 math,
+                                 // 2 generators only signal, 4 issuer skips the MMAs
 };
 
 struct Enc1Maps { CUtensorMap w; };            // conv2 packed weights, box {32, w_rows}
@@ -60,7 +66,7 @@ k_enc1_umma(const __grid_constant__ Enc1Maps maps, const Enc1Params p) {
     const uint32_t halo0 = base;
     const uint32_t wst0 = halo0 + (uint32_t)p.n_hbuf * kE1HaloBytes;
     const uint32_t ring0 = wst0 + (uint32_t)p.stages * stage_bytes;
-    const uint32_t xp0 = ring0 + kEpiWarps * 4096u;
+    const uint32_t xp0 = ring0 + kE1Epi * 4096u;
     const uint32_t w3s0 = xp0 + 2u * 4u * 240u * 4u;
     const uint32_t bar0 = (w3s0 + (uint32_t)(9 * p.C + 2) * coutp * 4u + 15u) & ~15u;
     auto wfull = [&](int s) { return bar0 + 8u * s; };
@@ -84,7 +90,7 @@ k_enc1_umma(const __grid_constant__ Enc1Maps maps, const Enc1Params p) {
             for (int b = 0; b < p.n_hbuf; ++b) { ptx::mbar_init(hfull(b), kE1Gen * (kPair ? 2 : 1)); ptx::mbar_init(hempty(b), 1); }
             for (int i = 0; i < 2; ++i) {
                 ptx::mbar_init(acc_full0 + 8u * i, 1);
-                ptx::mbar_init(acc_empty0 + 8u * i, kEpiWarps * (kPair ? 2 : 1));
+                ptx::mbar_init(acc_empty0 + 8u * i, kE1Epi * (kPair ? 2 : 1));
             }
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
@@ -164,6 +170,7 @@ k_enc1_umma(const __grid_constant__ Enc1Maps maps, const Enc1Params p) {
                             const uint64_t bd = umma_desc_sw128(wst0 + s * stage_bytes + j * wtap_bytes);
 #pragma unroll
                             for (int k = 0; k < 4; ++k) {
+                                if (p.debug & 4) break;
                                 if constexpr (!kPair) ptx::mma_tf32(d_tmem, ad + 2u * k, bd + 2u * k, idesc, accum);
                                 else ptx::mma_tf32_2sm(d_tmem, ad + 2u * k, bd + 2u * k, idesc, accum);
                                 accum = 1u;
@@ -180,10 +187,10 @@ k_enc1_umma(const __grid_constant__ Enc1Maps maps, const Enc1Params p) {
                 if (++acc == 2) { acc = 0; acc_ph ^= 1u; }
             }
         }
-    } else if (warp >= 2 + kEpiWarps) {
+    } else if (warp >= 2 + kE1Epi) {
         // ------------------------------------------------------------ generators: conv1 + BN + ReLU + time bias -> halo tiles
-        const int gt = threadIdx.x - 32 * (2 + kEpiWarps);         // 0..127
-        const int g = gt & 7, pl = gt >> 3;                         // float4 group inside the 32-channel chunk, pixel lane
+        const int gt = threadIdx.x - 32 * (2 + kE1Epi);            // 0..255
+        const int g = gt & 7, pl = gt >> 3;                         // float4 group inside the 32-channel chunk, pixel lane (0..31)
         const int C = p.C;
         int hb = 0;
         uint32_t hph = 0;
@@ -200,7 +207,7 @@ k_enc1_umma(const __grid_constant__ Enc1Maps maps, const Enc1Params p) {
                 const int c = i / 240, r = i - c * 240, yy = y0 - 2 + r / 12, xx = x0 - 2 + r % 12;
                 xp[i] = (real && yy >= 0 && yy < p.H && xx >= 0 && xx < p.W) ? __ldg(xs + ((size_t)c * p.H + yy) * p.W + xx) : 0.f;
             }
-            asm volatile("bar.sync 9, 128;" ::: "memory");
+            asm volatile("bar.sync 9, 256;" ::: "memory");
             const int var = (real && p.row_variant) ? p.row_variant[img] : 0;
             const float* tb = p.tbias + (size_t)var * p.tb_var_stride;
             for (int c = 0; c < p.n_chunks; ++c) {
@@ -214,37 +221,46 @@ k_enc1_umma(const __grid_constant__ Enc1Maps maps, const Enc1Params p) {
                 }
                 ptx::mbar_wait(hempty(hb), hph ^ 1u);               // the MMAs that read this buffer have retired
                 uint8_t* hbuf = gbase + (halo0 - base) + (size_t)hb * kE1HaloBytes;
-                for (int px = pl; px < kE1HaloRows; px += 16) {
+                // 32 pixel lanes x 6 rounds cover the 180 halo pixels; two pixels (px, px + 96) per trip keep eight
+                // independent FMA chains in flight
+                auto conv1_at = [&](int px) -> float4 {
                     const int ry = px / 10, rx = px - ry * 10;
                     const int yy = y0 - 1 + ry, xx = x0 - 1 + rx;
-                    float4 o = make_float4(0.f, 0.f, 0.f, 0.f);     // conv2's zero padding outside the image
-                    if (yy >= 0 && yy < p.H && xx >= 0 && xx < p.W) {
-                        float4 acc = b3;
-                        if (C == 1) {
+                    if (!(yy >= 0 && yy < p.H && xx >= 0 && xx < p.W)) return make_float4(0.f, 0.f, 0.f, 0.f);   // conv2's zero padding
+                    float4 acc = b3;
+                    if (C == 1) {
 #pragma unroll
-                            for (int ky = 0; ky < 3; ++ky)
+                        for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
-                                for (int kx = 0; kx < 3; ++kx) {
-                                    const float v = xp[(ry + ky) * 12 + rx + kx];
-                                    const float4 ww = w[ky * 3 + kx];
-                                    acc.x = fmaf(v, ww.x, acc.x); acc.y = fmaf(v, ww.y, acc.y);
-                                    acc.z = fmaf(v, ww.z, acc.z); acc.w = fmaf(v, ww.w, acc.w);
-                                }
-                        } else {
-                            for (int ci = 0; ci < C; ++ci)
+                            for (int kx = 0; kx < 3; ++kx) {
+                                const float v = xp[(ry + ky) * 12 + rx + kx];
+                                const float4 ww = w[ky * 3 + kx];
+                                acc.x = fmaf(v, ww.x, acc.x); acc.y = fmaf(v, ww.y, acc.y);
+                                acc.z = fmaf(v, ww.z, acc.z); acc.w = fmaf(v, ww.w, acc.w);
+                            }
+                    } else {
+                        for (int ci = 0; ci < C; ++ci)
 #pragma unroll
-                                for (int t9 = 0; t9 < 9; ++t9) {
-                                    const float v = xp[ci * 240 + (ry + t9 / 3) * 12 + rx + t9 % 3];
-                                    const float4 ww = *reinterpret_cast<const float4*>(w3s + (size_t)(t9 * C + ci) * coutp + ch);
-                                    acc.x = fmaf(v, ww.x, acc.x); acc.y = fmaf(v, ww.y, acc.y);
-                                    acc.z = fmaf(v, ww.z, acc.z); acc.w = fmaf(v, ww.w, acc.w);
-                                }
-                        }
-                        o = make_float4(fmaxf(acc.x, 0.f) + t4.x, fmaxf(acc.y, 0.f) + t4.y,
-                                        fmaxf(acc.z, 0.f) + t4.z, fmaxf(acc.w, 0.f) + t4.w);
-                        o = act_round4(o, p.act_mode);
+                            for (int t9 = 0; t9 < 9; ++t9) {
+                                const float v = xp[ci * 240 + (ry + t9 / 3) * 12 + rx + t9 % 3];
+                                const float4 ww = *reinterpret_cast<const float4*>(w3s + (size_t)(t9 * C + ci) * coutp + ch);
+                                acc.x = fmaf(v, ww.x, acc.x); acc.y = fmaf(v, ww.y, acc.y);
+                                acc.z = fmaf(v, ww.z, acc.z); acc.w = fmaf(v, ww.w, acc.w);
+                            }
                     }
-                    *reinterpret_cast<float4*>(hbuf + px * 128 + (((uint32_t)g ^ (uint32_t)(px & 7)) << 4)) = o;
+                    float4 o = make_float4(fmaxf(acc.x, 0.f) + t4.x, fmaxf(acc.y, 0.f) + t4.y,
+                                           fmaxf(acc.z, 0.f) + t4.z, fmaxf(acc.w, 0.f) + t4.w);
+                    return act_round4(o, p.act_mode);
+                };
+                for (int px = pl; px < 96 && !(p.debug & 2); px += 32) {
+                    const int px1 = px + 96;
+                    float4 o0 = make_float4(0.f, 0.f, 0.f, 0.f), o1 = o0;
+                    if (!(p.debug & 1)) {
+                        o0 = conv1_at(px);
+                        if (px1 < kE1HaloRows) o1 = conv1_at(px1);
+                    }
+                    *reinterpret_cast<float4*>(hbuf + px * 128 + (((uint32_t)g ^ (uint32_t)(px & 7)) << 4)) = o0;
+                    if (px1 < kE1HaloRows) *reinterpret_cast<float4*>(hbuf + px1 * 128 + (((uint32_t)g ^ (uint32_t)(px1 & 7)) << 4)) = o1;
                 }
                 ptx::fence_proxy_async();                           // generic-proxy writes -> visible to the tensor core
                 __syncwarp();
@@ -256,8 +272,9 @@ k_enc1_umma(const __grid_constant__ Enc1Maps maps, const Enc1Params p) {
             }
         }
     } else {
-        // ------------------------------------------------------------ epilogue (warps 2..9): thread = output pixel
-        const int q = warp & 3, h = (warp - 2) >> 2, ew = warp - 2;
+        // ------------------------------------------------------------ epilogue (warps 2..5): thread = output pixel
+        const int q = warp & 3, ew = warp - 2;
+        constexpr int h = 0;
         const int nchunk = coutp >> 5;
         uint8_t* bufp = gbase + (ring0 - base) + (size_t)ew * 4096;
         const uint32_t swz = (uint32_t)(lane & 7);
@@ -283,9 +300,8 @@ k_enc1_umma(const __grid_constant__ Enc1Maps maps, const Enc1Params p) {
             ptx::mbar_wait(acc_full0 + 8u * acc, acc_ph);
             ptx::tc_fence_after();
             const uint32_t t_acc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.acc_cols);
-            const int c_last = nchunk - 1 - ((nchunk - 1 - h) & 1);
-            if (c_last < h) { ptx::tc_fence_before(); __syncwarp(); if (lane == 0) arrive_acc_empty(); }
-            for (int c = h; c < nchunk; c += 2) {
+            const int c_last = nchunk - 1;
+            for (int c = h; c < nchunk; c += kE1Epi / 4) {
                 uint32_t raw[32];
                 ptx::tmem_ld32(t_acc + (uint32_t)(32 * c), raw);
                 ptx::tmem_ld_wait();
@@ -366,7 +382,7 @@ inline int build_enc1_launch(Enc1Launch* E, int C, int H, int coutp, int cout_re
     if (p.n_hbuf > 8) return fail(DTRAJ_EINVAL, "enc1: too many halo buffers");
     p.acc_cols = 32;
     while (p.acc_cols < coutp) p.acc_cols *= 2;
-    const size_t fixed = 1024 + (size_t)p.n_hbuf * kE1HaloBytes + kEpiWarps * 4096 + 2 * 4 * 240 * 4 + (size_t)(9 * C + 2) * coutp * 4 + 16 + 512;
+    const size_t fixed = 1024 + (size_t)p.n_hbuf * kE1HaloBytes + kE1Epi * 4096 + 2 * 4 * 240 * 4 + (size_t)(9 * C + 2) * coutp * 4 + 16 + 512;
     p.tps = 3;
     if ((227 * 1024 - fixed) / ((size_t)3 * p.w_rows * 128) < 3) p.tps = 1;
     const size_t stage = (size_t)p.tps * p.w_rows * 128;
@@ -379,6 +395,7 @@ inline int build_enc1_launch(Enc1Launch* E, int C, int H, int coutp, int cout_re
     if (E->pair) E->grid = (E->grid + 1) / 2 * 2;
     DTRAJ_TRY(make_w_map(&E->maps.w, w2, w2_rows, p.w_rows));
     E->flops = 2.0 * (double)R * H * H * cout_real * (double)cout_real * 9.0;
+    p.debug = getenv("DTRAJ_E1_DEBUG") ? atoi(getenv("DTRAJ_E1_DEBUG")) : 0;
     return 0;
 }
 
