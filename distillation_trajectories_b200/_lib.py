@@ -10,12 +10,12 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libdtraj.so")
 
-PREC_FP32, PREC_TF32, PREC_TF32X3 = 0, 1, 2
+PREC_FP32, PREC_TF32, PREC_TF32X3, PREC_F16 = 0, 1, 2, 3
 VAR_NONE, VAR_COND0, VAR_COND1 = 0, 1, 2
 RULE_S1, RULE_S2, RULE_S3 = 1, 2, 3
 METRIC_Q = 6
 
-PRECISIONS = {"fp32": PREC_FP32, "tf32": PREC_TF32, "tf32x3": PREC_TF32X3}
+PRECISIONS = {"fp32": PREC_FP32, "tf32": PREC_TF32, "tf32x3": PREC_TF32X3, "f16": PREC_F16}
 
 
 class DtrajError(RuntimeError):

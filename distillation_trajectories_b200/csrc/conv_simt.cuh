@@ -51,6 +51,8 @@ struct ConvLayer {
     const float* rsrc1;
     int rc0p, rc1p;
     const float* rbias;        //            residual_conv bias [coutp]
+    int f16;                   // DTRAJ_PREC_F16 (tcgen05 kernel only): src*/resid/out/pool_out/rsrc* point at __half maps,
+                               // channel counts are padded to 64
 };
 
 template <int BN>

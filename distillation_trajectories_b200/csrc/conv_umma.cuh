@@ -19,6 +19,7 @@
 // every producer of an activation (ACT_SPLIT) and the weights are split on the host.
 #pragma once
 #include <cstdlib>
+#include <cuda_fp16.h>
 #include "common.cuh"
 #include "conv_simt.cuh"
 
@@ -57,6 +58,7 @@ struct UmmaConv {
     int log2_hw;               // H*W is a power of two: image index of output row m is m >> log2_hw
     int log2_wh;               // log2(W / 2) (CONV_POOL)
     int debug;                 // timing experiments only (dtraj_bench_conv): bit2 skips the epilogue's global traffic
+    int f16;                   // 1: DTRAJ_PREC_F16 -- fp16 feature maps / weights (64 channels per 128-byte K block), kind::f16 MMAs
 };
 
 struct UmmaMaps {              // 64-byte aligned tensor maps, passed as __grid_constant__
@@ -182,6 +184,16 @@ __device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64
                  "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
                  ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
 }
+__device__ __forceinline__ void mma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void mma_f16_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
                  "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -206,6 +218,11 @@ __host__ __device__ inline uint32_t umma_idesc_tf32(int n) {
     return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 }
 
+// kind::f16 instruction descriptor: D fp32, A/B fp16 (format 0), both K-major, M=128; K = 16 per instruction
+__host__ __device__ inline uint32_t umma_idesc_f16(int n) {
+    return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+
 constexpr int kEpiWarps = 8;             // two per TMEM lane quarter, each takes every other 32-column chunk
 constexpr int kUmmaThreads = 64 + 32 * kEpiWarps;
 constexpr int kEpiBufsMax = 2;           // per-warp ring of 4 KB (32 rows x 32 columns) epilogue buffers: 1 or 2
@@ -216,9 +233,10 @@ constexpr int kATileBytes = 128 * 128;   // 128 rows x 32 fp32
 // epilogue warps drain accumulator buffer `acc` while the issuer fills the other one (TMEM holds two
 // accumulators whenever 2 x columns-per-tile <= 512), so neither the epilogue's latency nor its
 // instruction count sits on the tensor pipe's critical path.
-template <bool kPair>
+template <bool kPair, bool kF16>
 __global__ void __launch_bounds__(kUmmaThreads, 1)
 k_conv_umma_t(const __grid_constant__ UmmaMaps maps, const UmmaConv p) {
+    constexpr int kCh = kF16 ? 64 : 32;      // channels of one 128-byte K block
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // carve: [stages x (A 16 KB | B coutp*128 B)] [epilogue ring 4 warps x kEpiBufs x 4 KB] [barriers]
     const uint32_t base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -244,7 +262,7 @@ k_conv_umma_t(const __grid_constant__ UmmaMaps maps, const UmmaConv p) {
     const int crank = p.cluster > 1 ? (int)ptx::cluster_ctarank() : 0;
     const uint16_t cmask = (uint16_t)((1u << p.cluster) - 1u);
     const int work0 = (int)blockIdx.x - crank;   // first work item of this CTA's cluster; all its CTAs loop alike
-    const int nch0 = p.L.c0p / 32, nch = nch0 + p.L.c1p / 32;
+    const int nch0 = p.L.c0p / kCh, nch = nch0 + p.L.c1p / kCh;
     const int iters_per_pass = p.L.ntaps * nch;
     const int n_iters = p.npass * iters_per_pass;
 
@@ -319,7 +337,7 @@ k_conv_umma_t(const __grid_constant__ UmmaMaps maps, const UmmaConv p) {
                     if (!kPair || crank == 0) ptx::mbar_expect_tx(full_bar(s), tx_bytes);
                     for (int j = 0; j < p.kbs; ++j) {
                         const bool second = chunk >= n_first;
-                        const int c0 = (second ? chunk - n_first : chunk) * 32;
+                        const int c0 = (second ? chunk - n_first : chunk) * kCh;
                         if constexpr (!kPair) ptx::tma_load_4d(st0 + act_off + j * act_step, second ? am1 : am0, fb, c0, dx, y0 + dy, img0);
                         else ptx::tma_load_4d_2sm(st0 + act_off + j * act_step, second ? am1 : am0, fb, c0, dx, y0 + dy, img0);
                         if constexpr (kPair) ptx::tma_load_2d_2sm(st0 + w_base_off + j * w_step, wm, fb, 0, b_row);
@@ -350,7 +368,7 @@ k_conv_umma_t(const __grid_constant__ UmmaMaps maps, const UmmaConv p) {
     } else if (warp == 1) {
         // ------------------------------------------------------------ MMA issuer
         if (ptx::elect_one() && (!kPair || crank == 0)) {
-            const uint32_t idesc = umma_idesc_tf32(n_rows) + (kPair ? ((uint32_t)(128 >> 4) << 24) : 0u);   // pair: M = 256
+            const uint32_t idesc = (kF16 ? umma_idesc_f16(n_rows) : umma_idesc_tf32(n_rows)) + (kPair ? ((uint32_t)(128 >> 4) << 24) : 0u);   // pair: M = 256
             // descriptors differ between stages / K blocks only in their 14-bit start-address field
             const uint64_t desc0 = umma_desc_sw128(base);
             const uint32_t stage16 = stage_bytes >> 4;
@@ -372,9 +390,15 @@ k_conv_umma_t(const __grid_constant__ UmmaMaps maps, const UmmaConv p) {
                         const uint64_t md = desc0 + (uint64_t)(s * stage16), nd = md + n_off16;
                         for (int j = 0; j < p.kbs; ++j) {
 #pragma unroll
-                            for (int k = 0; k < 4; ++k) {   // 4 x (K = 8 tf32 = 32 bytes) inside the 128-byte swizzle atom
-                                if constexpr (!kPair) ptx::mma_tf32(d_tmem, md + (uint64_t)(j * m_step16 + 2 * k), nd + (uint64_t)(j * n_step16 + 2 * k), idesc, accum);
-                                else ptx::mma_tf32_2sm(d_tmem, md + (uint64_t)(j * m_step16 + 2 * k), nd + (uint64_t)(j * n_step16 + 2 * k), idesc, accum);
+                            for (int k = 0; k < 4; ++k) {   // 4 x (K = 8 tf32 / 16 fp16 = 32 bytes) inside the 128-byte swizzle atom
+                                const uint64_t mdk = md + (uint64_t)(j * m_step16 + 2 * k), ndk = nd + (uint64_t)(j * n_step16 + 2 * k);
+                                if constexpr (kF16) {
+                                    if constexpr (!kPair) ptx::mma_f16(d_tmem, mdk, ndk, idesc, accum);
+                                    else ptx::mma_f16_2sm(d_tmem, mdk, ndk, idesc, accum);
+                                } else {
+                                    if constexpr (!kPair) ptx::mma_tf32(d_tmem, mdk, ndk, idesc, accum);
+                                    else ptx::mma_tf32_2sm(d_tmem, mdk, ndk, idesc, accum);
+                                }
                                 accum = 1u;
                             }
                         }
@@ -411,7 +435,207 @@ k_conv_umma_t(const __grid_constant__ UmmaMaps maps, const UmmaConv p) {
         //                they are in registers; CONV_NOSTORE drops the main store when the full tensor
         //                has no other consumer
         // 3xTF32 (ACT_SPLIT) also writes the low plane y - trunc_tf32(y) through a second store.
-        if (p.swap) {
+        if constexpr (kF16) {
+        // ---- fp16 feature maps (DTRAJ_PREC_F16): same chunking (32 columns per warp step), but a ring buffer is
+        // [32 rows][32 channels] of HALFS: 64-byte rows, 64-byte swizzle (16-byte cell j of row r sits at
+        // j ^ ((r >> 1) & 3): thread = row stores are conflict-free), and one 16-byte cell holds 8 channels.
+        // Values are rounded to fp16 (rn) here, once; |v| > 65504 raises g_umma_error bit 1 instead of storing inf silently.
+        const int q = warp & 3;
+        const int h = (warp - 2) >> 2;
+        const int ew = warp - 2;
+        const int nchunk = ncols >> 5;
+        const int fl = p.L.flags;
+        const bool skip_io = (p.debug & 4) != 0;
+        const bool has_res = (fl & CONV_RESID) != 0 && !skip_io;
+        const bool do_store = !(fl & CONV_NOSTORE) && !skip_io;
+        const bool do_pool = (fl & CONV_POOL) != 0 && !skip_io;
+        const uint32_t buf0 = ring_base + (uint32_t)ew * kEpiBufs * 4096u;
+        const uint32_t rbar = res_bar0 + 8u * (ew * kEpiBufsMax);
+        const uint32_t swz = (uint32_t)((lane >> 1) & 3);
+        __half* const pool_h = reinterpret_cast<__half*>(p.L.pool_out);
+        uint32_t res_par = 0;
+        int acc = 0;
+        uint32_t acc_ph = 0;
+        float amax = 0.f;
+        for (int wk = work0; wk < p.n_work; wk += gridDim.x) {
+            const int work = wk + crank;
+            const int tile = work / p.n_split, n0 = (work % p.n_split) * ncols;
+            const int64_t m_warp = (int64_t)tile * 128 + q * 32;
+            const int row = (int)m_warp;
+            if (lane == 0) {
+                ptx::bulk_wait_read<0>();
+                if (has_res)
+                    for (int k = 0; k < kEpiBufs && h + 2 * k < nchunk; ++k) {
+                        ptx::mbar_expect_tx(rbar + 8u * k, 2048u);
+                        ptx::tma_load_2d(buf0 + 4096u * k, &maps.res, rbar + 8u * k, n0 + 32 * (h + 2 * k), row);
+                    }
+            }
+            __syncwarp();
+            const int64_t m = m_warp + lane;
+            const bool valid = m < p.L.M;
+            const int img = valid ? (int)(m >> p.log2_hw) : 0;
+            const float* tb = nullptr;
+            if (fl & CONV_TBIAS) tb = p.L.tbias + (size_t)(p.L.row_variant ? p.L.row_variant[img] : 0) * p.L.tb_var_stride;
+            float xv[4] = {0.f, 0.f, 0.f, 0.f}, fe[4] = {0.f, 0.f, 0.f, 0.f};
+            if ((fl & CONV_RESX) && valid) {
+                const int HWm = (1 << p.log2_hw);
+                const float* xs = p.L.xraw + (size_t)(p.L.row_sample ? p.L.row_sample[img] : img) * p.L.x_stride + (m & (HWm - 1));
+#pragma unroll
+                for (int ch = 0; ch < 4; ++ch) if (ch < p.L.xC) xv[ch] = xs[(size_t)ch * HWm];
+            }
+            ptx::mbar_wait(acc_full0 + 8u * acc, acc_ph);
+            ptx::tc_fence_after();
+            const uint32_t t_acc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.acc_cols);
+            const int c_last = nchunk - 1 - ((nchunk - 1 - h) & 1);
+            if (c_last < h) {
+                ptx::tc_fence_before();
+                __syncwarp();
+                if (lane == 0) arrive_acc_empty(acc);
+            }
+            for (int c = h, k = 0; c < nchunk; c += 2, ++k) {
+                const int b = k % kEpiBufs;
+                uint32_t raw[32];
+                ptx::tmem_ld32(t_acc + (uint32_t)(32 * c), raw);
+                ptx::tmem_ld_wait();
+                uint32_t rres[32];
+                if (fl & CONV_RESACC) {
+                    ptx::tmem_ld32(t_acc + (uint32_t)(p.res_col + 32 * c), rres);
+                    ptx::tmem_ld_wait();
+                }
+                if (c == c_last) {
+                    ptx::tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) arrive_acc_empty(acc);
+                }
+                if (has_res) { ptx::mbar_wait(rbar + 8u * b, (res_par >> b) & 1u); res_par ^= 1u << b; }
+                uint8_t* bufp = smem_raw + (buf0 + 4096u * b - ptx::smem_u32(smem_raw));
+                uint8_t* rowp = bufp + lane * 64;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int col = n0 + 32 * c + 8 * j;
+                    float v[8];
+                    {
+                        const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.L.bias + col));
+                        const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.L.bias + col + 4));
+                        v[0] = __uint_as_float(raw[8 * j]) + b0.x; v[1] = __uint_as_float(raw[8 * j + 1]) + b0.y;
+                        v[2] = __uint_as_float(raw[8 * j + 2]) + b0.z; v[3] = __uint_as_float(raw[8 * j + 3]) + b0.w;
+                        v[4] = __uint_as_float(raw[8 * j + 4]) + b1.x; v[5] = __uint_as_float(raw[8 * j + 5]) + b1.y;
+                        v[6] = __uint_as_float(raw[8 * j + 6]) + b1.z; v[7] = __uint_as_float(raw[8 * j + 7]) + b1.w;
+                    }
+                    if (fl & CONV_RELU) {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], 0.f);
+                    }
+                    if (tb) {
+                        const float4 t0 = __ldg(reinterpret_cast<const float4*>(tb + col));
+                        const float4 t1 = __ldg(reinterpret_cast<const float4*>(tb + col + 4));
+                        v[0] += t0.x; v[1] += t0.y; v[2] += t0.z; v[3] += t0.w;
+                        v[4] += t1.x; v[5] += t1.y; v[6] += t1.z; v[7] += t1.w;
+                    }
+                    if (fl & CONV_RESX) {
+#pragma unroll
+                        for (int hh = 0; hh < 2; ++hh) {
+                            float4 r4 = __ldg(reinterpret_cast<const float4*>(p.L.rb1 + col + 4 * hh));
+#pragma unroll
+                            for (int ch = 0; ch < 4; ++ch) {
+                                if (ch >= p.L.xC) break;
+                                const float4 w4 = __ldg(reinterpret_cast<const float4*>(p.L.rw1 + (size_t)ch * coutp + col + 4 * hh));
+                                r4.x = fmaf(xv[ch], w4.x, r4.x); r4.y = fmaf(xv[ch], w4.y, r4.y);
+                                r4.z = fmaf(xv[ch], w4.z, r4.z); r4.w = fmaf(xv[ch], w4.w, r4.w);
+                            }
+                            v[4 * hh] += r4.x; v[4 * hh + 1] += r4.y; v[4 * hh + 2] += r4.z; v[4 * hh + 3] += r4.w;
+                        }
+                    }
+                    if (fl & CONV_RESACC) {
+                        const float4 r0 = __ldg(reinterpret_cast<const float4*>(p.L.rbias + col));
+                        const float4 r1 = __ldg(reinterpret_cast<const float4*>(p.L.rbias + col + 4));
+                        v[0] += __uint_as_float(rres[8 * j]) + r0.x; v[1] += __uint_as_float(rres[8 * j + 1]) + r0.y;
+                        v[2] += __uint_as_float(rres[8 * j + 2]) + r0.z; v[3] += __uint_as_float(rres[8 * j + 3]) + r0.w;
+                        v[4] += __uint_as_float(rres[8 * j + 4]) + r1.x; v[5] += __uint_as_float(rres[8 * j + 5]) + r1.y;
+                        v[6] += __uint_as_float(rres[8 * j + 6]) + r1.z; v[7] += __uint_as_float(rres[8 * j + 7]) + r1.w;
+                    }
+                    uint4* cell = reinterpret_cast<uint4*>(rowp + (((uint32_t)j ^ swz) << 4));
+                    if (has_res) {
+                        const uint4 rr = *cell;
+                        const __half2* rh = reinterpret_cast<const __half2*>(&rr);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) { const float2 f = __half22float2(rh[i]); v[2 * i] += f.x; v[2 * i + 1] += f.y; }
+                    }
+                    uint4 pk;
+                    __half2* ph2 = reinterpret_cast<__half2*>(&pk);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        amax = fmaxf(amax, fmaxf(fabsf(v[2 * i]), fabsf(v[2 * i + 1])));
+                        ph2[i] = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+                    }
+                    if (fl & CONV_FINAL) {
+                        float vr[8];
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) { const float2 f = __half22float2(ph2[i]); vr[2 * i] = f.x; vr[2 * i + 1] = f.y; }
+#pragma unroll
+                        for (int o = 0; o < 4; ++o) {
+                            if (o >= p.L.finC) break;
+                            const float4 w0 = __ldg(reinterpret_cast<const float4*>(p.L.finw + (size_t)o * coutp + col));
+                            const float4 w1 = __ldg(reinterpret_cast<const float4*>(p.L.finw + (size_t)o * coutp + col + 4));
+                            fe[o] = fmaf(vr[0], w0.x, fmaf(vr[1], w0.y, fmaf(vr[2], w0.z, fmaf(vr[3], w0.w, fe[o]))));
+                            fe[o] = fmaf(vr[4], w1.x, fmaf(vr[5], w1.y, fmaf(vr[6], w1.z, fmaf(vr[7], w1.w, fe[o]))));
+                        }
+                    }
+                    if (do_store || do_pool) *cell = pk;
+                }
+                if (do_store) ptx::fence_proxy_async();
+                __syncwarp();
+                if (do_pool) {
+                    // 8 pooled rows x 4 cells (8 channels each) per chunk: one cell per lane
+                    const int W = p.L.W, pr = lane >> 2, x2 = pr & ((W >> 1) - 1), t = pr >> p.log2_wh;
+                    const int r00 = 2 * t * W + 2 * x2;
+                    if (m_warp + r00 < p.L.M) {
+                        const uint32_t jj = (uint32_t)(lane & 3);
+                        auto at = [&](int r) { return *reinterpret_cast<const uint4*>(bufp + r * 64 + ((jj ^ (((uint32_t)r >> 1) & 3u)) << 4)); };
+                        const uint4 a = at(r00), bq = at(r00 + 1), cq = at(r00 + W), d = at(r00 + W + 1);
+                        const __half2* ah = reinterpret_cast<const __half2*>(&a);
+                        const __half2* bh = reinterpret_cast<const __half2*>(&bq);
+                        const __half2* ch2 = reinterpret_cast<const __half2*>(&cq);
+                        const __half2* dh = reinterpret_cast<const __half2*>(&d);
+                        uint4 o4;
+                        __half2* oh = reinterpret_cast<__half2*>(&o4);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) oh[i] = __hmax2(__hmax2(ah[i], bh[i]), __hmax2(ch2[i], dh[i]));
+                        *reinterpret_cast<uint4*>(pool_h + ((m_warp >> 2) + pr) * coutp + n0 + 32 * c + 8 * (int)jj) = o4;
+                    }
+                    __syncwarp();
+                }
+                if (lane == 0 && do_store) { ptx::tma_store_2d(&maps.out, buf0 + 4096u * b, n0 + 32 * c, row); ptx::bulk_commit(); }
+                if (c + 2 < nchunk && k + 1 >= kEpiBufs && (has_res || do_store)) {
+                    if (lane == 0) {
+                        if (do_store) { if (kEpiBufs == 2) ptx::bulk_wait_read<1>(); else ptx::bulk_wait_read<0>(); }
+                        if (has_res) {
+                            const int nb = (k + 1) % kEpiBufs;
+                            ptx::mbar_expect_tx(rbar + 8u * nb, 2048u);
+                            ptx::tma_load_2d(buf0 + 4096u * nb, &maps.res, rbar + 8u * nb, n0 + 32 * (c + 2), row);
+                        }
+                    }
+                    __syncwarp();
+                }
+            }
+            if (fl & CONV_FINAL) {
+                float4* part = reinterpret_cast<float4*>(smem_raw + (fin_base - ptx::smem_u32(smem_raw))) + q * 32 + lane;
+                if (h == 1) *part = make_float4(fe[0], fe[1], fe[2], fe[3]);
+                asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
+                if (h == 0 && valid && !skip_io) {
+                    const float4 o4 = *part;
+                    const float other[4] = {o4.x, o4.y, o4.z, o4.w};
+#pragma unroll
+                    for (int o = 0; o < 4; ++o) if (o < p.L.finC) p.L.elow[m * p.L.finC + o] = (fe[o] + other[o]) + __ldg(p.L.finb + o);
+                }
+                asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
+            }
+            if (++acc == p.acc_stages) { acc = 0; acc_ph ^= 1u; }
+        }
+        if (!(amax <= 65504.f)) atomicOr(&g_umma_error, 2u);     // also catches NaN
+        if (lane == 0) ptx::bulk_wait_read<0>();
+        __syncwarp();
+        } else if (p.swap) {
             // ---- swapped operands: TMEM lane = output channel, TMEM column = pixel of the tile.  Warp (q, h)
             // owns channels [32q, 32q+32) and the pixel blocks h, h+2, ... of 32 pixels; a ring buffer is the
             // same [32 pixels][32 channels] swizzled box as in the other branch, accessed transposed (lane =
@@ -789,28 +1013,30 @@ inline PFN_encodeTiled get_encode_tiled() {
 }
 
 // NHWC activation map {cp, W, H, n_img} with box {32, W, box_h, box_n}
-inline int make_act_map(CUtensorMap* m, const float* base, int cp, int W, int H, int64_t n_img, int box_h, int box_n) {
+// (f16: elements are halfs and a box carries 64 channels -- the same 128 bytes per pixel)
+inline int make_act_map(CUtensorMap* m, const float* base, int cp, int W, int H, int64_t n_img, int box_h, int box_n, int f16 = 0) {
     PFN_encodeTiled enc = get_encode_tiled();
     if (!enc) return fail(DTRAJ_ECUDA, "cuTensorMapEncodeTiled not available");
+    const cuuint64_t es_b = f16 ? 2 : 4;
     cuuint64_t dims[4] = {(cuuint64_t)cp, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)n_img};
-    cuuint64_t strides[3] = {(cuuint64_t)cp * 4, (cuuint64_t)W * cp * 4, (cuuint64_t)H * W * cp * 4};
-    cuuint32_t box[4] = {32, (cuuint32_t)W, (cuuint32_t)box_h, (cuuint32_t)box_n};
+    cuuint64_t strides[3] = {(cuuint64_t)cp * es_b, (cuuint64_t)W * cp * es_b, (cuuint64_t)H * W * cp * es_b};
+    cuuint32_t box[4] = {f16 ? 64u : 32u, (cuuint32_t)W, (cuuint32_t)box_h, (cuuint32_t)box_n};
     cuuint32_t es[4] = {1, 1, 1, 1};
-    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)base, dims, strides, box, es,
+    CUresult r = enc(m, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)base, dims, strides, box, es,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(DTRAJ_ECUDA, "cuTensorMapEncodeTiled(act cp=%d W=%d H=%d n=%lld) -> %d", cp, W, H, (long long)n_img, (int)r);
     return 0;
 }
 // packed weights as a 2-d map {32, rows} with box {32, coutp}
-inline int make_w_map(CUtensorMap* m, const float* base, int64_t rows, int coutp) {
+inline int make_w_map(CUtensorMap* m, const float* base, int64_t rows, int coutp, int f16 = 0) {
     PFN_encodeTiled enc = get_encode_tiled();
     if (!enc) return fail(DTRAJ_ECUDA, "cuTensorMapEncodeTiled not available");
-    cuuint64_t dims[2] = {32, (cuuint64_t)rows};
+    cuuint64_t dims[2] = {f16 ? 64u : 32u, (cuuint64_t)rows};
     cuuint64_t strides[1] = {128};
-    cuuint32_t box[2] = {32, (cuuint32_t)coutp};
+    cuuint32_t box[2] = {f16 ? 64u : 32u, (cuuint32_t)coutp};
     cuuint32_t es[2] = {1, 1};
-    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, es,
+    CUresult r = enc(m, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, es,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(DTRAJ_ECUDA, "cuTensorMapEncodeTiled(weights rows=%lld) -> %d", (long long)rows, (int)r);
@@ -818,24 +1044,27 @@ inline int make_w_map(CUtensorMap* m, const float* base, int64_t rows, int coutp
 }
 
 // row-major [M, coutp] activation as a 2-d map {coutp, M} with box {32, 32} (epilogue chunks)
-inline int make_rows_map(CUtensorMap* m, const float* base, int64_t M, int coutp) {
+// (f16: 64-byte rows of 32 halfs, 64-byte swizzle)
+inline int make_rows_map(CUtensorMap* m, const float* base, int64_t M, int coutp, int f16 = 0) {
     PFN_encodeTiled enc = get_encode_tiled();
     if (!enc) return fail(DTRAJ_ECUDA, "cuTensorMapEncodeTiled not available");
     cuuint64_t dims[2] = {(cuuint64_t)coutp, (cuuint64_t)M};
-    cuuint64_t strides[1] = {(cuuint64_t)coutp * 4};
+    cuuint64_t strides[1] = {(cuuint64_t)coutp * (f16 ? 2 : 4)};
     cuuint32_t box[2] = {32, 32};
     cuuint32_t es[2] = {1, 1};
-    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, es,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+    CUresult r = enc(m, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, f16 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(DTRAJ_ECUDA, "cuTensorMapEncodeTiled(rows M=%lld cp=%d) -> %d", (long long)M, coutp, (int)r);
     return 0;
 }
 
 inline cudaError_t umma_set_smem_attr() {
-    cudaError_t e = cudaFuncSetAttribute(k_conv_umma_t<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(k_conv_umma_t<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(k_conv_umma_t<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_conv_umma_t<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_conv_umma_t<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_conv_umma_t<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    return e;
 }
 
 struct UmmaLaunch {            // everything a launch needs, built once per (layer, batch)
@@ -852,9 +1081,12 @@ inline int build_umma_launch(UmmaLaunch* U, const ConvLayer& L, int npass, const
     const int HW = L.H * L.W;
     if (L.W > 32 || L.H != L.W || (HW & (HW - 1)) != 0)
         return fail(DTRAJ_EINVAL, "umma conv: unsupported spatial size %dx%d", L.H, L.W);
-    if (L.coutp % 32 || L.coutp > 256 || L.c0p % 32 || L.c1p % 32) return fail(DTRAJ_EINVAL, "umma conv: bad channel padding");
+    const int f16 = L.f16 ? 1 : 0, kch = f16 ? 64 : 32;     // channels per 128-byte K block
+    if (L.coutp % 32 || L.coutp > 256 || L.c0p % kch || L.c1p % kch) return fail(DTRAJ_EINVAL, "umma conv: bad channel padding");
+    if (f16 && (npass != 1 || L.act_mode == ACT_SPLIT)) return fail(DTRAJ_EINVAL, "umma conv: fp16 mode is single-pass");
     UmmaConv& c = U->conv;
     c.L = L;
+    c.f16 = f16;
     c.npass = npass;
     // operand swap: with <= 128 output channels an M=128 x N=cout MMA reads (128 + cout) x 32 B of shared
     // memory for 128 x cout x 8 MACs and is shared-memory bound (measured 59 % of the tf32 peak at cout = 128
@@ -862,10 +1094,10 @@ inline int build_umma_launch(UmmaLaunch* U, const ConvLayer& L, int npass, const
     // Measured (tools/conv_bench.py): a win only for exactly 128 channels, K >= 1024 and enough 256-pixel tiles
     // to fill the GPU; narrower layers waste half of the 128 weight rows, short-K layers are epilogue-paced
     // and the transposed epilogue moves single words through shared memory.
-    const int nkb_all = L.ntaps * (L.c0p + L.c1p) / 32;
+    const int nkb_all = L.ntaps * (L.c0p + L.c1p) / kch;
     // ... and since CTA pairs exist (below) the pair form of the plain orientation beats it on every layer of
     // the bench workload (enc1.conv2 424 vs 497 us, dec1.conv1 370 vs 408 us), so it is opt-in.
-    c.swap = (L.coutp == 128 && nkb_all >= 32 && (L.M + 255) / 256 >= kNumSMs && !(L.flags & CONV_FINAL) &&
+    c.swap = (!f16 && L.coutp == 128 && nkb_all >= 32 && (L.M + 255) / 256 >= kNumSMs && !(L.flags & CONV_FINAL) &&
               getenv("DTRAJ_SWAP")) ? 1 : 0;
     c.tn = c.swap ? 256 : 128;
     c.box_h = HW >= c.tn ? c.tn / L.W : L.H;
@@ -892,17 +1124,17 @@ inline int build_umma_launch(UmmaLaunch* U, const ConvLayer& L, int npass, const
     c.corr_col = 0;
     if (npass == 3) { c.corr_col = c.acc_cols; c.acc_cols *= 2; }
     c.res_col = 0;
-    c.r_nch0 = L.rc0p / 32;
-    c.r_nch = (L.rc0p + L.rc1p) / 32;
+    c.r_nch0 = L.rc0p / kch;
+    c.r_nch = (L.rc0p + L.rc1p) / kch;
     if (L.flags & CONV_RESACC) {
-        if (npass != 1 || c.swap || !rwpk || L.rc0p % 32 || L.rc1p % 32 || !L.rsrc0 || (L.rc1p && !L.rsrc1))
+        if (npass != 1 || c.swap || !rwpk || L.rc0p % kch || L.rc1p % kch || !L.rsrc0 || (L.rc1p && !L.rsrc1))
             return fail(DTRAJ_EINVAL, "umma conv: fused residual conv needs single-pass TF32 and packed residual weights");
         c.res_col = c.acc_cols;
         c.acc_cols *= 2;
     }
     c.acc_stages = 2 * c.acc_cols <= 512 ? 2 : 1;
     c.tmem_cols = c.acc_stages * c.acc_cols;
-    const int nkb = L.ntaps * (L.c0p + L.c1p) / 32;
+    const int nkb = L.ntaps * (L.c0p + L.c1p) / kch;
     c.b_lo_row = nkb * L.coutp;
     c.cb = 0;
     c.log2_hw = 0;
@@ -920,7 +1152,7 @@ inline int build_umma_launch(UmmaLaunch* U, const ConvLayer& L, int npass, const
     // two K blocks per stage halve the single-thread loop overhead per MMA; worth it where an MMA is short
     // (N <= 128: <= 256 cycles per K block) and the stage stays small enough to keep >= 3 stages in flight
     const int n_stage_rows = c.pair ? n_rows / 2 : n_rows;
-    c.kbs = (n_stage_rows <= (c.pair ? 64 : 128) && c.r_nch0 % 2 == 0 && (c.r_nch - c.r_nch0) % 2 == 0 && (L.c0p / 32) % 2 == 0 && (L.c1p / 32) % 2 == 0 && !getenv("DTRAJ_KBS1")) ? 2 : 1;
+    c.kbs = (n_stage_rows <= (c.pair ? 64 : 128) && c.r_nch0 % 2 == 0 && (c.r_nch - c.r_nch0) % 2 == 0 && (L.c0p / kch) % 2 == 0 && (L.c1p / kch) % 2 == 0 && !getenv("DTRAJ_KBS1")) ? 2 : 1;
     const size_t stage = (size_t)c.kbs * (kATileBytes + (size_t)n_stage_rows * 128);
     const size_t misc = 1024 + 512 + ((L.flags & CONV_FINAL) ? 2048 : 0);
     auto stages_for = [&](int bufs) { return (int)((227 * 1024 - misc - (size_t)kEpiWarps * bufs * 4096) / stage); };
@@ -934,28 +1166,29 @@ inline int build_umma_launch(UmmaLaunch* U, const ConvLayer& L, int npass, const
     U->grid = (unsigned)(c.n_work < kNumSMs ? c.n_work : kNumSMs);
     if (c.cluster > 1) U->grid = (U->grid + c.cluster - 1) / c.cluster * c.cluster;
     const int64_t n_img = L.M / HW;
-    DTRAJ_TRY(make_act_map(&U->maps.a[0], L.src0, L.c0p, L.W, L.H, n_img, c.box_h, c.box_n));
-    if (L.c1p) DTRAJ_TRY(make_act_map(&U->maps.a[1], L.src1, L.c1p, L.W, L.H, n_img, c.box_h, c.box_n));
+    DTRAJ_TRY(make_act_map(&U->maps.a[0], L.src0, L.c0p, L.W, L.H, n_img, c.box_h, c.box_n, f16));
+    if (L.c1p) DTRAJ_TRY(make_act_map(&U->maps.a[1], L.src1, L.c1p, L.W, L.H, n_img, c.box_h, c.box_n, f16));
     if (npass == 3) {
         DTRAJ_TRY(make_act_map(&U->maps.a[2], L.src0_lo, L.c0p, L.W, L.H, n_img, c.box_h, c.box_n));
         if (L.c1p) DTRAJ_TRY(make_act_map(&U->maps.a[3], L.src1_lo, L.c1p, L.W, L.H, n_img, c.box_h, c.box_n));
     }
-    DTRAJ_TRY(make_w_map(&U->maps.b, wpk, w_rows, (c.swap ? 128 : c.ncols) / c.cluster));
+    DTRAJ_TRY(make_w_map(&U->maps.b, wpk, w_rows, (c.swap ? 128 : c.ncols) / c.cluster, f16));
     if (L.flags & CONV_RESACC) {
-        DTRAJ_TRY(make_act_map(&U->maps.ra[0], L.rsrc0, L.rc0p, L.W, L.H, n_img, c.box_h, c.box_n));
-        if (L.rc1p) DTRAJ_TRY(make_act_map(&U->maps.ra[1], L.rsrc1, L.rc1p, L.W, L.H, n_img, c.box_h, c.box_n));
-        DTRAJ_TRY(make_w_map(&U->maps.rb, rwpk, rw_rows, c.ncols / c.cluster));
+        DTRAJ_TRY(make_act_map(&U->maps.ra[0], L.rsrc0, L.rc0p, L.W, L.H, n_img, c.box_h, c.box_n, f16));
+        if (L.rc1p) DTRAJ_TRY(make_act_map(&U->maps.ra[1], L.rsrc1, L.rc1p, L.W, L.H, n_img, c.box_h, c.box_n, f16));
+        DTRAJ_TRY(make_w_map(&U->maps.rb, rwpk, rw_rows, c.ncols / c.cluster, f16));
     }
     if (L.M >= (int64_t)1 << 31) return fail(DTRAJ_EINVAL, "umma conv: M too large for 32-bit TMA coordinates");
-    if (!(L.flags & CONV_NOSTORE)) DTRAJ_TRY(make_rows_map(&U->maps.out, L.out, L.M, L.coutp));
+    if (!(L.flags & CONV_NOSTORE)) DTRAJ_TRY(make_rows_map(&U->maps.out, L.out, L.M, L.coutp, f16));
     if (L.act_mode == ACT_SPLIT) DTRAJ_TRY(make_rows_map(&U->maps.out_lo, L.out + L.lo_off, L.M, L.coutp));
-    if (L.flags & CONV_RESID) DTRAJ_TRY(make_rows_map(&U->maps.res, L.resid, L.M, L.coutp));
+    if (L.flags & CONV_RESID) DTRAJ_TRY(make_rows_map(&U->maps.res, L.resid, L.M, L.coutp, f16));
     return 0;
 }
 
 inline int launch_conv_umma(const UmmaLaunch& U, cudaStream_t st) {
     if (U.conv.cluster <= 1) {
-        k_conv_umma_t<false><<<U.grid, kUmmaThreads, U.smem, st>>>(U.maps, U.conv);
+        if (U.conv.f16) k_conv_umma_t<false, true><<<U.grid, kUmmaThreads, U.smem, st>>>(U.maps, U.conv);
+        else k_conv_umma_t<false, false><<<U.grid, kUmmaThreads, U.smem, st>>>(U.maps, U.conv);
         DTRAJ_LAUNCH_CHECK();
         return 0;
     }
@@ -972,8 +1205,10 @@ inline int launch_conv_umma(const UmmaLaunch& U, cudaStream_t st) {
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    if (U.conv.pair) DTRAJ_CUDA(cudaLaunchKernelEx(&cfg, k_conv_umma_t<true>, U.maps, U.conv));
-    else DTRAJ_CUDA(cudaLaunchKernelEx(&cfg, k_conv_umma_t<false>, U.maps, U.conv));
+    if (U.conv.pair && U.conv.f16) DTRAJ_CUDA(cudaLaunchKernelEx(&cfg, k_conv_umma_t<true, true>, U.maps, U.conv));
+    else if (U.conv.pair) DTRAJ_CUDA(cudaLaunchKernelEx(&cfg, k_conv_umma_t<true, false>, U.maps, U.conv));
+    else if (U.conv.f16) DTRAJ_CUDA(cudaLaunchKernelEx(&cfg, k_conv_umma_t<false, true>, U.maps, U.conv));
+    else DTRAJ_CUDA(cudaLaunchKernelEx(&cfg, k_conv_umma_t<false, false>, U.maps, U.conv));
     return 0;
 }
 

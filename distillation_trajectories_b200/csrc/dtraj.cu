@@ -5,6 +5,7 @@
 #include <vector>
 #include <cmath>
 #include <cstdlib>
+#include <cuda_fp16.h>
 
 #include "common.cuh"
 #include "elem.cuh"
@@ -105,14 +106,21 @@ int bn_fold(const TensorDict& sd, const std::string& conv, const std::string& no
     return 0;
 }
 
-// Pack [cout][c0+c1][k][k] into K-major 32-channel blocks [tap][chunk][coutp][32] (+ low plane)
+// channel padding unit = channels of one 128-byte K block: 32 fp32 / tf32 values, or 64 halfs (DTRAJ_PREC_F16)
+inline int cpad_of(int precision) { return precision == DTRAJ_PREC_F16 ? 64 : kCPad; }
+thread_local bool g_pack_overflow = false;   // a folded weight outside the fp16 range (DTRAJ_PREC_F16)
+
+// Pack [cout][c0+c1][k][k] into K-major blocks of one 128-byte row per output channel: [tap][chunk][coutp][32] floats
+// (+ low plane), or [tap][chunk][coutp][64] halfs in DTRAJ_PREC_F16
 void pack_conv(Arena* A, size_t* w_off, size_t* b_off, PackedConv* pc, const float* w, int cout, int c0, int c1,
                int ksize, bool centre_only, const double* scale, const double* shift, int precision) {
-    const int c0p = round_up(c0, kCPad), c1p = c1 ? round_up(c1, kCPad) : 0, coutp = round_up(cout, kCPad);
+    const int kch = cpad_of(precision);
+    const bool f16 = precision == DTRAJ_PREC_F16;
+    const int c0p = round_up(c0, kch), c1p = c1 ? round_up(c1, kch) : 0, coutp = round_up(cout, kch);
     const int ntaps = (ksize == 3 && !centre_only) ? 9 : 1;
-    const int nch0 = c0p / 32, nch = nch0 + c1p / 32, nkb = ntaps * nch;
+    const int nch0 = c0p / kch, nch = nch0 + c1p / kch, nkb = ntaps * nch;
     const int npl = precision == DTRAJ_PREC_TF32X3 ? 2 : 1;
-    const size_t plane = (size_t)nkb * coutp * 32;
+    const size_t plane = (size_t)nkb * coutp * 32;          // floats: one 128-byte row per (K block, output channel)
     *w_off = A->alloc(plane * npl);
     *b_off = A->alloc(coutp);
     const int cin = c0 + c1;
@@ -121,13 +129,19 @@ void pack_conv(Arena* A, size_t* w_off, size_t* b_off, PackedConv* pc, const flo
         if (ksize == 3) { ky = centre_only ? 1 : tap / 3; kx = centre_only ? 1 : tap % 3; }
         for (int chunk = 0; chunk < nch; ++chunk)
             for (int n = 0; n < cout; ++n)
-                for (int kk = 0; kk < 32; ++kk) {
+                for (int kk = 0; kk < kch; ++kk) {
                     int c, ci;
-                    if (chunk < nch0) { c = chunk * 32 + kk; ci = c < c0 ? c : -1; }
-                    else { c = (chunk - nch0) * 32 + kk; ci = c < c1 ? c0 + c : -1; }
+                    if (chunk < nch0) { c = chunk * kch + kk; ci = c < c0 ? c : -1; }
+                    else { c = (chunk - nch0) * kch + kk; ci = c < c1 ? c0 + c : -1; }
                     if (ci < 0) continue;
                     double v = (double)w[(((size_t)n * cin + ci) * ksize + ky) * ksize + kx] * (scale ? scale[n] : 1.0);
                     float f = (float)v;
+                    if (f16) {
+                        if (!(std::fabs(f) <= 65504.f)) g_pack_overflow = true;
+                        __half* hp = reinterpret_cast<__half*>(&A->h[*w_off]);
+                        hp[((size_t)(tap * nch + chunk) * coutp + n) * 64 + kk] = __float2half_rn(f);
+                        continue;
+                    }
                     size_t o = *w_off + (((size_t)(tap * nch + chunk) * coutp + n) * 32 + kk);
                     if (precision == DTRAJ_PREC_FP32) A->h[o] = f;
                     else {
@@ -157,7 +171,7 @@ extern "C" int dtraj_unet_create(const dtraj_unet_desc* desc, const char* const*
     if (C < 1 || C > 4) return fail(DTRAJ_EINVAL, "channels=%d unsupported (1..4)", C);
     if (H < 16 || H > 32 || (H % 16) != 0) return fail(DTRAJ_EINVAL, "image_size=%d unsupported (16 or 32)", H);
     if (temb < 2 || temb > 1024 || T < 1) return fail(DTRAJ_EINVAL, "bad temb_dim/n_timesteps");
-    if (desc->precision < 0 || desc->precision > 2) return fail(DTRAJ_EINVAL, "bad precision");
+    if (desc->precision < 0 || desc->precision > 3) return fail(DTRAJ_EINVAL, "bad precision");
     for (int i = 0; i < 4; ++i)
         if (desc->dims[i] < 1 || desc->dims[i] > 256) return fail(DTRAJ_EINVAL, "dims[%d]=%d unsupported (1..256)", i, desc->dims[i]);
     if (desc->dims[1] != desc->dims[2] || desc->dims[2] != desc->dims[3])
@@ -168,9 +182,11 @@ extern "C" int dtraj_unet_create(const dtraj_unet_desc* desc, const char* const*
 
     dtraj_unet* u = new dtraj_unet();
     u->d = *desc;
-    for (int i = 0; i < 4; ++i) u->dp[i] = round_up(desc->dims[i], kCPad);
+    const int cpad = cpad_of(desc->precision);
+    g_pack_overflow = false;
+    for (int i = 0; i < 4; ++i) u->dp[i] = round_up(desc->dims[i], cpad);
     for (int l = 0; l < 5; ++l) u->sizes[l] = H >> l;
-    u->act_mode = desc->precision == DTRAJ_PREC_FP32 ? ACT_PLAIN : desc->precision == DTRAJ_PREC_TF32 ? ACT_ROUND : ACT_SPLIT;
+    u->act_mode = desc->precision == DTRAJ_PREC_FP32 ? ACT_PLAIN : desc->precision == DTRAJ_PREC_TF32X3 ? ACT_SPLIT : ACT_ROUND;
     const int* d = desc->dims;
     // block geometry (models.py:137-154)
     const int cin0[8] = {C, d[0], d[1], d[2], d[3], d[3], d[2], d[1]};
@@ -260,10 +276,11 @@ extern "C" int dtraj_unet_create(const dtraj_unet_desc* desc, const char* const*
         }
     }
     if (err) { delete u; return err; }
+    if (g_pack_overflow) { delete u; return fail(DTRAJ_EINVAL, "a BatchNorm-folded conv weight exceeds the fp16 range: use precision tf32"); }
 
     // time table layout
     int tbs = 0;
-    for (int b = 0; b < 8; ++b) { u->tb_off[b] = tbs; tbs += round_up(cout[b], kCPad); }
+    for (int b = 0; b < 8; ++b) { u->tb_off[b] = tbs; tbs += round_up(cout[b], cpad); }
     u->tb_stride = tbs;
     const size_t o_table = A.alloc((size_t)T * 3 * tbs);
 
@@ -356,10 +373,12 @@ int64_t plan_floats(const dtraj_unet* u, int64_t R, dtraj_plan* P) {
     const int C = u->d.channels;
     const bool split = u->act_mode == ACT_SPLIT;
     int64_t off = 0;
-    auto take = [&](dtraj_plan::Buf* b, int64_t per_row, bool lo_plane) {
+    const bool f16 = u->d.precision == DTRAJ_PREC_F16;
+    // `act`: a feature map in the model's operand type (halfs in DTRAJ_PREC_F16: half the floats); else fp32
+    auto take = [&](dtraj_plan::Buf* b, int64_t per_row, bool lo_plane, bool act = true) {
         int64_t n = round_up64(R * per_row, 256);
         if (P) { b->p = P->ws + off; b->n = n; b->lo = (split && lo_plane) ? n : 0; }
-        off += n * ((split && lo_plane) ? 2 : 1);
+        off += (f16 && act) ? n / 2 : n * ((split && lo_plane) ? 2 : 1);
     };
     auto px = [&](int l) { return (int64_t)S[l] * S[l]; };
     dtraj_plan dummy;
@@ -384,7 +403,7 @@ int64_t plan_floats(const dtraj_unet* u, int64_t R, dtraj_plan* P) {
     take(&Q->u2, px(2) * dp[2], true);
     take(&Q->u1, px(1) * dp[1], true);
     take(&Q->y1, px(1) * dp[0], false);
-    take(&Q->elow, px(1) * C, false);
+    take(&Q->elow, px(1) * C, false, false);
     return off;
 }
 
@@ -413,6 +432,7 @@ int add_conv(dtraj_plan* P, const PackedConv& pc, const dtraj_plan::Buf& s0, con
     L.lo_off = out.lo;
     L.act_mode = is_residual_conv ? ACT_PLAIN : (u->act_mode == ACT_SPLIT && out.lo == 0 ? ACT_PLAIN : u->act_mode);
     L.flags = flags;
+    L.f16 = u->d.precision == DTRAJ_PREC_F16 ? 1 : 0;
     op.needs_x = false;
     if (tail.pool_out) { L.flags |= CONV_POOL; L.pool_out = tail.pool_out; }
     if (tail.nostore) L.flags |= CONV_NOSTORE;
@@ -455,7 +475,8 @@ int plan_build(const dtraj_unet* u, int64_t R, void* ws, int64_t ws_bytes, dtraj
     auto blk = [&](int b) -> const BlockW& { return u->blk[b]; };
     // Fused epilogue tails exist in the tcgen05 kernel's bulk path only (single-pass TF32, the mode the
     // sweeps run in); the exact modes keep the stand-alone pool / final / residual kernels.
-    const bool fused = u->d.precision == DTRAJ_PREC_TF32 && !getenv("DTRAJ_NO_FUSE");
+    const bool f16 = u->d.precision == DTRAJ_PREC_F16;
+    const bool fused = f16 || (u->d.precision == DTRAJ_PREC_TF32 && !getenv("DTRAJ_NO_FUSE"));
     P->fuse_resx = fused;
     P->fuse_final = fused;
     for (int l = 0; l < 4; ++l) P->fuse_pool[l] = fused && S[l] <= 16;
@@ -475,7 +496,7 @@ int plan_build(const dtraj_unet* u, int64_t R, void* ws, int64_t ws_bytes, dtraj
 #define ADD(...) if (!rc) rc = add_conv(P, __VA_ARGS__)
     // enc1: conv1/res by k_conv_first; conv2 here.  x1 itself is never a skip input (models.py:206-216):
     // with the pool fused, only the pooled tile is written.
-    P->fuse_enc1 = fused && S[0] % 16 == 0 && u->d.channels <= 4 && !getenv("DTRAJ_NO_ENC1");
+    P->fuse_enc1 = fused && !f16 && S[0] % 16 == 0 && u->d.channels <= 4 && !getenv("DTRAJ_NO_ENC1");
     if (P->fuse_enc1) {
         rc = build_enc1_launch(&P->enc1, u->d.channels, S[0], u->dp[0], blk(0).cout, P->R, blk(0).conv2.w, blk(0).conv2.rows);
         Enc1Params& e = P->enc1.p;
@@ -537,6 +558,7 @@ int plan_forward(dtraj_plan* P, const float* x, int64_t x_stride, const int32_t*
     const int C = u->d.channels;
     const int64_t R = P->R;
     const float* trow = u->table + (size_t)t * 3 * u->tb_stride;
+    const bool f16 = u->d.precision == DTRAJ_PREC_F16;
     int64_t nl = 0;
     if (P->fuse_enc1) {   // whole enc1 block + pool in one kernel
         Enc1Params& e = P->enc1.p;
@@ -553,7 +575,8 @@ int plan_forward(dtraj_plan* P, const float* x, int64_t x_stride, const int32_t*
         f.C = C; f.H = S[0]; f.W = S[0]; f.coutp = dp[0];
         f.w3 = u->fw3; f.b3 = u->fb3; f.w1 = u->fw1; f.b1 = u->fb1;
         f.tbias = trow + u->tb_off[0]; f.tb_var_stride = u->tb_stride;
-        f.h = P->tmp_h.p; f.r = P->fuse_resx ? nullptr : P->tmp_r.p; f.lo_off = P->tmp_h.lo; f.act_mode = u->act_mode;
+        f.h = P->tmp_h.p; f.r = P->fuse_resx ? nullptr : P->tmp_r.p; f.lo_off = P->tmp_h.lo;
+        f.f16 = f16 ? 1 : 0; f.act_mode = f16 ? ACT_PLAIN : u->act_mode;
         const size_t smem = (round_up(C * (S[0] + 2) * (S[0] + 2), 4) + 10 * C * dp[0]) * sizeof(float);
         PROF_BEGIN(prof, KC_FIRST);
         k_conv_first<<<(unsigned)R, 256, smem, st>>>(f);
@@ -582,7 +605,8 @@ int plan_forward(dtraj_plan* P, const float* x, int64_t x_stride, const int32_t*
         if (P->fuse_pool[level]) return 0;      // emitted by the producing conv's epilogue
         const int64_t n4 = R * So * So * (cp / 4);
         PROF_BEGIN(prof, KC_RESAMPLE);
-        k_pool2<<<blocks_for(n4, 256), 256, 0, st>>>(in.p, out.p, n4, So, So, cp / 4, out.lo, out.lo ? ACT_SPLIT : ACT_PLAIN);
+        if (f16) k_pool2_h<<<blocks_for(n4 / 2, 256), 256, 0, st>>>((const __half*)in.p, (__half*)out.p, n4 / 2, So, So, cp / 8);
+        else k_pool2<<<blocks_for(n4, 256), 256, 0, st>>>(in.p, out.p, n4, So, So, cp / 4, out.lo, out.lo ? ACT_SPLIT : ACT_PLAIN);
         PROF_END(prof);
         DTRAJ_LAUNCH_CHECK(); ++nl;
         return 0;
@@ -591,8 +615,9 @@ int plan_forward(dtraj_plan* P, const float* x, int64_t x_stride, const int32_t*
         const int64_t n4 = R * (2 * Si) * (2 * Si) * (cp / 4);
         if (n4 >= ((int64_t)1 << 31)) return fail(DTRAJ_EINVAL, "upsample: batch too large for 32-bit indexing");
         PROF_BEGIN(prof, KC_RESAMPLE);
-        k_upsample2<<<blocks_for(n4, 256), 256, 0, st>>>(in.p, out.p, n4, Si, Si, cp / 4, out.lo,
-                                                        (u->act_mode == ACT_SPLIT && !out.lo) ? ACT_PLAIN : u->act_mode);
+        if (f16) k_upsample2_h<<<blocks_for(n4 / 2, 256), 256, 0, st>>>((const __half*)in.p, (__half*)out.p, n4 / 2, Si, Si, cp / 8);
+        else k_upsample2<<<blocks_for(n4, 256), 256, 0, st>>>(in.p, out.p, n4, Si, Si, cp / 4, out.lo,
+                                                             (u->act_mode == ACT_SPLIT && !out.lo) ? ACT_PLAIN : u->act_mode);
         PROF_END(prof);
         DTRAJ_LAUNCH_CHECK(); ++nl;
         return 0;
@@ -857,7 +882,8 @@ extern "C" unsigned int dtraj_debug_umma_error(void) {
 extern "C" int dtraj_bench_conv(int32_t precision, int32_t c0, int32_t c1, int32_t cout, int64_t n, int32_t H, int32_t ksize,
                                 int32_t flags, int32_t iters, int32_t debug, float* ms_out) {
     if (precision == DTRAJ_PREC_FP32 && debug) return fail(DTRAJ_EINVAL, "bench_conv: debug needs a tcgen05 mode");
-    const int c0p = round_up(c0, kCPad), c1p = c1 ? round_up(c1, kCPad) : 0, coutp = round_up(cout, kCPad);
+    const int cpad = cpad_of(precision);
+    const int c0p = round_up(c0, cpad), c1p = c1 ? round_up(c1, cpad) : 0, coutp = round_up(cout, cpad);
     const int64_t M = n * H * H;
     std::vector<float> w((size_t)cout * (c0 + c1) * ksize * ksize, 0.01f);
     std::vector<double> shift(cout, 0.0);
@@ -883,6 +909,7 @@ extern "C" int dtraj_bench_conv(int32_t precision, int32_t c0, int32_t c1, int32
     L.resid = (flags & 4) ? res : nullptr; L.out = out; L.lo_off = (int64_t)M * coutp;
     L.flags = (flags & 1 ? CONV_RELU : 0) | (flags & 4 ? CONV_RESID : 0) | (flags & (CONV_POOL | CONV_NOSTORE | CONV_RESX | CONV_FINAL));
     L.act_mode = precision == DTRAJ_PREC_TF32 ? ACT_ROUND : precision == DTRAJ_PREC_TF32X3 ? ACT_SPLIT : ACT_PLAIN;
+    L.f16 = precision == DTRAJ_PREC_F16 ? 1 : 0;      // (buffers stay sized for fp32: zeros either way)
     float* aux = nullptr;      // pooled output | raw input | 1x1 weights | final weights | eps, all zero
     DTRAJ_CUDA(cudaMalloc(&aux, ((size_t)M / 4 * coutp + (size_t)n * 4 * H * H + 16 * coutp + (size_t)M * 4) * 4));
     DTRAJ_CUDA(cudaMemset(aux, 0, ((size_t)M / 4 * coutp + (size_t)n * 4 * H * H + 16 * coutp + (size_t)M * 4) * 4));
@@ -938,6 +965,7 @@ extern "C" int dtraj_test_conv(int32_t precision, const float* x0, int32_t c0, c
     L.H = H; L.W = W; L.M = M; L.ntaps = pc.ntaps; L.wpk = dev + wo; L.bias = dev + bo; L.coutp = pc.coutp;
     L.resid = resid; L.out = out; L.flags = (flags & 1 ? CONV_RELU : 0) | (resid ? CONV_RESID : 0);
     L.act_mode = (flags & 2) ? ACT_ROUND : ACT_PLAIN;
+    L.f16 = precision == DTRAJ_PREC_F16 ? 1 : 0;
     int rc = 0;
     float* lo = nullptr;
     if (precision == DTRAJ_PREC_FP32) rc = launch_conv_simt(L, st);

@@ -1,6 +1,7 @@
 // HBM/L2-bound kernels around the convolutions: time-embedding table, first conv (Cin<=4),
 // 2x2 max-pool, bilinear x2 upsample (align_corners), final 1x1 conv, fused sampler step.
 #pragma once
+#include <cuda_fp16.h>
 #include "common.cuh"
 
 namespace dtraj {
@@ -92,7 +93,19 @@ struct FirstConvParams {
     float* r;                // [R,H,W,coutp]   residual_conv(x); null when the consumer recomputes it (CONV_RESX)
     int64_t lo_off;          // ACT_SPLIT: h low plane offset
     int act_mode;
+    int f16;                 // DTRAJ_PREC_F16: h is a __half map (act_mode must be ACT_PLAIN, r null)
 };
+
+// four consecutive channels of a feature map at element index `idx`: fp32, or rounded to fp16 (rn)
+__device__ __forceinline__ void store_act4(float* base, size_t idx, float4 o, int f16) {
+    if (f16) {
+        __half2* d = reinterpret_cast<__half2*>(reinterpret_cast<__half*>(base) + idx);
+        d[0] = __floats2half2_rn(o.x, o.y);
+        d[1] = __floats2half2_rn(o.z, o.w);
+    } else {
+        *reinterpret_cast<float4*>(base + idx) = o;
+    }
+}
 
 __global__ void __launch_bounds__(256) k_conv_first(FirstConvParams p) {
     extern __shared__ float sm[];
@@ -114,8 +127,9 @@ __global__ void __launch_bounds__(256) k_conv_first(FirstConvParams p) {
     __syncthreads();
     const int groups = cp / 4;
     const float* tb = p.tbias + (size_t)variant * p.tb_var_stride;
-    float* hout = p.h + (size_t)row * H * W * cp;
-    float* rout = p.r + (size_t)row * H * W * cp;
+    const size_t hbase = (size_t)row * H * W * cp;       // element offset of this row's map
+    float* hout = p.h + hbase;                           // (fp32 maps only)
+    float* rout = p.r + hbase;
     // 256 threads and cp/4 <= 64 channel groups: a thread's group is the same for every item it owns when
     // 256 % groups == 0 (all padded widths except 96/160/192/224-style ones), so its 9*C weight vectors,
     // bias and time bias live in registers and the pixel loop is 9*C broadcast loads + 36*C FMAs.
@@ -143,7 +157,7 @@ __global__ void __launch_bounds__(256) k_conv_first(FirstConvParams p) {
                                    fmaxf(acc.z, 0.f) + t4.z, fmaxf(acc.w, 0.f) + t4.w);
             o = act_round4(o, p.act_mode);
             float* dst = hout + (size_t)pix * cp + g * 4;
-            *reinterpret_cast<float4*>(dst) = o;
+            store_act4(p.h, hbase + (size_t)pix * cp + g * 4, o, p.f16);
             if (p.act_mode == ACT_SPLIT) *reinterpret_cast<float4*>(dst + p.lo_off) = act_lo4(o);
             if (p.r) {
                 const float v = img[(y + 1) * PW + xq + 1];
@@ -177,7 +191,7 @@ __global__ void __launch_bounds__(256) k_conv_first(FirstConvParams p) {
                                fmaxf(acc.z, 0.f) + t4.z, fmaxf(acc.w, 0.f) + t4.w);
         o = act_round4(o, p.act_mode);
         float* dst = hout + (size_t)pix * cp + g * 4;
-        *reinterpret_cast<float4*>(dst) = o;
+        store_act4(p.h, hbase + (size_t)pix * cp + g * 4, o, p.f16);
         if (p.act_mode == ACT_SPLIT) *reinterpret_cast<float4*>(dst + p.lo_off) = act_lo4(o);
         if (p.r) *reinterpret_cast<float4*>(rout + (size_t)pix * cp + g * 4) = racc;
     }
@@ -205,6 +219,31 @@ __global__ void __launch_bounds__(256) k_pool2(const float* __restrict__ in, flo
                            fmaxf(fmaxf(a.z, b.z), fmaxf(c.z, d.z)), fmaxf(fmaxf(a.w, b.w), fmaxf(c.w, d.w)));
     reinterpret_cast<float4*>(out)[i] = o;
     if (act_mode == ACT_SPLIT) reinterpret_cast<float4*>(out + lo_off)[i] = act_lo4(o);
+}
+
+// fp16 maps (DTRAJ_PREC_F16): one thread = 8 channels (16 bytes) of one output pixel
+__global__ void __launch_bounds__(256) k_pool2_h(const __half* __restrict__ in, __half* __restrict__ out,
+                                                 int64_t n_out8, int Ho, int Wo, int cp8) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_out8) return;
+    int c8 = (int)(i % cp8);
+    int64_t pix = i / cp8;
+    int xo = (int)(pix % Wo);
+    int64_t t = pix / Wo;
+    int yo = (int)(t % Ho);
+    int64_t n = t / Ho;
+    const int Wi = Wo * 2;
+    const uint4* src = reinterpret_cast<const uint4*>(in) + (((n * (Ho * 2) + yo * 2) * Wi) + xo * 2) * cp8 + c8;
+    const uint4 a = src[0], b = src[cp8], c = src[(int64_t)Wi * cp8], d = src[(int64_t)Wi * cp8 + cp8];
+    const __half2* ah = reinterpret_cast<const __half2*>(&a);
+    const __half2* bh = reinterpret_cast<const __half2*>(&b);
+    const __half2* ch = reinterpret_cast<const __half2*>(&c);
+    const __half2* dh = reinterpret_cast<const __half2*>(&d);
+    uint4 o;
+    __half2* oh = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) oh[k] = __hmax2(__hmax2(ah[k], bh[k]), __hmax2(ch[k], dh[k]));
+    reinterpret_cast<uint4*>(out)[i] = o;
 }
 
 // =====================================================================================
@@ -249,6 +288,40 @@ __global__ void __launch_bounds__(256) k_upsample2(const float* __restrict__ in,
     o = act_round4(o, act_mode);
     reinterpret_cast<float4*>(out)[i] = o;
     if (act_mode == ACT_SPLIT) reinterpret_cast<float4*>(out + lo_off)[i] = act_lo4(o);
+}
+
+// fp16 maps (DTRAJ_PREC_F16): one thread = 8 channels of one output pixel; interpolation in fp32, one rounding
+__global__ void __launch_bounds__(256) k_upsample2_h(const __half* __restrict__ in, __half* __restrict__ out,
+                                                     int64_t n_out8, int Hi, int Wi, int cp8) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (uint32_t)n_out8) return;
+    const int Ho = Hi * 2, Wo = Wi * 2;
+    const uint32_t pix = i / (uint32_t)cp8, c8 = i - pix * (uint32_t)cp8;
+    const int lw = 31 - __clz(Wo), lh = 31 - __clz(Ho);
+    const int xo = (int)(pix & (uint32_t)(Wo - 1)), yo = (int)((pix >> lw) & (uint32_t)(Ho - 1));
+    const uint32_t n = pix >> (lw + lh);
+    const float sh = Ho > 1 ? (float)(Hi - 1) / (float)(Ho - 1) : 0.f;
+    const float sw = Wo > 1 ? (float)(Wi - 1) / (float)(Wo - 1) : 0.f;
+    int y0, y1, x0, x1; float ly, lx;
+    up2_coord(yo, Hi, sh, y0, y1, ly);
+    up2_coord(xo, Wi, sw, x0, x1, lx);
+    const float hy = 1.f - ly, hx = 1.f - lx;
+    const uint4* base = reinterpret_cast<const uint4*>(in) + (size_t)n * Hi * Wi * cp8 + c8;
+    const uint4 v00 = __ldg(base + (y0 * Wi + x0) * cp8), v01 = __ldg(base + (y0 * Wi + x1) * cp8);
+    const uint4 v10 = __ldg(base + (y1 * Wi + x0) * cp8), v11 = __ldg(base + (y1 * Wi + x1) * cp8);
+    const __half2* a = reinterpret_cast<const __half2*>(&v00);
+    const __half2* b = reinterpret_cast<const __half2*>(&v01);
+    const __half2* c = reinterpret_cast<const __half2*>(&v10);
+    const __half2* d = reinterpret_cast<const __half2*>(&v11);
+    uint4 o;
+    __half2* oh = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const float2 fa = __half22float2(a[k]), fb = __half22float2(b[k]), fc = __half22float2(c[k]), fd = __half22float2(d[k]);
+        oh[k] = __floats2half2_rn(hy * (hx * fa.x + lx * fb.x) + ly * (hx * fc.x + lx * fd.x),
+                                  hy * (hx * fa.y + lx * fb.y) + ly * (hx * fc.y + lx * fd.y));
+    }
+    reinterpret_cast<uint4*>(out)[i] = o;
 }
 
 // =====================================================================================

@@ -37,6 +37,10 @@ extern "C" {
 #define DTRAJ_PREC_FP32     0   /* CUDA-core fp32 implicit GEMM (exact mode)                 */
 #define DTRAJ_PREC_TF32     1   /* tcgen05.mma kind::tf32, one pass (fast mode)              */
 #define DTRAJ_PREC_TF32X3   2   /* tcgen05.mma kind::tf32, hi/lo split, 3 passes (~fp32)     */
+#define DTRAJ_PREC_F16      3   /* tcgen05.mma kind::f16: fp16 feature maps and weights (the  */
+                                /* same 11-bit significand as tf32), fp32 accumulation; twice */
+                                /* the MMA rate and half the operand bytes of DTRAJ_PREC_TF32. */
+                                /* Range-checked: |activation| or |weight| > 65504 is an error */
 
 /* conditioning variant of one forward row (reference models.py:181-185) */
 #define DTRAJ_VAR_NONE      0   /* cond=None: time embedding only                            */
@@ -209,7 +213,8 @@ int dtraj_wasserstein(const float* teacher, const float* student,
  * tests (tests/test_gpu_conv.py).  x0/x1 NHWC dev [n, H, W, c0p]/[.., c1p] (x1 may be
  * NULL); w host [Cout, c0+c1, k, k] (k = 1 or 3), bias host [Cout]; out dev NHWC
  * [n, H, W, coutp] with coutp = round_up(Cout, 32).  flags: bit0 relu, bit1 round
- * outputs to tf32. */
+ * outputs to tf32.  In DTRAJ_PREC_F16 x0/x1/resid/out are __half maps with channels
+ * padded to 64. */
 int dtraj_test_conv(int32_t precision, const float* x0, int32_t c0, const float* x1, int32_t c1,
                     int64_t n, int32_t H, int32_t W, const float* w_host, const float* bias_host,
                     int32_t cout, int32_t ksize, int32_t flags, const float* resid,

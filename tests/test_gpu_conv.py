@@ -32,15 +32,19 @@ def run_conv(prec, x0, x1, w, b, ksize, relu, resid):
     c1 = 0 if x1 is None else x1.shape[1]
     cout = w.shape[0]
 
+    f16 = prec == _lib.PREC_F16
+    pad = 64 if f16 else 32              # channels per 128-byte K block
+    dt = torch.float16 if f16 else torch.float32
+
     def nhwc(a, c):
-        t = torch.zeros(n, H, W, rup(c), dtype=torch.float32)
-        t[..., :c] = torch.from_numpy(a).permute(0, 2, 3, 1)
+        t = torch.zeros(n, H, W, rup(c, pad), dtype=dt)
+        t[..., :c] = torch.from_numpy(a).permute(0, 2, 3, 1).to(dt)
         return t.to(dev).contiguous()
 
     d0 = nhwc(x0, c0)
     d1 = None if x1 is None else nhwc(x1, c1)
     dr = None if resid is None else nhwc(resid, cout)
-    out = torch.full((n, H, W, rup(cout)), float("nan"), dtype=torch.float32, device=dev)
+    out = torch.full((n, H, W, rup(cout, pad)), float("nan"), dtype=dt, device=dev)
     wc = np.ascontiguousarray(w, np.float32)
     bc = np.ascontiguousarray(b, np.float32)
     rc = lib.dtraj_test_conv(prec, _lib.ptr(d0), c0, _lib.ptr(d1), c1, n, H, W, wc.ctypes.data_as(C.c_void_p),
@@ -49,9 +53,9 @@ def run_conv(prec, x0, x1, w, b, ksize, relu, resid):
     _lib.check(rc)
     torch.cuda.synchronize()
     assert umma_error_flag() == 0, "a tcgen05 role timed out on an mbarrier"
-    o = out.cpu()
+    o = out.float().cpu()
     assert torch.isfinite(o).all()
-    assert (o[..., cout:] == 0).all() or cout == rup(cout)      # pad channels carry only zeros
+    assert (o[..., cout:] == 0).all() or cout == rup(cout, pad)      # pad channels carry only zeros
     return o[..., :cout].permute(0, 3, 1, 2).numpy()
 
 
@@ -86,7 +90,12 @@ SHAPES = [
 ]
 
 
-@pytest.mark.parametrize("prec", [_lib.PREC_FP32, _lib.PREC_TF32, _lib.PREC_TF32X3], ids=["fp32", "tf32", "tf32x3"])
+def f16_round(a):
+    return a.astype(np.float16).astype(np.float32)
+
+
+@pytest.mark.parametrize("prec", [_lib.PREC_FP32, _lib.PREC_TF32, _lib.PREC_TF32X3, _lib.PREC_F16],
+                         ids=["fp32", "tf32", "tf32x3", "f16"])
 @pytest.mark.parametrize("shape", SHAPES, ids=lambda s: "n%d_c%d+%d_o%d_h%d_k%d" % s)
 def test_conv_layer(prec, shape):
     n, c0, c1, cout, H, ksize = shape
@@ -100,10 +109,21 @@ def test_conv_layer(prec, shape):
         # single-pass TF32 sees trunc_tf32(activations) x rna_tf32(weights): feed exact-tf32 activations
         x0 = tf32_trunc(x0)
         x1 = None if x1 is None else tf32_trunc(x1)
+    if prec == _lib.PREC_F16:
+        # fp16 operands (the same 11-bit significand as tf32), fp32 accumulation, ONE fp16 rounding of the output
+        x0 = f16_round(x0)
+        x1 = None if x1 is None else f16_round(x1)
+        resid = f16_round(resid)
+        w = f16_round(w)
     for relu, rs in ((True, resid), (False, None)):
         got = run_conv(prec, x0, x1, w, b, ksize, relu, rs)
         want = reference(x0, x1, w, b, ksize, relu, rs, round_w=(prec == _lib.PREC_TF32))
         scale = np.abs(want).max()
+        if prec == _lib.PREC_F16:
+            K = (c0 + c1) * ksize * ksize
+            bound = (4e-6 + 4e-9 * K) * scale + 2.0 ** -11 * np.abs(want) + 6e-8     # accumulate + output rounding (+ subnormal step)
+            assert (np.abs(got - want) <= bound).all(), f"max excess {np.max(np.abs(got - want) - bound):.3e}"
+            continue
         # CUDA-core path: fp32 FMA chain.  tcgen05 paths: the tensor core adds into its fp32 accumulator
         # with round-toward-zero, measured ~2e-9 * K of max|ref| (tools/probe_conv_accuracy.py); 3xTF32
         # additionally drops the lo*lo term (2^-22 relative).
