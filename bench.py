@@ -276,9 +276,13 @@ def run_ours(args, emit=print):
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tp):
         traffic = json.load(open(tp)).get("k_conv_umma_dram_bytes_per_launch")
-    roofline = {"kernel": "k_conv_umma (tcgen05 kind::tf32 implicit-GEMM conv)" if args.precision != "fp32" else "k_conv_simt",
+    kname = {"fp32": "k_conv_simt", "f16": "k_conv_umma (tcgen05 kind::f16 implicit-GEMM conv, fp32 accumulate)"}.get(
+        args.precision, "k_conv_umma (tcgen05 kind::tf32 implicit-GEMM conv)")
+    pnote = ": dense bf16 sustained" + ("; kind::f16 issues at the bf16 rate" if args.precision == "f16"
+                                        else "; kind::tf32 issues at half the bf16 rate")
+    roofline = {"kernel": kname,
                 "bound": "tensor", "achieved": ach, "peak": tc_sust, "unit": "TFLOP/s", "frac": ach / tc_sust,
-                "traffic": traffic, "peak_source": src + ": dense bf16 sustained; kind::tf32 issues at half the bf16 rate",
+                "traffic": traffic, "peak_source": src + pnote,
                 "launches_timed": conv_n, "avg_launch_us": conv_ms / max(conv_n, 1) * 1e3,
                 "flops_per_launch": conv_fl / max(conv_n, 1), "share_of_loop_time": conv_ms / all_ms,
                 "class_ms": {"conv": conv_ms, "first_conv": sum(p["ms"][1] for p in prof),
@@ -331,7 +335,7 @@ def run_ours(args, emit=print):
 
     out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-           "dtype": {"tf32": "tf32", "tf32x3": "tf32x3", "fp32": "f32"}[args.precision],
+           "dtype": {"tf32": "tf32", "tf32x3": "tf32x3", "fp32": "f32", "f16": "f16 (fp32 accumulate)"}[args.precision],
            "data": "synthetic (random-init weights, seeded N(0,1) noise)",
            "config": workload_config(S, world), "e2e": e2e, "gpu_launches": launches,
            "clocks": clk.summary(), "roofline": roofline, "roofline_other": side}
@@ -360,7 +364,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--seeds", type=int, default=296, help="seeds per GPU per step (x 8 guidance scales x 2 models)")
-    ap.add_argument("--precision", default="tf32", choices=["tf32", "tf32x3", "fp32"])
+    ap.add_argument("--precision", default="tf32", choices=["tf32", "tf32x3", "fp32", "f16"])
     ap.add_argument("--e2e-chunks", type=int, default=1,
                     help="chunks a sweep is cut into in the end-to-end leg (host staging of chunk i+1 overlaps chunk i on the GPU)")
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -14,7 +14,8 @@ pytestmark = pytest.mark.gpu
 # max |err| / max |ref| allowed for one forward.  fp32 / 3xTF32 differ from the reference only by
 # summation order and BatchNorm folding (3xTF32 also by the tensor core's round-toward-zero
 # accumulation, ~1e-5 per deep layer); single-pass TF32 carries 10-bit-mantissa operand rounding.
-FWD_TOL = {"fp32": 2e-5, "tf32x3": 6e-5, "tf32": 4e-3}
+# fp16 operands ("f16") have the same 11-bit significand as tf32, hence the same bound.
+FWD_TOL = {"fp32": 2e-5, "tf32x3": 6e-5, "tf32": 4e-3, "f16": 4e-3}
 
 
 @pytest.fixture(scope="module", params=["tiny16", "tiny32"])
@@ -22,7 +23,7 @@ def case(request):
     return golden_models(request.param, device="cuda")
 
 
-@pytest.mark.parametrize("prec", ["fp32", "tf32x3", "tf32"])
+@pytest.mark.parametrize("prec", ["fp32", "tf32x3", "tf32", "f16"])
 def test_forward_matches_reference_fixture(case, prec):
     g, cfg, teacher, student = case
     set_precision(prec, "forward")
@@ -58,7 +59,7 @@ def test_time_bias_table_matches_oracle(case):
 
 
 @pytest.mark.parametrize("sf,C,H", [(1.0, 1, 16), (0.5, 1, 16), (0.3, 3, 32), (1.0, 3, 32)])
-@pytest.mark.parametrize("prec", ["fp32", "tf32x3", "tf32"])
+@pytest.mark.parametrize("prec", ["fp32", "tf32x3", "tf32", "f16"])
 def test_forward_matches_oracle_real_widths(sf, C, H, prec):
     """teacher / student widths of the BASELINE configs, mixed conditioning variants in one batch."""
     cfg = Cfg(C, H, 50)

@@ -76,7 +76,7 @@ def test_s1_p_sample_single_step(case):
         assert_close(got.cpu().numpy(), want.numpy(), RTOL, ATOL, f"p_sample t={tval}")
 
 
-@pytest.mark.parametrize("prec", ["fp32", "tf32x3", "tf32"])
+@pytest.mark.parametrize("prec", ["fp32", "tf32x3", "tf32", "f16"])
 def test_s2_generate_trajectory_fixture(case, prec):
     g, cfg, teacher, student = case
     set_precision(prec, "S2")
@@ -91,7 +91,7 @@ def test_s2_generate_trajectory_fixture(case, prec):
     assert umma_error_flag() == 0
 
 
-@pytest.mark.parametrize("prec", ["fp32", "tf32"])
+@pytest.mark.parametrize("prec", ["fp32", "tf32", "f16"])
 def test_s3_trajectory_manager_fixture(case, prec, tmp_path):
     g, cfg, teacher, student = case
     T = cfg.timesteps
@@ -124,16 +124,19 @@ def test_s1_config1_batch64_teacher():
     assert umma_error_flag() == 0
 
 
+@pytest.mark.parametrize("prec", ["tf32", "f16"])
 @pytest.mark.parametrize("C,H,sf,w", [(1, 16, 1.0, 7.5), (1, 16, 0.5, 20.0), (3, 32, 1.0, 7.5), (3, 32, 0.1, 7.5)])
-def test_s2_full_length_vs_oracle(C, H, sf, w):
-    """BASELINE configs 2-3: 50 steps with CFG, default (single-pass TF32) arithmetic."""
+def test_s2_full_length_vs_oracle(C, H, sf, w, prec):
+    """BASELINE configs 2-3: 50 steps with CFG, in the two fast arithmetic modes (single-pass TF32, fp16)."""
+    set_precision(prec, "S2")
     cfg = Cfg(C, H, 50)
     model = make_model(cfg, sf, 1000 + int(sf * 100), stress=False, device="cuda")
     torch.manual_seed(42)
     noise = torch.randn(1, C, H, H)
     want = osmp.s2_generate_trajectory(oracle_fn(model), noise, 50, seed=42, guidance_scale=w)
     got = te.generate_trajectory(model, noise, 50, "cuda", seed=42, guidance_scale=w)
-    assert_close(stack(got), stack(want), RTOL, ATOL, f"S2 {C}x{H} sf={sf} w={w}")
+    set_precision("tf32", "S2")
+    assert_close(stack(got), stack(want), RTOL, ATOL, f"S2 {C}x{H} sf={sf} w={w} [{prec}]")
     assert umma_error_flag() == 0
 
 
