@@ -14,6 +14,7 @@
 #include "metrics.cuh"
 #include "probe.cuh"
 #include "enc1_umma.cuh"
+#include "enc1_f16.cuh"
 
 using namespace dtraj;
 
@@ -313,6 +314,7 @@ extern "C" int dtraj_unet_create(const dtraj_unet_desc* desc, const char* const*
     if (desc->precision != DTRAJ_PREC_FP32) {
         ce = umma_set_smem_attr();
         if (ce == cudaSuccess) ce = enc1_set_smem_attr();
+        if (ce == cudaSuccess) ce = enc1h_set_smem_attr();
         if (ce != cudaSuccess) { dtraj_unet_destroy(u); return fail(DTRAJ_ECUDA, "smem attribute -> %s", cudaGetErrorString(ce)); }
     }
     *out = u;
@@ -360,6 +362,7 @@ struct dtraj_plan {
     bool fuse_resx = false, fuse_final = false, fuse_res = false;
     bool fuse_enc1 = false;      // k_enc1_umma replaces k_conv_first + the enc1.conv2 launch
     Enc1Launch enc1;
+    Enc1hLaunch enc1h;           // its fp16 form (DTRAJ_PREC_F16): conv2 weights resident in shared memory
     bool fuse_pool[4] = {false, false, false, false};   // pool after enc1..enc4
     std::vector<ConvOp> convs;   // 15 3x3 + residual 1x1s
     int64_t launches_per_forward = 0;
@@ -496,8 +499,13 @@ int plan_build(const dtraj_unet* u, int64_t R, void* ws, int64_t ws_bytes, dtraj
 #define ADD(...) if (!rc) rc = add_conv(P, __VA_ARGS__)
     // enc1: conv1/res by k_conv_first; conv2 here.  x1 itself is never a skip input (models.py:206-216):
     // with the pool fused, only the pooled tile is written.
-    P->fuse_enc1 = fused && !f16 && S[0] % 16 == 0 && u->d.channels <= 4 && !getenv("DTRAJ_NO_ENC1");
-    if (P->fuse_enc1) {
+    P->fuse_enc1 = fused && S[0] % 16 == 0 && u->d.channels <= 4 && !getenv("DTRAJ_NO_ENC1");
+    if (P->fuse_enc1 && f16) {
+        rc = build_enc1h_launch(&P->enc1h, u->d.channels, S[0], u->dp[0], blk(0).cout, P->R, blk(0).conv2.w, blk(0).conv2.rows);
+        Enc1hParams& e = P->enc1h.p;
+        e.w3 = u->fw3; e.b3 = u->fb3; e.rw1 = u->fw1; e.rb1 = u->fb1; e.bias2 = blk(0).conv2.bias;
+        e.tb_var_stride = u->tb_stride; e.pool_out = (__half*)P->p1.p;
+    } else if (P->fuse_enc1) {
         rc = build_enc1_launch(&P->enc1, u->d.channels, S[0], u->dp[0], blk(0).cout, P->R, blk(0).conv2.w, blk(0).conv2.rows);
         Enc1Params& e = P->enc1.p;
         e.w3 = u->fw3; e.b3 = u->fb3; e.rw1 = u->fw1; e.rb1 = u->fb1; e.bias2 = blk(0).conv2.bias;
@@ -560,7 +568,16 @@ int plan_forward(dtraj_plan* P, const float* x, int64_t x_stride, const int32_t*
     const float* trow = u->table + (size_t)t * 3 * u->tb_stride;
     const bool f16 = u->d.precision == DTRAJ_PREC_F16;
     int64_t nl = 0;
-    if (P->fuse_enc1) {   // whole enc1 block + pool in one kernel
+    if (P->fuse_enc1 && f16) {
+        Enc1hParams& e = P->enc1h.p;
+        e.x = x; e.x_stride = x_stride; e.row_sample = row_sample; e.row_variant = row_variant;
+        e.tbias = trow + u->tb_off[0];
+        PROF_BEGIN(prof, KC_ENC1);
+        int rc1 = launch_enc1h(P->enc1h, st);
+        PROF_END(prof);
+        DTRAJ_TRY(rc1);
+        ++nl;
+    } else if (P->fuse_enc1) {   // whole enc1 block + pool in one kernel
         Enc1Params& e = P->enc1.p;
         e.x = x; e.x_stride = x_stride; e.row_sample = row_sample; e.row_variant = row_variant;
         e.tbias = trow + u->tb_off[0];
@@ -833,7 +850,7 @@ extern "C" int dtraj_sampler_profile(dtraj_sampler* s, void* stream, double* cla
     double f = 0.0;
     for (auto& op : s->plan->convs) f += op.flops;
     conv_flops[0] = f * s->d.n_updates;
-    conv_flops[1] = s->plan->fuse_enc1 ? s->plan->enc1.flops * s->d.n_updates : 0.0;
+    conv_flops[1] = s->plan->fuse_enc1 ? (s->u->d.precision == DTRAJ_PREC_F16 ? s->plan->enc1h.flops : s->plan->enc1.flops) * s->d.n_updates : 0.0;
     if (rc) return rc;
     if (ce != cudaSuccess) return fail(DTRAJ_ECUDA, "profile -> %s", cudaGetErrorString(ce));
     return 0;

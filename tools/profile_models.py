@@ -7,6 +7,7 @@ from distillation_trajectories_b200 import grid
 from distillation_trajectories_b200.engine import UNetEngine
 from distillation_trajectories_b200.models import DiffusionUNet
 seeds = int(sys.argv[1]) if len(sys.argv) > 1 else 296
+prec = sys.argv[2] if len(sys.argv) > 2 else "tf32"
 dev = torch.device("cuda", 0)
 models = []
 for sf, seed in ((1.0, 0), (0.5, 1050)):
@@ -14,10 +15,10 @@ for sf, seed in ((1.0, 0), (0.5, 1050)):
     with bench.quiet():
         models.append(DiffusionUNet(bench.Cfg, sf).eval().to(dev))
 ck = grid.stage_chunk(list(range(seeds)), bench.Cfg, bench.GUIDANCE, dev)
-grid.run_chunk(models[0], [models[1]], ck, dev, "tf32")
+grid.run_chunk(models[0], [models[1]], ck, dev, prec)
 torch.cuda.synchronize()
 for name, m in zip(("teacher", "student"), models):
-    s = next(iter(UNetEngine.for_model(m, 16, 50, "tf32", dev)._samplers.values()))
+    s = next(iter(UNetEngine.for_model(m, 16, 50, prec, dev)._samplers.values()))
     p = s.profile(); p = s.profile()
     n = s.n_updates
     print(f"{name}: per forward (us): conv {p['ms'][0]/n*1e3:.0f} ({p['conv_flops']/p['ms'][0]/1e9:.0f} TF/s)  first {p['ms'][1]/n*1e3:.0f}  "
