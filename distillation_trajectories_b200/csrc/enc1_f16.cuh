@@ -1,65 +1,90 @@
-// Fused enc1 block for sm_100a, fp16 mode (DTRAJ_PREC_F16): the same computation as enc1_umma.cuh,
+// Fused enc1 block for sm_100a, fp16 mode (DTRAJ_PREC_F16): one kernel from the raw C-channel frame to the max-pooled
+// enc1 output,
 //     h  = relu(bn1(conv1_3x3(x))) + relu(time_mlp(temb))          (models.py:62-77, C = config.channels <= 4)
 //     y  = relu(bn2(conv2_3x3(h))) + residual_conv_1x1(x)           (models.py:79-83)
 //     p1 = MaxPool2d(2)(y)                                          (models.py:191)
-// with two structural differences that fp16 operands make possible:
-//   * conv2's packed weights ([tap][64-channel chunk][coutp][64] halfs) are RESIDENT in shared memory: 288 KB for
-//     the teacher, 144 KB per CTA of a pair (each CTA holds its half of the output channels, tcgen05.mma.cta_group::2)
-//     -- they are loaded once per CTA, nothing streams from L2 inside the tile loop (the tf32 kernel re-read 295 KB
-//     of weights per 128-pixel tile, which paced it);
-//   * a halo chunk buffer holds 64 channels per 128-byte row, so the teacher's K loop is 2 chunks x 9 taps x 4 MMAs.
-// Output tile = 16 image rows x 8 columns; GENERATOR warps compute conv1 on the 18 x 10 halo with CUDA cores and write it
-// rounded to fp16 into the 128-byte-swizzled K-major layout; each conv2 tap is a descriptor VIEW of the halo tile
-// (start shifted by (dy*10 + dx) rows, 8-row groups 1280 bytes apart; profiles/r01_umma_view_probe.txt).
-// Epilogue: bias, ReLU, 1x1 residual recomputed from x, fp16 rounding, 2x2 max-pool, 16-byte stores.
+// with BOTH convolutions on the tensor cores and nothing but x and p1 touching global memory inside the tile loop:
+//   * conv2's packed weights ([tap][64-channel chunk][coutp][64] halfs) are RESIDENT in shared memory: 288 KB for the
+//     teacher, 144 KB per CTA of a pair (each CTA holds its half of the output channels, tcgen05.mma.cta_group::2),
+//     loaded once per CTA (the tf32 kernel re-read 295 KB of weights per 128-pixel tile);
+//   * output tile = 16 image rows x 8 columns, halo = 18 x 10 = 180 pixels.  conv1 is a small GEMM
+//     D1[halo pixel, cout] = A1[halo pixel, k] * W1[k, cout], k = tap * C + cin (9C <= 36 values, padded to K slices of
+//     16): the MID warps gather A1 (one halo pixel per thread, prefetched a tile ahead) into shared memory as fp16,
+//     the issuer runs it as one or two M = 256 MMAs per slice into a TMEM region of its own, and the mid warps read D1
+//     back, add bias / ReLU / time bias, round to fp16 and write the 128-byte-swizzled K-major halo chunk buffers
+//     (zero rows where the halo leaves the image: conv2's zero padding).  The first form of this kernel computed conv1
+//     with CUDA-core FMAs in "generator" warps: 115 instructions per 8 outputs made it issue-bound (572 us against
+//     ~170 us of conv2 MMAs for the teacher); the tensor-core form leaves ~25;
+//   * each conv2 tap is a descriptor VIEW of the halo tile (start shifted by (dy*10 + dx) rows, 8-row groups 1280 bytes
+//     apart; profiles/r01_umma_view_probe.txt): nothing is copied, no im2col re-reads;
+//   * epilogue: bias, ReLU, 1x1 residual recomputed from x (fp32 FMAs), fp16 rounding, 2x2 max-pool, 16-byte stores.
+// x enters conv1 rounded to fp16 like every other operand of this mode (11-bit significand; the range check of the
+// mode covers it).
 #pragma once
 #include "enc1_umma.cuh"
 
 namespace dtraj {
+
+constexpr int kE1Mid = 8;                        // mid warps (two per TMEM lane quarter)
+constexpr int kE1hThreads = 64 + 32 * kE1Epi + 32 * kE1Mid;
+constexpr int kA1SliceBytes = 256 * 32;          // 256 rows x 16 halfs
 
 struct Enc1hParams {
     int C, H, W, coutp;
     int n_chunks;                // coutp / 64: K chunks of conv2
     int n_tiles, tiles_x, tiles_per_img;
     int n_hbuf;                  // halo chunk buffers in the ring (>= 1; 2 x n_chunks when they fit)
-    int acc_cols;                // TMEM columns per accumulator
-    int w_rows;                  // weight rows (output channels) this CTA holds per (tap, chunk): coutp, or coutp / 2 in pair mode
+    int acc_cols;                // TMEM columns per accumulator; layout [acc0 | acc1 | D1 rows 0-127 | D1 rows 128-255]
+    int w_rows;                  // output channels this CTA holds: coutp, or coutp / 2 in pair mode
+    int n_slices;                // K slices (16 values) of conv1's GEMM: ceil(9C / 16)
+    int a1_mode;                 // shared-memory layout of the 32-byte-row operands: 0 SWIZZLE_32B, 1 SWIZZLE_NONE core matrices
     const float* x; int64_t x_stride; const int32_t* row_sample; const int32_t* row_variant;
-    const float* w3; const float* b3;          // conv1, BN folded: [9*C][coutp] tap-major then cin; [coutp]   (fp32)
-    const float* tbias; int tb_var_stride;
+    const float* w3; const float* b3;          // conv1, BN folded, fp32: [9*C][coutp] (k = tap * C + cin); [coutp]
+    const float* tbias; int tb_var_stride;     // relu(time_mlp(temb)) rows of enc1 for this t, 3 variants
     const float* bias2;                        // conv2 folded bias [coutp]
     const float* rw1; const float* rb1;        // residual 1x1: [C][coutp], [coutp]
     __half* pool_out;                          // [R, H/2, W/2, coutp]
-    int debug;                   // timing experiments (DTRAJ_E1_DEBUG): 1 generators store zeros, 2 generators only signal, 4 no MMAs
+    int debug;                   // timing experiments (DTRAJ_E1_DEBUG): 4 skips conv2's MMAs
 };
 
-template <bool kPair>
-__global__ void __launch_bounds__(kE1Threads, 1)
+// byte offset of 16-byte K chunk kc (0/1) of row r inside a [rows][16 halfs] operand slice
+__device__ __forceinline__ uint32_t k16_off(int r, int kc, int mode) {
+    return mode == 0 ? (uint32_t)(r * 32 + ((kc ^ ((r >> 2) & 1)) << 4))
+                     : (uint32_t)((r >> 3) * 256 + kc * 128 + (r & 7) * 16);
+}
+
+template <bool kPair, int kC>
+__global__ void __launch_bounds__(kE1hThreads, 1)
 k_enc1_f16(const __grid_constant__ Enc1Maps maps, const Enc1hParams p) {
+    constexpr int C = kC;                        // compile-time: the A1 gather is 9 * C loads, not 36 predicated ones
+    constexpr int kBiasK = 9 * kC;               // K slots 9C and 9C + 1 carry conv1's folded bias (hi, lo) against A1 = 1
     extern __shared__ __align__(1024) uint8_t e1_smem[];
     const uint32_t base = (ptx::smem_u32(e1_smem) + 1023u) & ~1023u;
     uint8_t* gbase = e1_smem + (base - ptx::smem_u32(e1_smem));
-    const int coutp = p.coutp, C = p.C;
+    const int coutp = p.coutp;
     const uint32_t wblk_bytes = (uint32_t)p.w_rows * 128u;                 // one (tap, chunk) weight block in this CTA
     const uint32_t w_bytes = 9u * (uint32_t)p.n_chunks * wblk_bytes;
-    // carve: [resident weights][halo ring][epilogue ring 4 x 2 KB][x patches 2 x 4 ch x 240][constants][barriers]
+    const uint32_t b1_slice = (uint32_t)p.w_rows * 32u;
+    // carve: [resident conv2 weights][halo ring][epilogue ring 4 x 2 KB][A1 slices][W1 slices][constants][barriers]
     const uint32_t wres0 = base;
-    const uint32_t halo0 = wres0 + w_bytes;                                // w_bytes is a multiple of 1024 (w_rows % 8 == 0, 9 blocks)
+    const uint32_t halo0 = wres0 + w_bytes;
     const uint32_t ring0 = halo0 + (uint32_t)p.n_hbuf * kE1HaloBytes;
-    const uint32_t xp0 = ring0 + kE1Epi * 2048u;
-    const uint32_t cst0 = xp0 + 2u * 4u * 240u * 4u;
-    // constants (floats): w3 [9C][coutp] | b3 | bias2 | rb1 | rw1 [C][coutp]
-    const int n_cst = (9 * C + 3 + C) * coutp;
+    const uint32_t a1_0 = ring0 + kE1Epi * 2048u;
+    const uint32_t b1_0 = a1_0 + (uint32_t)p.n_slices * kA1SliceBytes;
+    const uint32_t cst0 = b1_0 + (((uint32_t)p.n_slices * b1_slice + 1023u) & ~1023u);
+    // constants (floats): b3 | tbias [3][coutp] | bias2 | rb1 | rw1 [C][coutp]
+    const int n_cst = (6 + C) * coutp;
     const uint32_t bar0 = (cst0 + (uint32_t)n_cst * 4u + 15u) & ~15u;
     auto hfull = [&](int b) { return bar0 + 8u * b; };
     auto hempty = [&](int b) { return bar0 + 64u + 8u * b; };
-    const uint32_t acc_full0 = bar0 + 128u, acc_empty0 = bar0 + 144u, wbar = bar0 + 160u, tmem_slot = bar0 + 168u;
+    const uint32_t acc_full0 = bar0 + 128u, acc_empty0 = bar0 + 144u, wbar = bar0 + 160u;
+    const uint32_t a1_full = bar0 + 168u, a1_empty = bar0 + 176u, d1_full = bar0 + 184u, d1_empty = bar0 + 192u;
+    const uint32_t tmem_slot = bar0 + 200u;
     volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gbase + (tmem_slot - base));
-    float* xpatch = reinterpret_cast<float*>(gbase + (xp0 - base));       // [2][4][20][12]
     float* cst = reinterpret_cast<float*>(gbase + (cst0 - base));
-    const float* w3s = cst;
-    const float* b3s = cst + 9 * C * coutp;
-    const float* bias2s = b3s + coutp;
+    const float* b3s = cst;
+    const float* tbs = b3s + coutp;
+    const float* bias2s = tbs + 3 * coutp;
     const float* rb1s = bias2s + coutp;
     const float* rw1s = rb1s + coutp;
 
@@ -67,35 +92,57 @@ k_enc1_f16(const __grid_constant__ Enc1Maps maps, const Enc1hParams p) {
     const int crank = kPair ? (int)ptx::cluster_ctarank() : 0;
     const uint16_t cmask = kPair ? 3 : 1;
     const int work0 = (int)blockIdx.x - crank;
+    const uint32_t nrep = kPair ? 2u : 1u;                                 // CTAs reporting to the (leader's) barriers
 
     if (warp == 0) {
         if (ptx::elect_one()) {
             ptx::prefetch_tmap(&maps.w);
-            for (int b = 0; b < p.n_hbuf; ++b) { ptx::mbar_init(hfull(b), kE1Gen * (kPair ? 2 : 1)); ptx::mbar_init(hempty(b), 1); }
+            for (int b = 0; b < p.n_hbuf; ++b) { ptx::mbar_init(hfull(b), kE1Mid * nrep); ptx::mbar_init(hempty(b), 1); }
             for (int i = 0; i < 2; ++i) {
                 ptx::mbar_init(acc_full0 + 8u * i, 1);
-                ptx::mbar_init(acc_empty0 + 8u * i, kE1Epi * (kPair ? 2 : 1));
+                ptx::mbar_init(acc_empty0 + 8u * i, kE1Epi * nrep);
             }
             ptx::mbar_init(wbar, 1);
+            ptx::mbar_init(a1_full, kE1Mid * nrep);
+            ptx::mbar_init(a1_empty, 1);
+            ptx::mbar_init(d1_full, 1);
+            ptx::mbar_init(d1_empty, kE1Mid * nrep);
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
         __syncwarp();
         if constexpr (!kPair) {
-            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"((uint32_t)(2 * p.acc_cols)) : "memory");
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"((uint32_t)(4 * p.acc_cols)) : "memory");
             asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
         } else {
-            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"((uint32_t)(2 * p.acc_cols)) : "memory");
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"((uint32_t)(4 * p.acc_cols)) : "memory");
             asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
         }
     }
-    // constants into shared memory (all threads)
-    for (int i = threadIdx.x; i < 9 * C * coutp; i += blockDim.x) cst[i] = p.w3[i];
+    // constants, the conv1 weight operand W1 (fp16, this CTA's output channels) and zeroed A1 slices (all threads)
     for (int i = threadIdx.x; i < coutp; i += blockDim.x) {
-        cst[9 * C * coutp + i] = p.b3[i];
-        cst[(9 * C + 1) * coutp + i] = p.bias2[i];
-        cst[(9 * C + 2) * coutp + i] = p.rb1[i];
+        cst[i] = p.b3[i];
+        for (int v = 0; v < 3; ++v) cst[(1 + v) * coutp + i] = p.tbias[(size_t)v * p.tb_var_stride + i];
+        cst[4 * coutp + i] = p.bias2[i];
+        cst[5 * coutp + i] = p.rb1[i];
     }
-    for (int i = threadIdx.x; i < C * coutp; i += blockDim.x) cst[(9 * C + 3) * coutp + i] = p.rw1[i];
+    for (int i = threadIdx.x; i < C * coutp; i += blockDim.x) cst[6 * coutp + i] = p.rw1[i];
+    for (int i = threadIdx.x; i < p.n_slices * (kA1SliceBytes / 16); i += blockDim.x)
+        reinterpret_cast<uint4*>(gbase + (a1_0 - base))[i] = make_uint4(0u, 0u, 0u, 0u);
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * 256; i += blockDim.x) {             // the bias slots of every A1 row hold 1.0
+        const int r = i >> 1, k = kBiasK + (i & 1);
+        *reinterpret_cast<__half*>(gbase + (a1_0 - base) + (k >> 4) * kA1SliceBytes + k16_off(r, (k >> 3) & 1, p.a1_mode) + (k & 7) * 2) = __float2half_rn(1.f);
+    }
+    for (int i = threadIdx.x; i < p.n_slices * p.w_rows * 16; i += blockDim.x) {
+        const int s = i / (p.w_rows * 16), rem = i - s * p.w_rows * 16, nl = rem >> 4, e = rem & 15, k = 16 * s + e;
+        const int n = crank * p.w_rows + nl;
+        float v = 0.f;
+        if (k < 9 * C) v = p.w3[(size_t)k * coutp + n];
+        else if (k == kBiasK) v = __half2float(__float2half_rn(p.b3[n]));
+        else if (k == kBiasK + 1) v = p.b3[n] - __half2float(__float2half_rn(p.b3[n]));
+        *reinterpret_cast<__half*>(gbase + (b1_0 - base) + s * b1_slice + k16_off(nl, e >> 3, p.a1_mode) + (e & 7) * 2) = __float2half_rn(v);
+    }
+    ptx::fence_proxy_async();
     ptx::tc_fence_before();
     __syncthreads();
     if constexpr (kPair) ptx::cluster_sync_all();
@@ -114,7 +161,7 @@ k_enc1_f16(const __grid_constant__ Enc1Maps maps, const Enc1hParams p) {
         if (ptx::elect_one()) {
             uint32_t fb = wbar;
             if constexpr (kPair) fb = ptx::map_to_cta(fb, 0);              // both CTAs' bytes complete on the leader's barrier
-            if (!kPair || crank == 0) ptx::mbar_expect_tx(wbar, w_bytes * (kPair ? 2u : 1u));
+            if (!kPair || crank == 0) ptx::mbar_expect_tx(wbar, w_bytes * nrep);
             for (int b = 0; b < 9 * p.n_chunks; ++b) {                     // block b = tap * n_chunks + chunk
                 const int row = b * coutp + crank * p.w_rows;
                 if constexpr (kPair) ptx::tma_load_2d_2sm(wres0 + b * wblk_bytes, &maps.w, fb, 0, row);
@@ -127,17 +174,40 @@ k_enc1_f16(const __grid_constant__ Enc1Maps maps, const Enc1hParams p) {
             const uint32_t idesc = umma_idesc_f16(coutp) + (kPair ? ((uint32_t)(128 >> 4) << 24) : 0u);
             // halo view: K-major SWIZZLE_128B, 8-row groups one halo row (10 pixels = 1280 B) apart
             const uint64_t hdesc0 = ((uint64_t)1 << 16) | ((uint64_t)(1280 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
-            int hb = 0, acc = 0;
+            // 32-byte-row operands of conv1: 8-row groups 256 B apart; SWIZZLE_32B, or un-swizzled core matrices 128 B apart in K
+            const uint64_t kdesc0 = p.a1_mode == 0
+                ? (((uint64_t)1 << 16) | ((uint64_t)(256 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)6 << 61))
+                : (((uint64_t)(128 >> 4) << 16) | ((uint64_t)(256 >> 4) << 32) | ((uint64_t)1 << 46));
+            auto kdesc = [&](uint32_t addr) { return kdesc0 | (uint64_t)((addr >> 4) & 0x3fffu); };
+            const uint32_t d1_tmem = tmem_base + (uint32_t)(2 * p.acc_cols);
+            int hb = 0, acc = 0, it = 0;
             uint32_t hph = 0, acc_ph = 0;
             bool ok = ptx::mbar_wait(wbar, 0u);
-            ptx::tc_fence_after();
-            for (int wk = work0; wk < p.n_tiles && ok; wk += gridDim.x) {
+            // conv1 of tile-iteration `j`: D1[g] = A1[rows 128g ..] * W1^T, g = 0, 1
+            auto issue_conv1 = [&](int j) {
+                ok = ok && ptx::mbar_wait(a1_full, (uint32_t)(j & 1));
+                ok = ok && ptx::mbar_wait(d1_empty, (uint32_t)((j & 1) ^ 1));
+                ptx::tc_fence_after();
+                for (int g = 0; g < 2; ++g)
+                    for (int s = 0; s < p.n_slices; ++s) {
+                        const uint64_t ad = kdesc(a1_0 + (uint32_t)s * kA1SliceBytes + (uint32_t)g * 4096u);
+                        const uint64_t bd = kdesc(b1_0 + (uint32_t)s * b1_slice);
+                        if constexpr (!kPair) ptx::mma_f16(d1_tmem + (uint32_t)(g * p.acc_cols), ad, bd, idesc, s ? 1u : 0u);
+                        else ptx::mma_f16_2sm(d1_tmem + (uint32_t)(g * p.acc_cols), ad, bd, idesc, s ? 1u : 0u);
+                    }
+                if constexpr (kPair) { ptx::tc_commit_2sm(a1_empty, cmask); ptx::tc_commit_2sm(d1_full, cmask); }
+                else { ptx::tc_commit(a1_empty); ptx::tc_commit(d1_full); }
+            };
+            if (work0 < p.n_tiles) issue_conv1(0);
+            for (int wk = work0; wk < p.n_tiles && ok; wk += gridDim.x, ++it) {
                 ok = ptx::mbar_wait(acc_empty0 + 8u * acc, acc_ph ^ 1u);
                 ptx::tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.acc_cols);
                 uint32_t accum = 0u;
                 for (int c = 0; c < p.n_chunks && ok; ++c) {
-                    ok = ptx::mbar_wait(hfull(hb), hph);            // this chunk's halo tile is in shared memory (both CTAs)
+                    // the next tile's conv1 goes in front of this tile's last chunk: its halo is ready when that chunk retires
+                    if (c == p.n_chunks - 1 && wk + (int)gridDim.x < p.n_tiles) issue_conv1(it + 1);
+                    ok = ok && ptx::mbar_wait(hfull(hb), hph);      // this chunk's halo tile is in shared memory (both CTAs)
                     ptx::tc_fence_after();
                     const uint32_t hbuf = halo0 + (uint32_t)hb * kE1HaloBytes;
                     int dy = 0, dx = 0;
@@ -162,86 +232,118 @@ k_enc1_f16(const __grid_constant__ Enc1Maps maps, const Enc1hParams p) {
             }
         }
     } else if (warp >= 2 + kE1Epi) {
-        // ------------------------------------------------------------ generators: conv1 + BN + ReLU + time bias -> halo tiles
-        const int gt = threadIdx.x - 32 * (2 + kE1Epi);            // 0..255
-        const int g = gt & 7, pl = gt >> 3;                         // 16-byte cell (8 channels) of the 64-channel chunk, pixel lane (0..31)
-        int hb = 0;
+        // ------------------------------------------------------------ mid warps: A1 gather, D1 -> halo chunk buffers
+        const int mt = threadIdx.x - 32 * (2 + kE1Epi);            // 0..255 = A1 row = halo pixel (< 180)
+        const int q = warp & 3;                                     // TMEM lane quarter of this warp
+        const int h = (warp - (2 + kE1Epi)) >> 2;                   // the quarter's two warps split every 64-channel chunk: cells 4h..4h+3
+        const int HW = p.H * p.W;
+        const bool a1_row = mt < kE1HaloRows;
+        const int a_ry = mt / 10, a_rx = mt - a_ry * 10;            // halo coordinates of the A1 row
+        uint8_t* a1p = gbase + (a1_0 - base);
+        // the two halo pixels whose D1 rows this thread converts: px0 = 32q + lane (region 0), px1 = 128 + 32q + lane (region 1)
+        const int px0 = 32 * q + lane, px1 = 128 + 32 * q + lane;
+        const bool has1 = 128 + 32 * q < kE1HaloRows;               // warp-uniform: quarters 0 and 1 own rows of region 1
+        const int ry0 = px0 / 10, rx0 = px0 - ry0 * 10, ry1 = px1 / 10, rx1 = px1 - ry1 * 10;
+        float xr[kC][9];                                            // prefetched conv1 inputs of the A1 row: [cin][tap]
+        // per-image indices are fetched TWO tiles ahead and the pixels ONE tile ahead, so no load is waited for in the loop
+        int smp_n = 0, var_n = 0, var_c = 0;                        // sample of the next tile; variant of the next / current tile
+        auto fetch_idx = [&](int wk) {
+            const int tile = wk + crank;
+            const int img = tile / p.tiles_per_img;
+            const bool real = wk < p.n_tiles && tile < p.n_tiles;
+            smp_n = real ? (p.row_sample ? __ldg(p.row_sample + img) : img) : 0;
+            var_n = (real && p.row_variant) ? __ldg(p.row_variant + img) : 0;
+        };
+        auto prefetch = [&](int wk, int smp) {
+            const int tile = wk + crank;
+            int img, y0, x0;
+            tile_geom(tile, img, y0, x0);
+            const bool real = tile < p.n_tiles && a1_row;
+            const float* xs = p.x + (size_t)smp * p.x_stride;
+            const int yy = y0 - 1 + a_ry, xx = x0 - 1 + a_rx;
+#pragma unroll
+            for (int ci = 0; ci < kC; ++ci)
+#pragma unroll
+                for (int t9 = 0; t9 < 9; ++t9) {
+                    const int sy = yy - 1 + t9 / 3, sx = xx - 1 + t9 % 3;
+                    xr[ci][t9] = (real && sy >= 0 && sy < p.H && sx >= 0 && sx < p.W) ? __ldg(xs + (size_t)ci * HW + sy * p.W + sx) : 0.f;
+                }
+        };
+        int hb = 0, it = 0;
         uint32_t hph = 0;
-        int it = 0;
+        fetch_idx(work0);
+        prefetch(work0, smp_n);
+        var_c = var_n;
+        fetch_idx(work0 + (int)gridDim.x);
         for (int wk = work0; wk < p.n_tiles; wk += gridDim.x, ++it) {
             const int tile = wk + crank;
             int img, y0, x0;
             tile_geom(tile, img, y0, x0);
             const bool real = tile < p.n_tiles;
-            // x patch (zero outside the image): rows y0-2 .. y0+17, cols x0-2 .. x0+9, double-buffered across tiles
-            float* xp = xpatch + (it & 1) * 4 * 240;
-            const float* xs = p.x + (size_t)(real ? (p.row_sample ? p.row_sample[img] : img) : 0) * p.x_stride;
-            for (int i = gt; i < C * 240; i += 32 * kE1Gen) {
-                const int c = i / 240, r = i - c * 240, yy = y0 - 2 + r / 12, xx = x0 - 2 + r % 12;
-                xp[i] = (real && yy >= 0 && yy < p.H && xx >= 0 && xx < p.W) ? __ldg(xs + ((size_t)c * p.H + yy) * p.W + xx) : 0.f;
-            }
-            asm volatile("bar.sync 9, 256;" ::: "memory");
-            const int var = (real && p.row_variant) ? p.row_variant[img] : 0;
-            const float* tb = p.tbias + (size_t)var * p.tb_var_stride;
-            for (int c = 0; c < p.n_chunks; ++c) {
-                const int ch = 64 * c + 8 * g;
-                const float4 b3a = *reinterpret_cast<const float4*>(b3s + ch), b3b = *reinterpret_cast<const float4*>(b3s + ch + 4);
-                const float4 t4a = __ldg(reinterpret_cast<const float4*>(tb + ch)), t4b = __ldg(reinterpret_cast<const float4*>(tb + ch + 4));
-                float4 wa[9], wb[9];                                // C == 1: the nine taps of this thread's 8 channels stay in registers
-                if (C == 1) {
+            // ---- A1 row of this tile (the MMAs of the previous tile's conv1 have retired)
+            ptx::mbar_wait(a1_empty, (uint32_t)((it & 1) ^ 1));
+            if (a1_row) {
+#pragma unroll
+                for (int ci = 0; ci < kC; ++ci)
 #pragma unroll
                     for (int t9 = 0; t9 < 9; ++t9) {
-                        wa[t9] = *reinterpret_cast<const float4*>(w3s + (size_t)t9 * coutp + ch);
-                        wb[t9] = *reinterpret_cast<const float4*>(w3s + (size_t)t9 * coutp + ch + 4);
+                        const int k = t9 * kC + ci;
+                        *reinterpret_cast<__half*>(a1p + (k >> 4) * kA1SliceBytes + k16_off(mt, (k >> 3) & 1, p.a1_mode) + (k & 7) * 2) = __float2half_rn(xr[ci][t9]);
+                    }
+            }
+            ptx::fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+                if constexpr (!kPair) ptx::mbar_arrive(a1_full);
+                else ptx::mbar_arrive_cluster(ptx::map_to_cta(a1_full, 0));
+            }
+            const float* tb = tbs + var_c * coutp;
+            if (wk + (int)gridDim.x < p.n_tiles) {                  // loads stay in flight under the conversion below
+                prefetch(wk + (int)gridDim.x, smp_n);
+                var_c = var_n;
+                fetch_idx(wk + 2 * (int)gridDim.x);
+            }
+            // ---- D1 -> halo chunk buffers
+            const int yy0 = y0 - 1 + ry0, xx0 = x0 - 1 + rx0, yy1 = y0 - 1 + ry1, xx1 = x0 - 1 + rx1;
+            const bool in0 = real && yy0 >= 0 && yy0 < p.H && xx0 >= 0 && xx0 < p.W;                       // else: conv2's zero padding
+            const bool in1 = real && px1 < kE1HaloRows && yy1 >= 0 && yy1 < p.H && xx1 >= 0 && xx1 < p.W;
+            ptx::mbar_wait(d1_full, (uint32_t)(it & 1));
+            ptx::tc_fence_after();
+            const uint32_t t_d1 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(2 * p.acc_cols);
+            for (int c = 0; c < p.n_chunks; ++c) {
+                const int col0 = 64 * c + 32 * h;                   // this warp's 32 channels of the chunk
+                uint32_t r0[32], r1[32];
+                ptx::tmem_ld32(t_d1 + (uint32_t)col0, r0);
+                if (has1) ptx::tmem_ld32(t_d1 + (uint32_t)(p.acc_cols + col0), r1);
+                ptx::tmem_ld_wait();
+                if (c == p.n_chunks - 1) {                          // D1 may be overwritten by the next tile's conv1
+                    ptx::tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) {
+                        if constexpr (!kPair) ptx::mbar_arrive(d1_empty);
+                        else ptx::mbar_arrive_cluster(ptx::map_to_cta(d1_empty, 0));
                     }
                 }
-                ptx::mbar_wait(hempty(hb), hph ^ 1u);               // the MMAs that read this buffer have retired
+                ptx::mbar_wait(hempty(hb), hph ^ 1u);               // the conv2 MMAs that read this buffer have retired
                 uint8_t* hbuf = gbase + (halo0 - base) + (size_t)hb * kE1HaloBytes;
-                auto conv1_at = [&](int px) -> uint4 {
-                    const int ry = px / 10, rx = px - ry * 10;
-                    const int yy = y0 - 1 + ry, xx = x0 - 1 + rx;
-                    if (!(yy >= 0 && yy < p.H && xx >= 0 && xx < p.W)) return make_uint4(0u, 0u, 0u, 0u);   // conv2's zero padding
-                    float4 a0 = b3a, a1 = b3b;
-                    if (C == 1) {
+                // h = relu(D1) + time bias (conv1's folded bias is inside D1), rounded to fp16; zero rows outside the image
+                auto emit = [&](const uint32_t* raw, int px, bool inside) {
 #pragma unroll
-                        for (int ky = 0; ky < 3; ++ky)
-#pragma unroll
-                            for (int kx = 0; kx < 3; ++kx) {
-                                const float v = xp[(ry + ky) * 12 + rx + kx];
-                                const float4 u0 = wa[ky * 3 + kx], u1 = wb[ky * 3 + kx];
-                                a0.x = fmaf(v, u0.x, a0.x); a0.y = fmaf(v, u0.y, a0.y); a0.z = fmaf(v, u0.z, a0.z); a0.w = fmaf(v, u0.w, a0.w);
-                                a1.x = fmaf(v, u1.x, a1.x); a1.y = fmaf(v, u1.y, a1.y); a1.z = fmaf(v, u1.z, a1.z); a1.w = fmaf(v, u1.w, a1.w);
-                            }
-                    } else {
-                        for (int ci = 0; ci < C; ++ci)
-#pragma unroll
-                            for (int t9 = 0; t9 < 9; ++t9) {
-                                const float v = xp[ci * 240 + (ry + t9 / 3) * 12 + rx + t9 % 3];
-                                const float4 u0 = *reinterpret_cast<const float4*>(w3s + (size_t)(t9 * C + ci) * coutp + ch);
-                                const float4 u1 = *reinterpret_cast<const float4*>(w3s + (size_t)(t9 * C + ci) * coutp + ch + 4);
-                                a0.x = fmaf(v, u0.x, a0.x); a0.y = fmaf(v, u0.y, a0.y); a0.z = fmaf(v, u0.z, a0.z); a0.w = fmaf(v, u0.w, a0.w);
-                                a1.x = fmaf(v, u1.x, a1.x); a1.y = fmaf(v, u1.y, a1.y); a1.z = fmaf(v, u1.z, a1.z); a1.w = fmaf(v, u1.w, a1.w);
-                            }
+                    for (int j = 0; j < 4; ++j) {
+                        uint4 o = make_uint4(0u, 0u, 0u, 0u);
+                        if (inside) {
+                            const float4 ta = *reinterpret_cast<const float4*>(tb + col0 + 8 * j), tc = *reinterpret_cast<const float4*>(tb + col0 + 8 * j + 4);
+                            __half2* oh = reinterpret_cast<__half2*>(&o);
+                            oh[0] = __floats2half2_rn(fmaxf(__uint_as_float(raw[8 * j]), 0.f) + ta.x, fmaxf(__uint_as_float(raw[8 * j + 1]), 0.f) + ta.y);
+                            oh[1] = __floats2half2_rn(fmaxf(__uint_as_float(raw[8 * j + 2]), 0.f) + ta.z, fmaxf(__uint_as_float(raw[8 * j + 3]), 0.f) + ta.w);
+                            oh[2] = __floats2half2_rn(fmaxf(__uint_as_float(raw[8 * j + 4]), 0.f) + tc.x, fmaxf(__uint_as_float(raw[8 * j + 5]), 0.f) + tc.y);
+                            oh[3] = __floats2half2_rn(fmaxf(__uint_as_float(raw[8 * j + 6]), 0.f) + tc.z, fmaxf(__uint_as_float(raw[8 * j + 7]), 0.f) + tc.w);
+                        }
+                        *reinterpret_cast<uint4*>(hbuf + px * 128 + (((uint32_t)(4 * h + j) ^ (uint32_t)(px & 7)) << 4)) = o;
                     }
-                    uint4 o;
-                    __half2* oh = reinterpret_cast<__half2*>(&o);
-                    oh[0] = __floats2half2_rn(fmaxf(a0.x, 0.f) + t4a.x, fmaxf(a0.y, 0.f) + t4a.y);
-                    oh[1] = __floats2half2_rn(fmaxf(a0.z, 0.f) + t4a.z, fmaxf(a0.w, 0.f) + t4a.w);
-                    oh[2] = __floats2half2_rn(fmaxf(a1.x, 0.f) + t4b.x, fmaxf(a1.y, 0.f) + t4b.y);
-                    oh[3] = __floats2half2_rn(fmaxf(a1.z, 0.f) + t4b.z, fmaxf(a1.w, 0.f) + t4b.w);
-                    return o;
                 };
-                // 32 pixel lanes x 6 rounds cover the 180 halo pixels; two pixels (px, px + 96) per trip
-                for (int px = pl; px < 96 && !(p.debug & 2); px += 32) {
-                    const int px1 = px + 96;
-                    uint4 o0 = make_uint4(0u, 0u, 0u, 0u), o1 = o0;
-                    if (!(p.debug & 1)) {
-                        o0 = conv1_at(px);
-                        if (px1 < kE1HaloRows) o1 = conv1_at(px1);
-                    }
-                    *reinterpret_cast<uint4*>(hbuf + px * 128 + (((uint32_t)g ^ (uint32_t)(px & 7)) << 4)) = o0;
-                    if (px1 < kE1HaloRows) *reinterpret_cast<uint4*>(hbuf + px1 * 128 + (((uint32_t)g ^ (uint32_t)(px1 & 7)) << 4)) = o1;
-                }
+                emit(r0, px0, in0);
+                if (has1 && px1 < kE1HaloRows) emit(r1, px1, in1);
                 ptx::fence_proxy_async();                           // generic-proxy writes -> visible to the tensor core
                 __syncwarp();
                 if (lane == 0) {
@@ -257,7 +359,8 @@ k_enc1_f16(const __grid_constant__ Enc1Maps maps, const Enc1hParams p) {
         const int nchunk = coutp >> 5;                              // 32-column steps
         uint8_t* bufp = gbase + (ring0 - base) + (size_t)ew * 2048; // [32 rows][32 halfs], 64-byte swizzle
         const uint32_t swz = (uint32_t)((lane >> 1) & 3);
-        const int Wh = p.W >> 1;
+        const int Wh = p.W >> 1, HW = p.H * p.W;
+        const int r = 32 * q + lane, yl = r >> 3, xl = r & 7;      // row of the 16 x 8 tile
         int acc = 0;
         uint32_t acc_ph = 0;
         float amax = 0.f;
@@ -265,17 +368,37 @@ k_enc1_f16(const __grid_constant__ Enc1Maps maps, const Enc1hParams p) {
             if constexpr (!kPair) ptx::mbar_arrive(acc_empty0 + 8u * acc);
             else ptx::mbar_arrive_cluster(ptx::map_to_cta(acc_empty0 + 8u * acc, 0));
         };
+        float xn[4] = {0.f, 0.f, 0.f, 0.f};                        // this thread's pixel of x for the NEXT tile
+        int smp_n = 0;                                              // sample index of the next tile, fetched two tiles ahead
+        auto fetch_idx = [&](int wk) {
+            const int tile = wk + crank;
+            const int img = tile / p.tiles_per_img;
+            smp_n = (wk < p.n_tiles && tile < p.n_tiles) ? (p.row_sample ? __ldg(p.row_sample + img) : img) : 0;
+        };
+        auto prefetch = [&](int wk, int smp) {
+            const int tile = wk + crank;
+            int img, y0, x0;
+            tile_geom(tile, img, y0, x0);
+            if (tile < p.n_tiles) {
+                const float* xs = p.x + (size_t)smp * p.x_stride + (size_t)(y0 + yl) * p.W + x0 + xl;
+#pragma unroll
+                for (int ci = 0; ci < kC; ++ci) xn[ci] = __ldg(xs + (size_t)ci * HW);
+            }
+        };
+        fetch_idx(work0);
+        prefetch(work0, smp_n);
+        fetch_idx(work0 + (int)gridDim.x);
         for (int wk = work0; wk < p.n_tiles; wk += gridDim.x) {
             const int tile = wk + crank;
             int img, y0, x0;
             tile_geom(tile, img, y0, x0);
             const bool real = tile < p.n_tiles;
-            const int r = 32 * q + lane, yl = r >> 3, xl = r & 7;          // row of the 16 x 8 tile
-            float xv[4] = {0.f, 0.f, 0.f, 0.f};
-            if (real) {
-                const float* xs = p.x + (size_t)(p.row_sample ? p.row_sample[img] : img) * p.x_stride + (size_t)(y0 + yl) * p.W + x0 + xl;
+            float xv[4];
 #pragma unroll
-                for (int ci = 0; ci < 4; ++ci) if (ci < C) xv[ci] = __ldg(xs + (size_t)ci * p.H * p.W);
+            for (int ci = 0; ci < 4; ++ci) xv[ci] = xn[ci];
+            if (wk + (int)gridDim.x < p.n_tiles) {
+                prefetch(wk + (int)gridDim.x, smp_n);
+                fetch_idx(wk + 2 * (int)gridDim.x);
             }
             ptx::mbar_wait(acc_full0 + 8u * acc, acc_ph);
             ptx::tc_fence_after();
@@ -295,8 +418,7 @@ k_enc1_f16(const __grid_constant__ Enc1Maps maps, const Enc1hParams p) {
                         const float4 b4 = *reinterpret_cast<const float4*>(bias2s + col + 4 * hh);
                         float4 r4 = *reinterpret_cast<const float4*>(rb1s + col + 4 * hh);
 #pragma unroll
-                        for (int ci = 0; ci < 4; ++ci) {
-                            if (ci >= C) break;
+                        for (int ci = 0; ci < kC; ++ci) {
                             const float4 w4 = *reinterpret_cast<const float4*>(rw1s + (size_t)ci * coutp + col + 4 * hh);
                             r4.x = fmaf(xv[ci], w4.x, r4.x); r4.y = fmaf(xv[ci], w4.y, r4.y);
                             r4.z = fmaf(xv[ci], w4.z, r4.z); r4.w = fmaf(xv[ci], w4.w, r4.w);
@@ -345,8 +467,8 @@ k_enc1_f16(const __grid_constant__ Enc1Maps maps, const Enc1hParams p) {
     if constexpr (kPair) ptx::cluster_sync_all();
     if (warp == 0) {
         ptx::tc_fence_after();
-        if constexpr (!kPair) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(2 * p.acc_cols)) : "memory");
-        else asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(2 * p.acc_cols)) : "memory");
+        if constexpr (!kPair) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(4 * p.acc_cols)) : "memory");
+        else asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(4 * p.acc_cols)) : "memory");
     }
 }
 
@@ -362,10 +484,11 @@ struct Enc1hLaunch {
 // `w2` = conv2 weights packed by pack_conv in DTRAJ_PREC_F16 ([tap][chunk][coutp][64] halfs), `w2_rows` its 128-byte rows
 inline int build_enc1h_launch(Enc1hLaunch* E, int C, int H, int coutp, int cout_real, int64_t R, const float* w2, int64_t w2_rows) {
     memset(E, 0, sizeof(*E));
-    if (C < 1 || C > 4 || H % 16 || H > 32 || coutp % 64 || coutp > 256) return fail(DTRAJ_EINVAL, "enc1(f16): unsupported geometry");
+    if (C < 1 || C > 4 || H % 16 || H > 32 || coutp % 64 || coutp > 128) return fail(DTRAJ_EINVAL, "enc1(f16): unsupported geometry");
     Enc1hParams& p = E->p;
     p.C = C; p.H = H; p.W = H; p.coutp = coutp;
     p.n_chunks = coutp / 64;
+    p.n_slices = (9 * C + 2 + 15) / 16;          // 9C taps + two bias slots
     p.tiles_x = H / 8;
     p.tiles_per_img = (H / 16) * p.tiles_x;
     const int64_t nt = R * p.tiles_per_img;
@@ -374,19 +497,17 @@ inline int build_enc1h_launch(Enc1hLaunch* E, int C, int H, int coutp, int cout_
     p.acc_cols = 32;
     while (p.acc_cols < coutp) p.acc_cols *= 2;
     auto fixed_for = [&](int pair) {
-        return (size_t)1024 + (size_t)9 * p.n_chunks * (coutp / (pair ? 2 : 1)) * 128 + kE1Epi * 2048 + 2 * 4 * 240 * 4 +
-               (size_t)(9 * C + 3 + C) * coutp * 4 + 16 + 256;
+        const size_t wr = (size_t)coutp / (pair ? 2 : 1);
+        return (size_t)1024 + (size_t)9 * p.n_chunks * wr * 128 + kE1Epi * 2048 + (size_t)p.n_slices * kA1SliceBytes +
+               (((size_t)p.n_slices * wr * 32 + 1023) & ~(size_t)1023) + (size_t)(6 + C) * coutp * 4 + 16 + 256;
     };
     // pairs halve the resident weights per CTA; without them the weights must still fit next to one halo buffer
     E->pair = (p.n_tiles >= 2 * kNumSMs && !getenv("DTRAJ_NO_PAIR")) ? 1 : 0;
-    if (!E->pair && fixed_for(0) + kE1HaloBytes > 227 * 1024) {
-        if (p.n_tiles < 2) return fail(DTRAJ_EINVAL, "enc1(f16): weights do not fit without a CTA pair");
-        E->pair = 1;
-    }
+    if (!E->pair && fixed_for(0) + kE1HaloBytes > 227 * 1024) E->pair = 1;     // n_tiles >= 2 always (two tiles per 16-row band)
     p.w_rows = coutp / (E->pair ? 2 : 1);
     const size_t fixed = fixed_for(E->pair);
+    if (fixed + kE1HaloBytes > 227 * 1024) return fail(DTRAJ_EINVAL, "enc1(f16): shared memory does not fit (coutp=%d C=%d)", coutp, C);
     int nh = (int)((227 * 1024 - fixed) / kE1HaloBytes);
-    if (nh < 1) return fail(DTRAJ_EINVAL, "enc1(f16): shared memory does not fit (coutp=%d pair=%d)", coutp, E->pair);
     if (nh > 2 * p.n_chunks) nh = 2 * p.n_chunks;
     if (nh > 8) nh = 8;
     p.n_hbuf = nh;
@@ -396,25 +517,36 @@ inline int build_enc1h_launch(Enc1hLaunch* E, int C, int H, int coutp, int cout_
     DTRAJ_TRY(make_w_map(&E->maps.w, w2, w2_rows, p.w_rows, 1));
     E->flops = 2.0 * (double)R * H * H * cout_real * (double)cout_real * 9.0;
     p.debug = getenv("DTRAJ_E1_DEBUG") ? atoi(getenv("DTRAJ_E1_DEBUG")) : 0;
+    p.a1_mode = getenv("DTRAJ_E1_A1MODE") ? atoi(getenv("DTRAJ_E1_A1MODE")) : 0;
     return 0;
 }
 
+typedef void (*Enc1hKernel)(const Enc1Maps, const Enc1hParams);
+inline Enc1hKernel enc1h_kernel(int pair, int C) {
+    static const Enc1hKernel tab[2][4] = {{k_enc1_f16<false, 1>, k_enc1_f16<false, 2>, k_enc1_f16<false, 3>, k_enc1_f16<false, 4>},
+                                          {k_enc1_f16<true, 1>, k_enc1_f16<true, 2>, k_enc1_f16<true, 3>, k_enc1_f16<true, 4>}};
+    return tab[pair ? 1 : 0][C - 1];
+}
+
 inline cudaError_t enc1h_set_smem_attr() {
-    cudaError_t e = cudaFuncSetAttribute(k_enc1_f16<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(k_enc1_f16<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    for (int pair = 0; pair < 2; ++pair)
+        for (int C = 1; C <= 4; ++C) {
+            cudaError_t e = cudaFuncSetAttribute(enc1h_kernel(pair, C), cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+            if (e != cudaSuccess) return e;
+        }
+    return cudaSuccess;
 }
 
 inline int launch_enc1h(const Enc1hLaunch& E, cudaStream_t st) {
     if (!E.pair) {
-        k_enc1_f16<false><<<E.grid, kE1Threads, E.smem, st>>>(E.maps, E.p);
+        enc1h_kernel(0, E.p.C)<<<E.grid, kE1hThreads, E.smem, st>>>(E.maps, E.p);
         DTRAJ_LAUNCH_CHECK();
         return 0;
     }
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3(E.grid);
-    cfg.blockDim = dim3(kE1Threads);
+    cfg.blockDim = dim3(kE1hThreads);
     cfg.dynamicSmemBytes = E.smem;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
@@ -424,7 +556,7 @@ inline int launch_enc1h(const Enc1hLaunch& E, cudaStream_t st) {
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    DTRAJ_CUDA(cudaLaunchKernelEx(&cfg, k_enc1_f16<true>, E.maps, E.p));
+    DTRAJ_CUDA(cudaLaunchKernelEx(&cfg, enc1h_kernel(1, E.p.C), E.maps, E.p));
     return 0;
 }
 
