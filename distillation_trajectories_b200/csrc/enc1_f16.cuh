@@ -97,16 +97,18 @@ k_enc1_f16(const __grid_constant__ Enc1Maps maps, const Enc1hParams p) {
     if (warp == 0) {
         if (ptx::elect_one()) {
             ptx::prefetch_tmap(&maps.w);
-            for (int b = 0; b < p.n_hbuf; ++b) { ptx::mbar_init(hfull(b), kE1Mid * nrep); ptx::mbar_init(hempty(b), 1); }
+            // a role's warps meet at a named barrier and ONE thread arrives for the CTA: a cluster-scope release arrive
+            // costs ~500 cycles of ERRBAR stall per arriving warp (ncu: a third of the mid warps' time when all eight arrived)
+            for (int b = 0; b < p.n_hbuf; ++b) { ptx::mbar_init(hfull(b), nrep); ptx::mbar_init(hempty(b), 1); }
             for (int i = 0; i < 2; ++i) {
                 ptx::mbar_init(acc_full0 + 8u * i, 1);
-                ptx::mbar_init(acc_empty0 + 8u * i, kE1Epi * nrep);
+                ptx::mbar_init(acc_empty0 + 8u * i, nrep);
             }
             ptx::mbar_init(wbar, 1);
-            ptx::mbar_init(a1_full, kE1Mid * nrep);
+            ptx::mbar_init(a1_full, nrep);
             ptx::mbar_init(a1_empty, 1);
             ptx::mbar_init(d1_full, 1);
-            ptx::mbar_init(d1_empty, kE1Mid * nrep);
+            ptx::mbar_init(d1_empty, nrep);
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
         __syncwarp();
@@ -292,8 +294,8 @@ k_enc1_f16(const __grid_constant__ Enc1Maps maps, const Enc1hParams p) {
                     }
             }
             ptx::fence_proxy_async();
-            __syncwarp();
-            if (lane == 0) {
+            asm volatile("bar.sync 9, 256;" ::: "memory");
+            if (mt == 0) {
                 if constexpr (!kPair) ptx::mbar_arrive(a1_full);
                 else ptx::mbar_arrive_cluster(ptx::map_to_cta(a1_full, 0));
             }
@@ -316,14 +318,7 @@ k_enc1_f16(const __grid_constant__ Enc1Maps maps, const Enc1hParams p) {
                 ptx::tmem_ld32(t_d1 + (uint32_t)col0, r0);
                 if (has1) ptx::tmem_ld32(t_d1 + (uint32_t)(p.acc_cols + col0), r1);
                 ptx::tmem_ld_wait();
-                if (c == p.n_chunks - 1) {                          // D1 may be overwritten by the next tile's conv1
-                    ptx::tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) {
-                        if constexpr (!kPair) ptx::mbar_arrive(d1_empty);
-                        else ptx::mbar_arrive_cluster(ptx::map_to_cta(d1_empty, 0));
-                    }
-                }
+                ptx::tc_fence_before();
                 ptx::mbar_wait(hempty(hb), hph ^ 1u);               // the conv2 MMAs that read this buffer have retired
                 uint8_t* hbuf = gbase + (halo0 - base) + (size_t)hb * kE1HaloBytes;
                 // h = relu(D1) + time bias (conv1's folded bias is inside D1), rounded to fp16; zero rows outside the image
@@ -345,10 +340,15 @@ k_enc1_f16(const __grid_constant__ Enc1Maps maps, const Enc1hParams p) {
                 emit(r0, px0, in0);
                 if (has1 && px1 < kE1HaloRows) emit(r1, px1, in1);
                 ptx::fence_proxy_async();                           // generic-proxy writes -> visible to the tensor core
-                __syncwarp();
-                if (lane == 0) {
-                    if constexpr (!kPair) ptx::mbar_arrive(hfull(hb));
-                    else ptx::mbar_arrive_cluster(ptx::map_to_cta(hfull(hb), 0));
+                asm volatile("bar.sync 9, 256;" ::: "memory");
+                if (mt == 0) {
+                    if constexpr (!kPair) {
+                        ptx::mbar_arrive(hfull(hb));
+                        if (c == p.n_chunks - 1) ptx::mbar_arrive(d1_empty);      // D1 may be overwritten by the next tile's conv1
+                    } else {
+                        ptx::mbar_arrive_cluster(ptx::map_to_cta(hfull(hb), 0));
+                        if (c == p.n_chunks - 1) ptx::mbar_arrive_cluster(ptx::map_to_cta(d1_empty, 0));
+                    }
                 }
                 if (++hb == p.n_hbuf) { hb = 0; hph ^= 1u; }
             }
@@ -407,7 +407,11 @@ k_enc1_f16(const __grid_constant__ Enc1Maps maps, const Enc1hParams p) {
                 uint32_t raw[32];
                 ptx::tmem_ld32(t_acc + (uint32_t)(32 * c), raw);
                 ptx::tmem_ld_wait();
-                if (c == nchunk - 1) { ptx::tc_fence_before(); __syncwarp(); if (lane == 0) arrive_acc_empty(); }
+                if (c == nchunk - 1) {
+                    ptx::tc_fence_before();
+                    asm volatile("bar.sync 10, 128;" ::: "memory");
+                    if (ew == 0 && lane == 0) arrive_acc_empty();
+                }
                 uint8_t* rowp = bufp + lane * 64;
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
