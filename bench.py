@@ -364,7 +364,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--seeds", type=int, default=296, help="seeds per GPU per step (x 8 guidance scales x 2 models)")
-    ap.add_argument("--precision", default="tf32", choices=["tf32", "tf32x3", "fp32", "f16"])
+    ap.add_argument("--precision", default="f16", choices=["tf32", "tf32x3", "fp32", "f16"])
     ap.add_argument("--e2e-chunks", type=int, default=1,
                     help="chunks a sweep is cut into in the end-to-end leg (host staging of chunk i+1 overlaps chunk i on the GPU)")
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -11,7 +11,7 @@ import numpy as np
 import torch
 
 from .. import sampling
-from ..engine import UNetEngine, get_precision
+from ..engine import UNetEngine, check_device_errors, get_precision
 from .metrics import trajectory_metrics as tm
 
 
@@ -151,6 +151,7 @@ def compare_trajectories_batched(teacher_model, student_model, config, guidance_
         idx_set = torch.arange(len(samples), dtype=torch.int32).repeat_interleave(G)
         w1 = tm.wasserstein_frames(t_flat, s_flat, torch.from_numpy(idx), idx_set)
     sm = tm.scalar_metrics_batched(red, w1.cpu().numpy(), H * H, D)
+    check_device_errors()
     return {k: sm[k].reshape(len(samples), G) for k in tm.SCALAR_KEYS}, samples
 
 

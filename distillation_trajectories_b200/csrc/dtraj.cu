@@ -888,6 +888,16 @@ extern "C" int dtraj_probe_umma_view(int32_t rows, int32_t start_row, int32_t sb
     return 0;
 }
 
+extern "C" int dtraj_check_errors(void) {
+    unsigned int v = 0;
+    DTRAJ_CUDA(cudaMemcpyFromSymbol(&v, g_umma_error, sizeof(v)));
+    if (!v) return 0;
+    const unsigned int z = 0;
+    DTRAJ_CUDA(cudaMemcpyToSymbol(g_umma_error, &z, sizeof(z)));
+    if (v & 1u) return fail(DTRAJ_ECUDA, "a tcgen05 pipeline role timed out on an mbarrier: results are invalid");
+    return fail(DTRAJ_ERANGE, "fp16 mode: an activation left the fp16 range (|v| > 65504): rerun with precision 'tf32'");
+}
+
 extern "C" unsigned int dtraj_debug_umma_error(void) {
     unsigned int v = 0;
     cudaMemcpyFromSymbol(&v, g_umma_error, sizeof(v));

@@ -14,14 +14,16 @@ from ._lib import (PREC_FP32, PREC_TF32, PREC_TF32X3, RULE_S1, RULE_S2, RULE_S3,
                    VAR_NONE, DtrajError)
 
 _default_precision = {"S1": os.environ.get("DTRAJ_PRECISION_S1", os.environ.get("DTRAJ_PRECISION", "tf32x3")),
-                      "S2": os.environ.get("DTRAJ_PRECISION_S2", os.environ.get("DTRAJ_PRECISION", "tf32")),
-                      "S3": os.environ.get("DTRAJ_PRECISION_S3", os.environ.get("DTRAJ_PRECISION", "tf32")),
+                      "S2": os.environ.get("DTRAJ_PRECISION_S2", os.environ.get("DTRAJ_PRECISION", "f16")),
+                      "S3": os.environ.get("DTRAJ_PRECISION_S3", os.environ.get("DTRAJ_PRECISION", "f16")),
                       "forward": os.environ.get("DTRAJ_PRECISION", "tf32x3")}
 
 
 def set_precision(mode, path=None):
-    """Choose the conv arithmetic: 'fp32' (CUDA cores), 'tf32' (tcgen05, one pass) or 'tf32x3'
-    (tcgen05, error-compensated).  ``path`` in {'S1','S2','S3','forward'} or None for all."""
+    """Choose the conv arithmetic: 'fp32' (CUDA cores), 'tf32' (tcgen05 kind::tf32, one pass), 'tf32x3'
+    (tcgen05, error-compensated) or 'f16' (tcgen05 kind::f16: fp16 feature maps and weights -- the same 11-bit
+    significand as tf32 -- with fp32 accumulation; a value outside the fp16 range raises DtrajError instead of
+    overflowing silently).  ``path`` in {'S1','S2','S3','forward'} or None for all."""
     if mode not in _lib.PRECISIONS:
         raise ValueError(f"precision must be one of {sorted(_lib.PRECISIONS)}")
     for k in ([path] if path else list(_default_precision)):
@@ -236,6 +238,12 @@ def cached_sampler(engine, key, factory):
         s = factory()
         engine._samplers[key] = s
     return s
+
+
+def check_device_errors():
+    """Raise DtrajError if a kernel flagged a pipeline time-out or an fp16 overflow since the last check.
+    Synchronises the device: called where results are read back to the host anyway."""
+    _lib.check(_lib.load().dtraj_check_errors())
 
 
 def umma_error_flag():

@@ -166,6 +166,7 @@ def finish_chunk(red, w1, ck, config, sums):
     H, D = config.image_size, config.channels * config.image_size ** 2
     red_h = red if isinstance(red, np.ndarray) else red.cpu().numpy()
     w1_h = w1 if isinstance(w1, np.ndarray) else w1.cpu().numpy()
+    te.check_device_errors()                          # pipeline time-out / fp16 overflow flagged by a kernel of this chunk
     for i in range(red_h.shape[0]):
         sm = tm.scalar_metrics_batched(red_h[i], w1_h[i], H * H, D)
         for j, k in enumerate(tm.SCALAR_KEYS):

@@ -16,7 +16,7 @@ import torch
 
 from .. import sampling
 from . import trajectory_store as store
-from ..engine import UNetEngine, get_precision
+from ..engine import UNetEngine, check_device_errors, get_precision
 from ..analysis.metrics import trajectory_metrics as tm
 from ..analysis.metrics.trajectory_metrics import compute_trajectory_metrics
 
@@ -116,6 +116,7 @@ class TrajectoryManager:
             eng = UNetEngine.for_model(model, x_T.shape[2], max(ts) + 1, get_precision("S3"), self.device)
             traj = sampling.s3_sample(eng, x_T, ts, cfg.teacher_steps, None if noise is None else noise[:max(n_upd, 1)])
             out.append((traj.cpu().numpy(), ts))
+            check_device_errors()
         return store.write_pack(cfg.trajectory_dir, self.size_factor, list(sample_ids), out[0][0], out[1][0],
                                 out[0][1], out[1][1])
 

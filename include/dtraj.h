@@ -32,6 +32,7 @@ extern "C" {
 #define DTRAJ_ECUDA       (-2)  /* CUDA runtime or driver error                */
 #define DTRAJ_EMISSING    (-3)  /* a state_dict tensor the model needs is absent */
 #define DTRAJ_ENOMEM      (-4)  /* workspace too small                         */
+#define DTRAJ_ERANGE      (-5)  /* DTRAJ_PREC_F16: a value left the fp16 range  */
 
 /* arithmetic used for the 3x3 / 1x1 convolutions of the U-Net */
 #define DTRAJ_PREC_FP32     0   /* CUDA-core fp32 implicit GEMM (exact mode)                 */
@@ -207,6 +208,14 @@ int dtraj_wasserstein(const float* teacher, const float* student,
                       int64_t N, int32_t L, int32_t D,
                       const int32_t* idx, const int32_t* idx_set, int32_t K,
                       float* out, void* stream);
+
+/* ------------------------------------------------------------------ device-side error state
+ * Kernels never trap: a tcgen05 pipeline role whose mbarrier wait times out, or an
+ * activation that leaves the fp16 range in DTRAJ_PREC_F16, sets a sticky device flag.
+ * dtraj_check_errors() reads and clears it (it synchronises the device: call it where the
+ * results are read back anyway).  Returns 0, DTRAJ_ECUDA (pipeline time-out: results are
+ * invalid) or DTRAJ_ERANGE (fp16 overflow: rerun with DTRAJ_PREC_TF32). */
+int dtraj_check_errors(void);
 
 /* ------------------------------------------------------------------ test hooks
  * Single convolution layer through either implementation, for kernel-vs-kernel parity

@@ -105,7 +105,7 @@ def test_compare_trajectories_fixture(name):
         res = te.compare_trajectories(teacher, student, cfg, guidance_scales=[1.0, 3.0], size_factor=0.5, num_samples=2)
     finally:
         sampling.set_noise_device(None)
-        set_precision("tf32", "S2")
+        set_precision("f16", "S2")
     assert set(res) == {"teacher_metrics", "student_metrics"}
     for gs in (1.0, 3.0):
         d = res["student_metrics"][gs]

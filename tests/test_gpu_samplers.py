@@ -87,7 +87,7 @@ def test_s2_generate_trajectory_fixture(case, prec):
             assert len(traj) == cfg.timesteps + 1 and all(f.device.type == "cpu" and f.shape == noise.shape for f in traj)
             assert torch.equal(traj[-1], traj[-2]) and torch.equal(traj[0], noise)
             assert_close(stack(traj), g[f"s2_{who}_w{w}"], RTOL, ATOL, f"S2 {who} w={w} [{prec}]")
-    set_precision("tf32", "S2")
+    set_precision("f16", "S2")
     assert umma_error_flag() == 0
 
 
@@ -106,7 +106,7 @@ def test_s3_trajectory_manager_fixture(case, prec, tmp_path):
         assert_close(stack(tt), g[f"s3_{tag}_teacher"], RTOL, ATOL, f"S3 {tag} teacher [{prec}]")
         assert_close(stack(st), g[f"s3_{tag}_student"], RTOL, ATOL, f"S3 {tag} student [{prec}]")
     cfg.sample_steps = cfg.teacher_steps = cfg.student_steps = T
-    set_precision("tf32", "S3")
+    set_precision("f16", "S3")
 
 
 # ------------------------------------------------------------------ BASELINE-size cases vs the oracle
@@ -135,7 +135,7 @@ def test_s2_full_length_vs_oracle(C, H, sf, w, prec):
     noise = torch.randn(1, C, H, H)
     want = osmp.s2_generate_trajectory(oracle_fn(model), noise, 50, seed=42, guidance_scale=w)
     got = te.generate_trajectory(model, noise, 50, "cuda", seed=42, guidance_scale=w)
-    set_precision("tf32", "S2")
+    set_precision("f16", "S2")
     assert_close(stack(got), stack(want), RTOL, ATOL, f"S2 {C}x{H} sf={sf} w={w} [{prec}]")
     assert umma_error_flag() == 0
 
@@ -180,3 +180,20 @@ def test_private_generators_reproduce_global_seeding():
             torch.manual_seed(k)
             b = torch.randn(1, 3, 32, 32, device=dev)
             assert torch.equal(a, b), (dev, k)
+
+
+def test_f16_overflow_is_reported_not_hidden():
+    """fp16 mode: activations beyond 65504 must surface as DtrajError at the read-back, never as silent inf/NaN frames"""
+    from distillation_trajectories_b200 import DtrajError
+    cfg = Cfg(1, 16, 4)
+    model = make_model(cfg, 0.2, 21, device="cuda")
+    with torch.no_grad():
+        model.enc2.conv1.weight.mul_(3e4)          # folded weights stay inside the fp16 range, the activations do not
+    torch.manual_seed(1)
+    noise = torch.randn(1, 1, 16, 16)
+    set_precision("f16", "S2")
+    with pytest.raises(DtrajError, match="fp16 range"):
+        te.generate_trajectory(model, noise, 4, "cuda", seed=1, guidance_scale=2.0)
+    assert umma_error_flag() == 0                  # the check clears the sticky flag
+    traj = te.generate_trajectory(make_model(cfg, 0.2, 21, device="cuda"), noise, 4, "cuda", seed=1, guidance_scale=2.0)
+    assert all(torch.isfinite(f).all() for f in traj)

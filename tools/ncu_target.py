@@ -11,7 +11,7 @@ from distillation_trajectories_b200 import grid
 from distillation_trajectories_b200.models import DiffusionUNet
 
 seeds = int(sys.argv[1]) if len(sys.argv) > 1 else 32
-prec = sys.argv[2] if len(sys.argv) > 2 else "tf32"
+prec = sys.argv[2] if len(sys.argv) > 2 else "f16"
 use_graph = (sys.argv[3] != "eager") if len(sys.argv) > 3 else True
 dev = torch.device("cuda", 0)
 models = []

@@ -7,7 +7,7 @@ from distillation_trajectories_b200 import grid
 from distillation_trajectories_b200.engine import UNetEngine
 from distillation_trajectories_b200.models import DiffusionUNet
 seeds = int(sys.argv[1]) if len(sys.argv) > 1 else 296
-prec = sys.argv[2] if len(sys.argv) > 2 else "tf32"
+prec = sys.argv[2] if len(sys.argv) > 2 else "f16"
 dev = torch.device("cuda", 0)
 models = []
 for sf, seed in ((1.0, 0), (0.5, 1050)):
