@@ -33,8 +33,10 @@ struct Enc1hParams {
     int C, H, W, coutp;
     int n_chunks;                // coutp / 64: K chunks of conv2
     int n_tiles, tiles_x, tiles_per_img;
+    int lg_tx, lg_tpi;           // log2(tiles_x), log2(tiles_per_img): both are powers of two (H = 16 or 32)
     int n_hbuf;                  // halo chunk buffers in the ring (>= 1; 2 x n_chunks when they fit)
-    int acc_cols;                // TMEM columns per accumulator; layout [acc0 | acc1 | D1 rows 0-127 | D1 rows 128-255]
+    int acc_cols;                // TMEM columns per accumulator; layout [acc0 | acc1 | n_d1 x (D1 rows 0-127 | D1 rows 128-255)]
+    int n_d1;                    // D1 buffers: 2 when 6 x acc_cols <= 512 (conv1 of tile i+2 runs while tile i is converted), else 1
     int w_rows;                  // output channels this CTA holds: coutp, or coutp / 2 in pair mode
     int n_slices;                // K slices (16 values) of conv1's GEMM: ceil(9C / 16)
     int a1_mode;                 // shared-memory layout of the 32-byte-row operands: 0 SWIZZLE_32B, 1 SWIZZLE_NONE core matrices
@@ -78,8 +80,9 @@ k_enc1_f16(const __grid_constant__ Enc1Maps maps, const Enc1hParams p) {
     auto hfull = [&](int b) { return bar0 + 8u * b; };
     auto hempty = [&](int b) { return bar0 + 64u + 8u * b; };
     const uint32_t acc_full0 = bar0 + 128u, acc_empty0 = bar0 + 144u, wbar = bar0 + 160u;
-    const uint32_t a1_full = bar0 + 168u, a1_empty = bar0 + 176u, d1_full = bar0 + 184u, d1_empty = bar0 + 192u;
-    const uint32_t tmem_slot = bar0 + 200u;
+    const uint32_t a1_full = bar0 + 168u, d1_full0 = bar0 + 176u, d1_empty0 = bar0 + 192u;   // d1_*: [2]
+    const uint32_t tmem_slot = bar0 + 208u;
+    const uint32_t tmem_cols = (uint32_t)((2 + 2 * p.n_d1) * p.acc_cols) <= 256u ? 256u : 512u;
     volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gbase + (tmem_slot - base));
     float* cst = reinterpret_cast<float*>(gbase + (cst0 - base));
     const float* b3s = cst;
@@ -106,17 +109,15 @@ k_enc1_f16(const __grid_constant__ Enc1Maps maps, const Enc1hParams p) {
             }
             ptx::mbar_init(wbar, 1);
             ptx::mbar_init(a1_full, nrep);
-            ptx::mbar_init(a1_empty, 1);
-            ptx::mbar_init(d1_full, 1);
-            ptx::mbar_init(d1_empty, nrep);
+            for (int i = 0; i < 2; ++i) { ptx::mbar_init(d1_full0 + 8u * i, 1); ptx::mbar_init(d1_empty0 + 8u * i, nrep); }
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
         __syncwarp();
         if constexpr (!kPair) {
-            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"((uint32_t)(4 * p.acc_cols)) : "memory");
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(tmem_cols) : "memory");
             asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
         } else {
-            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"((uint32_t)(4 * p.acc_cols)) : "memory");
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(tmem_cols) : "memory");
             asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
         }
     }
@@ -152,10 +153,10 @@ k_enc1_f16(const __grid_constant__ Enc1Maps maps, const Enc1hParams p) {
     const uint32_t tmem_base = *tmem_slot_ptr;
 
     auto tile_geom = [&](int tile, int& img, int& y0, int& x0) {
-        img = tile / p.tiles_per_img;
-        const int r = tile - img * p.tiles_per_img;
-        y0 = (r / p.tiles_x) * 16;
-        x0 = (r % p.tiles_x) * 8;
+        img = tile >> p.lg_tpi;
+        const int r = tile & (p.tiles_per_img - 1);
+        y0 = (r >> p.lg_tx) * 16;
+        x0 = (r & (p.tiles_x - 1)) * 8;
     };
 
     if (warp == 0) {
@@ -181,15 +182,17 @@ k_enc1_f16(const __grid_constant__ Enc1Maps maps, const Enc1hParams p) {
                 ? (((uint64_t)1 << 16) | ((uint64_t)(256 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)6 << 61))
                 : (((uint64_t)(128 >> 4) << 16) | ((uint64_t)(256 >> 4) << 32) | ((uint64_t)1 << 46));
             auto kdesc = [&](uint32_t addr) { return kdesc0 | (uint64_t)((addr >> 4) & 0x3fffu); };
-            const uint32_t d1_tmem = tmem_base + (uint32_t)(2 * p.acc_cols);
             int hb = 0, acc = 0, it = 0;
             uint32_t hph = 0, acc_ph = 0;
             bool ok = ptx::mbar_wait(wbar, 0u);
-            // conv1 of tile-iteration `j`: D1[g] = A1[rows 128g ..] * W1^T, g = 0, 1
+            const int n_my = work0 < p.n_tiles ? (p.n_tiles - work0 + (int)gridDim.x - 1) / (int)gridDim.x : 0;   // tile iterations of this CTA (pair)
+            // conv1 of tile-iteration j into D1 buffer j % n_d1: D1[g] = A1[rows 128g ..] * W1^T, g = 0, 1
             auto issue_conv1 = [&](int j) {
+                const int b = j & (p.n_d1 - 1);
                 ok = ok && ptx::mbar_wait(a1_full, (uint32_t)(j & 1));
-                ok = ok && ptx::mbar_wait(d1_empty, (uint32_t)((j & 1) ^ 1));
+                ok = ok && ptx::mbar_wait(d1_empty0 + 8u * b, (uint32_t)(((j >> (p.n_d1 - 1)) & 1) ^ 1));
                 ptx::tc_fence_after();
+                const uint32_t d1_tmem = tmem_base + (uint32_t)((2 + 2 * b) * p.acc_cols);
                 for (int g = 0; g < 2; ++g)
                     for (int s = 0; s < p.n_slices; ++s) {
                         const uint64_t ad = kdesc(a1_0 + (uint32_t)s * kA1SliceBytes + (uint32_t)g * 4096u);
@@ -197,18 +200,21 @@ k_enc1_f16(const __grid_constant__ Enc1Maps maps, const Enc1hParams p) {
                         if constexpr (!kPair) ptx::mma_f16(d1_tmem + (uint32_t)(g * p.acc_cols), ad, bd, idesc, s ? 1u : 0u);
                         else ptx::mma_f16_2sm(d1_tmem + (uint32_t)(g * p.acc_cols), ad, bd, idesc, s ? 1u : 0u);
                     }
-                if constexpr (kPair) { ptx::tc_commit_2sm(a1_empty, cmask); ptx::tc_commit_2sm(d1_full, cmask); }
-                else { ptx::tc_commit(a1_empty); ptx::tc_commit(d1_full); }
+                // (its completion also frees A1: the mid warps write the next tile's A1 after seeing d1_full)
+                if constexpr (kPair) ptx::tc_commit_2sm(d1_full0 + 8u * b, cmask); else ptx::tc_commit(d1_full0 + 8u * b);
             };
-            if (work0 < p.n_tiles) issue_conv1(0);
+            // A1 is single-buffered: conv1(j + 1) can only be issued after the mid warps saw conv1(j) complete and wrote A1(j + 1)
+            if (n_my > 0) issue_conv1(0);
+            if (p.n_d1 == 2 && n_my > 1) issue_conv1(1);
             for (int wk = work0; wk < p.n_tiles && ok; wk += gridDim.x, ++it) {
                 ok = ptx::mbar_wait(acc_empty0 + 8u * acc, acc_ph ^ 1u);
                 ptx::tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.acc_cols);
                 uint32_t accum = 0u;
                 for (int c = 0; c < p.n_chunks && ok; ++c) {
-                    // the next tile's conv1 goes in front of this tile's last chunk: its halo is ready when that chunk retires
-                    if (c == p.n_chunks - 1 && wk + (int)gridDim.x < p.n_tiles) issue_conv1(it + 1);
+                    // one D1 buffer: the next tile's conv1 goes in front of this tile's last chunk, so that its conversion
+                    // overlaps that chunk's MMAs
+                    if (p.n_d1 == 1 && c == p.n_chunks - 1 && it + 1 < n_my) issue_conv1(it + 1);
                     ok = ok && ptx::mbar_wait(hfull(hb), hph);      // this chunk's halo tile is in shared memory (both CTAs)
                     ptx::tc_fence_after();
                     const uint32_t hbuf = halo0 + (uint32_t)hb * kE1HaloBytes;
@@ -231,6 +237,8 @@ k_enc1_f16(const __grid_constant__ Enc1Maps maps, const Enc1hParams p) {
                 }
                 if constexpr (kPair) ptx::tc_commit_2sm(acc_full0 + 8u * acc, cmask); else ptx::tc_commit(acc_full0 + 8u * acc);
                 if (++acc == 2) { acc = 0; acc_ph ^= 1u; }
+                // two D1 buffers: tile it's buffer is free once its conversion is done; refill it for tile it + 2
+                if (p.n_d1 == 2 && it + 2 < n_my) issue_conv1(it + 2);
             }
         }
     } else if (warp >= 2 + kE1Epi) {
@@ -248,10 +256,10 @@ k_enc1_f16(const __grid_constant__ Enc1Maps maps, const Enc1hParams p) {
         const int ry0 = px0 / 10, rx0 = px0 - ry0 * 10, ry1 = px1 / 10, rx1 = px1 - ry1 * 10;
         float xr[kC][9];                                            // prefetched conv1 inputs of the A1 row: [cin][tap]
         // per-image indices are fetched TWO tiles ahead and the pixels ONE tile ahead, so no load is waited for in the loop
-        int smp_n = 0, var_n = 0, var_c = 0;                        // sample of the next tile; variant of the next / current tile
+        int smp_n = 0, var_n = 0;                                   // indices of the tile fetched last (two tiles ahead of the pixels)
         auto fetch_idx = [&](int wk) {
             const int tile = wk + crank;
-            const int img = tile / p.tiles_per_img;
+            const int img = tile >> p.lg_tpi;
             const bool real = wk < p.n_tiles && tile < p.n_tiles;
             smp_n = real ? (p.row_sample ? __ldg(p.row_sample + img) : img) : 0;
             var_n = (real && p.row_variant) ? __ldg(p.row_variant + img) : 0;
@@ -271,47 +279,74 @@ k_enc1_f16(const __grid_constant__ Enc1Maps maps, const Enc1hParams p) {
                     xr[ci][t9] = (real && sy >= 0 && sy < p.H && sx >= 0 && sx < p.W) ? __ldg(xs + (size_t)ci * HW + sy * p.W + sx) : 0.f;
                 }
         };
-        int hb = 0, it = 0;
+        // xr -> this thread's A1 row: per K slice two 16-byte stores (taps, the two bias slots = 1.0, zero padding)
+        auto store_a1 = [&]() {
+            if (a1_row) {
+#pragma unroll
+                for (int sl = 0; sl < (9 * kC + 2 + 15) / 16; ++sl)
+#pragma unroll
+                    for (int kc = 0; kc < 2; ++kc) {
+                        float v[8];
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) {
+                            const int k = 16 * sl + 8 * kc + e;
+                            v[e] = k < 9 * kC ? xr[k % kC][k / kC] : ((k == kBiasK || k == kBiasK + 1) ? 1.f : 0.f);
+                        }
+                        uint4 o;
+                        __half2* oh = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) oh[e] = __floats2half2_rn(v[2 * e], v[2 * e + 1]);
+                        *reinterpret_cast<uint4*>(a1p + sl * kA1SliceBytes + k16_off(mt, kc, p.a1_mode)) = o;
+                    }
+            }
+        };
+        // the CTA's single arrival on (the leader's) barrier `bar`, after the role's warps met at a named barrier
+        auto arrive_one = [&](uint32_t bar) {
+            if constexpr (!kPair) ptx::mbar_arrive(bar);
+            else asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(ptx::map_to_cta(bar, 0)) : "memory");
+        };
+        auto release_fence = [&]() {
+            if constexpr (kPair) asm volatile("fence.acq_rel.cluster;" ::: "memory");
+        };
+        // Software pipeline, at the top of iteration `it`: A1(it) written (conv1(it) issued or done), xr = pixels of tile
+        // it + 1, var0 / var1 = variants of tiles it / it + 1, (smp_n, var_n) = indices of tile it + 2.
+        const int G = (int)gridDim.x;
+        int hb = 0, it = 0, var0 = 0, var1 = 0;
         uint32_t hph = 0;
-        fetch_idx(work0);
-        prefetch(work0, smp_n);
-        var_c = var_n;
-        fetch_idx(work0 + (int)gridDim.x);
-        for (int wk = work0; wk < p.n_tiles; wk += gridDim.x, ++it) {
+        if (work0 < p.n_tiles) {
+            fetch_idx(work0);
+            prefetch(work0, smp_n);
+            var0 = var_n;
+            fetch_idx(work0 + G);
+            store_a1();                                             // A1(0)
+            ptx::fence_proxy_async();
+            asm volatile("bar.sync 9, 256;" ::: "memory");
+            if (mt == 0) { release_fence(); arrive_one(a1_full); }
+            if (work0 + G < p.n_tiles) prefetch(work0 + G, smp_n);
+            var1 = var_n;
+            fetch_idx(work0 + 2 * G);
+        }
+        for (int wk = work0; wk < p.n_tiles; wk += G, ++it) {
             const int tile = wk + crank;
             int img, y0, x0;
             tile_geom(tile, img, y0, x0);
             const bool real = tile < p.n_tiles;
-            // ---- A1 row of this tile (the MMAs of the previous tile's conv1 have retired)
-            ptx::mbar_wait(a1_empty, (uint32_t)((it & 1) ^ 1));
-            if (a1_row) {
-#pragma unroll
-                for (int ci = 0; ci < kC; ++ci)
-#pragma unroll
-                    for (int t9 = 0; t9 < 9; ++t9) {
-                        const int k = t9 * kC + ci;
-                        *reinterpret_cast<__half*>(a1p + (k >> 4) * kA1SliceBytes + k16_off(mt, (k >> 3) & 1, p.a1_mode) + (k & 7) * 2) = __float2half_rn(xr[ci][t9]);
-                    }
+            const int b = it & (p.n_d1 - 1);
+            ptx::mbar_wait(d1_full0 + 8u * b, (uint32_t)((it >> (p.n_d1 - 1)) & 1));    // conv1(it) done: D1 readable, A1 free
+            ptx::tc_fence_after();
+            const bool next = wk + G < p.n_tiles;
+            if (next) {
+                store_a1();                                         // A1(it + 1); published together with the first halo chunk below
+                if (wk + 2 * G < p.n_tiles) prefetch(wk + 2 * G, smp_n);          // loads stay in flight under the conversion below
             }
-            ptx::fence_proxy_async();
-            asm volatile("bar.sync 9, 256;" ::: "memory");
-            if (mt == 0) {
-                if constexpr (!kPair) ptx::mbar_arrive(a1_full);
-                else ptx::mbar_arrive_cluster(ptx::map_to_cta(a1_full, 0));
-            }
-            const float* tb = tbs + var_c * coutp;
-            if (wk + (int)gridDim.x < p.n_tiles) {                  // loads stay in flight under the conversion below
-                prefetch(wk + (int)gridDim.x, smp_n);
-                var_c = var_n;
-                fetch_idx(wk + 2 * (int)gridDim.x);
-            }
+            const float* tb = tbs + var0 * coutp;
+            var0 = var1; var1 = var_n;
+            fetch_idx(wk + 3 * G);
             // ---- D1 -> halo chunk buffers
             const int yy0 = y0 - 1 + ry0, xx0 = x0 - 1 + rx0, yy1 = y0 - 1 + ry1, xx1 = x0 - 1 + rx1;
             const bool in0 = real && yy0 >= 0 && yy0 < p.H && xx0 >= 0 && xx0 < p.W;                       // else: conv2's zero padding
             const bool in1 = real && px1 < kE1HaloRows && yy1 >= 0 && yy1 < p.H && xx1 >= 0 && xx1 < p.W;
-            ptx::mbar_wait(d1_full, (uint32_t)(it & 1));
-            ptx::tc_fence_after();
-            const uint32_t t_d1 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(2 * p.acc_cols);
+            const uint32_t t_d1 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((2 + 2 * b) * p.acc_cols);
             for (int c = 0; c < p.n_chunks; ++c) {
                 const int col0 = 64 * c + 32 * h;                   // this warp's 32 channels of the chunk
                 uint32_t r0[32], r1[32];
@@ -341,14 +376,11 @@ k_enc1_f16(const __grid_constant__ Enc1Maps maps, const Enc1hParams p) {
                 if (has1 && px1 < kE1HaloRows) emit(r1, px1, in1);
                 ptx::fence_proxy_async();                           // generic-proxy writes -> visible to the tensor core
                 asm volatile("bar.sync 9, 256;" ::: "memory");
-                if (mt == 0) {
-                    if constexpr (!kPair) {
-                        ptx::mbar_arrive(hfull(hb));
-                        if (c == p.n_chunks - 1) ptx::mbar_arrive(d1_empty);      // D1 may be overwritten by the next tile's conv1
-                    } else {
-                        ptx::mbar_arrive_cluster(ptx::map_to_cta(hfull(hb), 0));
-                        if (c == p.n_chunks - 1) ptx::mbar_arrive_cluster(ptx::map_to_cta(d1_empty, 0));
-                    }
+                if (mt == 0) {                                      // one release fence, then relaxed arrivals
+                    release_fence();
+                    if (c == 0 && next) arrive_one(a1_full);
+                    arrive_one(hfull(hb));
+                    if (c == p.n_chunks - 1) arrive_one(d1_empty0 + 8u * b);      // this D1 buffer may be overwritten
                 }
                 if (++hb == p.n_hbuf) { hb = 0; hph ^= 1u; }
             }
@@ -372,7 +404,7 @@ k_enc1_f16(const __grid_constant__ Enc1Maps maps, const Enc1hParams p) {
         int smp_n = 0;                                              // sample index of the next tile, fetched two tiles ahead
         auto fetch_idx = [&](int wk) {
             const int tile = wk + crank;
-            const int img = tile / p.tiles_per_img;
+            const int img = tile >> p.lg_tpi;
             smp_n = (wk < p.n_tiles && tile < p.n_tiles) ? (p.row_sample ? __ldg(p.row_sample + img) : img) : 0;
         };
         auto prefetch = [&](int wk, int smp) {
@@ -471,8 +503,8 @@ k_enc1_f16(const __grid_constant__ Enc1Maps maps, const Enc1hParams p) {
     if constexpr (kPair) ptx::cluster_sync_all();
     if (warp == 0) {
         ptx::tc_fence_after();
-        if constexpr (!kPair) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(4 * p.acc_cols)) : "memory");
-        else asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(4 * p.acc_cols)) : "memory");
+        if constexpr (!kPair) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
+        else asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
     }
 }
 
@@ -495,11 +527,14 @@ inline int build_enc1h_launch(Enc1hLaunch* E, int C, int H, int coutp, int cout_
     p.n_slices = (9 * C + 2 + 15) / 16;          // 9C taps + two bias slots
     p.tiles_x = H / 8;
     p.tiles_per_img = (H / 16) * p.tiles_x;
+    p.lg_tx = H == 16 ? 1 : 2;
+    p.lg_tpi = H == 16 ? 1 : 3;
     const int64_t nt = R * p.tiles_per_img;
     if (nt >= ((int64_t)1 << 30)) return fail(DTRAJ_EINVAL, "enc1(f16): batch too large");
     p.n_tiles = (int)nt;
     p.acc_cols = 32;
     while (p.acc_cols < coutp) p.acc_cols *= 2;
+    p.n_d1 = (6 * p.acc_cols <= 512 && !getenv("DTRAJ_E1_D1SINGLE")) ? 2 : 1;
     auto fixed_for = [&](int pair) {
         const size_t wr = (size_t)coutp / (pair ? 2 : 1);
         return (size_t)1024 + (size_t)9 * p.n_chunks * wr * 128 + kE1Epi * 2048 + (size_t)p.n_slices * kA1SliceBytes +
