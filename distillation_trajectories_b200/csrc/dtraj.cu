@@ -898,6 +898,14 @@ extern "C" int dtraj_check_errors(void) {
     return fail(DTRAJ_ERANGE, "fp16 mode: an activation left the fp16 range (|v| > 65504): rerun with precision 'tf32'");
 }
 
+extern "C" int dtraj_error_flag_async(uint32_t* host_flag, void* stream) {
+    if (!host_flag) return fail(DTRAJ_EINVAL, "error_flag_async: null destination");
+    void* sym = nullptr;
+    DTRAJ_CUDA(cudaGetSymbolAddress(&sym, g_umma_error));
+    DTRAJ_CUDA(cudaMemcpyAsync(host_flag, sym, sizeof(uint32_t), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    return 0;
+}
+
 extern "C" unsigned int dtraj_debug_umma_error(void) {
     unsigned int v = 0;
     cudaMemcpyFromSymbol(&v, g_umma_error, sizeof(v));

@@ -16,7 +16,7 @@ of the per-frame reductions + the f64 scalar formulas).
 import numpy as np
 import torch
 
-from . import sampling
+from . import _lib, sampling
 from .analysis import trajectory_engine as te
 from .analysis.metrics import trajectory_metrics as tm
 
@@ -136,17 +136,21 @@ class _Readback:
         ready.record(torch.cuda.current_stream(device))
         self.red_h = torch.empty(red.shape, dtype=red.dtype, pin_memory=True)
         self.w1_h = torch.empty(w1.shape, dtype=w1.dtype, pin_memory=True)
+        self.flag_h = torch.zeros(1, dtype=torch.int32, pin_memory=True)   # device error word, read without a device-wide sync
         self.keep = (red, w1)                       # keep the device tensors alive until the copy is done
         with torch.cuda.stream(self.stream):
             self.stream.wait_event(ready)
             self.red_h.copy_(red, non_blocking=True)
             self.w1_h.copy_(w1, non_blocking=True)
+            _lib.check(_lib.load().dtraj_error_flag_async(self.flag_h.data_ptr(), self.stream.cuda_stream))
             self.done = torch.cuda.Event()
             self.done.record(self.stream)
 
     def wait(self):
         self.done.synchronize()
         self.keep = None
+        if int(self.flag_h[0]) != 0:
+            te.check_device_errors()                  # raises (pipeline time-out / fp16 overflow) and clears the flag
         return self.red_h.numpy(), self.w1_h.numpy()
 
 
@@ -164,9 +168,10 @@ def finish_chunk(red, w1, ck, config, sums):
     """Device-to-host copy of the reductions and the f64 scalar formulas; accumulates into ``sums``.
     ``red`` / ``w1`` are device tensors or the numpy arrays of a finished ``_Readback``.  Returns the bytes copied."""
     H, D = config.image_size, config.channels * config.image_size ** 2
-    red_h = red if isinstance(red, np.ndarray) else red.cpu().numpy()
-    w1_h = w1 if isinstance(w1, np.ndarray) else w1.cpu().numpy()
-    te.check_device_errors()                          # pipeline time-out / fp16 overflow flagged by a kernel of this chunk
+    if not isinstance(red, np.ndarray):               # (a finished _Readback has checked the device error word already)
+        red, w1 = red.cpu().numpy(), w1.cpu().numpy()
+        te.check_device_errors()                      # pipeline time-out / fp16 overflow flagged by a kernel of this chunk
+    red_h, w1_h = red, w1
     for i in range(red_h.shape[0]):
         sm = tm.scalar_metrics_batched(red_h[i], w1_h[i], H * H, D)
         for j, k in enumerate(tm.SCALAR_KEYS):

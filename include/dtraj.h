@@ -216,6 +216,9 @@ int dtraj_wasserstein(const float* teacher, const float* student,
  * results are read back anyway).  Returns 0, DTRAJ_ECUDA (pipeline time-out: results are
  * invalid) or DTRAJ_ERANGE (fp16 overflow: rerun with DTRAJ_PREC_TF32). */
 int dtraj_check_errors(void);
+/* Non-blocking form for pipelined callers: enqueue a copy of the flag word into `host_flag` (pinned host memory) on
+ * `stream`; a non-zero word read after the stream has reached that point means "call dtraj_check_errors()". */
+int dtraj_error_flag_async(uint32_t* host_flag, void* stream);
 
 /* ------------------------------------------------------------------ test hooks
  * Single convolution layer through either implementation, for kernel-vs-kernel parity
