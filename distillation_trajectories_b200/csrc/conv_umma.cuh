@@ -312,7 +312,8 @@ k_conv_umma_t(const __grid_constant__ UmmaMaps maps, const UmmaConv p) {
             const int w_half = w_rows / p.cluster;             // rows this CTA fetches (and multicasts, unless paired)
             const uint32_t w_off = kPair ? 0u : (uint32_t)(crank * w_half) * 128u;
             // pair: the LEADER's barrier collects the bytes of both CTAs' loads
-            const uint32_t tx_bytes = (uint32_t)p.kbs * (kATileBytes + b_bytes) * (kPair ? 2u : 1u);
+            // (timing experiments: debug bit 0 skips the pixel loads, bit 1 the weight loads -- the MMAs then read stale smem)
+            const uint32_t tx_bytes = (uint32_t)p.kbs * (((p.debug & 1) ? 0u : (uint32_t)kATileBytes) + ((p.debug & 2) ? 0u : b_bytes)) * (kPair ? 2u : 1u);
             const uint32_t act_off = p.swap ? (uint32_t)p.kbs * kATileBytes : 0u;   // N slots follow the M slots
             const uint32_t w_base_off = p.swap ? 0u : (uint32_t)p.kbs * kATileBytes;
             const uint32_t act_step = p.swap ? b_bytes : (uint32_t)kATileBytes;
@@ -338,11 +339,15 @@ k_conv_umma_t(const __grid_constant__ UmmaMaps maps, const UmmaConv p) {
                     for (int j = 0; j < p.kbs; ++j) {
                         const bool second = chunk >= n_first;
                         const int c0 = (second ? chunk - n_first : chunk) * kCh;
-                        if constexpr (!kPair) ptx::tma_load_4d(st0 + act_off + j * act_step, second ? am1 : am0, fb, c0, dx, y0 + dy, img0);
-                        else ptx::tma_load_4d_2sm(st0 + act_off + j * act_step, second ? am1 : am0, fb, c0, dx, y0 + dy, img0);
-                        if constexpr (kPair) ptx::tma_load_2d_2sm(st0 + w_base_off + j * w_step, wm, fb, 0, b_row);
-                        else if (p.cluster == 1) ptx::tma_load_2d(st0 + w_base_off + j * w_step, wm, fb, 0, b_row);
-                        else ptx::tma_load_2d_mc(st0 + w_base_off + j * w_step + w_off, wm, fb, 0, b_row, cmask);
+                        if (!(p.debug & 1)) {
+                            if constexpr (!kPair) ptx::tma_load_4d(st0 + act_off + j * act_step, second ? am1 : am0, fb, c0, dx, y0 + dy, img0);
+                            else ptx::tma_load_4d_2sm(st0 + act_off + j * act_step, second ? am1 : am0, fb, c0, dx, y0 + dy, img0);
+                        }
+                        if (!(p.debug & 2)) {
+                            if constexpr (kPair) ptx::tma_load_2d_2sm(st0 + w_base_off + j * w_step, wm, fb, 0, b_row);
+                            else if (p.cluster == 1) ptx::tma_load_2d(st0 + w_base_off + j * w_step, wm, fb, 0, b_row);
+                            else ptx::tma_load_2d_mc(st0 + w_base_off + j * w_step + w_off, wm, fb, 0, b_row, cmask);
+                        }
                         b_row += coutp;
                         if (++chunk == n_chunks) { chunk = 0; if (++dx == 2) { dx = -1; ++dy; } }
                     }
