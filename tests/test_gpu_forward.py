@@ -80,6 +80,31 @@ def test_forward_matches_oracle_real_widths(sf, C, H, prec):
     assert umma_error_flag() == 0
 
 
+@pytest.mark.parametrize("prec", ["tf32", "f16"])
+@pytest.mark.parametrize("sf", [1.0, 0.5])
+def test_forward_bench_sized_batch(sf, prec):
+    """A batch large enough for the persistent / CTA-pair forms of every kernel (160 rows: 320 enc1 tiles, 80+ conv
+    tiles at the 8x8 level; multiple tiles per CTA): sampled rows against the oracle, and the whole batch against the
+    same rows pushed through in small batches (other launch shapes of the same kernels)."""
+    cfg = Cfg(1, 16, 50)
+    model = make_model(cfg, sf, 11, device="cuda")
+    sd = cpu_sd(model)
+    torch.manual_seed(5)
+    R = 160
+    x = torch.randn(R, 1, 16, 16)
+    variants = (torch.arange(R) % 3).to(torch.int32)
+    eng = UNetEngine.for_model(model, 16, 50, prec)
+    got = eng.forward(x.cuda(), 23, variants.cuda()).cpu().numpy()
+    tt = torch.full((1,), 23, dtype=torch.long)
+    for r in (0, 1, 77, 158, 159):
+        cond = None if variants[r] == 0 else torch.full((1, 1), float(variants[r] - 1))
+        want = ounet.unet_forward(sd, x[r:r + 1], tt, cond).numpy()
+        assert_close(got[r:r + 1], want, 0.0, FWD_TOL[prec], f"row {r} [{prec}]")
+    small = np.concatenate([eng.forward(x[i:i + 8].cuda(), 23, variants[i:i + 8].cuda()).cpu().numpy() for i in range(0, R, 8)])
+    assert_close(got, small, 0.0, 1e-5, f"160-row batch vs 8-row batches [{prec}]")
+    assert umma_error_flag() == 0
+
+
 def test_training_mode_and_bad_input_fail_loudly():
     from distillation_trajectories_b200 import DtrajError
     cfg = Cfg(1, 16, 4)
