@@ -243,18 +243,26 @@ k_enc1_f16(const __grid_constant__ Enc1Maps maps, const Enc1hParams p) {
         }
     } else if (warp >= 2 + kE1Epi) {
         // ------------------------------------------------------------ mid warps: A1 gather, D1 -> halo chunk buffers
-        const int mt = threadIdx.x - 32 * (2 + kE1Epi);            // 0..255 = A1 row = halo pixel (< 180)
+        const int mt = threadIdx.x - 32 * (2 + kE1Epi);            // 0..255
         const int q = warp & 3;                                     // TMEM lane quarter of this warp
         const int h = (warp - (2 + kE1Epi)) >> 2;                   // the quarter's two warps split every 64-channel chunk: cells 4h..4h+3
         const int HW = p.H * p.W;
-        const bool a1_row = mt < kE1HaloRows;
-        const int a_ry = mt / 10, a_rx = mt - a_ry * 10;            // halo coordinates of the A1 row
+        // Work balance: quarters 0 and 1 convert two D1 rows per thread (regions 0 and 1), quarters 2 and 3 only one --
+        // so the four warps of quarters 2 and 3 (128 threads) gather ALL of A1: rows tq and tq + 128 (< 180).
+        // (debug bit 8 restores one row per mid thread)
+        const bool bal = !(p.debug & 8);
+        const bool a1_warp = q >= 2;
+        const int tq = (2 * h + (q & 1)) * 32 + lane;               // 0..127 over the A1-gathering threads
+        const int a_row[2] = {bal ? tq : mt, tq + 128};
+        const bool a_has[2] = {bal ? a1_warp : mt < kE1HaloRows, bal && a1_warp && tq + 128 < kE1HaloRows};
+        const int a_ry[2] = {a_row[0] / 10, a_row[1] / 10};
+        const int a_rx[2] = {a_row[0] - a_ry[0] * 10, a_row[1] - a_ry[1] * 10};
         uint8_t* a1p = gbase + (a1_0 - base);
         // the two halo pixels whose D1 rows this thread converts: px0 = 32q + lane (region 0), px1 = 128 + 32q + lane (region 1)
         const int px0 = 32 * q + lane, px1 = 128 + 32 * q + lane;
         const bool has1 = 128 + 32 * q < kE1HaloRows;               // warp-uniform: quarters 0 and 1 own rows of region 1
         const int ry0 = px0 / 10, rx0 = px0 - ry0 * 10, ry1 = px1 / 10, rx1 = px1 - ry1 * 10;
-        float xr[kC][9];                                            // prefetched conv1 inputs of the A1 row: [cin][tap]
+        float xr[2][kC][9];                                         // prefetched conv1 inputs of this thread's A1 rows: [row][cin][tap]
         // per-image indices are fetched TWO tiles ahead and the pixels ONE tile ahead, so no load is waited for in the loop
         int smp_n = 0, var_n = 0;                                   // indices of the tile fetched last (two tiles ahead of the pixels)
         auto fetch_idx = [&](int wk) {
@@ -268,20 +276,26 @@ k_enc1_f16(const __grid_constant__ Enc1Maps maps, const Enc1hParams p) {
             const int tile = wk + crank;
             int img, y0, x0;
             tile_geom(tile, img, y0, x0);
-            const bool real = tile < p.n_tiles && a1_row;
             const float* xs = p.x + (size_t)smp * p.x_stride;
-            const int yy = y0 - 1 + a_ry, xx = x0 - 1 + a_rx;
 #pragma unroll
-            for (int ci = 0; ci < kC; ++ci)
+            for (int rr = 0; rr < 2; ++rr) {
+                if (!a_has[rr]) continue;                           // (warp-uniform for rr = 0; the second row ends inside one warp)
+                const bool real = tile < p.n_tiles;
+                const int yy = y0 - 1 + a_ry[rr], xx = x0 - 1 + a_rx[rr];
 #pragma unroll
-                for (int t9 = 0; t9 < 9; ++t9) {
-                    const int sy = yy - 1 + t9 / 3, sx = xx - 1 + t9 % 3;
-                    xr[ci][t9] = (real && sy >= 0 && sy < p.H && sx >= 0 && sx < p.W) ? __ldg(xs + (size_t)ci * HW + sy * p.W + sx) : 0.f;
-                }
+                for (int ci = 0; ci < kC; ++ci)
+#pragma unroll
+                    for (int t9 = 0; t9 < 9; ++t9) {
+                        const int sy = yy - 1 + t9 / 3, sx = xx - 1 + t9 % 3;
+                        xr[rr][ci][t9] = (real && sy >= 0 && sy < p.H && sx >= 0 && sx < p.W) ? __ldg(xs + (size_t)ci * HW + sy * p.W + sx) : 0.f;
+                    }
+            }
         };
         // xr -> this thread's A1 row: per K slice two 16-byte stores (taps, the two bias slots = 1.0, zero padding)
         auto store_a1 = [&]() {
-            if (a1_row) {
+#pragma unroll
+            for (int rr = 0; rr < 2; ++rr) {
+                if (!a_has[rr]) continue;
 #pragma unroll
                 for (int sl = 0; sl < (9 * kC + 2 + 15) / 16; ++sl)
 #pragma unroll
@@ -290,13 +304,13 @@ k_enc1_f16(const __grid_constant__ Enc1Maps maps, const Enc1hParams p) {
 #pragma unroll
                         for (int e = 0; e < 8; ++e) {
                             const int k = 16 * sl + 8 * kc + e;
-                            v[e] = k < 9 * kC ? xr[k % kC][k / kC] : ((k == kBiasK || k == kBiasK + 1) ? 1.f : 0.f);
+                            v[e] = k < 9 * kC ? xr[rr][k % kC][k / kC] : ((k == kBiasK || k == kBiasK + 1) ? 1.f : 0.f);
                         }
                         uint4 o;
                         __half2* oh = reinterpret_cast<__half2*>(&o);
 #pragma unroll
                         for (int e = 0; e < 4; ++e) oh[e] = __floats2half2_rn(v[2 * e], v[2 * e + 1]);
-                        *reinterpret_cast<uint4*>(a1p + sl * kA1SliceBytes + k16_off(mt, kc, p.a1_mode)) = o;
+                        *reinterpret_cast<uint4*>(a1p + sl * kA1SliceBytes + k16_off(a_row[rr], kc, p.a1_mode)) = o;
                     }
             }
         };
