@@ -47,7 +47,7 @@ def workload_config(seeds, world):
             "seeds_per_gpu_per_step": seeds, "guidance_scales": GUIDANCE,
             "trajectories_per_step": 2 * seeds * len(GUIDANCE) * world,
             "parallelism": f"seed-sharded x{world}, one all-reduce of metric sums",
-            "l2": "per-step working set (2 x 124 MB trajectory buffers at 296 seeds + GBs of activations) "
+            "l2": f"per-step working set (2 x {seeds * 8 * 51 * 256 * 4 / 1e6:.0f} MB trajectory buffers + GBs of activations) "
                   "exceeds the 126 MB L2; no explicit flush"}
 
 
@@ -326,8 +326,9 @@ def run_ours(args, emit=print):
     del t5, s5
     side = [{"kernel": "k_step (+ k_copy_frame)", "bound": "hbm", "achieved": step_bytes / (step_ms / 1e3) / 1e9, "peak": hbm,
              "unit": "GB/s", "frac": step_bytes / (step_ms / 1e3) / 1e9 / hbm, "traffic": None,
-             "note": "10 MB per launch: launch-latency bound at this batch, 0.4 % of the step"},
-            {"kernel": "k_metrics_pairs (this workload: [2048, 51, 256] x 2)", "bound": "hbm",
+             "note": f"{step_bytes / (2 * (Cfg.timesteps - 1)) / 1e6:.0f} MB per launch: launch-latency bound at this batch, "
+                     f"{step_ms / all_ms * 100:.1f} % of the loop time"},
+            {"kernel": f"k_metrics_pairs (this workload: [{N}, {L}, {D}] x 2)", "bound": "hbm",
              "achieved": met_bytes / (met_ms / 1e3) / 1e9, "peak": hbm, "unit": "GB/s",
              "frac": met_bytes / (met_ms / 1e3) / 1e9 / hbm, "traffic": None,
              "note": f"{met_bytes / 1e6:.0f} MB per launch"},
@@ -366,7 +367,8 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--seeds", type=int, default=296, help="seeds per GPU per step (x 8 guidance scales x 2 models)")
+    ap.add_argument("--seeds", type=int, default=592, help="seeds per GPU per step (x 8 guidance scales x 2 models); "
+                    "a multiple of 148 keeps every conv grid a whole number of waves")
     ap.add_argument("--precision", default="f16", choices=["tf32", "tf32x3", "fp32", "f16"])
     ap.add_argument("--e2e-chunks", type=int, default=1,
                     help="chunks a sweep is cut into in the end-to-end leg (host staging of chunk i+1 overlaps chunk i on the GPU)")

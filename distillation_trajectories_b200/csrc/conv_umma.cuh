@@ -297,6 +297,8 @@ k_conv_umma_t(const __grid_constant__ UmmaMaps maps, const UmmaConv p) {
     if (p.cluster > 1) ptx::cluster_sync_all();   // peers' barriers exist before anything is multicast at them
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
+    pdl_launch_dependents();                   // the next kernel of the stream / graph may start its prologue
+    pdl_wait();                                // ... and this one touches activations only after its predecessor is complete
     auto arrive_acc_empty = [&](int acc) {     // "accumulator drained": to this CTA's issuer, or to the pair leader's
         if constexpr (!kPair) ptx::mbar_arrive(acc_empty0 + 8u * acc);
         else ptx::mbar_arrive_cluster(ptx::map_to_cta(acc_empty0 + 8u * acc, 0));
@@ -1192,9 +1194,13 @@ inline int build_umma_launch(UmmaLaunch* U, const ConvLayer& L, int npass, const
 }
 
 inline int launch_conv_umma(const UmmaLaunch& U, cudaStream_t st) {
+    if (U.conv.f16) {          // (the fp16 loop is the PDL-enabled one: every kernel around it waits on its predecessor explicitly)
+        if (U.conv.pair) DTRAJ_CUDA(launch_ex(k_conv_umma_t<true, true>, U.grid, kUmmaThreads, U.smem, st, U.conv.cluster, true, U.maps, U.conv));
+        else DTRAJ_CUDA(launch_ex(k_conv_umma_t<false, true>, U.grid, kUmmaThreads, U.smem, st, U.conv.cluster, true, U.maps, U.conv));
+        return 0;
+    }
     if (U.conv.cluster <= 1) {
-        if (U.conv.f16) k_conv_umma_t<false, true><<<U.grid, kUmmaThreads, U.smem, st>>>(U.maps, U.conv);
-        else k_conv_umma_t<false, false><<<U.grid, kUmmaThreads, U.smem, st>>>(U.maps, U.conv);
+        k_conv_umma_t<false, false><<<U.grid, kUmmaThreads, U.smem, st>>>(U.maps, U.conv);
         DTRAJ_LAUNCH_CHECK();
         return 0;
     }

@@ -632,7 +632,7 @@ int plan_forward(dtraj_plan* P, const float* x, int64_t x_stride, const int32_t*
         const int64_t n4 = R * (2 * Si) * (2 * Si) * (cp / 4);
         if (n4 >= ((int64_t)1 << 31)) return fail(DTRAJ_EINVAL, "upsample: batch too large for 32-bit indexing");
         PROF_BEGIN(prof, KC_RESAMPLE);
-        if (f16) k_upsample2_h<<<blocks_for(n4 / 2, 256), 256, 0, st>>>((const __half*)in.p, (__half*)out.p, n4 / 2, Si, Si, cp / 8);
+        if (f16) DTRAJ_CUDA(launch_ex(k_upsample2_h, blocks_for(n4 / 2, 256), 256, 0, st, 1, true, (const __half*)in.p, (__half*)out.p, n4 / 2, Si, Si, cp / 8));
         else k_upsample2<<<blocks_for(n4, 256), 256, 0, st>>>(in.p, out.p, n4, Si, Si, cp / 4, out.lo,
                                                              (u->act_mode == ACT_SPLIT && !out.lo) ? ACT_PLAIN : u->act_mode);
         PROF_END(prof);
@@ -748,15 +748,15 @@ int sampler_enqueue(dtraj_sampler* s, cudaStream_t st, int64_t* launches, Profil
         p.B = d.n_samples; p.C = C; p.H = H; p.W = H;
         const int64_t nthr = (int64_t)d.n_samples * C * H * (H / 4);
         PROF_BEGIN(prof, KC_STEP);
-        k_step<<<blocks_for(nthr, 256), 256, 0, st>>>(p);
+        DTRAJ_CUDA(launch_ex(k_step, blocks_for(nthr, 256), 256, 0, st, 1, s->u->d.precision == DTRAJ_PREC_F16, p));
         PROF_END(prof);
         DTRAJ_LAUNCH_CHECK(); ++nl;
     }
     if (d.copy_last) {
         const int64_t k = d.n_updates;
         PROF_BEGIN(prof, KC_STEP);
-        k_copy_frame<<<blocks_for((int64_t)d.n_samples * (D / 4), 256), 256, 0, st>>>(d.traj + k * D, d.traj + (k + 1) * D, fs,
-                                                                                      d.n_samples, (int)(D / 4));
+        DTRAJ_CUDA(launch_ex(k_copy_frame, blocks_for((int64_t)d.n_samples * (D / 4), 256), 256, 0, st, 1, s->u->d.precision == DTRAJ_PREC_F16,
+                             (const float*)(d.traj + k * D), d.traj + (k + 1) * D, fs, d.n_samples, (int)(D / 4)));
         PROF_END(prof);
         DTRAJ_LAUNCH_CHECK(); ++nl;
     }

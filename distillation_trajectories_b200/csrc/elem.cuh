@@ -293,6 +293,8 @@ __global__ void __launch_bounds__(256) k_upsample2(const float* __restrict__ in,
 // fp16 maps (DTRAJ_PREC_F16): one thread = 8 channels of one output pixel; interpolation in fp32, one rounding
 __global__ void __launch_bounds__(256) k_upsample2_h(const __half* __restrict__ in, __half* __restrict__ out,
                                                      int64_t n_out8, int Hi, int Wi, int cp8) {
+    pdl_launch_dependents();
+    pdl_wait();
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (uint32_t)n_out8) return;
     const int Ho = Hi * 2, Wo = Wi * 2;
@@ -418,6 +420,8 @@ struct StepParams {
 
 // one thread = 4 consecutive pixels along W of one (sample, channel, y)
 __global__ void __launch_bounds__(256) k_step(StepParams p) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int W4 = p.W / 4;
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     int64_t total = (int64_t)p.B * p.C * p.H * W4;
@@ -471,6 +475,8 @@ __global__ void __launch_bounds__(256) k_step_plain(int rule, float k0, float k1
 // duplicate frame (S2 at t == 0 records x unchanged, trajectory_engine.py:86,113)
 __global__ void __launch_bounds__(256) k_copy_frame(const float* __restrict__ in, float* __restrict__ out,
                                                     int64_t frame_stride, int B, int D4) {
+    pdl_launch_dependents();
+    pdl_wait();
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (int64_t)B * D4) return;
     int64_t b = i / D4, e = i % D4;

@@ -151,6 +151,8 @@ k_enc1_f16(const __grid_constant__ Enc1Maps maps, const Enc1hParams p) {
     if constexpr (kPair) ptx::cluster_sync_all();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
+    pdl_launch_dependents();
+    pdl_wait();                                // everything above read weights / tables only; x and pool_out belong to other kernels
 
     auto tile_geom = [&](int tile, int& img, int& y0, int& x0) {
         img = tile >> p.lg_tpi;
@@ -591,25 +593,7 @@ inline cudaError_t enc1h_set_smem_attr() {
 }
 
 inline int launch_enc1h(const Enc1hLaunch& E, cudaStream_t st) {
-    if (!E.pair) {
-        enc1h_kernel(0, E.p.C)<<<E.grid, kE1hThreads, E.smem, st>>>(E.maps, E.p);
-        DTRAJ_LAUNCH_CHECK();
-        return 0;
-    }
-    cudaLaunchConfig_t cfg;
-    memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = dim3(E.grid);
-    cfg.blockDim = dim3(kE1hThreads);
-    cfg.dynamicSmemBytes = E.smem;
-    cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    DTRAJ_CUDA(cudaLaunchKernelEx(&cfg, enc1h_kernel(1, E.p.C), E.maps, E.p));
+    DTRAJ_CUDA(launch_ex(enc1h_kernel(E.pair, E.p.C), E.grid, kE1hThreads, E.smem, st, E.pair ? 2 : 1, true, E.maps, E.p));
     return 0;
 }
 
