@@ -557,8 +557,10 @@ int plan_build(const dtraj_unet* u, int64_t R, void* ws, int64_t ws_bytes, dtraj
 inline unsigned blocks_for(int64_t n, int per) { return (unsigned)((n + per - 1) / per); }
 
 // Enqueue one U-Net forward (models.py:159-224 up to the half-resolution eps map).
+// `per_row`: row_variant holds t_i * 3 + variant_i (a row of the whole table) instead of the variant alone, `t` is 0.
 int plan_forward(dtraj_plan* P, const float* x, int64_t x_stride, const int32_t* row_sample,
-                 const int32_t* row_variant, int t, cudaStream_t st, int64_t* launches, Profiler* prof = nullptr) {
+                 const int32_t* row_variant, int t, cudaStream_t st, int64_t* launches, Profiler* prof = nullptr,
+                 bool per_row = false) {
     const dtraj_unet* u = P->u;
     if (t < 0 || t >= u->d.n_timesteps) return fail(DTRAJ_EINVAL, "timestep %d outside the time table (0..%d)", t, u->d.n_timesteps - 1);
     const int* S = u->sizes;
@@ -572,6 +574,7 @@ int plan_forward(dtraj_plan* P, const float* x, int64_t x_stride, const int32_t*
         Enc1hParams& e = P->enc1h.p;
         e.x = x; e.x_stride = x_stride; e.row_sample = row_sample; e.row_variant = row_variant;
         e.tbias = trow + u->tb_off[0];
+        e.tb_rows = per_row ? 1 : 0;
         PROF_BEGIN(prof, KC_ENC1);
         int rc1 = launch_enc1h(P->enc1h, st);
         PROF_END(prof);
@@ -696,6 +699,22 @@ extern "C" int dtraj_unet_forward(dtraj_unet* u, const float* x, int64_t n_rows,
     }
     const int C = u->d.channels, H = u->d.image_size;
     DTRAJ_TRY(plan_forward(u->plan, x, (int64_t)C * H * H, nullptr, row_variant, t, st, nullptr));
+    const int64_t n = n_rows * C * H * H;
+    k_eps_out<<<blocks_for(n, 256), 256, 0, st>>>(u->plan->elow.p, eps, n, C, H, H);
+    DTRAJ_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int dtraj_unet_forward_rows(dtraj_unet* u, const float* x, int64_t n_rows, const int32_t* row_tv, float* eps,
+                                       void* workspace, int64_t workspace_bytes, void* stream) {
+    if (!u || !x || !eps || !workspace || !row_tv) return fail(DTRAJ_EINVAL, "null argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!u->plan || u->plan->R != n_rows || u->plan->ws != (float*)workspace) {
+        if (u->plan) { delete u->plan; u->plan = nullptr; }
+        DTRAJ_TRY(plan_build(u, n_rows, workspace, workspace_bytes, &u->plan));
+    }
+    const int C = u->d.channels, H = u->d.image_size;
+    DTRAJ_TRY(plan_forward(u->plan, x, (int64_t)C * H * H, nullptr, row_tv, 0, st, nullptr, nullptr, true));
     const int64_t n = n_rows * C * H * H;
     k_eps_out<<<blocks_for(n, 256), 256, 0, st>>>(u->plan->elow.p, eps, n, C, H, H);
     DTRAJ_LAUNCH_CHECK();

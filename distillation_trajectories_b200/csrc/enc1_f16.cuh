@@ -43,6 +43,7 @@ struct Enc1hParams {
     const float* x; int64_t x_stride; const int32_t* row_sample; const int32_t* row_variant;
     const float* w3; const float* b3;          // conv1, BN folded, fp32: [9*C][coutp] (k = tap * C + cin); [coutp]
     const float* tbias; int tb_var_stride;     // relu(time_mlp(temb)) rows of enc1 for this t, 3 variants
+    int tb_rows;                 // 1: row_variant indexes the whole [T][3] table (per-row timesteps): read the bias from global memory
     const float* bias2;                        // conv2 folded bias [coutp]
     const float* rw1; const float* rb1;        // residual 1x1: [C][coutp], [coutp]
     __half* pool_out;                          // [R, H/2, W/2, coutp]
@@ -355,7 +356,7 @@ k_enc1_f16(const __grid_constant__ Enc1Maps maps, const Enc1hParams p) {
                 store_a1();                                         // A1(it + 1); published together with the first halo chunk below
                 if (wk + 2 * G < p.n_tiles) prefetch(wk + 2 * G, smp_n);          // loads stay in flight under the conversion below
             }
-            const float* tb = tbs + var0 * coutp;
+            const float* tb = p.tb_rows ? p.tbias + (size_t)var0 * p.tb_var_stride : tbs + var0 * coutp;
             var0 = var1; var1 = var_n;
             fetch_idx(wk + 3 * G);
             // ---- D1 -> halo chunk buffers

@@ -138,7 +138,8 @@ class UNetEngine:
         return out
 
     def forward(self, x, t, variants=None):
-        """eps = U-Net(x, t, cond) for rows sharing timestep ``t`` (int).  ``variants``: int32 [R] of VAR_*."""
+        """eps = U-Net(x, t, cond).  ``t``: one int for the whole batch (the sampling loops), or an int tensor [R]
+        with a timestep per row (p_losses, the distillation step).  ``variants``: int32 [R] of VAR_*."""
         x = x.to(self.device, torch.float32).contiguous()
         R = x.shape[0]
         if tuple(x.shape[1:]) != (self.channels, self.image_size, self.image_size):
@@ -148,6 +149,15 @@ class UNetEngine:
             variants = variants.to(self.device, torch.int32).contiguous()
         eps = torch.empty_like(x)
         ws = self.workspace(R)
+        if torch.is_tensor(t):
+            tv = t.reshape(R, -1)[:, 0].to(self.device, torch.int64)
+            if int(tv.min()) < 0 or int(tv.max()) >= self.n_timesteps:
+                raise DtrajError(f"timesteps outside the engine's table (0..{self.n_timesteps - 1})")
+            row_tv = (tv * 3 + (variants.to(torch.int64) if variants is not None else 0)).to(torch.int32).contiguous()
+            with torch.cuda.device(self.device):
+                _lib.check(self.lib.dtraj_unet_forward_rows(self.handle, _lib.ptr(x), R, _lib.ptr(row_tv), _lib.ptr(eps),
+                                                            _lib.ptr(ws), ws.numel(), _lib.stream_ptr()))
+            return eps
         with torch.cuda.device(self.device):
             _lib.check(self.lib.dtraj_unet_forward(self.handle, _lib.ptr(x), R, int(t), _lib.ptr(variants), _lib.ptr(eps),
                                                    _lib.ptr(ws), ws.numel(), _lib.stream_ptr()))

@@ -70,22 +70,24 @@ class DiffusionUNet(nn.Module):
 
     @torch.no_grad()
     def forward(self, x, t, cond=None):
-        """eps = U-Net(x, t, cond) (models.py:159-224).  ``t`` [B] (or [B,1]) must hold one value;
-        ``cond`` is None or a [B,1] tensor of 0/1 flags (the only values the hot path feeds)."""
+        """eps = U-Net(x, t, cond) (models.py:159-224).  ``t`` [B] (or [B,1]): one shared value (the sampling loops) or
+        a timestep per row (p_losses, the distillation step: scripts/train_students.py:131-141); ``cond`` is None or
+        a [B,1] tensor of 0/1 flags (the only values the reference feeds)."""
         if self.training:
             raise DtrajError("DiffusionUNet.forward: training mode is out of scope; call model.eval()")
         tv = t.reshape(t.shape[0], -1)[:, 0]
         t0 = int(tv[0].item())
-        if not bool((tv == t0).all()):
-            raise DtrajError("DiffusionUNet.forward: all rows must share one timestep")
-        eng = UNetEngine.for_model(self, x.shape[2], t0 + 1, get_precision("forward"))
+        shared = bool((tv == t0).all())
+        if int(tv.min()) < 0:
+            raise DtrajError("DiffusionUNet.forward: negative timestep")
+        eng = UNetEngine.for_model(self, x.shape[2], (t0 if shared else int(tv.max())) + 1, get_precision("forward"))
         variants = None
         if cond is not None:
             c = cond.reshape(cond.shape[0], -1)[:, 0].to(torch.float32)
             if not bool(((c == 0) | (c == 1)).all()):
                 raise DtrajError("DiffusionUNet.forward: cond must be 0/1 flags")
             variants = torch.where(c > 0.5, VAR_COND1, VAR_COND0).to(torch.int32)
-        return eng.forward(x, t0, variants)
+        return eng.forward(x, t0 if shared else tv, variants)
 
 
 class SimpleUNet(DiffusionUNet):

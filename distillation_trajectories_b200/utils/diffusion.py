@@ -3,8 +3,9 @@
 Same names, signatures and return types as the reference for ``linear_beta_schedule``,
 ``get_diffusion_params``, ``extract``, ``p_sample`` and ``p_sample_loop``; the U-Net forwards
 and the update run in libdtraj.so (two forward rows per sample, fused CFG + update + trajectory
-store, whole loop in one CUDA graph).  The training helpers ``q_sample`` / ``p_losses`` are out
-of scope.
+store, whole loop in one CUDA graph).  ``q_sample`` and the FORWARD value of ``p_losses`` are here too (SURVEY.md 8f
+rank 4: the forward-only half of the training-side steps -- per-row timesteps through the same kernels); gradients and
+optimizers stay out of scope.
 """
 import torch
 
@@ -42,6 +43,25 @@ def get_diffusion_params(sample_steps, config=None):
     force_cpu = bool(config and getattr(config, "force_cpu", False))
     device = torch.device("cpu" if force_cpu or not torch.cuda.is_available() else "cuda")
     return {k: v.to(device) for k, v in tables.items()}
+
+
+def q_sample(x_start, t, diffusion_params):
+    """utils/diffusion.py:68-80 with the reference's own torch ops (noise from the global generator on x_start's
+    device): returns (sqrt_alphas_cumprod_t * x_start + sqrt_one_minus_alphas_cumprod_t * noise, noise)."""
+    noise = torch.randn_like(x_start)
+    a = extract(diffusion_params["sqrt_alphas_cumprod"], t, x_start.shape)
+    b = extract(diffusion_params["sqrt_one_minus_alphas_cumprod"], t, x_start.shape)
+    return a * x_start + b * noise, noise
+
+
+@torch.no_grad()
+def p_losses(denoise_model, x_start, t, diffusion_params, cond=None):
+    """Forward value of utils/diffusion.py:82-100: mse(model(q_sample(x_start, t), t, cond), noise).  ``t`` holds a
+    timestep per row (scripts/train_teacher.py draws randint(0, T, (B,))); no autograd graph is built -- the backward
+    pass is out of scope, so this is a validation-loss / monitoring entry point."""
+    x_noisy, noise = q_sample(x_start, t, diffusion_params)
+    predicted = denoise_model(x_noisy, t, cond)
+    return torch.nn.functional.mse_loss(predicted, noise)
 
 
 def _engine(model, x_shape, n_timesteps, path):

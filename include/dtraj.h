@@ -104,6 +104,18 @@ int dtraj_unet_forward(dtraj_unet* unet, const float* x, int64_t n_rows, int32_t
                        const int32_t* row_variant, float* eps,
                        void* workspace, int64_t workspace_bytes, void* stream);
 
+/*
+ * The same forward with a timestep PER ROW: what the training-side callers feed
+ * (utils/diffusion.py:83-100 p_losses; the teacher half of the distillation step,
+ * scripts/train_students.py:131-141, where t = randint(0, teacher_steps, (B,))).
+ *   row_tv   dev int32 [n_rows]: t_i * 3 + DTRAJ_VAR_* of row i -- the row of the
+ *            [n_timesteps][3] time-bias table its epilogues read; the caller guarantees
+ *            0 <= t_i < n_timesteps.
+ */
+int dtraj_unet_forward_rows(dtraj_unet* unet, const float* x, int64_t n_rows,
+                            const int32_t* row_tv, float* eps,
+                            void* workspace, int64_t workspace_bytes, void* stream);
+
 /* ------------------------------------------------------------------ fused sampler step */
 
 /*

@@ -113,8 +113,13 @@ def test_training_mode_and_bad_input_fail_loudly():
     with pytest.raises(DtrajError):
         m(torch.zeros(1, 1, 16, 16, device="cuda"), torch.tensor([0], device="cuda"))
     m.eval()
+    # mixed timesteps in one batch are served by the per-row form and equal the rows run one at a time
+    xm = torch.randn(2, 1, 16, 16, device="cuda")
+    both = m(xm, torch.tensor([0, 3], device="cuda"))
+    one = torch.cat([m(xm[:1], torch.tensor([0], device="cuda")), m(xm[1:], torch.tensor([3], device="cuda"))])
+    assert torch.allclose(both, one, rtol=0, atol=1e-6 * float(one.abs().max()))
     with pytest.raises(DtrajError):
-        m(torch.zeros(2, 1, 16, 16, device="cuda"), torch.tensor([0, 1], device="cuda"))     # mixed timesteps
+        m(xm, torch.tensor([0, -1], device="cuda"))                                           # negative timestep
     eng = UNetEngine.for_model(m, 16, 4, "fp32")
     with pytest.raises(DtrajError):
         eng.forward(torch.zeros(1, 1, 16, 16, device="cuda"), 9)                              # t outside the table
