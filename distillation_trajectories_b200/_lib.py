@@ -58,6 +58,7 @@ SIGNATURES = {
     "dtraj_metrics_pairs": (C.c_int, [_P, _P, _I64, _I32, _I32, _P, _P]),
     "dtraj_wasserstein": (C.c_int, [_P, _P, _I64, _I32, _I32, _P, _P, _I32, _P, _P]),
     "dtraj_unet_forward_rows": (C.c_int, [_P, _P, _I64, _P, _P, _P, _I64, _P]),
+    "dtraj_project": (C.c_int, [_P, _I64, _I32, _P, _P, _I32, _P, _P]),
     "dtraj_check_errors": (C.c_int, []),
     "dtraj_error_flag_async": (C.c_int, [_P, _P]),
     "dtraj_test_conv": (C.c_int, [_I32, _P, _I32, _P, _I32, _I64, _I32, _I32, _P, _P, _I32, _I32, _I32,

@@ -891,6 +891,13 @@ extern "C" int dtraj_wasserstein(const float* teacher, const float* student, int
     return launch_wasserstein(teacher, student, N, L, D, idx, idx_set, K, out, (cudaStream_t)stream);
 }
 
+extern "C" int dtraj_project(const float* frames, int64_t n_frames, int32_t D, const float* comps, const float* offset, int32_t K,
+                             float* out, void* stream) {
+    if (n_frames == 0) return 0;
+    if (!frames || !comps || !offset || !out || n_frames < 0) return fail(DTRAJ_EINVAL, "project: bad argument");
+    return launch_project(frames, n_frames, D, comps, offset, K, out, (cudaStream_t)stream);
+}
+
 // ======================================================================================
 // test hooks
 // ======================================================================================

@@ -242,6 +242,62 @@ __global__ void __launch_bounds__(256) k_wasserstein_warp(const float* __restric
     if (lane == 0) out[pf] = (float)(acc / (double)K);
 }
 
+// Projection of trajectory frames onto K <= 8 principal directions (scripts/analysis/analyze_trajectories.py:66-80,100:
+// process_trajectory -> [L, D] features, PCA(3).fit(reference).transform(features) for every trajectory of a sweep):
+//   out[f][k] = sum_d x[f][d] * comps[k][d] - off[k],   off[k] = mean . comps[k]   (sklearn's transform order)
+// HBM-bound: every element of the frames is read once (algorithmic bytes 4 * F * D); the K x D directions sit in shared
+// memory, one warp per frame, 128-bit streaming loads, warp-shuffle reductions, persistent blocks.
+__global__ void __launch_bounds__(256) k_project(const float* __restrict__ x, int64_t F, int D4, const float* __restrict__ comps,
+                                                 const float* __restrict__ off, int K, float* __restrict__ out) {
+    extern __shared__ float4 pc[];                   // [K][D4]
+    for (int i = threadIdx.x; i < K * D4; i += blockDim.x) pc[i] = reinterpret_cast<const float4*>(comps)[i];
+    __syncthreads();
+    const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+    for (int64_t f = (int64_t)blockIdx.x * wpb + (threadIdx.x >> 5); f < F; f += (int64_t)gridDim.x * wpb) {
+        const float4* row = reinterpret_cast<const float4*>(x) + f * D4;
+        float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        for (int d0 = lane; d0 < D4; d0 += 128) {          // four independent 16-byte loads per lane in flight
+            float4 v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int d = d0 + 32 * u;
+                v[u] = d < D4 ? ld_stream4(reinterpret_cast<const float*>(row + d)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int d = d0 + 32 * u;
+                if (d < D4) {
+#pragma unroll
+                    for (int k = 0; k < 8; ++k)
+                        if (k < K) {
+                            const float4 c = pc[k * D4 + d];
+                            acc[k] = fmaf(v[u].x, c.x, fmaf(v[u].y, c.y, fmaf(v[u].z, c.z, fmaf(v[u].w, c.w, acc[k]))));
+                        }
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+            if (k < K) {
+                const float s = warp_sum(acc[k]);
+                if (lane == 0) out[f * K + k] = s - off[k];
+            }
+    }
+}
+
+inline int launch_project(const float* x, int64_t F, int D, const float* comps, const float* off, int K, float* out, cudaStream_t st) {
+    if (D % 4 != 0 || D <= 0 || K < 1 || K > 8) return fail(DTRAJ_EINVAL, "project: D=%d must be a positive multiple of 4, K=%d in 1..8", D, K);
+    const size_t smem = (size_t)K * D * sizeof(float);
+    if (smem > 200 * 1024) return fail(DTRAJ_EINVAL, "project: K*D=%d too large for shared memory", K * D);
+    if (F == 0) return 0;
+    if (smem > 48 * 1024) DTRAJ_CUDA(cudaFuncSetAttribute(k_project, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int64_t want = (F + 7) / 8;
+    const unsigned grid = (unsigned)(want < 6 * kNumSMs ? want : 6 * kNumSMs);
+    k_project<<<grid, 256, smem, st>>>(x, F, D / 4, comps, off, K, out);
+    DTRAJ_LAUNCH_CHECK();
+    return 0;
+}
+
 inline int launch_wasserstein(const float* T, const float* S, int64_t N, int L, int D, const int32_t* idx,
                               const int32_t* idx_set, int K, float* out, cudaStream_t st) {
     if (K < 1 || K > D || K > 4096) return fail(DTRAJ_EINVAL, "wasserstein: K=%d out of range (D=%d)", K, D);

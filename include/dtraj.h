@@ -221,6 +221,17 @@ int dtraj_wasserstein(const float* teacher, const float* student,
                       const int32_t* idx, const int32_t* idx_set, int32_t K,
                       float* out, void* stream);
 
+/* ------------------------------------------------------------------ PCA projection
+ * Replaces the per-trajectory `pca.transform(process_trajectory(traj))` of the visual analysis
+ * (scripts/analysis/analyze_trajectories.py:66-80,100; same in :232-246): frames of any number
+ * of trajectories are projected onto K <= 8 fitted directions in one streaming pass.
+ *   frames  dev [n_frames, D] fp32 (a [N, L, C, H, W] trajectory tensor, n_frames = N*L)
+ *   comps   dev [K, D] fp32 (sklearn PCA.components_), offset dev [K] = mean_ . components_[k]
+ *   out     dev [n_frames, K] fp32 = frames @ comps^T - offset
+ * Every element of `frames` is read exactly once (HBM-bound: 4 * n_frames * D bytes). */
+int dtraj_project(const float* frames, int64_t n_frames, int32_t D, const float* comps,
+                  const float* offset, int32_t K, float* out, void* stream);
+
 /* ------------------------------------------------------------------ device-side error state
  * Kernels never trap: a tcgen05 pipeline role whose mbarrier wait times out, or an
  * activation that leaves the fp16 range in DTRAJ_PREC_F16, sets a sticky device flag.

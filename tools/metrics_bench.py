@@ -24,3 +24,22 @@ for N, L, D in ((4096, 50, 3072), (16384, 50, 3072), (65536, 51, 256), (2048, 51
     gb = 2 * N * L * D * 4 / 1e9
     print(f"pair_reductions N={N} L={L} D={D}: {gb:.2f} GB in {ms:.3f} ms = {gb/ms*1e3:.0f} GB/s", flush=True)
     del T, S
+
+# PCA projection (dtraj_project): one pass over [N, L, D], K = 3 directions
+import numpy as np
+from distillation_trajectories_b200.analysis import trajectory_pca as tp
+for N, L, D in ((8192, 50, 3072), (65536, 51, 256)):
+    T, S = make(N, L, D, 1)
+    del S
+    pca = tp.fit_reference_pca(T[0].cpu().numpy())
+    for _ in range(3):
+        tp.project_trajectories(T, pca)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(10):
+        tp.project_trajectories(T, pca)
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 10
+    gb = N * L * D * 4 / 1e9
+    print(f"project_trajectories N={N} L={L} D={D}: {gb:.2f} GB in {ms:.3f} ms = {gb/ms*1e3:.0f} GB/s", flush=True)
+    del T
