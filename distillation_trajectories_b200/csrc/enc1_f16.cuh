@@ -73,7 +73,8 @@ k_enc1_f16(const __grid_constant__ Enc1Maps maps, const Enc1hParams p) {
     const uint32_t halo0 = wres0 + w_bytes;
     const uint32_t ring0 = halo0 + (uint32_t)p.n_hbuf * kE1HaloBytes;
     const uint32_t a1_0 = ring0 + kE1Epi * 2048u;
-    const uint32_t b1_0 = a1_0 + (uint32_t)p.n_slices * kA1SliceBytes;
+    const uint32_t a1_buf = (uint32_t)p.n_slices * kA1SliceBytes;         // one A1 buffer; there are n_d1 of them
+    const uint32_t b1_0 = a1_0 + (uint32_t)p.n_d1 * a1_buf;
     const uint32_t cst0 = b1_0 + (((uint32_t)p.n_slices * b1_slice + 1023u) & ~1023u);
     // constants (floats): b3 | tbias [3][coutp] | bias2 | rb1 | rw1 [C][coutp]
     const int n_cst = (6 + C) * coutp;
@@ -81,8 +82,8 @@ k_enc1_f16(const __grid_constant__ Enc1Maps maps, const Enc1hParams p) {
     auto hfull = [&](int b) { return bar0 + 8u * b; };
     auto hempty = [&](int b) { return bar0 + 64u + 8u * b; };
     const uint32_t acc_full0 = bar0 + 128u, acc_empty0 = bar0 + 144u, wbar = bar0 + 160u;
-    const uint32_t a1_full = bar0 + 168u, d1_full0 = bar0 + 176u, d1_empty0 = bar0 + 192u;   // d1_*: [2]
-    const uint32_t tmem_slot = bar0 + 208u;
+    const uint32_t a1_full0 = bar0 + 168u, d1_full0 = bar0 + 184u, d1_empty0 = bar0 + 200u;   // each [2]
+    const uint32_t tmem_slot = bar0 + 216u;
     const uint32_t tmem_cols = (uint32_t)((2 + 2 * p.n_d1) * p.acc_cols) <= 256u ? 256u : 512u;
     volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gbase + (tmem_slot - base));
     float* cst = reinterpret_cast<float*>(gbase + (cst0 - base));
@@ -109,8 +110,11 @@ k_enc1_f16(const __grid_constant__ Enc1Maps maps, const Enc1hParams p) {
                 ptx::mbar_init(acc_empty0 + 8u * i, nrep);
             }
             ptx::mbar_init(wbar, 1);
-            ptx::mbar_init(a1_full, nrep);
-            for (int i = 0; i < 2; ++i) { ptx::mbar_init(d1_full0 + 8u * i, 1); ptx::mbar_init(d1_empty0 + 8u * i, nrep); }
+            for (int i = 0; i < 2; ++i) {
+                ptx::mbar_init(a1_full0 + 8u * i, nrep);
+                ptx::mbar_init(d1_full0 + 8u * i, 1);
+                ptx::mbar_init(d1_empty0 + 8u * i, nrep);
+            }
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
         __syncwarp();
@@ -130,12 +134,12 @@ k_enc1_f16(const __grid_constant__ Enc1Maps maps, const Enc1hParams p) {
         cst[5 * coutp + i] = p.rb1[i];
     }
     for (int i = threadIdx.x; i < C * coutp; i += blockDim.x) cst[6 * coutp + i] = p.rw1[i];
-    for (int i = threadIdx.x; i < p.n_slices * (kA1SliceBytes / 16); i += blockDim.x)
+    for (int i = threadIdx.x; i < p.n_d1 * p.n_slices * (kA1SliceBytes / 16); i += blockDim.x)
         reinterpret_cast<uint4*>(gbase + (a1_0 - base))[i] = make_uint4(0u, 0u, 0u, 0u);
     __syncthreads();
-    for (int i = threadIdx.x; i < 2 * 256; i += blockDim.x) {             // the bias slots of every A1 row hold 1.0
-        const int r = i >> 1, k = kBiasK + (i & 1);
-        *reinterpret_cast<__half*>(gbase + (a1_0 - base) + (k >> 4) * kA1SliceBytes + k16_off(r, (k >> 3) & 1, p.a1_mode) + (k & 7) * 2) = __float2half_rn(1.f);
+    for (int i = threadIdx.x; i < p.n_d1 * 2 * 256; i += blockDim.x) {    // the bias slots of every A1 row hold 1.0
+        const int bb = i >> 9, r = (i >> 1) & 255, k = kBiasK + (i & 1);
+        *reinterpret_cast<__half*>(gbase + (a1_0 - base) + bb * a1_buf + (k >> 4) * kA1SliceBytes + k16_off(r, (k >> 3) & 1, p.a1_mode) + (k & 7) * 2) = __float2half_rn(1.f);
     }
     for (int i = threadIdx.x; i < p.n_slices * p.w_rows * 16; i += blockDim.x) {
         const int s = i / (p.w_rows * 16), rem = i - s * p.w_rows * 16, nl = rem >> 4, e = rem & 15, k = 16 * s + e;
@@ -192,13 +196,13 @@ k_enc1_f16(const __grid_constant__ Enc1Maps maps, const Enc1hParams p) {
             // conv1 of tile-iteration j into D1 buffer j % n_d1: D1[g] = A1[rows 128g ..] * W1^T, g = 0, 1
             auto issue_conv1 = [&](int j) {
                 const int b = j & (p.n_d1 - 1);
-                ok = ok && ptx::mbar_wait(a1_full, (uint32_t)(j & 1));
+                ok = ok && ptx::mbar_wait(a1_full0 + 8u * b, (uint32_t)((j >> (p.n_d1 - 1)) & 1));
                 ok = ok && ptx::mbar_wait(d1_empty0 + 8u * b, (uint32_t)(((j >> (p.n_d1 - 1)) & 1) ^ 1));
                 ptx::tc_fence_after();
                 const uint32_t d1_tmem = tmem_base + (uint32_t)((2 + 2 * b) * p.acc_cols);
                 for (int g = 0; g < 2; ++g)
                     for (int s = 0; s < p.n_slices; ++s) {
-                        const uint64_t ad = kdesc(a1_0 + (uint32_t)s * kA1SliceBytes + (uint32_t)g * 4096u);
+                        const uint64_t ad = kdesc(a1_0 + (uint32_t)b * a1_buf + (uint32_t)s * kA1SliceBytes + (uint32_t)g * 4096u);
                         const uint64_t bd = kdesc(b1_0 + (uint32_t)s * b1_slice);
                         if constexpr (!kPair) ptx::mma_f16(d1_tmem + (uint32_t)(g * p.acc_cols), ad, bd, idesc, s ? 1u : 0u);
                         else ptx::mma_f16_2sm(d1_tmem + (uint32_t)(g * p.acc_cols), ad, bd, idesc, s ? 1u : 0u);
@@ -206,7 +210,7 @@ k_enc1_f16(const __grid_constant__ Enc1Maps maps, const Enc1hParams p) {
                 // (its completion also frees A1: the mid warps write the next tile's A1 after seeing d1_full)
                 if constexpr (kPair) ptx::tc_commit_2sm(d1_full0 + 8u * b, cmask); else ptx::tc_commit(d1_full0 + 8u * b);
             };
-            // A1 is single-buffered: conv1(j + 1) can only be issued after the mid warps saw conv1(j) complete and wrote A1(j + 1)
+            // A1 and D1 have n_d1 buffers each: the mid warps publish A1(j + n_d1) once they have seen conv1(j) complete
             if (n_my > 0) issue_conv1(0);
             if (p.n_d1 == 2 && n_my > 1) issue_conv1(1);
             for (int wk = work0; wk < p.n_tiles && ok; wk += gridDim.x, ++it) {
@@ -295,7 +299,8 @@ k_enc1_f16(const __grid_constant__ Enc1Maps maps, const Enc1hParams p) {
             }
         };
         // xr -> this thread's A1 row: per K slice two 16-byte stores (taps, the two bias slots = 1.0, zero padding)
-        auto store_a1 = [&]() {
+        auto store_a1 = [&](int buf) {
+            uint8_t* const a1b = a1p + (uint32_t)buf * a1_buf;
 #pragma unroll
             for (int rr = 0; rr < 2; ++rr) {
                 if (!a_has[rr]) continue;
@@ -313,7 +318,7 @@ k_enc1_f16(const __grid_constant__ Enc1Maps maps, const Enc1hParams p) {
                         __half2* oh = reinterpret_cast<__half2*>(&o);
 #pragma unroll
                         for (int e = 0; e < 4; ++e) oh[e] = __floats2half2_rn(v[2 * e], v[2 * e + 1]);
-                        *reinterpret_cast<uint4*>(a1p + sl * kA1SliceBytes + k16_off(a_row[rr], kc, p.a1_mode)) = o;
+                        *reinterpret_cast<uint4*>(a1b + sl * kA1SliceBytes + k16_off(a_row[rr], kc, p.a1_mode)) = o;
                     }
             }
         };
@@ -325,40 +330,49 @@ k_enc1_f16(const __grid_constant__ Enc1Maps maps, const Enc1hParams p) {
         auto release_fence = [&]() {
             if constexpr (kPair) asm volatile("fence.acq_rel.cluster;" ::: "memory");
         };
-        // Software pipeline, at the top of iteration `it`: A1(it) written (conv1(it) issued or done), xr = pixels of tile
-        // it + 1, var0 / var1 = variants of tiles it / it + 1, (smp_n, var_n) = indices of tile it + 2.
-        const int G = (int)gridDim.x;
-        int hb = 0, it = 0, var0 = 0, var1 = 0;
+        // Software pipeline with lead Ld = n_d1 (buffers of A1 and of D1).  At the top of iteration `it`: A1(it .. it+Ld-1) are
+        // published (their conv1 issued or done), xr = pixels of tile it + Ld, vq[k] = variant of tile it + k (k <= Ld),
+        // (smp_n, var_n) = indices of tile it + Ld + 1.  With Ld = 2 the conv1 round trip (publish -> issue -> MMA -> commit)
+        // of tile it + 2 runs under the conversion of tile it + 1, so the mid warps never wait for it.
+        const int G = (int)gridDim.x, Ld = p.n_d1;
+        int hb = 0, it = 0, vq[3] = {0, 0, 0};
         uint32_t hph = 0;
         if (work0 < p.n_tiles) {
             fetch_idx(work0);
-            prefetch(work0, smp_n);
-            var0 = var_n;
-            fetch_idx(work0 + G);
-            store_a1();                                             // A1(0)
-            ptx::fence_proxy_async();
-            asm volatile("bar.sync 9, 256;" ::: "memory");
-            if (mt == 0) { release_fence(); arrive_one(a1_full); }
-            if (work0 + G < p.n_tiles) prefetch(work0 + G, smp_n);
-            var1 = var_n;
-            fetch_idx(work0 + 2 * G);
+            for (int j = 0; j < Ld; ++j) {                         // A1(0 .. Ld-1)
+                const bool ex = work0 + j * G < p.n_tiles;          // (CTA-uniform)
+                if (ex) prefetch(work0 + j * G, smp_n);
+                vq[j] = var_n;
+                fetch_idx(work0 + (j + 1) * G);
+                if (ex) {
+                    store_a1(j);
+                    ptx::fence_proxy_async();
+                    asm volatile("bar.sync 9, 256;" ::: "memory");
+                    if (mt == 0) { release_fence(); arrive_one(a1_full0 + 8u * j); }
+                }
+            }
+            if (work0 + Ld * G < p.n_tiles) prefetch(work0 + Ld * G, smp_n);
+            vq[Ld] = var_n;
+            fetch_idx(work0 + (Ld + 1) * G);
         }
         for (int wk = work0; wk < p.n_tiles; wk += G, ++it) {
             const int tile = wk + crank;
             int img, y0, x0;
             tile_geom(tile, img, y0, x0);
             const bool real = tile < p.n_tiles;
-            const int b = it & (p.n_d1 - 1);
-            ptx::mbar_wait(d1_full0 + 8u * b, (uint32_t)((it >> (p.n_d1 - 1)) & 1));    // conv1(it) done: D1 readable, A1 free
+            const int b = it & (Ld - 1);
+            ptx::mbar_wait(d1_full0 + 8u * b, (uint32_t)((it >> (Ld - 1)) & 1));    // conv1(it) done: D1 readable, A1 buffer b free
             ptx::tc_fence_after();
-            const bool next = wk + G < p.n_tiles;
+            const bool next = wk + Ld * G < p.n_tiles;
             if (next) {
-                store_a1();                                         // A1(it + 1); published together with the first halo chunk below
-                if (wk + 2 * G < p.n_tiles) prefetch(wk + 2 * G, smp_n);          // loads stay in flight under the conversion below
+                store_a1(b);                                        // A1(it + Ld); published together with the first halo chunk below
+                if (wk + (Ld + 1) * G < p.n_tiles) prefetch(wk + (Ld + 1) * G, smp_n);   // loads stay in flight under the conversion
             }
+            const int var0 = vq[0];
             const float* tb = p.tb_rows ? p.tbias + (size_t)var0 * p.tb_var_stride : tbs + var0 * coutp;
-            var0 = var1; var1 = var_n;
-            fetch_idx(wk + 3 * G);
+            vq[0] = vq[1];
+            if (Ld == 2) { vq[1] = vq[2]; vq[2] = var_n; } else vq[1] = var_n;
+            fetch_idx(wk + (Ld + 2) * G);
             // ---- D1 -> halo chunk buffers
             const int yy0 = y0 - 1 + ry0, xx0 = x0 - 1 + rx0, yy1 = y0 - 1 + ry1, xx1 = x0 - 1 + rx1;
             const bool in0 = real && yy0 >= 0 && yy0 < p.H && xx0 >= 0 && xx0 < p.W;                       // else: conv2's zero padding
@@ -395,7 +409,7 @@ k_enc1_f16(const __grid_constant__ Enc1Maps maps, const Enc1hParams p) {
                 asm volatile("bar.sync 9, 256;" ::: "memory");
                 if (mt == 0) {                                      // one release fence, then relaxed arrivals
                     release_fence();
-                    if (c == 0 && next) arrive_one(a1_full);
+                    if (c == 0 && next) arrive_one(a1_full0 + 8u * b);
                     arrive_one(hfull(hb));
                     if (c == p.n_chunks - 1) arrive_one(d1_empty0 + 8u * b);      // this D1 buffer may be overwritten
                 }
@@ -554,7 +568,7 @@ inline int build_enc1h_launch(Enc1hLaunch* E, int C, int H, int coutp, int cout_
     p.n_d1 = (6 * p.acc_cols <= 512 && !getenv("DTRAJ_E1_D1SINGLE")) ? 2 : 1;
     auto fixed_for = [&](int pair) {
         const size_t wr = (size_t)coutp / (pair ? 2 : 1);
-        return (size_t)1024 + (size_t)9 * p.n_chunks * wr * 128 + kE1Epi * 2048 + (size_t)p.n_slices * kA1SliceBytes +
+        return (size_t)1024 + (size_t)9 * p.n_chunks * wr * 128 + kE1Epi * 2048 + (size_t)p.n_d1 * p.n_slices * kA1SliceBytes +
                (((size_t)p.n_slices * wr * 32 + 1023) & ~(size_t)1023) + (size_t)(6 + C) * coutp * 4 + 16 + 256;
     };
     // pairs halve the resident weights per CTA; without them the weights must still fit next to one halo buffer
