@@ -635,7 +635,16 @@ int plan_forward(dtraj_plan* P, const float* x, int64_t x_stride, const int32_t*
         const int64_t n4 = R * (2 * Si) * (2 * Si) * (cp / 4);
         if (n4 >= ((int64_t)1 << 31)) return fail(DTRAJ_EINVAL, "upsample: batch too large for 32-bit indexing");
         PROF_BEGIN(prof, KC_RESAMPLE);
-        if (f16) DTRAJ_CUDA(launch_ex(k_upsample2_h, blocks_for(n4 / 2, 256), 256, 0, st, 1, true, (const __half*)in.p, (__half*)out.p, n4 / 2, Si, Si, cp / 8));
+        Up2Coef cf;
+        const int cp8 = cp / 8;
+        if (f16 && (cp8 & (cp8 - 1)) == 0 && !getenv("DTRAJ_UP_GENERIC") && up2_static_ok(Si, &cf)) {
+            int lg_hi = 0, lg_c = 0;
+            while ((1 << lg_hi) < Si) ++lg_hi;
+            while ((1 << lg_c) < cp8) ++lg_c;
+            const int64_t n_blk = R * Si * Si * cp8;
+            DTRAJ_CUDA(launch_ex(k_upsample2_h4, blocks_for(n_blk, 256), 256, 0, st, 1, true, (const __half*)in.p, (__half*)out.p,
+                                 (uint32_t)n_blk, Si, lg_hi, cp8, lg_c, cf));
+        } else if (f16) DTRAJ_CUDA(launch_ex(k_upsample2_h, blocks_for(n4 / 2, 256), 256, 0, st, 1, true, (const __half*)in.p, (__half*)out.p, n4 / 2, Si, Si, cp / 8));
         else k_upsample2<<<blocks_for(n4, 256), 256, 0, st>>>(in.p, out.p, n4, Si, Si, cp / 4, out.lo,
                                                              (u->act_mode == ACT_SPLIT && !out.lo) ? ACT_PLAIN : u->act_mode);
         PROF_END(prof);

@@ -326,6 +326,83 @@ __global__ void __launch_bounds__(256) k_upsample2_h(const __half* __restrict__ 
     reinterpret_cast<uint4*>(out)[i] = o;
 }
 
+// Block form of the same upsample: one thread = 8 channels of a 2 x 2 OUTPUT block.  With scale (in-1)/(2*in-1) the even
+// output row 2*yb interpolates source rows (yb-1, yb) and the odd row 2*yb+1 rows (yb, yb+1) (clamped) -- checked on the
+// host against ATen's fp32 index formula for the actual size (up2_static_ok) -- so the block needs a 3 x 3 source patch:
+// 9 loads and conversions for 4 outputs instead of 16, and the horizontal partial sums of the middle row are shared.
+// The generic kernel above was issue-bound (226 instructions per output vector, 88 % issue-active in ncu).
+struct Up2Coef { float ly_even[16], ly_odd[16]; };     // vertical (= horizontal) weights per block row, ATen's l1 = s - floor(s)
+
+__global__ void __launch_bounds__(256) k_upsample2_h4(const __half* __restrict__ in, __half* __restrict__ out,
+                                                      uint32_t n_blk, int Hi, int lg_hi, int cp8, int lg_cp8,
+                                                      const __grid_constant__ Up2Coef cf) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;        // (n, yb, xb, c8), c8 fastest
+    if (i >= n_blk) return;
+    const int c8 = (int)(i & (uint32_t)(cp8 - 1));
+    const uint32_t pix = i >> lg_cp8;
+    const int xb = (int)(pix & (uint32_t)(Hi - 1)), yb = (int)((pix >> lg_hi) & (uint32_t)(Hi - 1));
+    const uint32_t n = pix >> (2 * lg_hi);
+    const int ym = yb > 0 ? yb - 1 : 0, yp = yb < Hi - 1 ? yb + 1 : Hi - 1;
+    const int xm = xb > 0 ? xb - 1 : 0, xp = xb < Hi - 1 ? xb + 1 : Hi - 1;
+    const uint4* base = reinterpret_cast<const uint4*>(in) + (size_t)n * Hi * Hi * cp8 + c8;
+    const int rows[3] = {ym, yb, yp}, cols[3] = {xm, xb, xp};
+    const float lxe = cf.ly_even[xb], lxo = cf.ly_odd[xb], hxe = 1.f - lxe, hxo = 1.f - lxo;
+    const float lye = cf.ly_even[yb], lyo = cf.ly_odd[yb], hye = 1.f - lye, hyo = 1.f - lyo;
+    // horizontal partial sums per source row: he = hx*v[xm] + lx*v[xb] (even output column), ho = hx*v[xb] + lx*v[xp] (odd)
+    float he[3][8], ho[3][8];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        const uint4 a = __ldg(base + (rows[r] * Hi + cols[0]) * cp8);
+        const uint4 b = __ldg(base + (rows[r] * Hi + cols[1]) * cp8);
+        const uint4 c = __ldg(base + (rows[r] * Hi + cols[2]) * cp8);
+        const __half2* ah = reinterpret_cast<const __half2*>(&a);
+        const __half2* bh = reinterpret_cast<const __half2*>(&b);
+        const __half2* ch = reinterpret_cast<const __half2*>(&c);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float2 fa = __half22float2(ah[k]), fb = __half22float2(bh[k]), fc = __half22float2(ch[k]);
+            he[r][2 * k] = hxe * fa.x + lxe * fb.x; he[r][2 * k + 1] = hxe * fa.y + lxe * fb.y;
+            ho[r][2 * k] = hxo * fb.x + lxo * fc.x; ho[r][2 * k + 1] = hxo * fb.y + lxo * fc.y;
+        }
+    }
+    const int Wo = 2 * Hi;
+    uint4* obase = reinterpret_cast<uint4*>(out) + ((size_t)n * Wo * Wo + (size_t)(2 * yb) * Wo + 2 * xb) * cp8 + c8;
+    auto emit = [&](const float (&top)[8], const float (&bot)[8], float hy, float ly, uint4* dst) {
+        uint4 o;
+        __half2* oh = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) oh[k] = __floats2half2_rn(hy * top[2 * k] + ly * bot[2 * k], hy * top[2 * k + 1] + ly * bot[2 * k + 1]);
+        *dst = o;
+    };
+    emit(he[0], he[1], hye, lye, obase);                                  // (2yb,   2xb)
+    emit(ho[0], ho[1], hye, lye, obase + cp8);                            // (2yb,   2xb+1)
+    emit(he[1], he[2], hyo, lyo, obase + (size_t)Wo * cp8);               // (2yb+1, 2xb)
+    emit(ho[1], ho[2], hyo, lyo, obase + (size_t)Wo * cp8 + cp8);         // (2yb+1, 2xb+1)
+}
+
+// host: does ATen's fp32 coordinate formula pick (yb-1, yb) / (yb, yb+1) for every output row of this size?  Fills the weights.
+inline bool up2_static_ok(int Hi, Up2Coef* cf) {
+    if (Hi < 1 || Hi > 16 || (Hi & (Hi - 1))) return false;
+    const int Ho = 2 * Hi;
+    const float sc = Ho > 1 ? (float)(Hi - 1) / (float)(Ho - 1) : 0.f;
+    for (int yb = 0; yb < Hi; ++yb)
+        for (int par = 0; par < 2; ++par) {
+            const float s = sc * (float)(2 * yb + par);
+            int i0 = (int)s;
+            if (i0 > Hi - 1) i0 = Hi - 1;
+            const int i1 = i0 + (i0 < Hi - 1 ? 1 : 0);
+            const float l1 = s - (float)i0;
+            const int top = par == 0 ? (yb > 0 ? yb - 1 : 0) : yb;
+            const int bot = par == 0 ? yb : (yb < Hi - 1 ? yb + 1 : Hi - 1);
+            // the static pair must give the same value: identical rows, or all the weight on a shared first row
+            if (!((i0 == top && i1 == bot) || (l1 == 0.f && i0 == top))) return false;
+            (par == 0 ? cf->ly_even : cf->ly_odd)[yb] = l1;
+        }
+    return true;
+}
+
 // =====================================================================================
 // final 1x1 conv (models.py:157,224) evaluated at HALF resolution: a 1x1 conv commutes
 // with the per-channel bilinear resize (lerp weights sum to 1), so
