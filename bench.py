@@ -197,6 +197,8 @@ def run_ours(args, emit=print):
     if world > 1:
         os.environ["NCCL_DEBUG"] = os.environ.get("DTRAJ_NCCL_DEBUG", "WARN")   # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
+        # one process per GPU on one host: do not let every rank's tiny host-side torch ops spawn a full-size thread pool
+        torch.set_num_threads(max(1, (os.cpu_count() or world) // world))
 
     def barrier():
         if world > 1:
@@ -254,6 +256,9 @@ def run_ours(args, emit=print):
                      precision=args.precision, stats=stats)
     barrier()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
+    if os.environ.get("DTRAJ_SWEEP_TIMING"):
+        print(f"[rank {rank}] e2e {e2e_s * 1e3:.0f} ms; host ms per phase: " +
+              ", ".join(f"{k[7:]} {v * 1e3:.0f}" for k, v in stats.items() if k.startswith("host_s_")), file=sys.stderr)
     e2e = {"value": traj_per_step * K / e2e_s, "unit": UNIT, "h2d_bytes_per_step": stats["h2d_bytes"] // K,
            "d2h_bytes_per_step": stats["d2h_bytes"] // K, "ms_per_step": e2e_s / K * 1e3,
            "api": "distillation_trajectories_b200.grid.sweep (batched compare_trajectories): one call over steps x seeds, "

@@ -24,8 +24,13 @@ from .analysis.metrics import trajectory_metrics as tm
 
 
 def shard_samples(num_samples, rank, world_size):
-    """Round-robin seed ownership: sample s belongs to rank s % world_size."""
-    return list(range(rank, num_samples, world_size))
+    """Contiguous block ownership (sizes differ by at most one).  Contiguous, not round-robin, because the noise of
+    step t of sample s is the stream seeded 42 + s + t (analysis/trajectory_engine.py:88-95): a rank's noise bank holds
+    one entry per DISTINCT seed + t, i.e. n + T entries for n consecutive samples but up to n * T for samples spread
+    world_size apart (measured at 8 GPUs: 300 ms of host draws per 592-sample chunk, more than the chunk's device time)."""
+    base, extra = divmod(num_samples, world_size)
+    lo = rank * base + min(rank, extra)
+    return list(range(lo, lo + base + (1 if rank < extra else 0)))
 
 
 def reduce_sums(sums, group=None):
@@ -223,13 +228,24 @@ def sweep(teacher_model, students, config, guidance_scales, num_samples, device=
     n_traj = n_pairs = h2d = d2h = 0
     pending = None                                  # (readback, chunk) of the previous chunk
     nxt = stage_chunk(pieces[0], config, guidance_scales, device) if pieces else None
+    import time
+    tm_ = {"run": 0.0, "stage": 0.0, "wait": 0.0, "finish": 0.0}
     for i in range(len(pieces)):
         ck = nxt
+        t0 = time.perf_counter()
         red, w1, nt = run_chunk(teacher_model, models, ck, device, precision)      # queued, not waited for
         rb = _Readback(red, w1, device)
+        t1 = time.perf_counter()
         nxt = stage_chunk(pieces[i + 1], config, guidance_scales, device) if i + 1 < len(pieces) else None
+        t2 = time.perf_counter()
+        tm_["run"] += t1 - t0
+        tm_["stage"] += t2 - t1
         if pending is not None:
-            d2h += finish_chunk(*pending[0].wait(), pending[1], config, sums)
+            arrs = pending[0].wait()
+            t3 = time.perf_counter()
+            d2h += finish_chunk(*arrs, pending[1], config, sums)
+            tm_["wait"] += t3 - t2
+            tm_["finish"] += time.perf_counter() - t3
         pending = (rb, ck)
         h2d += ck.h2d_bytes
         n_traj += nt
@@ -239,6 +255,8 @@ def sweep(teacher_model, students, config, guidance_scales, num_samples, device=
     if stats is not None:
         for k, v in (("trajectories", n_traj), ("pairs", n_pairs), ("h2d_bytes", h2d), ("d2h_bytes", d2h)):
             stats[k] = stats.get(k, 0) + v
+        for k, v in tm_.items():                      # host seconds per phase (wait = blocked on the previous chunk's read-back)
+            stats["host_s_" + k] = stats.get("host_s_" + k, 0.0) + v
     if reduce:
         sums = reduce_sums(sums)
     return averages_from_sums(sums, names, guidance_scales)
