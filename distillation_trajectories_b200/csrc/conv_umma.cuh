@@ -1,22 +1,25 @@
-// tcgen05 / TMA implicit-GEMM convolution for sm_100a (DTRAJ_PREC_TF32, DTRAJ_PREC_TF32X3).
+// tcgen05 / TMA implicit-GEMM convolution for sm_100a (DTRAJ_PREC_F16, DTRAJ_PREC_TF32, DTRAJ_PREC_TF32X3).
 //
 // GEMM view of one conv layer (models.py:48-57):  D[M, N] = A[M, K] * B[K, N]
 //   M = n_img*H*W output pixels, N = coutp, K = ntaps * (c0p + c1p).
 // A is never materialised: with NHWC feature maps a 3x3 tap is a SHIFTED 4-d box of the
-// input tensor, so one TMA box load {32 ch, W, Hb, Nb} at coordinates
-// {c0, dx, y0+dy, img0} delivers the 128 x 32 im2col tile of tap (dy,dx) straight into the
+// input tensor, so one TMA box load {128 bytes of channels, W, Hb, Nb} at coordinates
+// {c0, dx, y0+dy, img0} delivers the 128-row im2col tile of tap (dy,dx) straight into the
 // 128-byte-swizzled K-major layout tcgen05.mma reads; out-of-bounds rows/columns (the
 // conv's zero padding) are zero-filled by the TMA unit.  The channel concat of the decoder
-// blocks (models.py:206,211,216) is two tensor maps feeding consecutive K blocks.
+// blocks (models.py:206,211,216) is two tensor maps feeding consecutive K blocks.  A K block
+// (128 bytes per row) is 32 fp32 channels (kind::tf32) or 64 fp16 channels (kind::f16).
 //
-// Roles (192 threads): warp 0 = TMA producer + TMEM allocator, warp 1 = MMA issuer (one
-// elected lane), warps 2-5 = epilogue (TMEM -> registers -> bias / ReLU / time-bias /
-// residual -> global).  A `stages`-deep mbarrier ring connects producer and issuer; the
-// fp32 accumulator (128 lanes x N columns) lives in TMEM.
+// Roles (320 threads, one persistent CTA per SM, optionally CTA pairs with cta_group::2):
+// warp 0 = TMA producer + TMEM allocator, warp 1 = MMA issuer (one elected lane), warps 2-9 =
+// epilogue (TMEM -> registers -> bias / ReLU / time-bias / residual / fused tails -> swizzled
+// ring buffer -> TMA store).  A `stages`-deep mbarrier ring connects producer and issuer; two
+// fp32 accumulator sets (128 lanes x N columns) live in TMEM so that the epilogue of tile i
+// overlaps the MMAs of tile i+1.
 //
 // 3xTF32 (DTRAJ_PREC_TF32X3): the K loop runs three passes  A_hi*B_hi + A_hi*B_lo + A_lo*B_hi
-// into the same accumulator, where x_lo = x - trunc_tf32(x) is kept in a second plane by
-// every producer of an activation (ACT_SPLIT) and the weights are split on the host.
+// (the two cross terms into a separate accumulator), where x_lo = x - trunc_tf32(x) is kept in a
+// second plane by every producer of an activation (ACT_SPLIT) and the weights are split on the host.
 #pragma once
 #include <cstdlib>
 #include <cuda_fp16.h>

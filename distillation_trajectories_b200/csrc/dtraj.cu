@@ -500,6 +500,8 @@ int plan_build(const dtraj_unet* u, int64_t R, void* ws, int64_t ws_bytes, dtraj
     // enc1: conv1/res by k_conv_first; conv2 here.  x1 itself is never a skip input (models.py:206-216):
     // with the pool fused, only the pooled tile is written.
     P->fuse_enc1 = fused && S[0] % 16 == 0 && u->d.channels <= 4 && !getenv("DTRAJ_NO_ENC1");
+    if (f16 && u->dp[0] > 128) P->fuse_enc1 = false;   // the fp16 fused kernel holds D1 + two accumulators in TMEM: widths up to 128;
+                                                        // wider first blocks take k_conv_first + the generic conv2 (RESX + POOL tails)
     if (P->fuse_enc1 && f16) {
         rc = build_enc1h_launch(&P->enc1h, u->d.channels, S[0], u->dp[0], blk(0).cout, P->R, blk(0).conv2.w, blk(0).conv2.rows);
         Enc1hParams& e = P->enc1h.p;

@@ -14,6 +14,7 @@ A chunk of the sweep goes through three stages so that the device part can be ti
 of the per-frame reductions + the f64 scalar formulas).
 """
 import os
+import time
 
 import numpy as np
 import torch
@@ -228,7 +229,6 @@ def sweep(teacher_model, students, config, guidance_scales, num_samples, device=
     n_traj = n_pairs = h2d = d2h = 0
     pending = None                                  # (readback, chunk) of the previous chunk
     nxt = stage_chunk(pieces[0], config, guidance_scales, device) if pieces else None
-    import time
     tm_ = {"run": 0.0, "stage": 0.0, "wait": 0.0, "finish": 0.0}
     for i in range(len(pieces)):
         ck = nxt

@@ -1,5 +1,6 @@
+"""GPU: host time of the three phases of one sweep chunk (stage / run / finish) at the bench batch."""
 import os, sys, time
-sys.path.insert(0, "/root/repo")
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch, numpy as np
 import bench
 from distillation_trajectories_b200 import grid
