@@ -105,6 +105,27 @@ def test_forward_bench_sized_batch(sf, prec):
     assert umma_error_flag() == 0
 
 
+@pytest.mark.parametrize("C,H", [(1, 16), (3, 32)])
+def test_forward_f16_unfused_first_block(C, H, monkeypatch):
+    """fp16 mode without the fused enc1 kernel (what first blocks wider than 128 channels take): k_conv_first writing
+    fp16, the generic conv2 with the recomputed 1x1 residual and the pool tail (16x16) or k_pool2_h (32x32)."""
+    monkeypatch.setenv("DTRAJ_NO_ENC1", "1")
+    cfg = Cfg(C, H, 50)
+    model = make_model(cfg, 0.3, 13, device="cuda")
+    sd = cpu_sd(model)
+    torch.manual_seed(4)
+    x = torch.randn(4, C, H, H)
+    variants = torch.tensor([0, 1, 2, 1], dtype=torch.int32)
+    eng = UNetEngine.for_model(model, H, 50, "f16")
+    got = eng.forward(x.cuda(), 31, variants.cuda()).cpu().numpy()
+    tt = torch.full((1,), 31, dtype=torch.long)
+    for r in range(4):
+        cond = None if variants[r] == 0 else torch.full((1, 1), float(variants[r] - 1))
+        want = ounet.unet_forward(sd, x[r:r + 1], tt, cond).numpy()
+        assert_close(got[r:r + 1], want, 0.0, FWD_TOL["f16"], f"row {r} unfused f16")
+    assert umma_error_flag() == 0
+
+
 def test_training_mode_and_bad_input_fail_loudly():
     from distillation_trajectories_b200 import DtrajError
     cfg = Cfg(1, 16, 4)
