@@ -1127,7 +1127,8 @@ inline int build_umma_launch(UmmaLaunch* U, const ConvLayer& L, int npass, const
     // latency-bound operand ring.  Wide, long layers with plenty of tiles only.
     const int pair_min = getenv("DTRAJ_PAIR_MIN") ? atoi(getenv("DTRAJ_PAIR_MIN")) : 64;
     const int pair_work = getenv("DTRAJ_PAIR_WORK") ? atoi(getenv("DTRAJ_PAIR_WORK")) : 2 * kNumSMs;
-    c.pair = (!c.swap && c.n_split == 1 && L.coutp >= pair_min && nkb_all >= 16 && c.n_work >= pair_work &&
+    const int pair_nkb = getenv("DTRAJ_PAIR_NKB") ? atoi(getenv("DTRAJ_PAIR_NKB")) : 16;
+    c.pair = (!c.swap && c.n_split == 1 && L.coutp >= pair_min && nkb_all >= pair_nkb && c.n_work >= pair_work &&
               !getenv("DTRAJ_NO_PAIR")) ? 1 : 0;
     c.cluster = (c.pair || (c.n_split == 1 && c.n_work >= 2 * kNumSMs && getenv("DTRAJ_CLUSTER"))) ? 2 : 1;
     c.acc_cols = 32;

@@ -3,6 +3,8 @@ metric kernels) at a reduced seed count.  Used under ncu for the launch list and
 import os
 import sys
 
+os.environ.setdefault("DTRAJ_OVERLAP_MODELS", "0")     # one stream: a deterministic launch order for --launch-skip
+
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 
