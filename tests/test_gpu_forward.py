@@ -126,6 +126,35 @@ def test_forward_f16_unfused_first_block(C, H, monkeypatch):
     assert umma_error_flag() == 0
 
 
+@pytest.mark.parametrize("prec", ["fp32", "tf32x3", "tf32", "f16"])
+@pytest.mark.parametrize("sf,C,H,R", [(1.0, 1, 16, 37), (0.5, 1, 16, 5), (0.2, 3, 32, 3)])
+def test_forward_stays_inside_its_workspace(sf, C, H, R, prec):
+    """Guard bands around the caller-owned workspace and the eps output: a forward (ragged row counts: partial tiles,
+    padded pair tiles) must not write a byte outside dtraj_unet_workspace_bytes / the eps tensor."""
+    import ctypes as Ct
+    cfg = Cfg(C, H, 8)
+    model = make_model(cfg, sf, 17, device="cuda")
+    eng = UNetEngine.for_model(model, H, 8, prec)
+    lib = _lib.load()
+    need = eng.workspace_bytes(R)
+    guard = 1 << 20
+    ws = torch.full((guard + need + guard,), 0xAB, dtype=torch.uint8, device="cuda")
+    base = ws.data_ptr() + guard
+    assert base % 256 == 0
+    x = torch.randn(R, C, H, H, device="cuda")
+    out = torch.full((R + 2, C, H, H), 7.0, device="cuda")           # rows 0 and R + 1 are guards
+    variants = (torch.arange(R, device="cuda") % 3).to(torch.int32)
+    _lib.check(lib.dtraj_unet_forward(eng.handle, _lib.ptr(x), R, 3, _lib.ptr(variants), Ct.c_void_p(out[1:].data_ptr()),
+                                      Ct.c_void_p(base), need, _lib.stream_ptr()))
+    torch.cuda.synchronize()
+    assert bool((ws[:guard] == 0xAB).all()) and bool((ws[guard + need:] == 0xAB).all()), "wrote outside the workspace"
+    assert bool((out[0] == 7.0).all()) and bool((out[R + 1] == 7.0).all()), "wrote outside the eps tensor"
+    assert torch.isfinite(out[1:R + 1]).all()
+    ref = eng.forward(x, 3, variants)
+    assert torch.equal(out[1:R + 1], ref)
+    assert umma_error_flag() == 0
+
+
 def test_training_mode_and_bad_input_fail_loudly():
     from distillation_trajectories_b200 import DtrajError
     cfg = Cfg(1, 16, 4)
