@@ -47,6 +47,9 @@ def workload_config(seeds, world):
             "seeds_per_gpu_per_step": seeds, "guidance_scales": GUIDANCE,
             "trajectories_per_step": 2 * seeds * len(GUIDANCE) * world,
             "parallelism": f"seed-sharded x{world}, one all-reduce of metric sums",
+            "dedup": "teacher trajectories computed once per (seed, w); at the first step the 8 scales of a seed still hold "
+                     "the same x_T, so its forward rows are evaluated once per (seed, conditioning variant) -- bit-identical "
+                     "frames (tests/test_gpu_samplers.py::test_first_step_row_sharing_is_exact)",
             "l2": f"per-step working set (2 x {seeds * 8 * 51 * 256 * 4 / 1e6:.0f} MB trajectory buffers + GBs of activations) "
                   "exceeds the 126 MB L2; no explicit flush"}
 

@@ -30,12 +30,14 @@ class UNetDesc(C.Structure):
 class SamplerDesc(C.Structure):
     _fields_ = [("rule", C.c_int32), ("n_samples", C.c_int32), ("n_rows", C.c_int32),
                 ("n_updates", C.c_int32), ("copy_last", C.c_int32), ("n_frames", C.c_int32),
-                ("use_graph", C.c_int32), ("reserved", C.c_int32),
+                ("use_graph", C.c_int32), ("n_rows0", C.c_int32),
                 ("step_timestep", C.c_void_p), ("step_coef", C.c_void_p),
                 ("row_sample", C.c_void_p), ("row_variant", C.c_void_p),
                 ("sample_row_u", C.c_void_p), ("sample_row_c", C.c_void_p),
                 ("guidance", C.c_void_p), ("z_bank", C.c_void_p), ("z_index", C.c_void_p),
-                ("traj", C.c_void_p), ("workspace", C.c_void_p), ("workspace_bytes", C.c_int64)]
+                ("traj", C.c_void_p), ("workspace", C.c_void_p), ("workspace_bytes", C.c_int64),
+                ("row_sample0", C.c_void_p), ("row_variant0", C.c_void_p),
+                ("sample_row_u0", C.c_void_p), ("sample_row_c0", C.c_void_p)]
 
 
 # every symbol include/dtraj.h declares: name -> (restype, argtypes)

@@ -85,16 +85,18 @@ def _noise_bank(base_seeds, shape, device, timesteps):
 
 
 @torch.no_grad()
-def generate_trajectories_batched(model, noises, seeds, guidance, timesteps, device, precision=None):
+def generate_trajectories_batched(model, noises, seeds, guidance, timesteps, device, precision=None, groups=None):
     """S2 for B independent (noise, seed, w) triples in one captured loop.
-    noises [B, C, H, W]; seeds list[int]; guidance list[float|None].  Returns DEVICE [B, T+1, C, H, W]."""
+    noises [B, C, H, W]; seeds list[int]; guidance list[float|None]; ``groups``: optional group id per triple --
+    triples of a group have IDENTICAL noise rows, which lets the first step share forward rows.
+    Returns DEVICE [B, T+1, C, H, W]."""
     model.eval()
     device = torch.device(device)
     eng = UNetEngine.for_model(model, noises.shape[2], timesteps, precision or get_precision("S2"), device)
     bank, first = _noise_bank(seeds, (1,) + tuple(noises.shape[1:]), sampling.noise_device(device), timesteps)
     ts = np.arange(timesteps - 1, 0, -1)
     z_index = (np.asarray(seeds)[None, :] + ts[:, None] - first).astype(np.int32) if len(ts) else np.zeros((1, len(seeds)), np.int32)
-    return sampling.s2_sample(eng, noises.to(device), timesteps, list(guidance), bank, z_index)
+    return sampling.s2_sample(eng, noises.to(device), timesteps, list(guidance), bank, z_index, groups=groups)
 
 
 def wasserstein_index_sets(seeds, timesteps, n_frames, numel, sample_size=1000):
@@ -134,13 +136,14 @@ def compare_trajectories_batched(teacher_model, student_model, config, guidance_
     x = torch.cat(noises).repeat_interleave(G, dim=0)   # pair p = sample-major, guidance-minor
     seeds = [42 + s for s in samples for _ in range(G)]
     ws = [gs for _ in samples for gs in guidance_scales]
-    tt = generate_trajectories_batched(teacher_model, x, seeds, ws, T, device, precision)
+    groups = [i for i in range(len(samples)) for _ in range(G)]      # every scale of a sample starts from the same noise
+    tt = generate_trajectories_batched(teacher_model, x, seeds, ws, T, device, precision, groups)
     t_flat = tt.reshape(tt.shape[0], tt.shape[1], -1)
     if student_model is teacher_model:
         s_flat = t_flat
     else:
         t_flat = t_flat.clone()                         # the sampler's buffer is reused by the next run
-        st = generate_trajectories_batched(student_model, x, seeds, ws, T, device, precision)
+        st = generate_trajectories_batched(student_model, x, seeds, ws, T, device, precision, groups)
         s_flat = st.reshape(st.shape[0], st.shape[1], -1)
     red = tm.pair_reductions(t_flat, s_flat).cpu().numpy()
     L, D = t_flat.shape[1], t_flat.shape[2]

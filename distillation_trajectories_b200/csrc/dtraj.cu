@@ -754,6 +754,7 @@ struct dtraj_sampler {
     std::vector<int32_t> ts;
     std::vector<float> coef;
     dtraj_plan* plan = nullptr;
+    dtraj_plan* plan0 = nullptr;    // first step with shared rows (desc.n_rows0 > 0); same workspace
     cudaGraph_t graph = nullptr;
     cudaGraphExec_t exec = nullptr;
     int64_t launches = 0;
@@ -768,10 +769,14 @@ int sampler_enqueue(dtraj_sampler* s, cudaStream_t st, int64_t* launches, Profil
     int64_t nl = 0;
     for (int k = 0; k < d.n_updates; ++k) {
         const float* xin = d.traj + (int64_t)k * D;
-        DTRAJ_TRY(plan_forward(s->plan, xin, fs, d.row_sample, d.row_variant, s->ts[k], st, &nl, prof));
+        const bool first = k == 0 && s->plan0 != nullptr;            // shared rows: every sample of a group still has x_T
+        dtraj_plan* P = first ? s->plan0 : s->plan;
+        DTRAJ_TRY(plan_forward(P, xin, fs, first ? d.row_sample0 : d.row_sample, first ? d.row_variant0 : d.row_variant,
+                               s->ts[k], st, &nl, prof));
         StepParams p;
         p.rule = d.rule; p.k0 = s->coef[3 * k]; p.k1 = s->coef[3 * k + 1]; p.k2 = s->coef[3 * k + 2];
-        p.elow = s->plan->elow.p; p.sample_row_u = d.sample_row_u; p.sample_row_c = d.sample_row_c;
+        p.elow = P->elow.p; p.sample_row_u = first ? d.sample_row_u0 : d.sample_row_u;
+        p.sample_row_c = first ? d.sample_row_c0 : d.sample_row_c;
         p.guidance = d.guidance; p.z_bank = d.z_bank;
         p.z_index = d.z_index ? d.z_index + (int64_t)k * d.n_samples : nullptr;
         p.x_in = xin; p.x_out = d.traj + (int64_t)(k + 1) * D; p.frame_stride = fs;
@@ -801,6 +806,7 @@ extern "C" int dtraj_sampler_destroy(dtraj_sampler* s) {
     if (s->exec) cudaGraphExecDestroy(s->exec);
     if (s->graph) cudaGraphDestroy(s->graph);
     if (s->plan) delete s->plan;
+    if (s->plan0) delete s->plan0;
     delete s;
     return 0;
 }
@@ -827,6 +833,14 @@ extern "C" int dtraj_sampler_create(dtraj_unet* u, const dtraj_sampler_desc* d, 
         }
     int rc = plan_build(u, d->n_rows, d->workspace, d->workspace_bytes, &s->plan);
     if (rc) { delete s; return rc; }
+    if (d->n_rows0 > 0) {
+        if (d->n_rows0 > d->n_rows || !d->row_sample0 || !d->row_variant0 || !d->sample_row_u0 || (d->sample_row_c && !d->sample_row_c0)) {
+            dtraj_sampler_destroy(s);
+            return fail(DTRAJ_EINVAL, "bad first-step row layout");
+        }
+        rc = plan_build(u, d->n_rows0, d->workspace, d->workspace_bytes, &s->plan0);
+        if (rc) { dtraj_sampler_destroy(s); return rc; }
+    }
     if (d->use_graph) {
         cudaStream_t cs;
         cudaError_t ce = cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking);
@@ -877,10 +891,18 @@ extern "C" int dtraj_sampler_profile(dtraj_sampler* s, void* stream, double* cla
         }
         cudaEventDestroy(r.a); cudaEventDestroy(r.b);
     }
-    double f = 0.0;
-    for (auto& op : s->plan->convs) f += op.flops;
-    conv_flops[0] = f * s->d.n_updates;
-    conv_flops[1] = s->plan->fuse_enc1 ? (s->u->d.precision == DTRAJ_PREC_F16 ? s->plan->enc1h.flops : s->plan->enc1.flops) * s->d.n_updates : 0.0;
+    auto plan_flops = [&](dtraj_plan* P, double* conv, double* e1) {
+        double f = 0.0;
+        for (auto& op : P->convs) f += op.flops;
+        *conv = f;
+        *e1 = P->fuse_enc1 ? (s->u->d.precision == DTRAJ_PREC_F16 ? P->enc1h.flops : P->enc1.flops) : 0.0;
+    };
+    double fc = 0.0, fe = 0.0, fc0 = 0.0, fe0 = 0.0;
+    plan_flops(s->plan, &fc, &fe);
+    if (s->plan0) plan_flops(s->plan0, &fc0, &fe0); else { fc0 = fc; fe0 = fe; }
+    const int nu = s->d.n_updates;
+    conv_flops[0] = nu > 0 ? fc0 + fc * (nu - 1) : 0.0;       // executed flops: the first step runs the shared-row plan
+    conv_flops[1] = nu > 0 ? fe0 + fe * (nu - 1) : 0.0;
     if (rc) return rc;
     if (ce != cudaSuccess) return fail(DTRAJ_ECUDA, "profile -> %s", cudaGetErrorString(ce));
     return 0;

@@ -172,7 +172,7 @@ class TrajectorySampler:
     """
 
     def __init__(self, engine, rule, n_samples, row_sample, row_variant, sample_row_u, sample_row_c,
-                 timesteps, coefs, copy_last, n_noise, use_graph=True):
+                 timesteps, coefs, copy_last, n_noise, use_graph=True, first_layout=None):
         self.engine = engine
         self.lib = engine.lib
         dev = engine.device
@@ -207,6 +207,11 @@ class TrajectorySampler:
         d.guidance = self.guidance.data_ptr()
         d.z_bank, d.z_index = self.z_bank.data_ptr(), self.z_index.data_ptr()
         d.traj, d.workspace, d.workspace_bytes = self.traj.data_ptr(), self.ws.data_ptr(), self.ws.numel()
+        if first_layout is not None:          # (row_sample0, row_variant0, sample_row_u0, sample_row_c0): shared rows at step 0
+            self.first = [torch.as_tensor(np.asarray(a, np.int32), **i32) for a in first_layout]
+            d.n_rows0 = len(first_layout[0])
+            d.row_sample0, d.row_variant0 = self.first[0].data_ptr(), self.first[1].data_ptr()
+            d.sample_row_u0, d.sample_row_c0 = self.first[2].data_ptr(), self.first[3].data_ptr()
         h = C.c_void_p()
         with torch.cuda.device(dev):
             torch.cuda.synchronize(dev)

@@ -60,7 +60,7 @@ def averages_from_sums(sums, student_keys, guidance_scales):
 
 class Chunk:
     """Device-resident inputs of one batch of (seed, guidance) pairs; pair p = seed-major, guidance-minor."""
-    __slots__ = ("samples", "G", "x", "seeds", "ws", "ws_dev", "bank", "z_index", "idx", "idx_set", "T", "h2d_bytes")
+    __slots__ = ("samples", "G", "x", "seeds", "groups", "ws", "ws_dev", "bank", "z_index", "idx", "idx_set", "T", "h2d_bytes")
 
 
 def stage_chunk(samples, config, guidance_scales, device):
@@ -80,6 +80,7 @@ def stage_chunk(samples, config, guidance_scales, device):
         noises.append(torch.randn(1, C, H, H, generator=gen))
     x = torch.cat(noises).repeat_interleave(G, dim=0)
     ck.seeds = [42 + s for s in ck.samples for _ in range(G)]
+    ck.groups = [i for i in range(len(ck.samples)) for _ in range(G)]      # pairs of one sample share x_T: first-step rows are shared
     ck.ws = [gs for _ in ck.samples for gs in guidance_scales]
     ndev = sampling.noise_device(device)
     bank, first = te._noise_bank(ck.seeds, (1, C, H, H), ndev, T)
@@ -116,7 +117,8 @@ def run_chunk(teacher_model, student_models, ck, device, precision=None):
     def gen(model):
         model.eval()
         eng = te.UNetEngine.for_model(model, ck.x.shape[2], ck.T, prec, device)
-        return sampling.s2_sample(eng, ck.x, ck.T, ck.ws, ck.bank, ck.z_index, guidance_dev=ck.ws_dev)
+        return sampling.s2_sample(eng, ck.x, ck.T, ck.ws, ck.bank, ck.z_index, guidance_dev=ck.ws_dev,
+                                  groups=getattr(ck, "groups", None))
 
     # The teacher's and the students' loops are independent until the metrics: the students run on a side stream, so that
     # their CTAs fill the tails of the teacher's persistent kernels and vice versa (+2.3 % trajectories/s on the bench

@@ -147,7 +147,7 @@ typedef struct {
                                   trajectory_engine.py:86,113)                               */
     int32_t n_frames;          /* L = 1 + n_updates + copy_last                              */
     int32_t use_graph;         /* capture the whole loop in one CUDA graph                   */
-    int32_t reserved;
+    int32_t n_rows0;           /* > 0: the FIRST step uses its own, smaller row layout (below) */
     const int32_t* step_timestep;  /* host [n_updates]  timestep value fed to the model      */
     const float*   step_coef;      /* host [n_updates*3] k0,k1,k2 of the rule, per step      */
     const int32_t* row_sample;     /* dev [n_rows]   sample whose x this row evaluates       */
@@ -160,6 +160,14 @@ typedef struct {
     float*         traj;           /* dev [n_samples, n_frames, C, H, W]; frame 0 = x_T in   */
     void*          workspace;      /* dev, >= dtraj_unet_workspace_bytes(unet, n_rows)       */
     int64_t        workspace_bytes;
+    /* First-step row sharing (n_rows0 > 0): samples that start from the SAME x_T and differ only in their guidance
+     * scale (compare_trajectories feeds one noise to every scale, analysis/trajectory_engine.py:147-156) need one
+     * forward row per (x_T, variant) at the first step instead of one or two per sample.  Same meaning as the four
+     * arrays above, for step 0 only; n_rows0 <= n_rows. */
+    const int32_t* row_sample0;    /* dev [n_rows0]                                          */
+    const int32_t* row_variant0;   /* dev [n_rows0]                                          */
+    const int32_t* sample_row_u0;  /* dev [n_samples]                                        */
+    const int32_t* sample_row_c0;  /* dev [n_samples], -1 = no guidance                      */
 } dtraj_sampler_desc;
 
 /*

@@ -34,4 +34,4 @@ def test_version_and_error_string_without_gpu():
 
 def test_struct_sizes_match_header():
     assert ctypes.sizeof(_lib.UNetDesc) == 9 * 4
-    assert ctypes.sizeof(_lib.SamplerDesc) == 8 * 4 + 11 * 8 + 8
+    assert ctypes.sizeof(_lib.SamplerDesc) == 8 * 4 + 11 * 8 + 8 + 4 * 8

@@ -197,3 +197,25 @@ def test_f16_overflow_is_reported_not_hidden():
     assert umma_error_flag() == 0                  # the check clears the sticky flag
     traj = te.generate_trajectory(make_model(cfg, 0.2, 21, device="cuda"), noise, 4, "cuda", seed=1, guidance_scale=2.0)
     assert all(torch.isfinite(f).all() for f in traj)
+
+
+@pytest.mark.parametrize("prec", ["tf32", "f16"])
+def test_first_step_row_sharing_is_exact(prec):
+    """samples of one group start from the same x_T: sharing their first-step forward rows (3 rows per group instead of
+    up to 2 per sample) must reproduce the unshared loop bit for bit"""
+    from distillation_trajectories_b200.engine import UNetEngine
+    cfg = Cfg(1, 16, 7)
+    model = make_model(cfg, 0.2, 23, device="cuda")
+    eng = UNetEngine.for_model(model, 16, 7, prec)
+    torch.manual_seed(2)
+    ws = [1.0, 2.0, 7.5, None, 20.0]
+    G, S = len(ws), 6
+    x = torch.randn(S, 1, 16, 16).repeat_interleave(G, dim=0)
+    guidance = ws * S
+    groups = [i for i in range(S) for _ in range(G)]
+    bank = torch.randn(6 * 4, 256)
+    zi = np.random.RandomState(0).randint(0, 24, size=(6, S * G)).astype(np.int32)
+    a = sampling.s2_sample(eng, x, 7, guidance, bank, zi, groups=groups).cpu().numpy().copy()
+    b = sampling.s2_sample(eng, x, 7, guidance, bank, zi, groups=None).cpu().numpy()
+    np.testing.assert_array_equal(a, b)
+    assert umma_error_flag() == 0
