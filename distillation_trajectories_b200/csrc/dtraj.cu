@@ -965,6 +965,36 @@ extern "C" int dtraj_error_flag_async(uint32_t* host_flag, void* stream) {
     return 0;
 }
 
+// hardware probe, see probe.cuh: [n_img][8][8][64] fp16 map with element (n, y, x, c) = n*64 + y*8 + x + 1, loaded through a
+// tensor map over {c, x, image, y}; out_host[200] = first channel of every shared-memory row of the box at image `img0`
+extern "C" int dtraj_probe_tma_permuted(int32_t n_img, int32_t img0, float* out_host) {
+    PFN_encodeTiled enc = get_encode_tiled();
+    if (!enc) return fail(DTRAJ_ECUDA, "cuTensorMapEncodeTiled not available");
+    std::vector<__half> h((size_t)n_img * 64 * 64);
+    for (int n = 0; n < n_img; ++n)
+        for (int p = 0; p < 64; ++p)
+            for (int c = 0; c < 64; ++c) h[((size_t)n * 64 + p) * 64 + c] = __float2half_rn((float)(n * 64 + p + 1));
+    __half* d = nullptr; float* o = nullptr;
+    DTRAJ_CUDA(cudaMalloc(&d, h.size() * 2));
+    DTRAJ_CUDA(cudaMalloc(&o, 200 * sizeof(float)));
+    DTRAJ_CUDA(cudaMemcpy(d, h.data(), h.size() * 2, cudaMemcpyHostToDevice));
+    CUtensorMap m;
+    cuuint64_t dims[4] = {64, 8, (cuuint64_t)n_img, 8};                       // c, x, image, y
+    cuuint64_t strides[3] = {64 * 2, 64 * 64 * 2, 8 * 64 * 2};                  // x, image, y  (bytes): NOT increasing
+    cuuint32_t box[4] = {64, 10, 2, 10};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, (void*)d, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { cudaFree(d); cudaFree(o); return fail(DTRAJ_ECUDA, "cuTensorMapEncodeTiled(permuted dims) -> %d", (int)r); }
+    cudaFuncSetAttribute(k_probe_tma_perm, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * 1024);
+    k_probe_tma_perm<<<1, 128, 28 * 1024>>>(m, img0, o);
+    cudaError_t ce = cudaDeviceSynchronize();
+    if (ce == cudaSuccess) ce = cudaMemcpy(out_host, o, 200 * sizeof(float), cudaMemcpyDeviceToHost);
+    cudaFree(d); cudaFree(o);
+    if (ce != cudaSuccess) return fail(DTRAJ_ECUDA, "tma permuted probe -> %s", cudaGetErrorString(ce));
+    return 0;
+}
+
 extern "C" unsigned int dtraj_debug_umma_error(void) {
     unsigned int v = 0;
     cudaMemcpyFromSymbol(&v, g_umma_error, sizeof(v));

@@ -53,4 +53,26 @@ __global__ void __launch_bounds__(128) k_probe_view(int rows, int start_row, int
     if (threadIdx.x < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(32u) : "memory");
 }
 
+// Second probe (for the next step of the conv kernel): does a TMA box over PERMUTED dimensions {c, x, image, y} of an
+// NHWC fp16 map -- global strides not in increasing order -- deliver the halo rows of two 8x8 images interleaved in
+// shared memory as [halo row (10)][image (2)][halo column (10)][64 channels], with out-of-bounds rows / columns
+// zero-filled?  (Interleaved rows make consecutive 8-pixel row groups always 10 pixels apart, which is what a tap VIEW of
+// a two-image tile needs.)  The map is encoded on the host; out[r] = first channel of shared-memory row r.
+__global__ void __launch_bounds__(128) k_probe_tma_perm(const __grid_constant__ CUtensorMap map, int img0, float* out) {
+    extern __shared__ __align__(1024) uint8_t probe_sm[];
+    const uint32_t base = (ptx::smem_u32(probe_sm) + 1023u) & ~1023u;
+    uint8_t* a = probe_sm + (base - ptx::smem_u32(probe_sm));
+    __shared__ uint64_t bar;
+    for (int i = threadIdx.x; i < 200 * 128 / 4; i += blockDim.x) reinterpret_cast<float*>(a)[i] = -1.f;
+    if (threadIdx.x == 0) { ptx::mbar_init(ptx::smem_u32(&bar), 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    ptx::fence_proxy_async();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        ptx::mbar_expect_tx(ptx::smem_u32(&bar), 200u * 128u);
+        ptx::tma_load_4d(base, &map, ptx::smem_u32(&bar), 0, -1, img0, -1);
+    }
+    ptx::mbar_wait(ptx::smem_u32(&bar), 0);
+    for (int r = threadIdx.x; r < 200; r += blockDim.x) out[r] = __half2float(*reinterpret_cast<const __half*>(a + r * 128));
+}
+
 }  // namespace dtraj
