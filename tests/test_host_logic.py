@@ -148,3 +148,38 @@ def test_product_never_imports_oracle():
             if f.endswith(".py"):
                 src = open(os.path.join(dp, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), os.path.join(dp, f)
+
+
+def test_s2_first_step_layout_shares_rows_per_group_and_variant():
+    """first-step row sharing (sampling.s2_first_step_layout): one row per (group, conditioning variant in use); every
+    sample points at the rows of its own group; nothing is shared across groups"""
+    from distillation_trajectories_b200 import sampling
+    from distillation_trajectories_b200._lib import VAR_COND0, VAR_COND1, VAR_NONE
+    ws = [1.0, 2.0, 7.5, None, 20.0]
+    S = 4
+    guidance = ws * S
+    groups = [i for i in range(S) for _ in range(len(ws))]
+    rs, rv, ru, rc = sampling.s2_first_step_layout(guidance, groups)
+    assert len(rs) == 3 * S and sorted(set(rv)) == sorted({VAR_NONE, VAR_COND0, VAR_COND1})
+    full = sampling.s2_layout(guidance)
+    assert len(full[0]) == S * (2 + 2 * 3)                       # unshared: 1 row for w <= 1 / None, 2 rows for w > 1
+    for b, w in enumerate(guidance):
+        g = groups[b]
+        assert groups[rs[ru[b]]] == g                             # the row evaluates a member of the same group (same x_T)
+        if w is not None and w > 1.0:
+            assert rv[ru[b]] == VAR_COND0 and rv[rc[b]] == VAR_COND1 and groups[rs[rc[b]]] == g
+        else:
+            assert rv[ru[b]] == VAR_NONE and rc[b] == -1
+    # all guided samples of a group share the same two rows
+    for g in range(S):
+        guided = [b for b in range(len(guidance)) if groups[b] == g and guidance[b] is not None and guidance[b] > 1.0]
+        assert len({ru[b] for b in guided}) == 1 and len({rc[b] for b in guided}) == 1
+
+
+def test_shard_samples_blocks_are_contiguous_and_balanced():
+    for n, w in ((10, 4), (7, 2), (65536, 8), (5, 8)):
+        parts = [grid.shard_samples(n, r, w) for r in range(w)]
+        sizes = [len(p) for p in parts]
+        assert max(sizes) - min(sizes) <= 1
+        for p in parts:
+            assert p == list(range(p[0], p[0] + len(p))) if p else True
