@@ -267,7 +267,6 @@ k_conv_umma_t(const __grid_constant__ UmmaMaps maps, const UmmaConv p) {
     const int work0 = (int)blockIdx.x - crank;   // first work item of this CTA's cluster; all its CTAs loop alike
     const int nch0 = p.L.c0p / kCh, nch = nch0 + p.L.c1p / kCh;
     const int iters_per_pass = p.L.ntaps * nch;
-    const int n_iters = p.npass * iters_per_pass;
 
     if (warp == 0) {
         if (ptx::elect_one()) {
