@@ -62,7 +62,13 @@ struct UmmaConv {
     int log2_wh;               // log2(W / 2) (CONV_POOL)
     int debug;                 // timing experiments only (dtraj_bench_conv): bit2 skips the epilogue's global traffic
     int f16;                   // 1: DTRAJ_PREC_F16 -- fp16 feature maps / weights (64 channels per 128-byte K block), kind::f16 MMAs
+    int halo;                  // 1: HALO mode (fp16, 8x8 maps, 3x3): a tile is two images whose halos [10 rows][2 images][10 pixels]
+                               //    arrive by ONE TMA box per 64-channel chunk; the nine taps are descriptor views of it
+    int n_hb;                  // halo ring depth
 };
+
+constexpr uint32_t kHaloBytes = 26624;     // 200 halo pixels x 128 B, rounded up to 1024
+constexpr uint32_t kHaloTx = 200 * 128;    // bytes one halo box delivers
 
 struct UmmaMaps {              // 64-byte aligned tensor maps, passed as __grid_constant__
     CUtensorMap a[4];          // [src0 hi, src1 hi, src0 lo, src1 lo]
@@ -123,6 +129,10 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
                  ::"l"(map), "r"(src), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                 ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N>
@@ -247,8 +257,10 @@ k_conv_umma_t(const __grid_constant__ UmmaMaps maps, const UmmaConv p) {
     const int ncols = p.ncols;                                 // columns this CTA computes per work item (coutp / n_split)
     const int n_rows = p.swap ? p.tn : ncols;                  // rows of the N operand tile (UMMA N)
     const uint32_t b_bytes = (uint32_t)(kPair ? n_rows / 2 : n_rows) * 128u;   // N-operand bytes staged in THIS CTA
-    const uint32_t stage_bytes = (uint32_t)p.kbs * (kATileBytes + b_bytes);   // kbs x [M tile 16 KB] then kbs x [N tile]
-    const uint32_t ring_base = base + p.stages * stage_bytes;
+    // halo mode: a stage holds ONE weight tile (a tap of a chunk); the pixels live in the halo ring behind the stages
+    const uint32_t stage_bytes = p.halo ? b_bytes : (uint32_t)p.kbs * (kATileBytes + b_bytes);   // kbs x [M tile 16 KB] then kbs x [N tile]
+    const uint32_t halo_base = base + p.stages * stage_bytes;
+    const uint32_t ring_base = halo_base + (p.halo ? (uint32_t)p.n_hb * kHaloBytes : 0u);
     const int kEpiBufs = p.epi_bufs;
     const uint32_t bar_base = ring_base + (uint32_t)(kEpiWarps * kEpiBufs * 4096);
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
@@ -257,7 +269,9 @@ k_conv_umma_t(const __grid_constant__ UmmaMaps maps, const UmmaConv p) {
     const uint32_t acc_empty0 = acc_full0 + 16u;               // [2] accumulator drained (epilogue -> issuer)
     const uint32_t res_bar0 = acc_empty0 + 16u;                // [kEpiWarps][kEpiBufs] residual-chunk barriers
     const uint32_t tmem_slot = res_bar0 + 8u * kEpiWarps * kEpiBufsMax;
-    const uint32_t fin_base = tmem_slot + 16u;                 // CONV_FINAL partial sums [4 quarters][32 lanes][4]
+    const uint32_t hfull0 = tmem_slot + 16u;                   // [4] halo buffer loaded   (TMA -> issuer)
+    const uint32_t hempty0 = hfull0 + 32u;                     // [4] halo buffer consumed (issuer -> TMA)
+    const uint32_t fin_base = hempty0 + 32u;                   // CONV_FINAL partial sums [4 quarters][32 lanes][4]
     volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(
         smem_raw + (tmem_slot - ptx::smem_u32(smem_raw)));
 
@@ -279,6 +293,7 @@ k_conv_umma_t(const __grid_constant__ UmmaMaps maps, const UmmaConv p) {
                 ptx::mbar_init(acc_empty0 + 8u * i, kEpiWarps * (kPair ? 2 : 1));   // pair: both CTAs' epilogues report to the leader
             }
             for (int i = 0; i < kEpiWarps * kEpiBufsMax; ++i) ptx::mbar_init(res_bar0 + 8u * i, 1);
+            for (int i = 0; i < 4; ++i) { ptx::mbar_init(hfull0 + 8u * i, 1); ptx::mbar_init(hempty0 + 8u * i, 1); }
             if (!(p.L.flags & CONV_NOSTORE)) ptx::prefetch_tmap(&maps.out);
             if (p.L.flags & CONV_RESID) ptx::prefetch_tmap(&maps.res);
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -325,6 +340,48 @@ k_conv_umma_t(const __grid_constant__ UmmaMaps maps, const UmmaConv p) {
             int s = 0;
             uint32_t ph = 0;
             bool ok = true;
+            if constexpr (kF16) if (p.halo) {
+                // ---- halo mode: per 64-channel chunk ONE box {64 ch, 10, 2 images, 10} over the permuted dimensions
+                // {c, x, image, y} (out-of-bounds rows / columns zero-filled = the conv's padding), then the nine weight tiles
+                int hb = 0;
+                uint32_t hph = 0;
+                auto weight_stage = [&](const CUtensorMap* wm, int b_row) -> bool {
+                    if (!ptx::mbar_wait(empty_bar(s), ph ^ 1u)) return false;
+                    uint32_t fb = full_bar(s);
+                    if constexpr (kPair) fb = ptx::map_to_cta(fb, 0);
+                    if (!kPair || crank == 0) ptx::mbar_expect_tx(full_bar(s), b_bytes * (kPair ? 2u : 1u));
+                    if constexpr (kPair) ptx::tma_load_2d_2sm(base + s * stage_bytes, wm, fb, 0, b_row);
+                    else ptx::tma_load_2d(base + s * stage_bytes, wm, fb, 0, b_row);
+                    if (++s == p.stages) { s = 0; ph ^= 1u; }
+                    return true;
+                };
+                auto pixel_box = [&](const CUtensorMap* am, int c0, int xy0, int img0, uint32_t bytes) -> bool {
+                    if (!ptx::mbar_wait(hempty0 + 8u * hb, hph ^ 1u)) return false;
+                    uint32_t fb = hfull0 + 8u * hb;
+                    if constexpr (kPair) fb = ptx::map_to_cta(fb, 0);
+                    if (!kPair || crank == 0) ptx::mbar_expect_tx(hfull0 + 8u * hb, bytes * (kPair ? 2u : 1u));
+                    if constexpr (kPair) ptx::tma_load_4d_2sm(halo_base + hb * kHaloBytes, am, fb, c0, xy0, img0, xy0);
+                    else ptx::tma_load_4d(halo_base + hb * kHaloBytes, am, fb, c0, xy0, img0, xy0);
+                    if (++hb == p.n_hb) { hb = 0; hph ^= 1u; }
+                    return true;
+                };
+                const int w_half = ncols / p.cluster;
+                for (int wk = work0; wk < p.n_work && ok; wk += gridDim.x) {
+                    const int img0 = 2 * (wk + crank);             // a tile = two images (a padding tile loads zeros)
+                    for (int chunk = 0; chunk < nch && ok; ++chunk) {
+                        const bool second = chunk >= nch0;
+                        ok = pixel_box(second ? &maps.a[1] : &maps.a[0], (second ? chunk - nch0 : chunk) * kCh, -1, img0, kHaloTx);
+                        for (int tap = 0; tap < 9 && ok; ++tap) ok = weight_stage(&maps.b, (tap * nch + chunk) * coutp + crank * w_half);
+                    }
+                    if (p.L.flags & CONV_RESACC)                   // 1x1 residual conv: the un-shifted 128 pixels of the block input
+                        for (int rc = 0; rc < p.r_nch && ok; ++rc) {
+                            const bool second = rc >= p.r_nch0;
+                            ok = pixel_box(second ? &maps.ra[1] : &maps.ra[0], (second ? rc - p.r_nch0 : rc) * kCh, 0, img0, (uint32_t)kATileBytes);
+                            if (ok) ok = weight_stage(&maps.rb, rc * coutp + crank * w_half);
+                        }
+                }
+                ok = false;                                        // (skip the im2col loop below)
+            }
             for (int wk = work0; wk < p.n_work && ok; wk += gridDim.x) {
                 const int work = wk + crank;                   // may be a padding item past n_work: loads hit OOB zeros
                 const int tile = work / p.n_split, n0 = (work % p.n_split) * ncols;
@@ -385,6 +442,64 @@ k_conv_umma_t(const __grid_constant__ UmmaMaps maps, const UmmaConv p) {
             int s = 0, acc = 0;
             uint32_t ph = 0, acc_ph = 0;
             bool ok = true;
+            if constexpr (kF16) if (p.halo) {
+                // ---- halo mode: tap (dy, dx) of a chunk = view of the halo buffer starting (dy*20 + dx) pixel rows in, 8-row groups
+                // (one image row of 8 pixels) 10 pixel rows = 1280 B apart: [halo row][image][halo column] makes that uniform
+                const uint64_t hdesc0 = ((uint64_t)1 << 16) | ((uint64_t)(1280 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+                int hb = 0;
+                uint32_t hph = 0;
+                auto mma4 = [&](uint32_t d_tmem, uint64_t ad, uint64_t bd, uint32_t& accum) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        if constexpr (!kPair) ptx::mma_f16(d_tmem, ad + 2u * k, bd + 2u * k, idesc, accum);
+                        else ptx::mma_f16_2sm(d_tmem, ad + 2u * k, bd + 2u * k, idesc, accum);
+                        accum = 1u;
+                    }
+                };
+                auto free_stage = [&]() {
+                    if constexpr (kPair) ptx::tc_commit_2sm(empty_bar(s), cmask); else ptx::tc_commit(empty_bar(s));
+                    if (++s == p.stages) { s = 0; ph ^= 1u; }
+                };
+                auto free_halo = [&]() {
+                    if constexpr (kPair) ptx::tc_commit_2sm(hempty0 + 8u * hb, cmask); else ptx::tc_commit(hempty0 + 8u * hb);
+                    if (++hb == p.n_hb) { hb = 0; hph ^= 1u; }
+                };
+                for (int wk = work0; wk < p.n_work && ok; wk += gridDim.x) {
+                    ok = ptx::mbar_wait(acc_empty0 + 8u * acc, acc_ph ^ 1u);
+                    ptx::tc_fence_after();
+                    const uint32_t d_set = tmem_base + (uint32_t)(acc * p.acc_cols);
+                    uint32_t accum = 0u;
+                    for (int chunk = 0; chunk < nch && ok; ++chunk) {
+                        ok = ptx::mbar_wait(hfull0 + 8u * hb, hph);
+                        ptx::tc_fence_after();
+                        const uint32_t hbuf = halo_base + (uint32_t)hb * kHaloBytes;
+                        int dy = 0, dx = 0;
+                        for (int tap = 0; tap < 9 && ok; ++tap) {
+                            ok = ptx::mbar_wait(full_bar(s), ph);
+                            ptx::tc_fence_after();
+                            const uint32_t a_addr = hbuf + (uint32_t)(dy * 20 + dx) * 128u;
+                            mma4(d_set, hdesc0 | (uint64_t)((a_addr >> 4) & 0x3fffu), umma_desc_sw128(base + s * stage_bytes), accum);
+                            free_stage();
+                            if (++dx == 3) { dx = 0; ++dy; }
+                        }
+                        free_halo();
+                    }
+                    if (p.L.flags & CONV_RESACC) {
+                        uint32_t accum_r = 0u;
+                        for (int rc = 0; rc < p.r_nch && ok; ++rc) {
+                            ok = ptx::mbar_wait(hfull0 + 8u * hb, hph);
+                            ok = ok && ptx::mbar_wait(full_bar(s), ph);
+                            ptx::tc_fence_after();
+                            mma4(d_set + (uint32_t)p.res_col, umma_desc_sw128(halo_base + (uint32_t)hb * kHaloBytes), umma_desc_sw128(base + s * stage_bytes), accum_r);
+                            free_stage();
+                            free_halo();
+                        }
+                    }
+                    if constexpr (kPair) ptx::tc_commit_2sm(acc_full0 + 8u * acc, cmask); else ptx::tc_commit(acc_full0 + 8u * acc);
+                    if (++acc == p.acc_stages) { acc = 0; acc_ph ^= 1u; }
+                }
+                ok = false;                                        // (skip the im2col loop below)
+            }
             for (int wk = work0; wk < p.n_work && ok; wk += gridDim.x) {
                 ok = ptx::mbar_wait(acc_empty0 + 8u * acc, acc_ph ^ 1u);      // epilogue has drained this buffer
                 ptx::tc_fence_after();
@@ -480,9 +595,17 @@ k_conv_umma_t(const __grid_constant__ UmmaMaps maps, const UmmaConv p) {
                     }
             }
             __syncwarp();
-            const int64_t m = m_warp + lane;
-            const bool valid = m < p.L.M;
-            const int img = valid ? (int)(m >> p.log2_hw) : 0;
+            // halo mode: the tile's rows are ordered (y, image, x); `m` stays the row index of the standard [image][y][x] layout
+            int64_t m = m_warp + lane;
+            bool valid = m < p.L.M;
+            int img = valid ? (int)(m >> p.log2_hw) : 0;
+            if (p.halo) {
+                const int r = q * 32 + lane;
+                img = 2 * tile + ((r >> 3) & 1);
+                valid = (int64_t)img * 64 < p.L.M;
+                m = (int64_t)img * 64 + (r >> 4) * 8 + (r & 7);
+                if (!valid) img = 0;
+            }
             const float* tb = nullptr;
             if (fl & CONV_TBIAS) tb = p.L.tbias + (size_t)(p.L.row_variant ? p.L.row_variant[img] : 0) * p.L.tb_var_stride;
             float xv[4] = {0.f, 0.f, 0.f, 0.f}, fe[4] = {0.f, 0.f, 0.f, 0.f};
@@ -597,11 +720,19 @@ k_conv_umma_t(const __grid_constant__ UmmaMaps maps, const UmmaConv p) {
                 if (do_pool) {
                     // 8 pooled rows x 4 cells (8 channels each) per chunk: one cell per lane
                     const int W = p.L.W, pr = lane >> 2, x2 = pr & ((W >> 1) - 1), t = pr >> p.log2_wh;
-                    const int r00 = 2 * t * W + 2 * x2;
-                    if (m_warp + r00 < p.L.M) {
+                    int r00 = 2 * t * W + 2 * x2, rdn = W;               // window rows r00, r00 + 1, r00 + rdn, r00 + rdn + 1 of the warp's buffer
+                    int64_t prow = (m_warp >> 2) + pr;                   // pooled pixel (row of the [M/4, coutp] output)
+                    bool pvalid = m_warp + r00 < p.L.M;
+                    if (p.halo) {                                        // warp rows = (y in {2q, 2q+1}, image, x): lane -> (image, window column)
+                        const int im2 = pr >> 2, wx = pr & 3;
+                        r00 = im2 * 8 + 2 * wx; rdn = 16;
+                        prow = ((int64_t)(2 * tile + im2) * 4 + q) * 4 + wx;
+                        pvalid = (int64_t)(2 * tile + im2) * 64 < p.L.M;
+                    }
+                    if (pvalid) {
                         const uint32_t jj = (uint32_t)(lane & 3);
                         auto at = [&](int r) { return *reinterpret_cast<const uint4*>(bufp + r * 64 + ((jj ^ (((uint32_t)r >> 1) & 3u)) << 4)); };
-                        const uint4 a = at(r00), bq = at(r00 + 1), cq = at(r00 + W), d = at(r00 + W + 1);
+                        const uint4 a = at(r00), bq = at(r00 + 1), cq = at(r00 + rdn), d = at(r00 + rdn + 1);
                         const __half2* ah = reinterpret_cast<const __half2*>(&a);
                         const __half2* bh = reinterpret_cast<const __half2*>(&bq);
                         const __half2* ch2 = reinterpret_cast<const __half2*>(&cq);
@@ -610,11 +741,15 @@ k_conv_umma_t(const __grid_constant__ UmmaMaps maps, const UmmaConv p) {
                         __half2* oh = reinterpret_cast<__half2*>(&o4);
 #pragma unroll
                         for (int i = 0; i < 4; ++i) oh[i] = __hmax2(__hmax2(ah[i], bh[i]), __hmax2(ch2[i], dh[i]));
-                        *reinterpret_cast<uint4*>(pool_h + ((m_warp >> 2) + pr) * coutp + n0 + 32 * c + 8 * (int)jj) = o4;
+                        *reinterpret_cast<uint4*>(pool_h + prow * coutp + n0 + 32 * c + 8 * (int)jj) = o4;
                     }
                     __syncwarp();
                 }
-                if (lane == 0 && do_store) { ptx::tma_store_2d(&maps.out, buf0 + 4096u * b, n0 + 32 * c, row); ptx::bulk_commit(); }
+                if (lane == 0 && do_store) {
+                    if (p.halo) ptx::tma_store_4d(&maps.out, buf0 + 4096u * b, n0 + 32 * c, 0, 2 * tile, 2 * q);   // box {32 ch, 8 x, 2 images, 2 rows}
+                    else ptx::tma_store_2d(&maps.out, buf0 + 4096u * b, n0 + 32 * c, row);
+                    ptx::bulk_commit();
+                }
                 if (c + 2 < nchunk && k + 1 >= kEpiBufs && (has_res || do_store)) {
                     if (lane == 0) {
                         if (do_store) { if (kEpiBufs == 2) ptx::bulk_wait_read<1>(); else ptx::bulk_wait_read<0>(); }
@@ -1068,6 +1203,22 @@ inline int make_rows_map(CUtensorMap* m, const float* base, int64_t M, int coutp
     return 0;
 }
 
+// fp16 NHWC map [n_img][8][8][cp] seen through the PERMUTED dimensions {c, x, image, y} (global strides not increasing;
+// profiles/r01_tma_permuted_probe.txt): a box {box_c, box_x, 2, box_y} lands / leaves shared memory as [y][image][x] rows
+inline int make_perm8_map(CUtensorMap* m, const float* base, int cp, int64_t n_img, int box_c, int box_x, int box_y, bool sw64) {
+    PFN_encodeTiled enc = get_encode_tiled();
+    if (!enc) return fail(DTRAJ_ECUDA, "cuTensorMapEncodeTiled not available");
+    cuuint64_t dims[4] = {(cuuint64_t)cp, 8, (cuuint64_t)n_img, 8};
+    cuuint64_t strides[3] = {(cuuint64_t)cp * 2, (cuuint64_t)64 * cp * 2, (cuuint64_t)8 * cp * 2};
+    cuuint32_t box[4] = {(cuuint32_t)box_c, (cuuint32_t)box_x, 2, (cuuint32_t)box_y};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, (void*)base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     sw64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(DTRAJ_ECUDA, "cuTensorMapEncodeTiled(permuted 8x8 map cp=%d n=%lld) -> %d", cp, (long long)n_img, (int)r);
+    return 0;
+}
+
 inline cudaError_t umma_set_smem_attr() {
     cudaError_t e = cudaFuncSetAttribute(k_conv_umma_t<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_conv_umma_t<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
@@ -1164,11 +1315,17 @@ inline int build_umma_launch(UmmaLaunch* U, const ConvLayer& L, int npass, const
     // (N <= 128: <= 256 cycles per K block) and the stage stays small enough to keep >= 3 stages in flight
     const int n_stage_rows = c.pair ? n_rows / 2 : n_rows;
     c.kbs = (n_stage_rows <= (c.pair ? 64 : 128) && c.r_nch0 % 2 == 0 && (c.r_nch - c.r_nch0) % 2 == 0 && (L.c0p / kch) % 2 == 0 && (L.c1p / kch) % 2 == 0 && !getenv("DTRAJ_KBS1")) ? 2 : 1;
-    const size_t stage = (size_t)c.kbs * (kATileBytes + (size_t)n_stage_rows * 128);
-    const size_t misc = 1024 + 512 + ((L.flags & CONV_FINAL) ? 2048 : 0);
+    // halo mode (fp16, 8x8 maps, 3x3, no identity residual): two images per tile, pixels through the halo ring
+    c.halo = (f16 && L.H == 8 && L.W == 8 && L.ntaps == 9 && !(L.flags & (CONV_RESID | CONV_RESX)) && c.n_split == 1 && !c.swap &&
+              L.act_mode != ACT_SPLIT && !(getenv("DTRAJ_HALO") && atoi(getenv("DTRAJ_HALO")) == 0)) ? 1 : 0;
+    c.n_hb = 0;
+    if (c.halo) { c.kbs = 1; c.n_hb = 3; }
+    const size_t stage = c.halo ? (size_t)n_stage_rows * 128 : (size_t)c.kbs * (kATileBytes + (size_t)n_stage_rows * 128);
+    const size_t misc = 1024 + 512 + ((L.flags & CONV_FINAL) ? 2048 : 0) + (size_t)c.n_hb * kHaloBytes;
     auto stages_for = [&](int bufs) { return (int)((227 * 1024 - misc - (size_t)kEpiWarps * bufs * 4096) / stage); };
     c.epi_bufs = 2;
     if (nkb_all >= 16 && stages_for(1) > stages_for(2) && stages_for(2) < 8 && !getenv("DTRAJ_EPI2")) c.epi_bufs = 1;
+    if (c.halo) c.epi_bufs = 1;
     int stages = stages_for(c.epi_bufs);
     if (stages < 2) return fail(DTRAJ_EINVAL, "umma conv: operand ring does not fit");
     if (stages > 8) stages = 8;
@@ -1190,6 +1347,16 @@ inline int build_umma_launch(UmmaLaunch* U, const ConvLayer& L, int npass, const
         DTRAJ_TRY(make_w_map(&U->maps.rb, rwpk, rw_rows, c.ncols / c.cluster, f16));
     }
     if (L.M >= (int64_t)1 << 31) return fail(DTRAJ_EINVAL, "umma conv: M too large for 32-bit TMA coordinates");
+    if (c.halo) {      // every pixel-side map goes through the permuted dimensions {c, x, image, y}
+        DTRAJ_TRY(make_perm8_map(&U->maps.a[0], L.src0, L.c0p, n_img, 64, 10, 10, false));
+        if (L.c1p) DTRAJ_TRY(make_perm8_map(&U->maps.a[1], L.src1, L.c1p, n_img, 64, 10, 10, false));
+        if (L.flags & CONV_RESACC) {
+            DTRAJ_TRY(make_perm8_map(&U->maps.ra[0], L.rsrc0, L.rc0p, n_img, 64, 8, 8, false));
+            if (L.rc1p) DTRAJ_TRY(make_perm8_map(&U->maps.ra[1], L.rsrc1, L.rc1p, n_img, 64, 8, 8, false));
+        }
+        if (!(L.flags & CONV_NOSTORE)) DTRAJ_TRY(make_perm8_map(&U->maps.out, L.out, L.coutp, n_img, 32, 8, 2, true));
+        return 0;
+    }
     if (!(L.flags & CONV_NOSTORE)) DTRAJ_TRY(make_rows_map(&U->maps.out, L.out, L.M, L.coutp, f16));
     if (L.act_mode == ACT_SPLIT) DTRAJ_TRY(make_rows_map(&U->maps.out_lo, L.out + L.lo_off, L.M, L.coutp));
     if (L.flags & CONV_RESID) DTRAJ_TRY(make_rows_map(&U->maps.res, L.resid, L.M, L.coutp, f16));

@@ -101,7 +101,9 @@ def test_forward_bench_sized_batch(sf, prec):
         want = ounet.unet_forward(sd, x[r:r + 1], tt, cond).numpy()
         assert_close(got[r:r + 1], want, 0.0, FWD_TOL[prec], f"row {r} [{prec}]")
     small = np.concatenate([eng.forward(x[i:i + 8].cuda(), 23, variants[i:i + 8].cuda()).cpu().numpy() for i in range(0, R, 8)])
-    assert_close(got, small, 0.0, 1e-5, f"160-row batch vs 8-row batches [{prec}]")
+    # (fp16: the halo form of the 8x8-level convs sums its K blocks chunk-major, the im2col form the small batches take
+    # tap-major: the fp32 accumulators differ in their last bits and an output may round to the neighbouring fp16 value)
+    assert_close(got, small, 0.0, 1e-5 if prec == "tf32" else 1.5e-3, f"160-row batch vs 8-row batches [{prec}]")
     assert umma_error_flag() == 0
 
 
