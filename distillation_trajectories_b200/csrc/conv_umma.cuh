@@ -1319,13 +1319,13 @@ inline int build_umma_launch(UmmaLaunch* U, const ConvLayer& L, int npass, const
     c.halo = (f16 && L.H == 8 && L.W == 8 && L.ntaps == 9 && !(L.flags & (CONV_RESID | CONV_RESX)) && c.n_split == 1 && !c.swap &&
               L.act_mode != ACT_SPLIT && !(getenv("DTRAJ_HALO") && atoi(getenv("DTRAJ_HALO")) == 0)) ? 1 : 0;
     c.n_hb = 0;
-    if (c.halo) { c.kbs = 1; c.n_hb = 3; }
+    if (c.halo) { c.kbs = 1; c.n_hb = getenv("DTRAJ_HALO_NHB") ? atoi(getenv("DTRAJ_HALO_NHB")) : 3; }
     const size_t stage = c.halo ? (size_t)n_stage_rows * 128 : (size_t)c.kbs * (kATileBytes + (size_t)n_stage_rows * 128);
     const size_t misc = 1024 + 512 + ((L.flags & CONV_FINAL) ? 2048 : 0) + (size_t)c.n_hb * kHaloBytes;
     auto stages_for = [&](int bufs) { return (int)((227 * 1024 - misc - (size_t)kEpiWarps * bufs * 4096) / stage); };
     c.epi_bufs = 2;
     if (nkb_all >= 16 && stages_for(1) > stages_for(2) && stages_for(2) < 8 && !getenv("DTRAJ_EPI2")) c.epi_bufs = 1;
-    if (c.halo) c.epi_bufs = 1;
+    if (c.halo) c.epi_bufs = getenv("DTRAJ_HALO_EPI") ? atoi(getenv("DTRAJ_HALO_EPI")) : 2;
     int stages = stages_for(c.epi_bufs);
     if (stages < 2) return fail(DTRAJ_EINVAL, "umma conv: operand ring does not fit");
     if (stages > 8) stages = 8;
