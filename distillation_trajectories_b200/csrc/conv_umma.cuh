@@ -591,7 +591,8 @@ k_conv_umma_t(const __grid_constant__ UmmaMaps maps, const UmmaConv p) {
                 if (has_res)
                     for (int k = 0; k < kEpiBufs && h + 2 * k < nchunk; ++k) {
                         ptx::mbar_expect_tx(rbar + 8u * k, 2048u);
-                        ptx::tma_load_2d(buf0 + 4096u * k, &maps.res, rbar + 8u * k, n0 + 32 * (h + 2 * k), row);
+                        if (p.halo) ptx::tma_load_4d(buf0 + 4096u * k, &maps.res, rbar + 8u * k, n0 + 32 * (h + 2 * k), 0, 2 * tile, 2 * q);
+                        else ptx::tma_load_2d(buf0 + 4096u * k, &maps.res, rbar + 8u * k, n0 + 32 * (h + 2 * k), row);
                     }
             }
             __syncwarp();
@@ -756,7 +757,8 @@ k_conv_umma_t(const __grid_constant__ UmmaMaps maps, const UmmaConv p) {
                         if (has_res) {
                             const int nb = (k + 1) % kEpiBufs;
                             ptx::mbar_expect_tx(rbar + 8u * nb, 2048u);
-                            ptx::tma_load_2d(buf0 + 4096u * nb, &maps.res, rbar + 8u * nb, n0 + 32 * (c + 2), row);
+                            if (p.halo) ptx::tma_load_4d(buf0 + 4096u * nb, &maps.res, rbar + 8u * nb, n0 + 32 * (c + 2), 0, 2 * tile, 2 * q);
+                            else ptx::tma_load_2d(buf0 + 4096u * nb, &maps.res, rbar + 8u * nb, n0 + 32 * (c + 2), row);
                         }
                     }
                     __syncwarp();
@@ -1316,7 +1318,7 @@ inline int build_umma_launch(UmmaLaunch* U, const ConvLayer& L, int npass, const
     const int n_stage_rows = c.pair ? n_rows / 2 : n_rows;
     c.kbs = (n_stage_rows <= (c.pair ? 64 : 128) && c.r_nch0 % 2 == 0 && (c.r_nch - c.r_nch0) % 2 == 0 && (L.c0p / kch) % 2 == 0 && (L.c1p / kch) % 2 == 0 && !getenv("DTRAJ_KBS1")) ? 2 : 1;
     // halo mode (fp16, 8x8 maps, 3x3, no identity residual): two images per tile, pixels through the halo ring
-    c.halo = (f16 && L.H == 8 && L.W == 8 && L.ntaps == 9 && !(L.flags & (CONV_RESID | CONV_RESX)) && c.n_split == 1 && !c.swap &&
+    c.halo = (f16 && L.H == 8 && L.W == 8 && L.ntaps == 9 && !(L.flags & CONV_RESX) && c.n_split == 1 && !c.swap &&
               L.act_mode != ACT_SPLIT && !(getenv("DTRAJ_HALO") && atoi(getenv("DTRAJ_HALO")) == 0)) ? 1 : 0;
     c.n_hb = 0;
     if (c.halo) { c.kbs = 1; c.n_hb = getenv("DTRAJ_HALO_NHB") ? atoi(getenv("DTRAJ_HALO_NHB")) : 3; }
@@ -1355,6 +1357,7 @@ inline int build_umma_launch(UmmaLaunch* U, const ConvLayer& L, int npass, const
             if (L.rc1p) DTRAJ_TRY(make_perm8_map(&U->maps.ra[1], L.rsrc1, L.rc1p, n_img, 64, 8, 8, false));
         }
         if (!(L.flags & CONV_NOSTORE)) DTRAJ_TRY(make_perm8_map(&U->maps.out, L.out, L.coutp, n_img, 32, 8, 2, true));
+        if (L.flags & CONV_RESID) DTRAJ_TRY(make_perm8_map(&U->maps.res, L.resid, L.coutp, n_img, 32, 8, 2, true));
         return 0;
     }
     if (!(L.flags & CONV_NOSTORE)) DTRAJ_TRY(make_rows_map(&U->maps.out, L.out, L.M, L.coutp, f16));
