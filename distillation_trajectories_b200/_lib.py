@@ -61,8 +61,14 @@ SIGNATURES = {
     "dtraj_wasserstein": (C.c_int, [_P, _P, _I64, _I32, _I32, _P, _P, _I32, _P, _P]),
     "dtraj_unet_forward_rows": (C.c_int, [_P, _P, _I64, _P, _P, _P, _I64, _P]),
     "dtraj_project": (C.c_int, [_P, _I64, _I32, _P, _P, _I32, _P, _P]),
+    "dtraj_sampler_flops": (C.c_int, [_P, C.POINTER(C.c_double)]),
+    "dtraj_sampler_profile_text": (C.c_int, [_P, _P, _I32, C.c_char_p, _I64]),
+    "dtraj_unet_check_errors": (C.c_int, [_P]),
+    "dtraj_unet_error_flag_async": (C.c_int, [_P, _P, _P]),
     "dtraj_check_errors": (C.c_int, []),
     "dtraj_error_flag_async": (C.c_int, [_P, _P]),
+    "dtraj_bench_conv": (C.c_int, [_I32, _I32, _I32, _I32, _I64, _I32, _I32, _I32, _I32, _I32, C.POINTER(C.c_float)]),
+    "dtraj_debug_umma_error": (C.c_uint, []),
     "dtraj_test_conv": (C.c_int, [_I32, _P, _I32, _P, _I32, _I64, _I32, _I32, _P, _P, _I32, _I32, _I32,
                                   _P, _P, _P]),
 }
@@ -84,10 +90,6 @@ def load():
         fn = getattr(lib, name)       # AttributeError if the .so is stale / incomplete
         fn.restype = res
         fn.argtypes = args
-    lib.dtraj_bench_conv.restype = C.c_int
-    lib.dtraj_bench_conv.argtypes = [_I32, _I32, _I32, _I32, _I64, _I32, _I32, _I32, _I32, _I32, C.POINTER(C.c_float)]
-    lib.dtraj_debug_umma_error.restype = C.c_uint
-    lib.dtraj_debug_umma_error.argtypes = []
     _lib = lib
     return lib
 

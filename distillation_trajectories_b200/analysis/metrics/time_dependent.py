@@ -36,17 +36,8 @@ def _velocities(trajs_a, trajs_b, dev):
 
 
 def _reduce(a, b):
-    n, L, D = a.shape
-    if D <= 4096:
-        return pair_reductions(a, b).cpu().numpy()
-    # frames with a batch axis: split so one kernel group owns <= 4096 elements, then add
-    parts = 1
-    while D // parts > 4096 or D % parts:
-        parts += 1
-    ra = a.reshape(n, L, parts, D // parts).permute(0, 2, 1, 3).reshape(n * parts, L, D // parts)
-    rb = b.reshape(n, L, parts, D // parts).permute(0, 2, 1, 3).reshape(n * parts, L, D // parts)
-    r = pair_reductions(ra.contiguous(), rb.contiguous()).cpu().numpy().astype(np.float64)
-    return r.reshape(n, parts, L, -1).sum(axis=1).astype(np.float32)
+    """[n, L, D] x2 -> host [n, L, 6]; frames wider than one kernel group are split inside pair_reductions."""
+    return pair_reductions(a, b).cpu().numpy()
 
 
 def _to_lists(sq):

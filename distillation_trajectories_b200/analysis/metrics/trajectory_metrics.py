@@ -24,7 +24,15 @@ SCALAR_KEYS = (
     "student_efficiency", "efficiency_similarity", "mean_velocity_similarity", "mean_position_difference",
     "max_position_difference", "mean_directional_consistency", "weighted_directional_consistency",
     "mean_wasserstein", "distribution_similarity",
-)   # the 18 keys compare_trajectories averages (np.float32 path_alignment and the lists are dropped there)
+)   # the 18 keys compare_trajectories averages.  path_alignment is left out on purpose: the reference computes it as
+#     np.exp(-10.0 * np.float32) -- an np.float32 under NumPy >= 2 promotion rules (NEP 50), which fails the
+#     isinstance(v, (int, float)) filter of analysis/trajectory_engine.py:173, so it is dropped from the averages;
+#     with the reference's pinned numpy==1.26.4 (value-based promotion) the same expression is an np.float64 and the
+#     reference would average 19 keys.  The goldens (tests/golden) were made under NumPy 2.3 and pin the 18-key form;
+#     compute_trajectory_metrics still returns path_alignment per pair (25 keys) for callers that want it.
+
+
+MAX_GROUP_ELEMS = 4096      # elements of one frame a kernel group of dtraj_metrics_pairs holds in registers
 
 
 # ----------------------------------------------------------------------------- kernels
@@ -41,6 +49,15 @@ def pair_reductions(teacher, student):
     if teacher.shape != student.shape or teacher.dim() != 3:
         raise ValueError("pair_reductions expects two [N, L, D] tensors of equal shape")
     N, L, D = teacher.shape
+    if D > MAX_GROUP_ELEMS:
+        # one kernel group owns at most 4096 elements of a frame (include/dtraj.h): wider frames (a batch axis folded
+        # into D, or images beyond 32x32x4) are cut into equal parts that are reduced separately and added in f64
+        parts = 2
+        while D // parts > MAX_GROUP_ELEMS or D % parts:
+            parts += 1
+        cut = lambda x: x.reshape(N, L, parts, D // parts).permute(0, 2, 1, 3).reshape(N * parts, L, D // parts).contiguous()
+        r = pair_reductions(cut(teacher), cut(student))
+        return r.reshape(N, parts, L, -1).double().sum(dim=1).float()
     out = torch.empty(N, L, _lib.METRIC_Q, dtype=torch.float32, device=teacher.device)
     with torch.cuda.device(teacher.device):
         _lib.check(lib.dtraj_metrics_pairs(_lib.ptr(teacher), _lib.ptr(student), N, L, D, _lib.ptr(out), _lib.stream_ptr()))

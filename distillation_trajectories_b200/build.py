@@ -39,21 +39,25 @@ def nvcc_path():
     return "nvcc"
 
 
-def build(force=False, verbose=False):
-    dig = _digest()
-    if not force and os.path.exists(LIB) and os.path.exists(STAMP) and open(STAMP).read().strip() == dig:
-        return LIB
-    cmd = [nvcc_path()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
-          [os.path.join(CSRC, s) for s in SOURCES] + ["-o", LIB]
+def build(force=False, verbose=False, probes=False):
+    """``probes=True`` builds csrc/libdtraj_probes.so instead: the same library plus the hardware probes of csrc/probe.cuh
+    (-DDTRAJ_PROBES; tools/probe_*.py).  The product library never contains them."""
+    dig = _digest() + ("+probes" if probes else "")
+    lib = LIB.replace("libdtraj.so", "libdtraj_probes.so") if probes else LIB
+    stamp = STAMP + (".probes" if probes else "")
+    if not force and os.path.exists(lib) and os.path.exists(stamp) and open(stamp).read().strip() == dig:
+        return lib
+    cmd = [nvcc_path()] + NVCC_FLAGS + (["-DDTRAJ_PROBES"] if probes else []) + (["-Xptxas", "-v"] if verbose else []) + \
+          [os.path.join(CSRC, s) for s in SOURCES] + ["-o", lib]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + res.stdout + res.stderr)
     if verbose:
         print(res.stderr)
-    with open(STAMP, "w") as fh:
+    with open(stamp, "w") as fh:
         fh.write(dig)
-    return LIB
+    return lib
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, probes="--probes" in sys.argv))

@@ -53,6 +53,7 @@ struct ConvLayer {
     const float* rbias;        //            residual_conv bias [coutp]
     int f16;                   // DTRAJ_PREC_F16 (tcgen05 kernel only): src*/resid/out/pool_out/rsrc* point at __half maps,
                                // channel counts are padded to 64
+    unsigned int* err;         // the owning handle's device error word (null: the library-wide word), tcgen05 kernels only
 };
 
 template <int BN>

@@ -28,7 +28,10 @@
 
 namespace dtraj {
 
-// set by any role that timed out on an mbarrier (would otherwise hang the GPU)
+// Device-side error words (bit 0: a pipeline role timed out on an mbarrier -- it would otherwise hang the GPU; bit 1:
+// fp16 mode, an activation left the fp16 range).  Every dtraj_unet handle owns one word (ConvLayer::err, Enc1*Params::err), so
+// that two models running on two streams can tell whose launch failed; launches without a handle (dtraj_test_conv,
+// dtraj_bench_conv) report to this library-wide word.
 __device__ unsigned int g_umma_error = 0;
 
 struct UmmaConv {
@@ -45,22 +48,16 @@ struct UmmaConv {
     int n_split;               // column split of a tile when there are fewer tiles than SMs (power of two)
     int ncols;                 // coutp / n_split: columns per work item (multiple of 32)
     int n_work;                // n_tiles * n_split work items; CTA b handles b, b + gridDim.x, ...
-    int swap;                  // 1: operands swapped (coutp <= 128): the WEIGHTS are the 128-row M operand and
-                               //    `tn` output pixels the N operand, D^T[cout, pixel] accumulates in TMEM
-    int tn;                    // pixels per tile in swap mode (256, 128 or 64); 128 otherwise
     int pair;                  // 1: CTA pairs run tcgen05.mma.cta_group::2 -- M = 256 (two 128-row tiles, one per CTA), each CTA
                                //    stages only ITS half of the weight tile, the leader CTA issues for both
     int kbs;                   // 32-channel K blocks per pipeline stage (2 when both sources have an even number of them)
     int epi_bufs;              // epilogue ring depth per warp (1 when the freed 32 KB buy another operand stage)
-    int cluster;               // 1, or 2: CTA pairs (thread-block clusters) share the weight tile -- each CTA loads half
-                               // of it and TMA-multicasts that half into both CTAs' shared memory
     int box_h, box_n;          // A box = {32, W, box_h, box_n}
     int tiles_per_img;         // >= 1
     int b_lo_row;              // row offset of the low-plane weights inside the B tensor map
     int cb;                    // epilogue column block: 128, 64 or 32 (largest that divides coutp)
     int log2_hw;               // H*W is a power of two: image index of output row m is m >> log2_hw
     int log2_wh;               // log2(W / 2) (CONV_POOL)
-    int debug;                 // timing experiments only (dtraj_bench_conv): bit2 skips the epilogue's global traffic
     int f16;                   // 1: DTRAJ_PREC_F16 -- fp16 feature maps / weights (64 channels per 128-byte K block), kind::f16 MMAs
     int halo;                  // 1: HALO mode (fp16, 8x8 maps, 3x3): a tile is two images whose halos [10 rows][2 images][10 pixels]
                                //    arrive by ONE TMA box per 64-channel chunk; the nine taps are descriptor views of it
@@ -104,16 +101,16 @@ __device__ __forceinline__ uint32_t mbar_try(uint32_t bar, uint32_t parity) {
                  : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
     return ok;
 }
-__device__ __noinline__ bool mbar_wait_slow(uint32_t bar, uint32_t parity) {
+__device__ __noinline__ bool mbar_wait_slow(unsigned int* err, uint32_t bar, uint32_t parity) {
 #pragma unroll 1
     for (uint32_t i = 0; i < (1u << 22); ++i)
         if (mbar_try(bar, parity)) return true;
-    atomicOr(&g_umma_error, 1u);
+    atomicOr(err, 1u);
     return false;
 }
-__device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity) {
+__device__ __forceinline__ bool mbar_wait(unsigned int* err, uint32_t bar, uint32_t parity) {
     if (mbar_try(bar, parity)) return true;
-    return mbar_wait_slow(bar, parity);
+    return mbar_wait_slow(err, bar, parity);
 }
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar,
                                             int c0, int c1, int c2, int c3) {
@@ -138,15 +135,6 @@ __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.comm
 template <int N>
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, uint16_t mask) {
-    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster "
-                 "[%0], [%1, {%3, %4}], [%2], %5;"
-                 ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "h"(mask) : "memory");
-}
-__device__ __forceinline__ void tc_commit_mc(uint32_t bar, uint16_t mask) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-                 ::"r"(bar), "h"(mask) : "memory");
-}
 // ---- CTA-pair (cta_group::2) forms
 __device__ __forceinline__ void tma_load_4d_2sm(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
     asm volatile("cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes "
@@ -255,7 +243,7 @@ k_conv_umma_t(const __grid_constant__ UmmaMaps maps, const UmmaConv p) {
     const uint32_t base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
     const int coutp = p.L.coutp;
     const int ncols = p.ncols;                                 // columns this CTA computes per work item (coutp / n_split)
-    const int n_rows = p.swap ? p.tn : ncols;                  // rows of the N operand tile (UMMA N)
+    const int n_rows = ncols;                                  // rows of the N operand tile (UMMA N)
     const uint32_t b_bytes = (uint32_t)(kPair ? n_rows / 2 : n_rows) * 128u;   // N-operand bytes staged in THIS CTA
     // halo mode: a stage holds ONE weight tile (a tap of a chunk); the pixels live in the halo ring behind the stages
     const uint32_t stage_bytes = p.halo ? b_bytes : (uint32_t)p.kbs * (kATileBytes + b_bytes);   // kbs x [M tile 16 KB] then kbs x [N tile]
@@ -276,8 +264,9 @@ k_conv_umma_t(const __grid_constant__ UmmaMaps maps, const UmmaConv p) {
         smem_raw + (tmem_slot - ptx::smem_u32(smem_raw)));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int crank = p.cluster > 1 ? (int)ptx::cluster_ctarank() : 0;
-    const uint16_t cmask = (uint16_t)((1u << p.cluster) - 1u);
+    unsigned int* const errw = p.L.err ? p.L.err : &g_umma_error;
+    const int crank = kPair ? (int)ptx::cluster_ctarank() : 0;
+    const uint16_t cmask = kPair ? 3 : 1;
     const int work0 = (int)blockIdx.x - crank;   // first work item of this CTA's cluster; all its CTAs loop alike
     const int nch0 = p.L.c0p / kCh, nch = nch0 + p.L.c1p / kCh;
     const int iters_per_pass = p.L.ntaps * nch;
@@ -287,7 +276,7 @@ k_conv_umma_t(const __grid_constant__ UmmaMaps maps, const UmmaConv p) {
             ptx::prefetch_tmap(&maps.a[0]);
             ptx::prefetch_tmap(&maps.b);
             if (p.L.c1p) ptx::prefetch_tmap(&maps.a[1]);
-            for (int s = 0; s < p.stages; ++s) { ptx::mbar_init(full_bar(s), 1); ptx::mbar_init(empty_bar(s), kPair ? 1 : p.cluster); }
+            for (int s = 0; s < p.stages; ++s) { ptx::mbar_init(full_bar(s), 1); ptx::mbar_init(empty_bar(s), 1); }
             for (int i = 0; i < 2; ++i) {
                 ptx::mbar_init(acc_full0 + 8u * i, 1);
                 ptx::mbar_init(acc_empty0 + 8u * i, kEpiWarps * (kPair ? 2 : 1));   // pair: both CTAs' epilogues report to the leader
@@ -311,7 +300,7 @@ k_conv_umma_t(const __grid_constant__ UmmaMaps maps, const UmmaConv p) {
     }
     ptx::tc_fence_before();
     __syncthreads();
-    if (p.cluster > 1) ptx::cluster_sync_all();   // peers' barriers exist before anything is multicast at them
+    if constexpr (kPair) ptx::cluster_sync_all(); // the peer's barriers exist before anything arrives on them
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
     pdl_launch_dependents();                   // the next kernel of the stream / graph may start its prologue
@@ -327,16 +316,10 @@ k_conv_umma_t(const __grid_constant__ UmmaMaps maps, const UmmaConv p) {
         // iteration of the first persistent version against 128 cycles of MMA work at N = 64), so every index
         // is carried incrementally and a stage holds `kbs` (1 or 2) 32-channel K blocks per barrier round trip.
         if (ptx::elect_one()) {
-            const int w_rows = p.swap ? 128 : ncols;           // rows of the weight tile
-            const int w_half = w_rows / p.cluster;             // rows this CTA fetches (and multicasts, unless paired)
-            const uint32_t w_off = kPair ? 0u : (uint32_t)(crank * w_half) * 128u;
+            const int w_half = kPair ? ncols / 2 : ncols;      // weight rows this CTA fetches (pair: its half of the tile)
             // pair: the LEADER's barrier collects the bytes of both CTAs' loads
-            // (timing experiments: debug bit 0 skips the pixel loads, bit 1 the weight loads -- the MMAs then read stale smem)
-            const uint32_t tx_bytes = (uint32_t)p.kbs * (((p.debug & 1) ? 0u : (uint32_t)kATileBytes) + ((p.debug & 2) ? 0u : b_bytes)) * (kPair ? 2u : 1u);
-            const uint32_t act_off = p.swap ? (uint32_t)p.kbs * kATileBytes : 0u;   // N slots follow the M slots
-            const uint32_t w_base_off = p.swap ? 0u : (uint32_t)p.kbs * kATileBytes;
-            const uint32_t act_step = p.swap ? b_bytes : (uint32_t)kATileBytes;
-            const uint32_t w_step = p.swap ? (uint32_t)kATileBytes : b_bytes;
+            const uint32_t tx_bytes = (uint32_t)p.kbs * ((uint32_t)kATileBytes + b_bytes) * (kPair ? 2u : 1u);
+            const uint32_t w_base_off = (uint32_t)p.kbs * kATileBytes;      // the N (weight) slots follow the M (pixel) slots
             int s = 0;
             uint32_t ph = 0;
             bool ok = true;
@@ -346,7 +329,7 @@ k_conv_umma_t(const __grid_constant__ UmmaMaps maps, const UmmaConv p) {
                 int hb = 0;
                 uint32_t hph = 0;
                 auto weight_stage = [&](const CUtensorMap* wm, int b_row) -> bool {
-                    if (!ptx::mbar_wait(empty_bar(s), ph ^ 1u)) return false;
+                    if (!ptx::mbar_wait(errw, empty_bar(s), ph ^ 1u)) return false;
                     uint32_t fb = full_bar(s);
                     if constexpr (kPair) fb = ptx::map_to_cta(fb, 0);
                     if (!kPair || crank == 0) ptx::mbar_expect_tx(full_bar(s), b_bytes * (kPair ? 2u : 1u));
@@ -356,7 +339,7 @@ k_conv_umma_t(const __grid_constant__ UmmaMaps maps, const UmmaConv p) {
                     return true;
                 };
                 auto pixel_box = [&](const CUtensorMap* am, int c0, int xy0, int img0, uint32_t bytes) -> bool {
-                    if (!ptx::mbar_wait(hempty0 + 8u * hb, hph ^ 1u)) return false;
+                    if (!ptx::mbar_wait(errw, hempty0 + 8u * hb, hph ^ 1u)) return false;
                     uint32_t fb = hfull0 + 8u * hb;
                     if constexpr (kPair) fb = ptx::map_to_cta(fb, 0);
                     if (!kPair || crank == 0) ptx::mbar_expect_tx(hfull0 + 8u * hb, bytes * (kPair ? 2u : 1u));
@@ -365,7 +348,6 @@ k_conv_umma_t(const __grid_constant__ UmmaMaps maps, const UmmaConv p) {
                     if (++hb == p.n_hb) { hb = 0; hph ^= 1u; }
                     return true;
                 };
-                const int w_half = ncols / p.cluster;
                 for (int wk = work0; wk < p.n_work && ok; wk += gridDim.x) {
                     const int img0 = 2 * (wk + crank);             // a tile = two images (a padding tile loads zeros)
                     for (int chunk = 0; chunk < nch && ok; ++chunk) {
@@ -391,7 +373,7 @@ k_conv_umma_t(const __grid_constant__ UmmaMaps maps, const UmmaConv p) {
                 // one pipeline stage: kbs K blocks = (activation box at tap (dx, dy), weight rows) pairs
                 auto fill_stage = [&](const CUtensorMap* am0, const CUtensorMap* am1, const CUtensorMap* wm, int n_first,
                                       int& chunk, int n_chunks, int& dx, int& dy, int& b_row) -> bool {
-                    if (!ptx::mbar_wait(empty_bar(s), ph ^ 1u)) return false;
+                    if (!ptx::mbar_wait(errw, empty_bar(s), ph ^ 1u)) return false;
                     const uint32_t st0 = base + s * stage_bytes;
                     // pair: complete_tx goes to the leader's barrier (same offset, CTA 0 of the cluster)
                     uint32_t fb = full_bar(s);
@@ -400,14 +382,12 @@ k_conv_umma_t(const __grid_constant__ UmmaMaps maps, const UmmaConv p) {
                     for (int j = 0; j < p.kbs; ++j) {
                         const bool second = chunk >= n_first;
                         const int c0 = (second ? chunk - n_first : chunk) * kCh;
-                        if (!(p.debug & 1)) {
-                            if constexpr (!kPair) ptx::tma_load_4d(st0 + act_off + j * act_step, second ? am1 : am0, fb, c0, dx, y0 + dy, img0);
-                            else ptx::tma_load_4d_2sm(st0 + act_off + j * act_step, second ? am1 : am0, fb, c0, dx, y0 + dy, img0);
-                        }
-                        if (!(p.debug & 2)) {
-                            if constexpr (kPair) ptx::tma_load_2d_2sm(st0 + w_base_off + j * w_step, wm, fb, 0, b_row);
-                            else if (p.cluster == 1) ptx::tma_load_2d(st0 + w_base_off + j * w_step, wm, fb, 0, b_row);
-                            else ptx::tma_load_2d_mc(st0 + w_base_off + j * w_step + w_off, wm, fb, 0, b_row, cmask);
+                        if constexpr (!kPair) {
+                            ptx::tma_load_4d(st0 + j * kATileBytes, second ? am1 : am0, fb, c0, dx, y0 + dy, img0);
+                            ptx::tma_load_2d(st0 + w_base_off + j * b_bytes, wm, fb, 0, b_row);
+                        } else {
+                            ptx::tma_load_4d_2sm(st0 + j * kATileBytes, second ? am1 : am0, fb, c0, dx, y0 + dy, img0);
+                            ptx::tma_load_2d_2sm(st0 + w_base_off + j * b_bytes, wm, fb, 0, b_row);
                         }
                         b_row += coutp;
                         if (++chunk == n_chunks) { chunk = 0; if (++dx == 2) { dx = -1; ++dy; } }
@@ -465,17 +445,17 @@ k_conv_umma_t(const __grid_constant__ UmmaMaps maps, const UmmaConv p) {
                     if (++hb == p.n_hb) { hb = 0; hph ^= 1u; }
                 };
                 for (int wk = work0; wk < p.n_work && ok; wk += gridDim.x) {
-                    ok = ptx::mbar_wait(acc_empty0 + 8u * acc, acc_ph ^ 1u);
+                    ok = ptx::mbar_wait(errw, acc_empty0 + 8u * acc, acc_ph ^ 1u);
                     ptx::tc_fence_after();
                     const uint32_t d_set = tmem_base + (uint32_t)(acc * p.acc_cols);
                     uint32_t accum = 0u;
                     for (int chunk = 0; chunk < nch && ok; ++chunk) {
-                        ok = ptx::mbar_wait(hfull0 + 8u * hb, hph);
+                        ok = ptx::mbar_wait(errw, hfull0 + 8u * hb, hph);
                         ptx::tc_fence_after();
                         const uint32_t hbuf = halo_base + (uint32_t)hb * kHaloBytes;
                         int dy = 0, dx = 0;
                         for (int tap = 0; tap < 9 && ok; ++tap) {
-                            ok = ptx::mbar_wait(full_bar(s), ph);
+                            ok = ptx::mbar_wait(errw, full_bar(s), ph);
                             ptx::tc_fence_after();
                             const uint32_t a_addr = hbuf + (uint32_t)(dy * 20 + dx) * 128u;
                             mma4(d_set, hdesc0 | (uint64_t)((a_addr >> 4) & 0x3fffu), umma_desc_sw128(base + s * stage_bytes), accum);
@@ -487,8 +467,8 @@ k_conv_umma_t(const __grid_constant__ UmmaMaps maps, const UmmaConv p) {
                     if (p.L.flags & CONV_RESACC) {
                         uint32_t accum_r = 0u;
                         for (int rc = 0; rc < p.r_nch && ok; ++rc) {
-                            ok = ptx::mbar_wait(hfull0 + 8u * hb, hph);
-                            ok = ok && ptx::mbar_wait(full_bar(s), ph);
+                            ok = ptx::mbar_wait(errw, hfull0 + 8u * hb, hph);
+                            ok = ok && ptx::mbar_wait(errw, full_bar(s), ph);
                             ptx::tc_fence_after();
                             mma4(d_set + (uint32_t)p.res_col, umma_desc_sw128(halo_base + (uint32_t)hb * kHaloBytes), umma_desc_sw128(base + s * stage_bytes), accum_r);
                             free_stage();
@@ -501,7 +481,7 @@ k_conv_umma_t(const __grid_constant__ UmmaMaps maps, const UmmaConv p) {
                 ok = false;                                        // (skip the im2col loop below)
             }
             for (int wk = work0; wk < p.n_work && ok; wk += gridDim.x) {
-                ok = ptx::mbar_wait(acc_empty0 + 8u * acc, acc_ph ^ 1u);      // epilogue has drained this buffer
+                ok = ptx::mbar_wait(errw, acc_empty0 + 8u * acc, acc_ph ^ 1u);      // epilogue has drained this buffer
                 ptx::tc_fence_after();
                 // 3xTF32: the two small cross terms go to their own accumulator.  The tensor core adds into the
                 // accumulator with round-toward-zero; adding 2^-11-sized terms to a full-size accumulator for 2/3 of
@@ -509,7 +489,7 @@ k_conv_umma_t(const __grid_constant__ UmmaMaps maps, const UmmaConv p) {
                 // accumulator keeps that at the single-pass level.
                 auto run_stages = [&](uint32_t d_tmem, uint32_t accum, int n_kblocks) {
                     for (int it = 0; it < n_kblocks && ok; it += p.kbs) {
-                        ok = ptx::mbar_wait(full_bar(s), ph);
+                        ok = ptx::mbar_wait(errw, full_bar(s), ph);
                         ptx::tc_fence_after();
                         const uint64_t md = desc0 + (uint64_t)(s * stage16), nd = md + n_off16;
                         for (int j = 0; j < p.kbs; ++j) {
@@ -528,8 +508,7 @@ k_conv_umma_t(const __grid_constant__ UmmaMaps maps, const UmmaConv p) {
                         }
                         // frees the smem slot when these MMAs retire -- in every CTA that multicasts into it
                         if constexpr (kPair) ptx::tc_commit_2sm(empty_bar(s), cmask);
-                        else if (p.cluster == 1) ptx::tc_commit(empty_bar(s));
-                        else ptx::tc_commit_mc(empty_bar(s), cmask);
+                        else ptx::tc_commit(empty_bar(s));
                         if (++s == p.stages) { s = 0; ph ^= 1u; }
                     }
                 };
@@ -569,10 +548,9 @@ k_conv_umma_t(const __grid_constant__ UmmaMaps maps, const UmmaConv p) {
         const int ew = warp - 2;
         const int nchunk = ncols >> 5;
         const int fl = p.L.flags;
-        const bool skip_io = (p.debug & 4) != 0;
-        const bool has_res = (fl & CONV_RESID) != 0 && !skip_io;
-        const bool do_store = !(fl & CONV_NOSTORE) && !skip_io;
-        const bool do_pool = (fl & CONV_POOL) != 0 && !skip_io;
+        const bool has_res = (fl & CONV_RESID) != 0;
+        const bool do_store = !(fl & CONV_NOSTORE);
+        const bool do_pool = (fl & CONV_POOL) != 0;
         const uint32_t buf0 = ring_base + (uint32_t)ew * kEpiBufs * 4096u;
         const uint32_t rbar = res_bar0 + 8u * (ew * kEpiBufsMax);
         const uint32_t swz = (uint32_t)((lane >> 1) & 3);
@@ -616,7 +594,7 @@ k_conv_umma_t(const __grid_constant__ UmmaMaps maps, const UmmaConv p) {
 #pragma unroll
                 for (int ch = 0; ch < 4; ++ch) if (ch < p.L.xC) xv[ch] = xs[(size_t)ch * HWm];
             }
-            ptx::mbar_wait(acc_full0 + 8u * acc, acc_ph);
+            ptx::mbar_wait(errw, acc_full0 + 8u * acc, acc_ph);
             ptx::tc_fence_after();
             const uint32_t t_acc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.acc_cols);
             const int c_last = nchunk - 1 - ((nchunk - 1 - h) & 1);
@@ -640,7 +618,7 @@ k_conv_umma_t(const __grid_constant__ UmmaMaps maps, const UmmaConv p) {
                     __syncwarp();
                     if (lane == 0) arrive_acc_empty(acc);
                 }
-                if (has_res) { ptx::mbar_wait(rbar + 8u * b, (res_par >> b) & 1u); res_par ^= 1u << b; }
+                if (has_res) { ptx::mbar_wait(errw, rbar + 8u * b, (res_par >> b) & 1u); res_par ^= 1u << b; }
                 uint8_t* bufp = smem_raw + (buf0 + 4096u * b - ptx::smem_u32(smem_raw));
                 uint8_t* rowp = bufp + lane * 64;
 #pragma unroll
@@ -768,7 +746,7 @@ k_conv_umma_t(const __grid_constant__ UmmaMaps maps, const UmmaConv p) {
                 float4* part = reinterpret_cast<float4*>(smem_raw + (fin_base - ptx::smem_u32(smem_raw))) + q * 32 + lane;
                 if (h == 1) *part = make_float4(fe[0], fe[1], fe[2], fe[3]);
                 asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
-                if (h == 0 && valid && !skip_io) {
+                if (h == 0 && valid) {
                     const float4 o4 = *part;
                     const float other[4] = {o4.x, o4.y, o4.z, o4.w};
 #pragma unroll
@@ -778,180 +756,18 @@ k_conv_umma_t(const __grid_constant__ UmmaMaps maps, const UmmaConv p) {
             }
             if (++acc == p.acc_stages) { acc = 0; acc_ph ^= 1u; }
         }
-        if (!(amax <= 65504.f)) atomicOr(&g_umma_error, 2u);     // also catches NaN
+        if (!(amax <= 65504.f)) atomicOr(errw, 2u);              // also catches NaN
         if (lane == 0) ptx::bulk_wait_read<0>();
         __syncwarp();
-        } else if (p.swap) {
-            // ---- swapped operands: TMEM lane = output channel, TMEM column = pixel of the tile.  Warp (q, h)
-            // owns channels [32q, 32q+32) and the pixel blocks h, h+2, ... of 32 pixels; a ring buffer is the
-            // same [32 pixels][32 channels] swizzled box as in the other branch, accessed transposed (lane =
-            // channel: 32 consecutive words per pixel row, conflict-free).  Bias, time bias and the enc1
-            // residual weights are per-thread constants here.
-            const int q = warp & 3, h = (warp - 2) >> 2, ew = warp - 2;
-            const int fl = p.L.flags;
-            const bool skip_io = (p.debug & 4) != 0;
-            const bool has_res = (fl & CONV_RESID) != 0 && !skip_io;
-            const bool do_store = !(fl & CONV_NOSTORE) && !skip_io;
-            const bool do_pool = (fl & CONV_POOL) != 0 && !skip_io;
-            const bool split = p.L.act_mode == ACT_SPLIT;
-            const bool live = 32 * q < coutp;       // quarters beyond the real width only keep the barriers going
-            const int npb = p.tn >> 5;
-            const uint32_t buf0 = ring_base + (uint32_t)ew * kEpiBufs * 4096u;
-            const uint32_t rbar = res_bar0 + 8u * (ew * kEpiBufsMax);
-            const int ch = 32 * q + lane;
-            float bias_r = 0.f, tbr[3] = {0.f, 0.f, 0.f}, rw[4] = {0.f, 0.f, 0.f, 0.f}, rb = 0.f;
-            if (live) {
-                bias_r = __ldg(p.L.bias + ch);
-                if (fl & CONV_TBIAS)
-                    for (int v = 0; v < 3; ++v) tbr[v] = __ldg(p.L.tbias + (size_t)v * p.L.tb_var_stride + ch);
-                if (fl & CONV_RESX) {
-                    rb = __ldg(p.L.rb1 + ch);
-                    for (int c = 0; c < 4; ++c) if (c < p.L.xC) rw[c] = __ldg(p.L.rw1 + (size_t)c * coutp + ch);
-                }
-            }
-            // byte offset of this lane's word inside pixel row r of a ring buffer: r*128 + cell[r & 7]
-            uint32_t cell[8];
-#pragma unroll
-            for (int r = 0; r < 8; ++r) cell[r] = ((((uint32_t)lane >> 2) ^ (uint32_t)r) << 4) + ((uint32_t)lane & 3u) * 4u;
-            uint32_t res_par = 0;
-            int acc = 0;
-            uint32_t acc_ph = 0;
-            const int HWm = 1 << p.log2_hw;
-            for (int wk = work0; wk < p.n_work; wk += gridDim.x) {
-                const int work = wk + crank;
-                const int64_t m_tile = (int64_t)work * p.tn;
-                if (lane == 0 && live) {
-                    ptx::bulk_wait_read<0>();
-                    if (has_res)
-                        for (int k = 0; k < kEpiBufs && h + 2 * k < npb; ++k) {
-                            ptx::mbar_expect_tx(rbar + 8u * k, 4096u);
-                            ptx::tma_load_2d(buf0 + 4096u * k, &maps.res, rbar + 8u * k, 32 * q, (int)m_tile + 32 * (h + 2 * k));
-                        }
-                }
-                __syncwarp();
-                ptx::mbar_wait(acc_full0 + 8u * acc, acc_ph);
-                ptx::tc_fence_after();
-                const uint32_t t_acc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.acc_cols);
-                const int pb_last = npb - 1 - ((npb - 1 - h) & 1);
-                if (!live || pb_last < h) {
-                    ptx::tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) arrive_acc_empty(acc);
-                }
-                if (live)
-                for (int pb = h, k = 0; pb < npb; pb += 2, ++k) {
-                    const int b = k % kEpiBufs;
-                    const int64_t m_chunk = m_tile + 32 * pb;
-                    uint32_t raw[32];
-                    ptx::tmem_ld32(t_acc + (uint32_t)(32 * pb), raw);
-                    if (p.npass == 3) {
-                        uint32_t raw2[32];
-                        ptx::tmem_ld32(t_acc + (uint32_t)(p.corr_col + 32 * pb), raw2);
-                        ptx::tmem_ld_wait();
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) raw[j] = __float_as_uint(__uint_as_float(raw[j]) + __uint_as_float(raw2[j]));
-                    } else {
-                        ptx::tmem_ld_wait();
-                    }
-                    if (pb == pb_last) {
-                        ptx::tc_fence_before();
-                        __syncwarp();
-                        if (lane == 0) arrive_acc_empty(acc);
-                    }
-                    // per-pixel side inputs, one pixel per lane, broadcast by shuffle in the loop below
-                    const int64_t m_l = m_chunk + lane;
-                    const bool valid_l = m_l < p.L.M;
-                    const int img_l = valid_l ? (int)(m_l >> p.log2_hw) : 0;
-                    int var_l = 0;
-                    if ((fl & CONV_TBIAS) && p.L.row_variant) var_l = p.L.row_variant[img_l];
-                    float xl[4] = {0.f, 0.f, 0.f, 0.f};
-                    if ((fl & CONV_RESX) && valid_l) {
-                        const float* xs = p.L.xraw + (size_t)(p.L.row_sample ? p.L.row_sample[img_l] : img_l) * p.L.x_stride + (m_l & (HWm - 1));
-#pragma unroll
-                        for (int c = 0; c < 4; ++c) if (c < p.L.xC) xl[c] = xs[(size_t)c * HWm];
-                    }
-                    if (has_res) { ptx::mbar_wait(rbar + 8u * b, (res_par >> b) & 1u); res_par ^= 1u << b; }
-                    uint8_t* bufp = smem_raw + (buf0 + 4096u * b - ptx::smem_u32(smem_raw));
-                    float keep[32];
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        float v = __uint_as_float(raw[j]) + bias_r;
-                        if (fl & CONV_RELU) v = fmaxf(v, 0.f);
-                        if (fl & CONV_TBIAS) {
-                            const int var = __shfl_sync(0xffffffffu, var_l, j);
-                            v += var == 0 ? tbr[0] : (var == 1 ? tbr[1] : tbr[2]);
-                        }
-                        if (fl & CONV_RESX) {
-                            float r = rb;
-#pragma unroll
-                            for (int c = 0; c < 4; ++c) {
-                                if (c >= p.L.xC) break;
-                                r = fmaf(__shfl_sync(0xffffffffu, xl[c], j), rw[c], r);
-                            }
-                            v += r;
-                        }
-                        float* wp = reinterpret_cast<float*>(bufp + j * 128 + cell[j & 7]);
-                        if (has_res) v += *wp;
-                        v = act_store_value(v, p.L.act_mode);
-                        if (do_store || do_pool) *wp = v;
-                        if (split) keep[j] = v;
-                    }
-                    if (do_store) ptx::fence_proxy_async();
-                    __syncwarp();
-                    if (do_pool) {
-                        const int W = p.L.W, pr = lane >> 2, x2 = pr & ((W >> 1) - 1), t = pr >> p.log2_wh;
-                        const int r00 = 2 * t * W + 2 * x2;
-                        if (m_chunk + r00 < p.L.M) {
-                            float* dst = p.L.pool_out + ((m_chunk >> 2) + pr) * coutp + 32 * q;
-#pragma unroll
-                            for (int jj = (lane & 3) * 2; jj < (lane & 3) * 2 + 2; ++jj) {
-                                auto at = [&](int r) { return *reinterpret_cast<const float4*>(bufp + r * 128 + (((uint32_t)jj ^ (uint32_t)(r & 7)) << 4)); };
-                                const float4 a = at(r00), bq = at(r00 + 1), cq = at(r00 + W), d = at(r00 + W + 1);
-                                *reinterpret_cast<float4*>(dst + 4 * jj) =
-                                    make_float4(fmaxf(fmaxf(a.x, bq.x), fmaxf(cq.x, d.x)), fmaxf(fmaxf(a.y, bq.y), fmaxf(cq.y, d.y)),
-                                                fmaxf(fmaxf(a.z, bq.z), fmaxf(cq.z, d.z)), fmaxf(fmaxf(a.w, bq.w), fmaxf(cq.w, d.w)));
-                            }
-                        }
-                        __syncwarp();
-                    }
-                    if (lane == 0 && do_store) { ptx::tma_store_2d(&maps.out, buf0 + 4096u * b, 32 * q, (int)m_chunk); ptx::bulk_commit(); }
-                    if (split && do_store) {
-                        if (lane == 0) ptx::bulk_wait_read<0>();
-                        __syncwarp();
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) *reinterpret_cast<float*>(bufp + j * 128 + cell[j & 7]) = keep[j] - tf32_trunc(keep[j]);
-                        ptx::fence_proxy_async();
-                        __syncwarp();
-                        if (lane == 0) { ptx::tma_store_2d(&maps.out_lo, buf0 + 4096u * b, 32 * q, (int)m_chunk); ptx::bulk_commit(); }
-                    }
-                    // ring upkeep (depth B = kEpiBufs): my next chunk reuses buffer (k + 1) % B, last read by the store
-                    // of my chunk k + 1 - B -- allow B - 1 younger stores to stay in flight, then refill / rewrite it
-                    if (pb + 2 < npb && k + 1 >= kEpiBufs && (has_res || do_store)) {
-                        if (lane == 0) {
-                            if (do_store) { if (kEpiBufs == 2) ptx::bulk_wait_read<1>(); else ptx::bulk_wait_read<0>(); }
-                            if (has_res) {
-                                const int nb = (k + 1) % kEpiBufs;
-                                ptx::mbar_expect_tx(rbar + 8u * nb, 4096u);
-                                ptx::tma_load_2d(buf0 + 4096u * nb, &maps.res, rbar + 8u * nb, 32 * q, (int)m_tile + 32 * (pb + 2));
-                            }
-                        }
-                        __syncwarp();
-                    }
-                }
-                if (++acc == p.acc_stages) { acc = 0; acc_ph ^= 1u; }
-            }
-            if (lane == 0) ptx::bulk_wait_read<0>();
-            __syncwarp();
         } else {
         const int q = warp & 3;
         const int h = (warp - 2) >> 2;          // which of the quarter's two warps: takes chunks h, h + 2, ...
         const int ew = warp - 2;
         const int nchunk = ncols >> 5;
         const int fl = p.L.flags;
-        const bool skip_io = (p.debug & 4) != 0;
-        const bool has_res = (fl & CONV_RESID) != 0 && !skip_io;
-        const bool do_store = !(fl & CONV_NOSTORE) && !skip_io;
-        const bool do_pool = (fl & CONV_POOL) != 0 && !skip_io;
+        const bool has_res = (fl & CONV_RESID) != 0;
+        const bool do_store = !(fl & CONV_NOSTORE);
+        const bool do_pool = (fl & CONV_POOL) != 0;
         const bool split = p.L.act_mode == ACT_SPLIT;
         const uint32_t buf0 = ring_base + (uint32_t)ew * kEpiBufs * 4096u;
         const uint32_t rbar = res_bar0 + 8u * (ew * kEpiBufsMax);
@@ -985,7 +801,7 @@ k_conv_umma_t(const __grid_constant__ UmmaMaps maps, const UmmaConv p) {
 #pragma unroll
                 for (int ch = 0; ch < 4; ++ch) if (ch < p.L.xC) xv[ch] = xs[(size_t)ch * HWm];
             }
-            ptx::mbar_wait(acc_full0 + 8u * acc, acc_ph);
+            ptx::mbar_wait(errw, acc_full0 + 8u * acc, acc_ph);
             ptx::tc_fence_after();
             const uint32_t t_acc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.acc_cols);
             const int c_last = nchunk - 1 - ((nchunk - 1 - h) & 1);   // this warp's last chunk (< h: it has none)
@@ -1018,7 +834,7 @@ k_conv_umma_t(const __grid_constant__ UmmaMaps maps, const UmmaConv p) {
                     __syncwarp();
                     if (lane == 0) arrive_acc_empty(acc);
                 }
-                if (has_res) { ptx::mbar_wait(rbar + 8u * b, (res_par >> b) & 1u); res_par ^= 1u << b; }
+                if (has_res) { ptx::mbar_wait(errw, rbar + 8u * b, (res_par >> b) & 1u); res_par ^= 1u << b; }
                 uint8_t* bufp = smem_raw + (buf0 + 4096u * b - ptx::smem_u32(smem_raw));
                 uint8_t* rowp = bufp + lane * 128;
                 float4 keep[8];                 // ACT_SPLIT: values for the low-plane store
@@ -1117,7 +933,7 @@ k_conv_umma_t(const __grid_constant__ UmmaMaps maps, const UmmaConv p) {
                 float4* part = reinterpret_cast<float4*>(smem_raw + (fin_base - ptx::smem_u32(smem_raw))) + q * 32 + lane;
                 if (h == 1) *part = make_float4(fe[0], fe[1], fe[2], fe[3]);
                 asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
-                if (h == 0 && valid && !skip_io) {
+                if (h == 0 && valid) {
                     const float4 o4 = *part;
                     const float other[4] = {o4.x, o4.y, o4.z, o4.w};
 #pragma unroll
@@ -1133,7 +949,7 @@ k_conv_umma_t(const __grid_constant__ UmmaMaps maps, const UmmaConv p) {
     }
     ptx::tc_fence_before();
     __syncthreads();
-    if (p.cluster > 1) ptx::cluster_sync_all();   // no CTA leaves while a peer can still write its smem / barriers
+    if constexpr (kPair) ptx::cluster_sync_all(); // no CTA leaves while its peer can still write its smem / barriers
     if (warp == 0) {
         ptx::tc_fence_after();
         if constexpr (!kPair) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols) : "memory");
@@ -1250,39 +1066,24 @@ inline int build_umma_launch(UmmaLaunch* U, const ConvLayer& L, int npass, const
     c.L = L;
     c.f16 = f16;
     c.npass = npass;
-    // operand swap: with <= 128 output channels an M=128 x N=cout MMA reads (128 + cout) x 32 B of shared
-    // memory for 128 x cout x 8 MACs and is shared-memory bound (measured 59 % of the tf32 peak at cout = 128
-    // with no loads at all); M = 128 weight rows x N = 256 pixels reads 1.5x the bytes for 2x the MACs.
-    // Measured (tools/conv_bench.py): a win only for exactly 128 channels, K >= 1024 and enough 256-pixel tiles
-    // to fill the GPU; narrower layers waste half of the 128 weight rows, short-K layers are epilogue-paced
-    // and the transposed epilogue moves single words through shared memory.
-    const int nkb_all = L.ntaps * (L.c0p + L.c1p) / kch;
-    // ... and since CTA pairs exist (below) the pair form of the plain orientation beats it on every layer of
-    // the bench workload (enc1.conv2 424 vs 497 us, dec1.conv1 370 vs 408 us), so it is opt-in.
-    c.swap = (!f16 && L.coutp == 128 && nkb_all >= 32 && (L.M + 255) / 256 >= kNumSMs && !(L.flags & CONV_FINAL) &&
-              getenv("DTRAJ_SWAP")) ? 1 : 0;
-    c.tn = c.swap ? 256 : 128;
-    c.box_h = HW >= c.tn ? c.tn / L.W : L.H;
-    c.box_n = HW >= c.tn ? 1 : c.tn / HW;
-    c.tiles_per_img = HW >= c.tn ? HW / c.tn : 1;
-    c.n_tiles = (int)((L.M + c.tn - 1) / c.tn);
+    const int nkb_all = L.ntaps * (L.c0p + L.c1p) / kch;       // K blocks (128 bytes of channels per row) of the whole K loop
+    // a tile = 128 output pixels: box_h image rows of box_n images
+    c.box_h = HW >= 128 ? 128 / L.W : L.H;
+    c.box_n = HW >= 128 ? 1 : 128 / HW;
+    c.tiles_per_img = HW >= 128 ? HW / 128 : 1;
+    c.n_tiles = (int)((L.M + 127) / 128);
+    // fewer tiles than SMs (deep levels, small batches): split a tile's columns over up to 4 CTAs
     c.n_split = 1;
-    if (!c.swap && !(L.flags & CONV_FINAL))
+    if (!(L.flags & CONV_FINAL))
         while (c.n_tiles * c.n_split * 2 <= kNumSMs && (L.coutp / (c.n_split * 2)) % 32 == 0 && L.coutp / (c.n_split * 2) >= 64)
             c.n_split *= 2;
-    if (getenv("DTRAJ_NO_NSPLIT")) c.n_split = 1;
     c.ncols = L.coutp / c.n_split;
     c.n_work = c.n_tiles * c.n_split;
-    const int n_rows = c.swap ? c.tn : c.ncols;
+    const int n_rows = c.ncols;
     // CTA pairs (tcgen05.mma.cta_group::2): each CTA stages its own 128 pixels and HALF of the weight tile, so a K
     // block costs 16 + N/4 KB of its shared memory instead of 16 + N/2 KB -- more K blocks in flight in the
-    // latency-bound operand ring.  Wide, long layers with plenty of tiles only.
-    const int pair_min = getenv("DTRAJ_PAIR_MIN") ? atoi(getenv("DTRAJ_PAIR_MIN")) : 64;
-    const int pair_work = getenv("DTRAJ_PAIR_WORK") ? atoi(getenv("DTRAJ_PAIR_WORK")) : 2 * kNumSMs;
-    const int pair_nkb = getenv("DTRAJ_PAIR_NKB") ? atoi(getenv("DTRAJ_PAIR_NKB")) : 16;
-    c.pair = (!c.swap && c.n_split == 1 && L.coutp >= pair_min && nkb_all >= pair_nkb && c.n_work >= pair_work &&
-              !getenv("DTRAJ_NO_PAIR")) ? 1 : 0;
-    c.cluster = (c.pair || (c.n_split == 1 && c.n_work >= 2 * kNumSMs && getenv("DTRAJ_CLUSTER"))) ? 2 : 1;
+    // latency-bound operand ring.  Wide, long layers with at least two waves of tiles only (profiles/r01c_conv_layers.txt).
+    c.pair = (c.n_split == 1 && L.coutp >= 64 && nkb_all >= 16 && c.n_work >= 2 * kNumSMs) ? 1 : 0;
     c.acc_cols = 32;
     while (c.acc_cols < n_rows) c.acc_cols *= 2;
     c.corr_col = 0;
@@ -1291,15 +1092,14 @@ inline int build_umma_launch(UmmaLaunch* U, const ConvLayer& L, int npass, const
     c.r_nch0 = L.rc0p / kch;
     c.r_nch = (L.rc0p + L.rc1p) / kch;
     if (L.flags & CONV_RESACC) {
-        if (npass != 1 || c.swap || !rwpk || L.rc0p % kch || L.rc1p % kch || !L.rsrc0 || (L.rc1p && !L.rsrc1))
-            return fail(DTRAJ_EINVAL, "umma conv: fused residual conv needs single-pass TF32 and packed residual weights");
+        if (npass != 1 || !rwpk || L.rc0p % kch || L.rc1p % kch || !L.rsrc0 || (L.rc1p && !L.rsrc1))
+            return fail(DTRAJ_EINVAL, "umma conv: fused residual conv needs a single-pass mode and packed residual weights");
         c.res_col = c.acc_cols;
         c.acc_cols *= 2;
     }
     c.acc_stages = 2 * c.acc_cols <= 512 ? 2 : 1;
     c.tmem_cols = c.acc_stages * c.acc_cols;
-    const int nkb = L.ntaps * (L.c0p + L.c1p) / kch;
-    c.b_lo_row = nkb * L.coutp;
+    c.b_lo_row = nkb_all * L.coutp;
     c.cb = 0;
     c.log2_hw = 0;
     while ((1 << c.log2_hw) < HW) ++c.log2_hw;
@@ -1316,25 +1116,23 @@ inline int build_umma_launch(UmmaLaunch* U, const ConvLayer& L, int npass, const
     // two K blocks per stage halve the single-thread loop overhead per MMA; worth it where an MMA is short
     // (N <= 128: <= 256 cycles per K block) and the stage stays small enough to keep >= 3 stages in flight
     const int n_stage_rows = c.pair ? n_rows / 2 : n_rows;
-    c.kbs = (n_stage_rows <= (c.pair ? 64 : 128) && c.r_nch0 % 2 == 0 && (c.r_nch - c.r_nch0) % 2 == 0 && (L.c0p / kch) % 2 == 0 && (L.c1p / kch) % 2 == 0 && !getenv("DTRAJ_KBS1")) ? 2 : 1;
+    c.kbs = (n_stage_rows <= (c.pair ? 64 : 128) && c.r_nch0 % 2 == 0 && (c.r_nch - c.r_nch0) % 2 == 0 && (L.c0p / kch) % 2 == 0 && (L.c1p / kch) % 2 == 0) ? 2 : 1;
     // halo mode (fp16, 8x8 maps, 3x3, no identity residual): two images per tile, pixels through the halo ring
-    c.halo = (f16 && L.H == 8 && L.W == 8 && L.ntaps == 9 && !(L.flags & CONV_RESX) && c.n_split == 1 && !c.swap &&
-              L.act_mode != ACT_SPLIT && !(getenv("DTRAJ_HALO") && atoi(getenv("DTRAJ_HALO")) == 0)) ? 1 : 0;
+    c.halo = (f16 && L.H == 8 && L.W == 8 && L.ntaps == 9 && !(L.flags & CONV_RESX) && c.n_split == 1 && L.act_mode != ACT_SPLIT) ? 1 : 0;
     c.n_hb = 0;
-    if (c.halo) { c.kbs = 1; c.n_hb = getenv("DTRAJ_HALO_NHB") ? atoi(getenv("DTRAJ_HALO_NHB")) : 3; }
+    if (c.halo) { c.kbs = 1; c.n_hb = 3; }
     const size_t stage = c.halo ? (size_t)n_stage_rows * 128 : (size_t)c.kbs * (kATileBytes + (size_t)n_stage_rows * 128);
     const size_t misc = 1024 + 512 + ((L.flags & CONV_FINAL) ? 2048 : 0) + (size_t)c.n_hb * kHaloBytes;
     auto stages_for = [&](int bufs) { return (int)((227 * 1024 - misc - (size_t)kEpiWarps * bufs * 4096) / stage); };
     c.epi_bufs = 2;
-    if (nkb_all >= 16 && stages_for(1) > stages_for(2) && stages_for(2) < 8 && !getenv("DTRAJ_EPI2")) c.epi_bufs = 1;
-    if (c.halo) c.epi_bufs = getenv("DTRAJ_HALO_EPI") ? atoi(getenv("DTRAJ_HALO_EPI")) : 2;
+    if (!c.halo && nkb_all >= 16 && stages_for(1) > stages_for(2) && stages_for(2) < 8) c.epi_bufs = 1;
     int stages = stages_for(c.epi_bufs);
     if (stages < 2) return fail(DTRAJ_EINVAL, "umma conv: operand ring does not fit");
     if (stages > 8) stages = 8;
     c.stages = stages;
     U->smem = misc + (size_t)kEpiWarps * c.epi_bufs * 4096 + stages * stage;
     U->grid = (unsigned)(c.n_work < kNumSMs ? c.n_work : kNumSMs);
-    if (c.cluster > 1) U->grid = (U->grid + c.cluster - 1) / c.cluster * c.cluster;
+    if (c.pair) U->grid = (U->grid + 1) / 2 * 2;
     const int64_t n_img = L.M / HW;
     DTRAJ_TRY(make_act_map(&U->maps.a[0], L.src0, L.c0p, L.W, L.H, n_img, c.box_h, c.box_n, f16));
     if (L.c1p) DTRAJ_TRY(make_act_map(&U->maps.a[1], L.src1, L.c1p, L.W, L.H, n_img, c.box_h, c.box_n, f16));
@@ -1342,11 +1140,11 @@ inline int build_umma_launch(UmmaLaunch* U, const ConvLayer& L, int npass, const
         DTRAJ_TRY(make_act_map(&U->maps.a[2], L.src0_lo, L.c0p, L.W, L.H, n_img, c.box_h, c.box_n));
         if (L.c1p) DTRAJ_TRY(make_act_map(&U->maps.a[3], L.src1_lo, L.c1p, L.W, L.H, n_img, c.box_h, c.box_n));
     }
-    DTRAJ_TRY(make_w_map(&U->maps.b, wpk, w_rows, (c.swap ? 128 : c.ncols) / c.cluster, f16));
+    DTRAJ_TRY(make_w_map(&U->maps.b, wpk, w_rows, c.ncols / (c.pair ? 2 : 1), f16));
     if (L.flags & CONV_RESACC) {
         DTRAJ_TRY(make_act_map(&U->maps.ra[0], L.rsrc0, L.rc0p, L.W, L.H, n_img, c.box_h, c.box_n, f16));
         if (L.rc1p) DTRAJ_TRY(make_act_map(&U->maps.ra[1], L.rsrc1, L.rc1p, L.W, L.H, n_img, c.box_h, c.box_n, f16));
-        DTRAJ_TRY(make_w_map(&U->maps.rb, rwpk, rw_rows, c.ncols / c.cluster, f16));
+        DTRAJ_TRY(make_w_map(&U->maps.rb, rwpk, rw_rows, c.ncols / (c.pair ? 2 : 1), f16));
     }
     if (L.M >= (int64_t)1 << 31) return fail(DTRAJ_EINVAL, "umma conv: M too large for 32-bit TMA coordinates");
     if (c.halo) {      // every pixel-side map goes through the permuted dimensions {c, x, image, y}
@@ -1367,33 +1165,14 @@ inline int build_umma_launch(UmmaLaunch* U, const ConvLayer& L, int npass, const
 }
 
 inline int launch_conv_umma(const UmmaLaunch& U, cudaStream_t st) {
-    if (U.conv.f16) {          // (the fp16 loop is the PDL-enabled one: every kernel around it waits on its predecessor explicitly)
-        if (U.conv.pair) DTRAJ_CUDA(launch_ex(k_conv_umma_t<true, true>, U.grid, kUmmaThreads, U.smem, st, U.conv.cluster, true, U.maps, U.conv));
-        else DTRAJ_CUDA(launch_ex(k_conv_umma_t<false, true>, U.grid, kUmmaThreads, U.smem, st, U.conv.cluster, true, U.maps, U.conv));
-        return 0;
+    // (only the fp16 loop carries the PDL attribute: every kernel around it waits on its predecessor explicitly)
+    if (U.conv.f16) {
+        if (U.conv.pair) DTRAJ_CUDA(launch_ex(k_conv_umma_t<true, true>, U.grid, kUmmaThreads, U.smem, st, 2, true, U.maps, U.conv));
+        else DTRAJ_CUDA(launch_ex(k_conv_umma_t<false, true>, U.grid, kUmmaThreads, U.smem, st, 1, true, U.maps, U.conv));
+    } else {
+        if (U.conv.pair) DTRAJ_CUDA(launch_ex(k_conv_umma_t<true, false>, U.grid, kUmmaThreads, U.smem, st, 2, false, U.maps, U.conv));
+        else DTRAJ_CUDA(launch_ex(k_conv_umma_t<false, false>, U.grid, kUmmaThreads, U.smem, st, 1, false, U.maps, U.conv));
     }
-    if (U.conv.cluster <= 1) {
-        k_conv_umma_t<false, false><<<U.grid, kUmmaThreads, U.smem, st>>>(U.maps, U.conv);
-        DTRAJ_LAUNCH_CHECK();
-        return 0;
-    }
-    cudaLaunchConfig_t cfg;
-    memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = dim3(U.grid);
-    cfg.blockDim = dim3(kUmmaThreads);
-    cfg.dynamicSmemBytes = U.smem;
-    cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = (unsigned)U.conv.cluster;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    if (U.conv.pair && U.conv.f16) DTRAJ_CUDA(cudaLaunchKernelEx(&cfg, k_conv_umma_t<true, true>, U.maps, U.conv));
-    else if (U.conv.pair) DTRAJ_CUDA(cudaLaunchKernelEx(&cfg, k_conv_umma_t<true, false>, U.maps, U.conv));
-    else if (U.conv.f16) DTRAJ_CUDA(cudaLaunchKernelEx(&cfg, k_conv_umma_t<false, true>, U.maps, U.conv));
-    else DTRAJ_CUDA(cudaLaunchKernelEx(&cfg, k_conv_umma_t<false, false>, U.maps, U.conv));
     return 0;
 }
 

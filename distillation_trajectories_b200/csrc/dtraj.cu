@@ -12,9 +12,11 @@
 #include "conv_simt.cuh"
 #include "conv_umma.cuh"
 #include "metrics.cuh"
-#include "probe.cuh"
 #include "enc1_umma.cuh"
 #include "enc1_f16.cuh"
+#ifdef DTRAJ_PROBES
+#include "probe.cuh"        // hardware probes (tools/probe_*.py): built only with -DDTRAJ_PROBES, never part of the product library
+#endif
 
 using namespace dtraj;
 
@@ -66,6 +68,7 @@ struct dtraj_unet {
     float* table = nullptr;     // [T][3][tb_stride]
     int tb_stride = 0;
     int tb_off[8];
+    unsigned int* err = nullptr;   // this handle's device error word (inside the arena): bit 0 pipeline time-out, bit 1 fp16 overflow
     // cached forward plan for dtraj_unet_forward
     struct dtraj_plan* plan = nullptr;
 };
@@ -284,6 +287,7 @@ extern "C" int dtraj_unet_create(const dtraj_unet_desc* desc, const char* const*
     for (int b = 0; b < 8; ++b) { u->tb_off[b] = tbs; tbs += round_up(cout[b], cpad); }
     u->tb_stride = tbs;
     const size_t o_table = A.alloc((size_t)T * 3 * tbs);
+    const size_t o_err = A.alloc(64);                 // (zero-initialised like the rest of the arena)
 
     u->dev_floats = A.h.size();
     cudaError_t ce = cudaMalloc(&u->dev, u->dev_floats * sizeof(float));
@@ -299,6 +303,7 @@ extern "C" int dtraj_unet_create(const dtraj_unet_desc* desc, const char* const*
     u->fw3 = D + o_fw3; u->fb3 = D + o_fb3; u->fw1 = D + o_fw1; u->fb1 = D + o_fb1;
     u->finw = D + o_finw; u->finb = D + o_finb;
     u->table = D + o_table;
+    u->err = reinterpret_cast<unsigned int*>(D + o_err);
 
     // time table on the device
     TimeTableParams tp;
@@ -335,18 +340,19 @@ extern "C" int dtraj_unet_time_bias(const dtraj_unet* u, int32_t t, int32_t vari
 // Optional per-launch timing (dtraj_sampler_profile): one event pair per launch, summed per class.
 enum KernelClass : int { KC_CONV = 0, KC_FIRST = 1, KC_RESAMPLE = 2, KC_STEP = 3, KC_ENC1 = 4, KC_COUNT = 5 };
 struct Profiler {
-    struct Rec { int cls; cudaEvent_t a, b; };
+    struct Rec { int cls; cudaEvent_t a, b; const char* name; int step; unsigned grid; double flops; };
     std::vector<Rec> recs;
     cudaStream_t st = nullptr;
-    void begin(int cls) {
-        Rec r; r.cls = cls;
+    int step = 0;               // sampler step the launches belong to
+    void begin(int cls, const char* name = "", unsigned grid = 0, double flops = 0.0) {
+        Rec r; r.cls = cls; r.name = name; r.step = step; r.grid = grid; r.flops = flops;
         cudaEventCreate(&r.a); cudaEventCreate(&r.b);
         cudaEventRecord(r.a, st);
         recs.push_back(r);
     }
     void end() { cudaEventRecord(recs.back().b, st); }
 };
-#define PROF_BEGIN(prof, cls) do { if (prof) (prof)->begin(cls); } while (0)
+#define PROF_BEGIN(prof, ...) do { if (prof) (prof)->begin(__VA_ARGS__); } while (0)
 #define PROF_END(prof) do { if (prof) (prof)->end(); } while (0)
 
 struct dtraj_plan {
@@ -357,7 +363,7 @@ struct dtraj_plan {
     struct Buf { float* p = nullptr; int64_t n = 0; int64_t lo = 0; };
     Buf tmp_h, tmp_r, tmp_x, p1, x2, p2, x3, p3, x4, p4, u3, u2, u1, y1, elow;
     // generic conv launches in execution order
-    struct ConvOp { ConvLayer L; bool umma; UmmaLaunch U; int tb_block; double flops; bool needs_x; };
+    struct ConvOp { ConvLayer L; bool umma; UmmaLaunch U; int tb_block; double flops; bool needs_x; char name[40]; };
     // fused tails (single-pass TF32 mode): which stand-alone kernels the conv epilogues replace
     bool fuse_resx = false, fuse_final = false, fuse_res = false;
     bool fuse_enc1 = false;      // k_enc1_umma replaces k_conv_first + the enc1.conv2 launch
@@ -419,7 +425,7 @@ struct Tail {                // optional fused epilogue tails of one conv
     const dtraj_plan::Buf* rs1 = nullptr;
 };
 
-int add_conv(dtraj_plan* P, const PackedConv& pc, const dtraj_plan::Buf& s0, const dtraj_plan::Buf* s1, int S,
+int add_conv(dtraj_plan* P, const char* name, const PackedConv& pc, const dtraj_plan::Buf& s0, const dtraj_plan::Buf* s1, int S,
              const dtraj_plan::Buf& out, const float* resid, int flags, int tb_block, bool is_residual_conv,
              const Tail& tail = Tail()) {
     const dtraj_unet* u = P->u;
@@ -436,6 +442,8 @@ int add_conv(dtraj_plan* P, const PackedConv& pc, const dtraj_plan::Buf& s0, con
     L.act_mode = is_residual_conv ? ACT_PLAIN : (u->act_mode == ACT_SPLIT && out.lo == 0 ? ACT_PLAIN : u->act_mode);
     L.flags = flags;
     L.f16 = u->d.precision == DTRAJ_PREC_F16 ? 1 : 0;
+    L.err = u->err;
+    snprintf(op.name, sizeof(op.name), "%s%s%s%s", name, tail.res ? " +res" : "", tail.pool_out ? " +pool" : "", tail.final1x1 ? " +final" : "");
     op.needs_x = false;
     if (tail.pool_out) { L.flags |= CONV_POOL; L.pool_out = tail.pool_out; }
     if (tail.nostore) L.flags |= CONV_NOSTORE;
@@ -479,12 +487,12 @@ int plan_build(const dtraj_unet* u, int64_t R, void* ws, int64_t ws_bytes, dtraj
     // Fused epilogue tails exist in the tcgen05 kernel's bulk path only (single-pass TF32, the mode the
     // sweeps run in); the exact modes keep the stand-alone pool / final / residual kernels.
     const bool f16 = u->d.precision == DTRAJ_PREC_F16;
-    const bool fused = f16 || (u->d.precision == DTRAJ_PREC_TF32 && !getenv("DTRAJ_NO_FUSE"));
+    const bool fused = f16 || u->d.precision == DTRAJ_PREC_TF32;
     P->fuse_resx = fused;
     P->fuse_final = fused;
     for (int l = 0; l < 4; ++l) P->fuse_pool[l] = fused && S[l] <= 16;
     // residual 1x1 convs as extra MMAs of the block's conv2 (CONV_RESACC): no r tensor, no extra launch
-    P->fuse_res = fused && !getenv("DTRAJ_NO_RESACC");
+    P->fuse_res = fused;
     const bool fr = P->fuse_res;
     auto with_res = [&](Tail t, int b, const dtraj_plan::Buf* s0, const dtraj_plan::Buf* s1) {
         if (fr && blk(b).has_res) { t.res = &u->blk[b].res; t.rs0 = s0; t.rs1 = s1; }
@@ -499,30 +507,30 @@ int plan_build(const dtraj_unet* u, int64_t R, void* ws, int64_t ws_bytes, dtraj
 #define ADD(...) if (!rc) rc = add_conv(P, __VA_ARGS__)
     // enc1: conv1/res by k_conv_first; conv2 here.  x1 itself is never a skip input (models.py:206-216):
     // with the pool fused, only the pooled tile is written.
-    P->fuse_enc1 = fused && S[0] % 16 == 0 && u->d.channels <= 4 && !getenv("DTRAJ_NO_ENC1");
+    P->fuse_enc1 = fused && S[0] % 16 == 0 && u->d.channels <= 4;
     if (f16 && u->dp[0] > 128) P->fuse_enc1 = false;   // the fp16 fused kernel holds D1 + two accumulators in TMEM: widths up to 128;
                                                         // wider first blocks take k_conv_first + the generic conv2 (RESX + POOL tails)
     if (P->fuse_enc1 && f16) {
         rc = build_enc1h_launch(&P->enc1h, u->d.channels, S[0], u->dp[0], blk(0).cout, P->R, blk(0).conv2.w, blk(0).conv2.rows);
         Enc1hParams& e = P->enc1h.p;
         e.w3 = u->fw3; e.b3 = u->fb3; e.rw1 = u->fw1; e.rb1 = u->fb1; e.bias2 = blk(0).conv2.bias;
-        e.tb_var_stride = u->tb_stride; e.pool_out = (__half*)P->p1.p;
+        e.tb_var_stride = u->tb_stride; e.pool_out = (__half*)P->p1.p; e.err = u->err;
     } else if (P->fuse_enc1) {
         rc = build_enc1_launch(&P->enc1, u->d.channels, S[0], u->dp[0], blk(0).cout, P->R, blk(0).conv2.w, blk(0).conv2.rows);
         Enc1Params& e = P->enc1.p;
         e.w3 = u->fw3; e.b3 = u->fb3; e.rw1 = u->fw1; e.rb1 = u->fb1; e.bias2 = blk(0).conv2.bias;
-        e.tb_var_stride = u->tb_stride; e.pool_out = P->p1.p; e.act_mode = u->act_mode;
+        e.tb_var_stride = u->tb_stride; e.pool_out = P->p1.p; e.act_mode = u->act_mode; e.err = u->err;
     } else {
         Tail t = tail_for(0);
         t.resx = P->fuse_resx;
         t.nostore = P->fuse_pool[0];
-        ADD(blk(0).conv2, P->tmp_h, nullptr, S[0], P->tmp_x, t.resx ? nullptr : P->tmp_r.p, t.resx ? CONV_RELU : RR, -1, false, t);
+        ADD("enc1.conv2", blk(0).conv2, P->tmp_h, nullptr, S[0], P->tmp_x, t.resx ? nullptr : P->tmp_r.p, t.resx ? CONV_RELU : RR, -1, false, t);
     }
     // enc2 @ level 1
     if (!blk(1).has_res) rc = fail(DTRAJ_EINVAL, "enc2 without residual_conv unsupported");
-    if (!fr) ADD(blk(1).res, P->p1, nullptr, S[1], P->tmp_r, nullptr, 0, -1, true);
-    ADD(blk(1).conv1, P->p1, nullptr, S[1], P->tmp_h, nullptr, RT, 1, false);
-    ADD(blk(1).conv2, P->tmp_h, nullptr, S[1], P->x2, fr ? nullptr : P->tmp_r.p, fr ? CONV_RELU : RR, -1, false,
+    if (!fr) ADD("enc2.res", blk(1).res, P->p1, nullptr, S[1], P->tmp_r, nullptr, 0, -1, true);
+    ADD("enc2.conv1", blk(1).conv1, P->p1, nullptr, S[1], P->tmp_h, nullptr, RT, 1, false);
+    ADD("enc2.conv2", blk(1).conv2, P->tmp_h, nullptr, S[1], P->x2, fr ? nullptr : P->tmp_r.p, fr ? CONV_RELU : RR, -1, false,
         with_res(tail_for(1), 1, &P->p1, nullptr));
     // enc3 @ level 2 (identity residual = pooled input)
     const dtraj_plan::Buf* pin[3] = {&P->p2, &P->p3, &P->p4};
@@ -531,9 +539,10 @@ int plan_build(const dtraj_unet* u, int64_t R, void* ws, int64_t ws_bytes, dtraj
         const int b = 2 + k, lv = 2 + k;
         const float* resid = pin[k]->p;
         const bool fused_here = fr && blk(b).has_res;
-        if (blk(b).has_res && !fr) { ADD(blk(b).res, *pin[k], nullptr, S[lv], P->tmp_r, nullptr, 0, -1, true); resid = P->tmp_r.p; }
-        ADD(blk(b).conv1, *pin[k], nullptr, S[lv], P->tmp_h, nullptr, RT, b, false);
-        ADD(blk(b).conv2, P->tmp_h, nullptr, S[lv], *xo[k], fused_here ? nullptr : resid, fused_here ? CONV_RELU : RR, -1, false,
+        const std::string bn = kBlockNames[b];
+        if (blk(b).has_res && !fr) { ADD((bn + ".res").c_str(), blk(b).res, *pin[k], nullptr, S[lv], P->tmp_r, nullptr, 0, -1, true); resid = P->tmp_r.p; }
+        ADD((bn + ".conv1").c_str(), blk(b).conv1, *pin[k], nullptr, S[lv], P->tmp_h, nullptr, RT, b, false);
+        ADD((bn + ".conv2").c_str(), blk(b).conv2, P->tmp_h, nullptr, S[lv], *xo[k], fused_here ? nullptr : resid, fused_here ? CONV_RELU : RR, -1, false,
             with_res(k < 2 ? tail_for(2 + k) : Tail(), b, pin[k], nullptr));
     }
     // decoders: [upsampled | skip]
@@ -543,11 +552,12 @@ int plan_build(const dtraj_unet* u, int64_t R, void* ws, int64_t ws_bytes, dtraj
     for (int k = 0; k < 3 && !rc; ++k) {
         const int b = 5 + k, lv = 3 - k;
         if (!blk(b).has_res) { rc = fail(DTRAJ_EINVAL, "%s without residual_conv unsupported", kBlockNames[b]); break; }
-        if (!fr) ADD(blk(b).res, *up[k], skip[k], S[lv], P->tmp_r, nullptr, 0, -1, true);
-        ADD(blk(b).conv1, *up[k], skip[k], S[lv], P->tmp_h, nullptr, RT, b, false);
+        const std::string bn = kBlockNames[b];
+        if (!fr) ADD((bn + ".res").c_str(), blk(b).res, *up[k], skip[k], S[lv], P->tmp_r, nullptr, 0, -1, true);
+        ADD((bn + ".conv1").c_str(), blk(b).conv1, *up[k], skip[k], S[lv], P->tmp_h, nullptr, RT, b, false);
         Tail t;
         if (k == 2 && P->fuse_final) { t.final1x1 = true; t.nostore = true; }   // y1 only feeds the final 1x1
-        ADD(blk(b).conv2, P->tmp_h, nullptr, S[lv], *yo[k], fr ? nullptr : P->tmp_r.p, fr ? CONV_RELU : RR, -1, false,
+        ADD((bn + ".conv2").c_str(), blk(b).conv2, P->tmp_h, nullptr, S[lv], *yo[k], fr ? nullptr : P->tmp_r.p, fr ? CONV_RELU : RR, -1, false,
             with_res(t, b, up[k], skip[k]));
     }
 #undef ADD
@@ -577,7 +587,7 @@ int plan_forward(dtraj_plan* P, const float* x, int64_t x_stride, const int32_t*
         e.x = x; e.x_stride = x_stride; e.row_sample = row_sample; e.row_variant = row_variant;
         e.tbias = trow + u->tb_off[0];
         e.tb_rows = per_row ? 1 : 0;
-        PROF_BEGIN(prof, KC_ENC1);
+        PROF_BEGIN(prof, KC_ENC1, "enc1 fused (k_enc1_f16)", P->enc1h.grid, P->enc1h.flops);
         int rc1 = launch_enc1h(P->enc1h, st);
         PROF_END(prof);
         DTRAJ_TRY(rc1);
@@ -586,7 +596,7 @@ int plan_forward(dtraj_plan* P, const float* x, int64_t x_stride, const int32_t*
         Enc1Params& e = P->enc1.p;
         e.x = x; e.x_stride = x_stride; e.row_sample = row_sample; e.row_variant = row_variant;
         e.tbias = trow + u->tb_off[0];
-        PROF_BEGIN(prof, KC_ENC1);
+        PROF_BEGIN(prof, KC_ENC1, "enc1 fused (k_enc1_umma)", P->enc1.grid, P->enc1.flops);
         int rc1 = launch_enc1(P->enc1, st);
         PROF_END(prof);
         DTRAJ_TRY(rc1);
@@ -600,7 +610,7 @@ int plan_forward(dtraj_plan* P, const float* x, int64_t x_stride, const int32_t*
         f.h = P->tmp_h.p; f.r = P->fuse_resx ? nullptr : P->tmp_r.p; f.lo_off = P->tmp_h.lo;
         f.f16 = f16 ? 1 : 0; f.act_mode = f16 ? ACT_PLAIN : u->act_mode;
         const size_t smem = (round_up(C * (S[0] + 2) * (S[0] + 2), 4) + 10 * C * dp[0]) * sizeof(float);
-        PROF_BEGIN(prof, KC_FIRST);
+        PROF_BEGIN(prof, KC_FIRST, "enc1.conv1 + res (k_conv_first)", (unsigned)R);
         k_conv_first<<<(unsigned)R, 256, smem, st>>>(f);
         PROF_END(prof);
         DTRAJ_LAUNCH_CHECK(); ++nl;
@@ -611,7 +621,7 @@ int plan_forward(dtraj_plan* P, const float* x, int64_t x_stride, const int32_t*
         const float* tb = op.tb_block >= 0 ? trow + u->tb_off[op.tb_block] : nullptr;
         ++nl;
         int rc;
-        PROF_BEGIN(prof, KC_CONV);
+        PROF_BEGIN(prof, KC_CONV, op.name, op.umma ? op.U.grid : 0u, op.flops);
         if (op.umma) {
             op.U.conv.L.tbias = tb; op.U.conv.L.row_variant = row_variant;
             if (op.needs_x) { op.U.conv.L.xraw = x; op.U.conv.L.x_stride = x_stride; op.U.conv.L.row_sample = row_sample; }
@@ -626,7 +636,7 @@ int plan_forward(dtraj_plan* P, const float* x, int64_t x_stride, const int32_t*
     auto pool = [&](const dtraj_plan::Buf& in, const dtraj_plan::Buf& out, int So, int cp, int level) -> int {
         if (P->fuse_pool[level]) return 0;      // emitted by the producing conv's epilogue
         const int64_t n4 = R * So * So * (cp / 4);
-        PROF_BEGIN(prof, KC_RESAMPLE);
+        PROF_BEGIN(prof, KC_RESAMPLE, "maxpool 2x2");
         if (f16) k_pool2_h<<<blocks_for(n4 / 2, 256), 256, 0, st>>>((const __half*)in.p, (__half*)out.p, n4 / 2, So, So, cp / 8);
         else k_pool2<<<blocks_for(n4, 256), 256, 0, st>>>(in.p, out.p, n4, So, So, cp / 4, out.lo, out.lo ? ACT_SPLIT : ACT_PLAIN);
         PROF_END(prof);
@@ -636,10 +646,10 @@ int plan_forward(dtraj_plan* P, const float* x, int64_t x_stride, const int32_t*
     auto upsample = [&](const dtraj_plan::Buf& in, const dtraj_plan::Buf& out, int Si, int cp) -> int {
         const int64_t n4 = R * (2 * Si) * (2 * Si) * (cp / 4);
         if (n4 >= ((int64_t)1 << 31)) return fail(DTRAJ_EINVAL, "upsample: batch too large for 32-bit indexing");
-        PROF_BEGIN(prof, KC_RESAMPLE);
+        PROF_BEGIN(prof, KC_RESAMPLE, Si == 1 ? "upsample 1->2" : Si == 2 ? "upsample 2->4" : Si == 4 ? "upsample 4->8" : Si == 8 ? "upsample 8->16" : "upsample");
         Up2Coef cf;
         const int cp8 = cp / 8;
-        if (f16 && (cp8 & (cp8 - 1)) == 0 && !getenv("DTRAJ_UP_GENERIC") && up2_static_ok(Si, &cf)) {
+        if (f16 && (cp8 & (cp8 - 1)) == 0 && up2_static_ok(Si, &cf)) {
             int lg_hi = 0, lg_c = 0;
             while ((1 << lg_hi) < Si) ++lg_hi;
             while ((1 << lg_c) < cp8) ++lg_c;
@@ -676,7 +686,7 @@ int plan_forward(dtraj_plan* P, const float* x, int64_t x_stride, const int32_t*
     }
     if (!P->fuse_final) {   // final 1x1 at half resolution (else: dec1.conv2's epilogue)
         const int64_t npix = R * S[1] * S[1];
-        PROF_BEGIN(prof, KC_RESAMPLE);
+        PROF_BEGIN(prof, KC_RESAMPLE, "final 1x1");
         k_final1x1<<<blocks_for(npix * 32, 256), 256, 0, st>>>(P->y1.p, u->finw, u->finb, P->elow.p, npix, dp[0], C);
         PROF_END(prof);
         DTRAJ_LAUNCH_CHECK(); ++nl;
@@ -768,6 +778,7 @@ int sampler_enqueue(dtraj_sampler* s, cudaStream_t st, int64_t* launches, Profil
     const int64_t D = (int64_t)C * H * H, fs = (int64_t)d.n_frames * D;
     int64_t nl = 0;
     for (int k = 0; k < d.n_updates; ++k) {
+        if (prof) prof->step = k;
         const float* xin = d.traj + (int64_t)k * D;
         const bool first = k == 0 && s->plan0 != nullptr;            // shared rows: every sample of a group still has x_T
         dtraj_plan* P = first ? s->plan0 : s->plan;
@@ -782,14 +793,14 @@ int sampler_enqueue(dtraj_sampler* s, cudaStream_t st, int64_t* launches, Profil
         p.x_in = xin; p.x_out = d.traj + (int64_t)(k + 1) * D; p.frame_stride = fs;
         p.B = d.n_samples; p.C = C; p.H = H; p.W = H;
         const int64_t nthr = (int64_t)d.n_samples * C * H * (H / 4);
-        PROF_BEGIN(prof, KC_STEP);
+        PROF_BEGIN(prof, KC_STEP, "k_step (CFG + update + store)");
         DTRAJ_CUDA(launch_ex(k_step, blocks_for(nthr, 256), 256, 0, st, 1, s->u->d.precision == DTRAJ_PREC_F16, p));
         PROF_END(prof);
         DTRAJ_LAUNCH_CHECK(); ++nl;
     }
     if (d.copy_last) {
         const int64_t k = d.n_updates;
-        PROF_BEGIN(prof, KC_STEP);
+        PROF_BEGIN(prof, KC_STEP, "k_copy_frame");
         DTRAJ_CUDA(launch_ex(k_copy_frame, blocks_for((int64_t)d.n_samples * (D / 4), 256), 256, 0, st, 1, s->u->d.precision == DTRAJ_PREC_F16,
                              (const float*)(d.traj + k * D), d.traj + (k + 1) * D, fs, d.n_samples, (int)(D / 4)));
         PROF_END(prof);
@@ -876,6 +887,32 @@ extern "C" int dtraj_sampler_run(dtraj_sampler* s, void* stream) {
 
 extern "C" int64_t dtraj_sampler_launches(const dtraj_sampler* s) { return s ? s->launches : -1; }
 
+namespace {
+
+// executed conv flops of a whole loop (real channels, evaluated taps): [0] generic convs, [1] the fused enc1 kernel's conv2
+void sampler_flops(const dtraj_sampler* s, double* out2) {
+    auto plan_flops = [&](const dtraj_plan* P, double* conv, double* e1) {
+        double f = 0.0;
+        for (auto& op : P->convs) f += op.flops;
+        *conv = f;
+        *e1 = P->fuse_enc1 ? (s->u->d.precision == DTRAJ_PREC_F16 ? P->enc1h.flops : P->enc1.flops) : 0.0;
+    };
+    double fc = 0.0, fe = 0.0, fc0 = 0.0, fe0 = 0.0;
+    plan_flops(s->plan, &fc, &fe);
+    if (s->plan0) plan_flops(s->plan0, &fc0, &fe0); else { fc0 = fc; fe0 = fe; }
+    const int nu = s->d.n_updates;
+    out2[0] = nu > 0 ? fc0 + fc * (nu - 1) : 0.0;       // the first step runs the shared-row plan
+    out2[1] = nu > 0 ? fe0 + fe * (nu - 1) : 0.0;
+}
+
+}  // namespace
+
+extern "C" int dtraj_sampler_flops(const dtraj_sampler* s, double* conv_flops2) {
+    if (!s || !conv_flops2) return fail(DTRAJ_EINVAL, "sampler_flops: null argument");
+    sampler_flops(s, conv_flops2);
+    return 0;
+}
+
 extern "C" int dtraj_sampler_profile(dtraj_sampler* s, void* stream, double* class_ms, int64_t* class_launches, double* conv_flops) {
     if (!s || !class_ms || !class_launches || !conv_flops) return fail(DTRAJ_EINVAL, "profile: null argument");
     Profiler prof;
@@ -891,20 +928,29 @@ extern "C" int dtraj_sampler_profile(dtraj_sampler* s, void* stream, double* cla
         }
         cudaEventDestroy(r.a); cudaEventDestroy(r.b);
     }
-    auto plan_flops = [&](dtraj_plan* P, double* conv, double* e1) {
-        double f = 0.0;
-        for (auto& op : P->convs) f += op.flops;
-        *conv = f;
-        *e1 = P->fuse_enc1 ? (s->u->d.precision == DTRAJ_PREC_F16 ? P->enc1h.flops : P->enc1.flops) : 0.0;
-    };
-    double fc = 0.0, fe = 0.0, fc0 = 0.0, fe0 = 0.0;
-    plan_flops(s->plan, &fc, &fe);
-    if (s->plan0) plan_flops(s->plan0, &fc0, &fe0); else { fc0 = fc; fe0 = fe; }
-    const int nu = s->d.n_updates;
-    conv_flops[0] = nu > 0 ? fc0 + fc * (nu - 1) : 0.0;       // executed flops: the first step runs the shared-row plan
-    conv_flops[1] = nu > 0 ? fe0 + fe * (nu - 1) : 0.0;
+    sampler_flops(s, conv_flops);
     if (rc) return rc;
     if (ce != cudaSuccess) return fail(DTRAJ_ECUDA, "profile -> %s", cudaGetErrorString(ce));
+    return 0;
+}
+
+extern "C" int dtraj_sampler_profile_text(dtraj_sampler* s, void* stream, int32_t step, char* buf, int64_t buf_len) {
+    if (!s || !buf || buf_len < 64) return fail(DTRAJ_EINVAL, "profile_text: bad argument");
+    if (step < 0 || step >= s->d.n_updates) return fail(DTRAJ_EINVAL, "profile_text: step %d outside 0..%d", step, s->d.n_updates - 1);
+    Profiler prof;
+    prof.st = (cudaStream_t)stream;
+    int rc = sampler_enqueue(s, prof.st, nullptr, &prof);
+    cudaError_t ce = cudaStreamSynchronize(prof.st);
+    int64_t off = 0;
+    buf[0] = 0;
+    for (auto& r : prof.recs) {
+        float ms = 0.f;
+        if (rc == 0 && ce == cudaSuccess && r.step == step && cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess && off + 128 < buf_len)
+            off += snprintf(buf + off, (size_t)(buf_len - off), "%s\t%u\t%.2f\t%.6g\n", r.name, r.grid, ms * 1e3, r.flops);
+        cudaEventDestroy(r.a); cudaEventDestroy(r.b);
+    }
+    if (rc) return rc;
+    if (ce != cudaSuccess) return fail(DTRAJ_ECUDA, "profile_text -> %s", cudaGetErrorString(ce));
     return 0;
 }
 
@@ -934,6 +980,47 @@ extern "C" int dtraj_project(const float* frames, int64_t n_frames, int32_t D, c
 // ======================================================================================
 // test hooks
 // ======================================================================================
+namespace {
+int report_error_word(unsigned int v) {
+    if (!v) return 0;
+    if (v & 1u) return fail(DTRAJ_ECUDA, "a tcgen05 pipeline role timed out on an mbarrier: results are invalid");
+    return fail(DTRAJ_ERANGE, "fp16 mode: an activation left the fp16 range (|v| > 65504): rerun with precision 'tf32'");
+}
+}  // namespace
+
+extern "C" int dtraj_check_errors(void) {
+    unsigned int v = 0;
+    DTRAJ_CUDA(cudaMemcpyFromSymbol(&v, g_umma_error, sizeof(v)));
+    if (!v) return 0;
+    const unsigned int z = 0;
+    DTRAJ_CUDA(cudaMemcpyToSymbol(g_umma_error, &z, sizeof(z)));
+    return report_error_word(v);
+}
+
+extern "C" int dtraj_unet_check_errors(dtraj_unet* u) {
+    if (!u) return fail(DTRAJ_EINVAL, "unet_check_errors: null handle");
+    unsigned int v = 0;
+    DTRAJ_CUDA(cudaMemcpy(&v, u->err, sizeof(v), cudaMemcpyDeviceToHost));
+    if (!v) return 0;
+    DTRAJ_CUDA(cudaMemset(u->err, 0, sizeof(v)));
+    return report_error_word(v);
+}
+
+extern "C" int dtraj_unet_error_flag_async(dtraj_unet* u, uint32_t* host_flag, void* stream) {
+    if (!u || !host_flag) return fail(DTRAJ_EINVAL, "unet_error_flag_async: null argument");
+    DTRAJ_CUDA(cudaMemcpyAsync(host_flag, u->err, sizeof(uint32_t), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    return 0;
+}
+
+extern "C" int dtraj_error_flag_async(uint32_t* host_flag, void* stream) {
+    if (!host_flag) return fail(DTRAJ_EINVAL, "error_flag_async: null destination");
+    void* sym = nullptr;
+    DTRAJ_CUDA(cudaGetSymbolAddress(&sym, g_umma_error));
+    DTRAJ_CUDA(cudaMemcpyAsync(host_flag, sym, sizeof(uint32_t), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    return 0;
+}
+
+#ifdef DTRAJ_PROBES
 // hardware probe, see probe.cuh; out_host[128] = row id fetched for each of the 128 output rows
 extern "C" int dtraj_probe_umma_view(int32_t rows, int32_t start_row, int32_t sbo_bytes, int32_t base_off_mode, float* out_host) {
     float* d = nullptr;
@@ -944,24 +1031,6 @@ extern "C" int dtraj_probe_umma_view(int32_t rows, int32_t start_row, int32_t sb
     if (ce == cudaSuccess) ce = cudaMemcpy(out_host, d, 128 * sizeof(float), cudaMemcpyDeviceToHost);
     cudaFree(d);
     if (ce != cudaSuccess) return fail(DTRAJ_ECUDA, "probe -> %s", cudaGetErrorString(ce));
-    return 0;
-}
-
-extern "C" int dtraj_check_errors(void) {
-    unsigned int v = 0;
-    DTRAJ_CUDA(cudaMemcpyFromSymbol(&v, g_umma_error, sizeof(v)));
-    if (!v) return 0;
-    const unsigned int z = 0;
-    DTRAJ_CUDA(cudaMemcpyToSymbol(g_umma_error, &z, sizeof(z)));
-    if (v & 1u) return fail(DTRAJ_ECUDA, "a tcgen05 pipeline role timed out on an mbarrier: results are invalid");
-    return fail(DTRAJ_ERANGE, "fp16 mode: an activation left the fp16 range (|v| > 65504): rerun with precision 'tf32'");
-}
-
-extern "C" int dtraj_error_flag_async(uint32_t* host_flag, void* stream) {
-    if (!host_flag) return fail(DTRAJ_EINVAL, "error_flag_async: null destination");
-    void* sym = nullptr;
-    DTRAJ_CUDA(cudaGetSymbolAddress(&sym, g_umma_error));
-    DTRAJ_CUDA(cudaMemcpyAsync(host_flag, sym, sizeof(uint32_t), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
     return 0;
 }
 
@@ -995,6 +1064,8 @@ extern "C" int dtraj_probe_tma_permuted(int32_t n_img, int32_t img0, float* out_
     return 0;
 }
 
+#endif  // DTRAJ_PROBES
+
 extern "C" unsigned int dtraj_debug_umma_error(void) {
     unsigned int v = 0;
     cudaMemcpyFromSymbol(&v, g_umma_error, sizeof(v));
@@ -1002,10 +1073,10 @@ extern "C" unsigned int dtraj_debug_umma_error(void) {
 }
 
 // Kernel-only timing of one conv layer shape (tools/conv_bench.py): device buffers are allocated and
-// zero-filled here, `iters` launches are timed with one event pair.  debug: see g_umma_debug.
+// zero-filled here, `iters` launches are timed with one event pair.  `debug` must be 0.
 extern "C" int dtraj_bench_conv(int32_t precision, int32_t c0, int32_t c1, int32_t cout, int64_t n, int32_t H, int32_t ksize,
                                 int32_t flags, int32_t iters, int32_t debug, float* ms_out) {
-    if (precision == DTRAJ_PREC_FP32 && debug) return fail(DTRAJ_EINVAL, "bench_conv: debug needs a tcgen05 mode");
+    if (debug) return fail(DTRAJ_EINVAL, "bench_conv: the operand knock-out experiments (profiles/r01f_conv_knockout.txt) were removed from the kernels");
     const int cpad = cpad_of(precision);
     const int c0p = round_up(c0, cpad), c1p = c1 ? round_up(c1, cpad) : 0, coutp = round_up(cout, cpad);
     const int64_t M = n * H * H;
@@ -1047,7 +1118,6 @@ extern "C" int dtraj_bench_conv(int32_t precision, int32_t c0, int32_t c1, int32
     if (precision != DTRAJ_PREC_FP32) {
         umma_set_smem_attr();
         rc = build_umma_launch(&U, L, precision == DTRAJ_PREC_TF32X3 ? 3 : 1, dev + wo, pc.rows);
-        U.conv.debug = debug;
     }
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0); cudaEventCreate(&e1);

@@ -39,7 +39,6 @@ struct Enc1hParams {
     int n_d1;                    // D1 buffers: 2 when 6 x acc_cols <= 512 (conv1 of tile i+2 runs while tile i is converted), else 1
     int w_rows;                  // output channels this CTA holds: coutp, or coutp / 2 in pair mode
     int n_slices;                // K slices (16 values) of conv1's GEMM: ceil(9C / 16)
-    int a1_mode;                 // shared-memory layout of the 32-byte-row operands: 0 SWIZZLE_32B, 1 SWIZZLE_NONE core matrices
     const float* x; int64_t x_stride; const int32_t* row_sample; const int32_t* row_variant;
     const float* w3; const float* b3;          // conv1, BN folded, fp32: [9*C][coutp] (k = tap * C + cin); [coutp]
     const float* tbias; int tb_var_stride;     // relu(time_mlp(temb)) rows of enc1 for this t, 3 variants
@@ -47,14 +46,11 @@ struct Enc1hParams {
     const float* bias2;                        // conv2 folded bias [coutp]
     const float* rw1; const float* rb1;        // residual 1x1: [C][coutp], [coutp]
     __half* pool_out;                          // [R, H/2, W/2, coutp]
-    int debug;                   // timing experiments (DTRAJ_E1_DEBUG): 4 skips conv2's MMAs
+    unsigned int* err;           // the owning handle's device error word (null: the library-wide word)
 };
 
-// byte offset of 16-byte K chunk kc (0/1) of row r inside a [rows][16 halfs] operand slice
-__device__ __forceinline__ uint32_t k16_off(int r, int kc, int mode) {
-    return mode == 0 ? (uint32_t)(r * 32 + ((kc ^ ((r >> 2) & 1)) << 4))
-                     : (uint32_t)((r >> 3) * 256 + kc * 128 + (r & 7) * 16);
-}
+// byte offset of 16-byte K chunk kc (0/1) of row r inside a [rows][16 halfs] operand slice (32-byte rows, SWIZZLE_32B)
+__device__ __forceinline__ uint32_t k16_off(int r, int kc) { return (uint32_t)(r * 32 + ((kc ^ ((r >> 2) & 1)) << 4)); }
 
 template <bool kPair, int kC>
 __global__ void __launch_bounds__(kE1hThreads, 1)
@@ -94,6 +90,7 @@ k_enc1_f16(const __grid_constant__ Enc1Maps maps, const Enc1hParams p) {
     const float* rw1s = rb1s + coutp;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    unsigned int* const errw = p.err ? p.err : &g_umma_error;
     const int crank = kPair ? (int)ptx::cluster_ctarank() : 0;
     const uint16_t cmask = kPair ? 3 : 1;
     const int work0 = (int)blockIdx.x - crank;
@@ -139,7 +136,7 @@ k_enc1_f16(const __grid_constant__ Enc1Maps maps, const Enc1hParams p) {
     __syncthreads();
     for (int i = threadIdx.x; i < p.n_d1 * 2 * 256; i += blockDim.x) {    // the bias slots of every A1 row hold 1.0
         const int bb = i >> 9, r = (i >> 1) & 255, k = kBiasK + (i & 1);
-        *reinterpret_cast<__half*>(gbase + (a1_0 - base) + bb * a1_buf + (k >> 4) * kA1SliceBytes + k16_off(r, (k >> 3) & 1, p.a1_mode) + (k & 7) * 2) = __float2half_rn(1.f);
+        *reinterpret_cast<__half*>(gbase + (a1_0 - base) + bb * a1_buf + (k >> 4) * kA1SliceBytes + k16_off(r, (k >> 3) & 1) + (k & 7) * 2) = __float2half_rn(1.f);
     }
     for (int i = threadIdx.x; i < p.n_slices * p.w_rows * 16; i += blockDim.x) {
         const int s = i / (p.w_rows * 16), rem = i - s * p.w_rows * 16, nl = rem >> 4, e = rem & 15, k = 16 * s + e;
@@ -148,7 +145,7 @@ k_enc1_f16(const __grid_constant__ Enc1Maps maps, const Enc1hParams p) {
         if (k < 9 * C) v = p.w3[(size_t)k * coutp + n];
         else if (k == kBiasK) v = __half2float(__float2half_rn(p.b3[n]));
         else if (k == kBiasK + 1) v = p.b3[n] - __half2float(__float2half_rn(p.b3[n]));
-        *reinterpret_cast<__half*>(gbase + (b1_0 - base) + s * b1_slice + k16_off(nl, e >> 3, p.a1_mode) + (e & 7) * 2) = __float2half_rn(v);
+        *reinterpret_cast<__half*>(gbase + (b1_0 - base) + s * b1_slice + k16_off(nl, e >> 3) + (e & 7) * 2) = __float2half_rn(v);
     }
     ptx::fence_proxy_async();
     ptx::tc_fence_before();
@@ -184,20 +181,18 @@ k_enc1_f16(const __grid_constant__ Enc1Maps maps, const Enc1hParams p) {
             const uint32_t idesc = umma_idesc_f16(coutp) + (kPair ? ((uint32_t)(128 >> 4) << 24) : 0u);
             // halo view: K-major SWIZZLE_128B, 8-row groups one halo row (10 pixels = 1280 B) apart
             const uint64_t hdesc0 = ((uint64_t)1 << 16) | ((uint64_t)(1280 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
-            // 32-byte-row operands of conv1: 8-row groups 256 B apart; SWIZZLE_32B, or un-swizzled core matrices 128 B apart in K
-            const uint64_t kdesc0 = p.a1_mode == 0
-                ? (((uint64_t)1 << 16) | ((uint64_t)(256 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)6 << 61))
-                : (((uint64_t)(128 >> 4) << 16) | ((uint64_t)(256 >> 4) << 32) | ((uint64_t)1 << 46));
+            // 32-byte-row operands of conv1: 8-row groups 256 B apart, SWIZZLE_32B
+            const uint64_t kdesc0 = ((uint64_t)1 << 16) | ((uint64_t)(256 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)6 << 61);
             auto kdesc = [&](uint32_t addr) { return kdesc0 | (uint64_t)((addr >> 4) & 0x3fffu); };
             int hb = 0, acc = 0, it = 0;
             uint32_t hph = 0, acc_ph = 0;
-            bool ok = ptx::mbar_wait(wbar, 0u);
+            bool ok = ptx::mbar_wait(errw, wbar, 0u);
             const int n_my = work0 < p.n_tiles ? (p.n_tiles - work0 + (int)gridDim.x - 1) / (int)gridDim.x : 0;   // tile iterations of this CTA (pair)
             // conv1 of tile-iteration j into D1 buffer j % n_d1: D1[g] = A1[rows 128g ..] * W1^T, g = 0, 1
             auto issue_conv1 = [&](int j) {
                 const int b = j & (p.n_d1 - 1);
-                ok = ok && ptx::mbar_wait(a1_full0 + 8u * b, (uint32_t)((j >> (p.n_d1 - 1)) & 1));
-                ok = ok && ptx::mbar_wait(d1_empty0 + 8u * b, (uint32_t)(((j >> (p.n_d1 - 1)) & 1) ^ 1));
+                ok = ok && ptx::mbar_wait(errw, a1_full0 + 8u * b, (uint32_t)((j >> (p.n_d1 - 1)) & 1));
+                ok = ok && ptx::mbar_wait(errw, d1_empty0 + 8u * b, (uint32_t)(((j >> (p.n_d1 - 1)) & 1) ^ 1));
                 ptx::tc_fence_after();
                 const uint32_t d1_tmem = tmem_base + (uint32_t)((2 + 2 * b) * p.acc_cols);
                 for (int g = 0; g < 2; ++g)
@@ -214,7 +209,7 @@ k_enc1_f16(const __grid_constant__ Enc1Maps maps, const Enc1hParams p) {
             if (n_my > 0) issue_conv1(0);
             if (p.n_d1 == 2 && n_my > 1) issue_conv1(1);
             for (int wk = work0; wk < p.n_tiles && ok; wk += gridDim.x, ++it) {
-                ok = ptx::mbar_wait(acc_empty0 + 8u * acc, acc_ph ^ 1u);
+                ok = ptx::mbar_wait(errw, acc_empty0 + 8u * acc, acc_ph ^ 1u);
                 ptx::tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.acc_cols);
                 uint32_t accum = 0u;
@@ -222,7 +217,7 @@ k_enc1_f16(const __grid_constant__ Enc1Maps maps, const Enc1hParams p) {
                     // one D1 buffer: the next tile's conv1 goes in front of this tile's last chunk, so that its conversion
                     // overlaps that chunk's MMAs
                     if (p.n_d1 == 1 && c == p.n_chunks - 1 && it + 1 < n_my) issue_conv1(it + 1);
-                    ok = ok && ptx::mbar_wait(hfull(hb), hph);      // this chunk's halo tile is in shared memory (both CTAs)
+                    ok = ok && ptx::mbar_wait(errw, hfull(hb), hph);      // this chunk's halo tile is in shared memory (both CTAs)
                     ptx::tc_fence_after();
                     const uint32_t hbuf = halo0 + (uint32_t)hb * kE1HaloBytes;
                     int dy = 0, dx = 0;
@@ -232,7 +227,6 @@ k_enc1_f16(const __grid_constant__ Enc1Maps maps, const Enc1hParams p) {
                         const uint64_t bd = umma_desc_sw128(wres0 + (uint32_t)(t * p.n_chunks + c) * wblk_bytes);
 #pragma unroll
                         for (int k = 0; k < 4; ++k) {
-                            if (p.debug & 4) break;
                             if constexpr (!kPair) ptx::mma_f16(d_tmem, ad + 2u * k, bd + 2u * k, idesc, accum);
                             else ptx::mma_f16_2sm(d_tmem, ad + 2u * k, bd + 2u * k, idesc, accum);
                             accum = 1u;
@@ -256,8 +250,7 @@ k_enc1_f16(const __grid_constant__ Enc1Maps maps, const Enc1hParams p) {
         const int HW = p.H * p.W;
         // Work balance: quarters 0 and 1 convert two D1 rows per thread (regions 0 and 1), quarters 2 and 3 only one --
         // so the four warps of quarters 2 and 3 (128 threads) gather ALL of A1: rows tq and tq + 128 (< 180).
-        // (debug bit 8 restores one row per mid thread)
-        const bool bal = !(p.debug & 8);
+        constexpr bool bal = true;
         const bool a1_warp = q >= 2;
         const int tq = (2 * h + (q & 1)) * 32 + lane;               // 0..127 over the A1-gathering threads
         const int a_row[2] = {bal ? tq : mt, tq + 128};
@@ -318,7 +311,7 @@ k_enc1_f16(const __grid_constant__ Enc1Maps maps, const Enc1hParams p) {
                         __half2* oh = reinterpret_cast<__half2*>(&o);
 #pragma unroll
                         for (int e = 0; e < 4; ++e) oh[e] = __floats2half2_rn(v[2 * e], v[2 * e + 1]);
-                        *reinterpret_cast<uint4*>(a1b + sl * kA1SliceBytes + k16_off(a_row[rr], kc, p.a1_mode)) = o;
+                        *reinterpret_cast<uint4*>(a1b + sl * kA1SliceBytes + k16_off(a_row[rr], kc)) = o;
                     }
             }
         };
@@ -361,7 +354,7 @@ k_enc1_f16(const __grid_constant__ Enc1Maps maps, const Enc1hParams p) {
             tile_geom(tile, img, y0, x0);
             const bool real = tile < p.n_tiles;
             const int b = it & (Ld - 1);
-            ptx::mbar_wait(d1_full0 + 8u * b, (uint32_t)((it >> (Ld - 1)) & 1));    // conv1(it) done: D1 readable, A1 buffer b free
+            ptx::mbar_wait(errw, d1_full0 + 8u * b, (uint32_t)((it >> (Ld - 1)) & 1));    // conv1(it) done: D1 readable, A1 buffer b free
             ptx::tc_fence_after();
             const bool next = wk + Ld * G < p.n_tiles;
             if (next) {
@@ -385,7 +378,7 @@ k_enc1_f16(const __grid_constant__ Enc1Maps maps, const Enc1hParams p) {
                 if (has1) ptx::tmem_ld32(t_d1 + (uint32_t)(p.acc_cols + col0), r1);
                 ptx::tmem_ld_wait();
                 ptx::tc_fence_before();
-                ptx::mbar_wait(hempty(hb), hph ^ 1u);               // the conv2 MMAs that read this buffer have retired
+                ptx::mbar_wait(errw, hempty(hb), hph ^ 1u);               // the conv2 MMAs that read this buffer have retired
                 uint8_t* hbuf = gbase + (halo0 - base) + (size_t)hb * kE1HaloBytes;
                 // h = relu(D1) + time bias (conv1's folded bias is inside D1), rounded to fp16; zero rows outside the image
                 auto emit = [&](const uint32_t* raw, int px, bool inside) {
@@ -463,7 +456,7 @@ k_enc1_f16(const __grid_constant__ Enc1Maps maps, const Enc1hParams p) {
                 prefetch(wk + (int)gridDim.x, smp_n);
                 fetch_idx(wk + 2 * (int)gridDim.x);
             }
-            ptx::mbar_wait(acc_full0 + 8u * acc, acc_ph);
+            ptx::mbar_wait(errw, acc_full0 + 8u * acc, acc_ph);
             ptx::tc_fence_after();
             const uint32_t t_acc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.acc_cols);
             for (int c = 0; c < nchunk; ++c) {
@@ -527,7 +520,7 @@ k_enc1_f16(const __grid_constant__ Enc1Maps maps, const Enc1hParams p) {
             }
             if (++acc == 2) { acc = 0; acc_ph ^= 1u; }
         }
-        if (!(amax <= 65504.f)) atomicOr(&g_umma_error, 2u);
+        if (!(amax <= 65504.f)) atomicOr(errw, 2u);
     }
     ptx::tc_fence_before();
     __syncthreads();
@@ -565,14 +558,14 @@ inline int build_enc1h_launch(Enc1hLaunch* E, int C, int H, int coutp, int cout_
     p.n_tiles = (int)nt;
     p.acc_cols = 32;
     while (p.acc_cols < coutp) p.acc_cols *= 2;
-    p.n_d1 = (6 * p.acc_cols <= 512 && !getenv("DTRAJ_E1_D1SINGLE")) ? 2 : 1;
+    p.n_d1 = 6 * p.acc_cols <= 512 ? 2 : 1;
     auto fixed_for = [&](int pair) {
         const size_t wr = (size_t)coutp / (pair ? 2 : 1);
         return (size_t)1024 + (size_t)9 * p.n_chunks * wr * 128 + kE1Epi * 2048 + (size_t)p.n_d1 * p.n_slices * kA1SliceBytes +
                (((size_t)p.n_slices * wr * 32 + 1023) & ~(size_t)1023) + (size_t)(6 + C) * coutp * 4 + 16 + 256;
     };
     // pairs halve the resident weights per CTA; without them the weights must still fit next to one halo buffer
-    E->pair = (p.n_tiles >= 2 * kNumSMs && !getenv("DTRAJ_NO_PAIR")) ? 1 : 0;
+    E->pair = p.n_tiles >= 2 * kNumSMs ? 1 : 0;
     if (!E->pair && fixed_for(0) + kE1HaloBytes > 227 * 1024) E->pair = 1;     // n_tiles >= 2 always (two tiles per 16-row band)
     p.w_rows = coutp / (E->pair ? 2 : 1);
     const size_t fixed = fixed_for(E->pair);
@@ -586,8 +579,6 @@ inline int build_enc1h_launch(Enc1hLaunch* E, int C, int H, int coutp, int cout_
     if (E->pair) E->grid = (E->grid + 1) / 2 * 2;
     DTRAJ_TRY(make_w_map(&E->maps.w, w2, w2_rows, p.w_rows, 1));
     E->flops = 2.0 * (double)R * H * H * cout_real * (double)cout_real * 9.0;
-    p.debug = getenv("DTRAJ_E1_DEBUG") ? atoi(getenv("DTRAJ_E1_DEBUG")) : 0;
-    p.a1_mode = getenv("DTRAJ_E1_A1MODE") ? atoi(getenv("DTRAJ_E1_A1MODE")) : 0;
     return 0;
 }
 

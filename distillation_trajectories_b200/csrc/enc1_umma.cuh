@@ -47,8 +47,7 @@ struct Enc1Params {
     const float* rw1; const float* rb1;        // residual 1x1: [C][coutp], [coutp]
     float* pool_out;                           // [R, H/2, W/2, coutp]
     int act_mode;
-    int debug;                   // timing experiments (DTRAJ_E1_DEBUG): 1 generators store zeros without conv1 math,
-                                 // 2 generators only signal, 4 issuer skips the MMAs
+    unsigned int* err;           // the owning handle's device error word (null: the library-wide word)
 };
 
 struct Enc1Maps { CUtensorMap w; };            // conv2 packed weights, box {32, w_rows}
@@ -79,6 +78,7 @@ k_enc1_umma(const __grid_constant__ Enc1Maps maps, const Enc1Params p) {
     float* w3s = reinterpret_cast<float*>(gbase + (w3s0 - base));         // [9*C][coutp], then b3 [coutp], tb unused
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    unsigned int* const errw = p.err ? p.err : &g_umma_error;
     const int crank = kPair ? (int)ptx::cluster_ctarank() : 0;
     const uint16_t cmask = kPair ? 3 : 1;
     const int work0 = (int)blockIdx.x - crank;
@@ -128,7 +128,7 @@ k_enc1_umma(const __grid_constant__ Enc1Maps maps, const Enc1Params p) {
             for (int wk = work0; wk < p.n_tiles && ok; wk += gridDim.x) {
                 for (int c = 0; c < p.n_chunks && ok; ++c)
                     for (int t0 = 0; t0 < 9 && ok; t0 += p.tps) {
-                        ok = ptx::mbar_wait(wempty(s), ph ^ 1u);
+                        ok = ptx::mbar_wait(errw, wempty(s), ph ^ 1u);
                         uint32_t fb = wfull(s);
                         if constexpr (kPair) fb = ptx::map_to_cta(fb, 0);
                         if (!kPair || crank == 0) ptx::mbar_expect_tx(wfull(s), stage_bytes * (kPair ? 2u : 1u));
@@ -152,17 +152,17 @@ k_enc1_umma(const __grid_constant__ Enc1Maps maps, const Enc1Params p) {
             uint32_t ph = 0, hph = 0, acc_ph = 0;
             bool ok = true;
             for (int wk = work0; wk < p.n_tiles && ok; wk += gridDim.x) {
-                ok = ptx::mbar_wait(acc_empty0 + 8u * acc, acc_ph ^ 1u);
+                ok = ptx::mbar_wait(errw, acc_empty0 + 8u * acc, acc_ph ^ 1u);
                 ptx::tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.acc_cols);
                 uint32_t accum = 0u;
                 for (int c = 0; c < p.n_chunks && ok; ++c) {
-                    ok = ptx::mbar_wait(hfull(hb), hph);            // this chunk's halo tile is in shared memory (both CTAs)
+                    ok = ptx::mbar_wait(errw, hfull(hb), hph);            // this chunk's halo tile is in shared memory (both CTAs)
                     ptx::tc_fence_after();
                     const uint32_t hbuf = halo0 + (uint32_t)hb * kE1HaloBytes;
                     int dy = 0, dx = 0;                              // tap (dy, dx) in 0..2
                     for (int t0 = 0; t0 < 9 && ok; t0 += p.tps) {
-                        ok = ptx::mbar_wait(wfull(s), ph);
+                        ok = ptx::mbar_wait(errw, wfull(s), ph);
                         ptx::tc_fence_after();
                         for (int j = 0; j < p.tps; ++j) {
                             const uint32_t a_addr = hbuf + (uint32_t)(dy * 10 + dx) * 128u;
@@ -170,7 +170,6 @@ k_enc1_umma(const __grid_constant__ Enc1Maps maps, const Enc1Params p) {
                             const uint64_t bd = umma_desc_sw128(wst0 + s * stage_bytes + j * wtap_bytes);
 #pragma unroll
                             for (int k = 0; k < 4; ++k) {
-                                if (p.debug & 4) break;
                                 if constexpr (!kPair) ptx::mma_tf32(d_tmem, ad + 2u * k, bd + 2u * k, idesc, accum);
                                 else ptx::mma_tf32_2sm(d_tmem, ad + 2u * k, bd + 2u * k, idesc, accum);
                                 accum = 1u;
@@ -219,7 +218,7 @@ k_enc1_umma(const __grid_constant__ Enc1Maps maps, const Enc1Params p) {
 #pragma unroll
                     for (int t9 = 0; t9 < 9; ++t9) w[t9] = *reinterpret_cast<const float4*>(w3s + (size_t)t9 * coutp + ch);
                 }
-                ptx::mbar_wait(hempty(hb), hph ^ 1u);               // the MMAs that read this buffer have retired
+                ptx::mbar_wait(errw, hempty(hb), hph ^ 1u);               // the MMAs that read this buffer have retired
                 uint8_t* hbuf = gbase + (halo0 - base) + (size_t)hb * kE1HaloBytes;
                 // 32 pixel lanes x 6 rounds cover the 180 halo pixels; two pixels (px, px + 96) per trip keep eight
                 // independent FMA chains in flight
@@ -252,13 +251,10 @@ k_enc1_umma(const __grid_constant__ Enc1Maps maps, const Enc1Params p) {
                                            fmaxf(acc.z, 0.f) + t4.z, fmaxf(acc.w, 0.f) + t4.w);
                     return act_round4(o, p.act_mode);
                 };
-                for (int px = pl; px < 96 && !(p.debug & 2); px += 32) {
+                for (int px = pl; px < 96; px += 32) {
                     const int px1 = px + 96;
-                    float4 o0 = make_float4(0.f, 0.f, 0.f, 0.f), o1 = o0;
-                    if (!(p.debug & 1)) {
-                        o0 = conv1_at(px);
-                        if (px1 < kE1HaloRows) o1 = conv1_at(px1);
-                    }
+                    float4 o0 = conv1_at(px), o1 = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (px1 < kE1HaloRows) o1 = conv1_at(px1);
                     *reinterpret_cast<float4*>(hbuf + px * 128 + (((uint32_t)g ^ (uint32_t)(px & 7)) << 4)) = o0;
                     if (px1 < kE1HaloRows) *reinterpret_cast<float4*>(hbuf + px1 * 128 + (((uint32_t)g ^ (uint32_t)(px1 & 7)) << 4)) = o1;
                 }
@@ -297,7 +293,7 @@ k_enc1_umma(const __grid_constant__ Enc1Maps maps, const Enc1Params p) {
 #pragma unroll
                 for (int ci = 0; ci < 4; ++ci) if (ci < p.C) xv[ci] = __ldg(xs + (size_t)ci * p.H * p.W);
             }
-            ptx::mbar_wait(acc_full0 + 8u * acc, acc_ph);
+            ptx::mbar_wait(errw, acc_full0 + 8u * acc, acc_ph);
             ptx::tc_fence_after();
             const uint32_t t_acc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.acc_cols);
             const int c_last = nchunk - 1;
@@ -376,7 +372,7 @@ inline int build_enc1_launch(Enc1Launch* E, int C, int H, int coutp, int cout_re
     const int64_t nt = R * p.tiles_per_img;
     if (nt >= ((int64_t)1 << 30)) return fail(DTRAJ_EINVAL, "enc1: batch too large");
     p.n_tiles = (int)nt;
-    E->pair = (p.n_tiles >= 2 * kNumSMs && coutp >= 64 && !getenv("DTRAJ_NO_PAIR")) ? 1 : 0;
+    E->pair = (p.n_tiles >= 2 * kNumSMs && coutp >= 64) ? 1 : 0;
     p.w_rows = coutp / (E->pair ? 2 : 1);
     p.n_hbuf = p.n_chunks;       // chunk c of the next tile reuses chunk c's buffer as soon as its nine taps have retired
     if (p.n_hbuf > 8) return fail(DTRAJ_EINVAL, "enc1: too many halo buffers");
@@ -395,7 +391,6 @@ inline int build_enc1_launch(Enc1Launch* E, int C, int H, int coutp, int cout_re
     if (E->pair) E->grid = (E->grid + 1) / 2 * 2;
     DTRAJ_TRY(make_w_map(&E->maps.w, w2, w2_rows, p.w_rows));
     E->flops = 2.0 * (double)R * H * H * cout_real * (double)cout_real * 9.0;
-    p.debug = getenv("DTRAJ_E1_DEBUG") ? atoi(getenv("DTRAJ_E1_DEBUG")) : 0;
     return 0;
 }
 

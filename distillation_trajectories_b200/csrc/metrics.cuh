@@ -308,12 +308,12 @@ inline int launch_wasserstein(const float* T, const float* S, int64_t N, int L, 
     while (P < K) P *= 2;
     const int64_t NL = N * L;
     const unsigned wgrid = (unsigned)((NL + 7) / 8);
-    if (P <= 256 && !getenv("DTRAJ_W1_BLOCK")) {
+    if (P <= 256) {
         k_wasserstein_warp<8><<<wgrid, 256, 0, st>>>(T, S, NL, L, D, idx, idx_set, K, out);
         DTRAJ_LAUNCH_CHECK();
         return 0;
     }
-    if (P <= 1024 && !getenv("DTRAJ_W1_BLOCK")) {
+    if (P <= 1024) {
         k_wasserstein_warp<32><<<wgrid, 256, 0, st>>>(T, S, NL, L, D, idx, idx_set, K, out);
         DTRAJ_LAUNCH_CHECK();
         return 0;

@@ -42,7 +42,7 @@ __global__ void __launch_bounds__(128) k_probe_view(int rows, int start_row, int
         ptx::mma_tf32(tmem, ad, bd, umma_idesc_tf32(16), 0u);
         ptx::tc_commit(ptx::smem_u32(&bar));
     }
-    ptx::mbar_wait(ptx::smem_u32(&bar), 0);
+    ptx::mbar_wait(&g_umma_error, ptx::smem_u32(&bar), 0);
     ptx::tc_fence_after();
     uint32_t v[32];
     ptx::tmem_ld32(tmem + ((uint32_t)((threadIdx.x >> 5) * 32) << 16), v);
@@ -71,7 +71,7 @@ __global__ void __launch_bounds__(128) k_probe_tma_perm(const __grid_constant__ 
         ptx::mbar_expect_tx(ptx::smem_u32(&bar), 200u * 128u);
         ptx::tma_load_4d(base, &map, ptx::smem_u32(&bar), 0, -1, img0, -1);
     }
-    ptx::mbar_wait(ptx::smem_u32(&bar), 0);
+    ptx::mbar_wait(&g_umma_error, ptx::smem_u32(&bar), 0);
     for (int r = threadIdx.x; r < 200; r += blockDim.x) out[r] = __half2float(*reinterpret_cast<const __half*>(a + r * 128));
 }
 

@@ -5,6 +5,7 @@ the reference's noise; all arithmetic of the hot path runs inside libdtraj.so.
 """
 import ctypes as C
 import os
+import weakref
 
 import numpy as np
 import torch
@@ -49,7 +50,25 @@ def _model_geometry(model):
 
 
 def _weights_fingerprint(model):
-    return tuple((id(t), t._version) for t in list(model.parameters()) + list(model.buffers()))
+    """Identity of the weight STORAGE: tensor ids, autograd versions and data pointers.  Catches ``load_state_dict``,
+    optimizer steps, ``p.data = new`` and re-allocations; an in-place write through ``p.data`` (the EMA idiom
+    ``p.data.mul_(d).add_(...)``) bumps none of them -- that is what ``_weights_checksum`` is for."""
+    return tuple((id(t), t._version, t.data_ptr()) for t in list(model.parameters()) + list(model.buffers()))
+
+
+def _weights_checksum(model):
+    """Content check of every floating-point parameter / buffer: position-weighted sums of the per-tensor L1 and L2
+    norms, two multi-tensor kernels and one scalar read-back (synchronises the current stream, so it runs where an
+    entry point hands results to the host anyway -- not between the chunks of a sweep, see ``for_model(verify=)``)."""
+    ts = [t.detach() for t in list(model.parameters()) + list(model.buffers()) if torch.is_floating_point(t)]
+    if not ts:
+        return 0.0
+    v = torch.stack(torch._foreach_norm(ts, 1) + torch._foreach_norm(ts, 2)).double()
+    w = torch.arange(1, v.numel() + 1, dtype=torch.float64, device=v.device)
+    return float((v * w).sum())
+
+
+_live_engines = weakref.WeakSet()      # every UNetEngine with an open handle: check_device_errors() polls their error words
 
 
 class UNetEngine:
@@ -80,10 +99,16 @@ class UNetEngine:
         self.handle = handle
         self._ws = None
         self._samplers = {}
+        self.label = f"U-Net dims={list(dims)} {channels}x{image_size}x{image_size} [{ {v: k for k, v in _lib.PRECISIONS.items()}[self.precision] }]"
+        _live_engines.add(self)
 
     @classmethod
-    def for_model(cls, model, image_size, n_timesteps, precision, device=None):
-        """Engine cached on the module; rebuilt when weights, precision or table size change."""
+    def for_model(cls, model, image_size, n_timesteps, precision, device=None, verify=True):
+        """Engine cached on the module; rebuilt when weights, precision or table size change.
+        ``verify=True`` also compares a content checksum of the weights with the one taken when the cached engine was
+        packed, so that in-place ``.data`` updates (which leave tensor versions untouched) are noticed; it costs one
+        host-device synchronisation.  Loops that must stay asynchronous (the chunks of ``grid.sweep``) verify once up
+        front and pass ``verify=False`` afterwards; ``invalidate(model)`` drops the cache explicitly."""
         if getattr(model, "training", False):
             raise DtrajError("model is in training mode; the hot path needs model.eval() "
                              "(eval-mode BatchNorm/Dropout, as every reference caller does)")
@@ -96,22 +121,45 @@ class UNetEngine:
         fp = _weights_fingerprint(model)
         ent = cache.get(key)
         if ent is not None and ent[0] == fp and ent[1].n_timesteps >= n_timesteps:
-            return ent[1]
+            if not verify or _weights_checksum(model) == ent[2]:
+                return ent[1]
         if ent is not None:
             n_timesteps = max(n_timesteps, ent[1].n_timesteps)
             ent[1].close()
         g = _model_geometry(model)
         eng = cls(model.state_dict(), g["channels"], int(image_size), g["dims"], g["temb_dim"], n_timesteps, prec, device)
-        cache[key] = (fp, eng)
+        cache[key] = (fp, eng, _weights_checksum(model))
         return eng
+
+    @staticmethod
+    def invalidate(model):
+        """Drop every cached engine of ``model`` (and the CUDA graphs captured on them)."""
+        for ent in model.__dict__.pop("_dtraj_engines", {}).values():
+            ent[1].close()
 
     def close(self):
         for s in self._samplers.values():
             s.close()
         self._samplers = {}
+        _live_engines.discard(self)
         if getattr(self, "handle", None):
             self.lib.dtraj_unet_destroy(self.handle)
             self.handle = None
+
+    def check_errors(self):
+        """Read and clear THIS engine's device error word (pipeline time-out / fp16 overflow flagged by one of its
+        kernels); raises DtrajError naming the model.  Synchronises the device."""
+        if not getattr(self, "handle", None):
+            return
+        with torch.cuda.device(self.device):
+            rc = self.lib.dtraj_unet_check_errors(self.handle)
+        if rc != 0:
+            msg = self.lib.dtraj_last_error()
+            raise DtrajError(f"libdtraj error {rc} in {self.label}: {msg.decode() if msg else '?'}")
+
+    def error_flag_async(self, host_flag_ptr, stream_ptr):
+        """Enqueue a copy of this engine's error word into pinned host memory (non-blocking form of check_errors)."""
+        _lib.check(self.lib.dtraj_unet_error_flag_async(self.handle, C.c_void_p(host_flag_ptr), C.c_void_p(stream_ptr)))
 
     def __del__(self):
         try:
@@ -232,6 +280,24 @@ class TrajectorySampler:
             _lib.check(self.lib.dtraj_sampler_profile(self.handle, _lib.stream_ptr(), ms, nl, fl))
         return dict(ms=list(ms), launches=list(nl), conv_flops=fl[0], enc1_flops=fl[1])
 
+    def flops(self):
+        """Algorithmic conv flops of one run() (real channels, evaluated taps): (generic convs, fused enc1 kernel)."""
+        fl = (C.c_double * 2)()
+        _lib.check(self.lib.dtraj_sampler_flops(self.handle, fl))
+        return float(fl[0]), float(fl[1])
+
+    def profile_layers(self, step=1):
+        """One un-captured run with an event pair around every launch; returns [(name, grid, microseconds, flops)] for the
+        launches of sampler step ``step`` (diagnostics, tools/profile_layers.py)."""
+        buf = C.create_string_buffer(1 << 16)
+        with torch.cuda.device(self.engine.device):
+            _lib.check(self.lib.dtraj_sampler_profile_text(self.handle, _lib.stream_ptr(), int(min(step, self.n_updates - 1)), buf, len(buf)))
+        rows = []
+        for ln in buf.value.decode().splitlines():
+            name, grid, us, fl = ln.split("\t")
+            rows.append((name, int(grid), float(us), float(fl)))
+        return rows
+
     def close(self):
         if getattr(self, "handle", None):
             self.lib.dtraj_sampler_destroy(self.handle)
@@ -255,12 +321,36 @@ def cached_sampler(engine, key, factory):
     return s
 
 
-def check_device_errors():
+def check_device_errors(device=None):
     """Raise DtrajError if a kernel flagged a pipeline time-out or an fp16 overflow since the last check.
-    Synchronises the device: called where results are read back to the host anyway."""
-    _lib.check(_lib.load().dtraj_check_errors())
+    Synchronises the device: called where results leave the library.  ``device``: the engine's device (the error
+    word lives in that device's copy of the library's globals); default = the current device."""
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    if dev.index is None:
+        dev = torch.device("cuda", torch.cuda.current_device())
+    first = None
+    for eng in list(_live_engines):          # every word is read (and cleared) before the first failure is raised
+        if eng.device.index in (None, dev.index):
+            try:
+                eng.check_errors()
+            except DtrajError as e:
+                first = first or e
+    with torch.cuda.device(dev):
+        rc = _lib.load().dtraj_check_errors()     # launches without a handle (test hooks)
+    if first is not None:
+        raise first
+    _lib.check(rc)
 
 
 def umma_error_flag():
-    """Non-zero if any tcgen05 kernel timed out on a barrier since the library was loaded."""
-    return int(_lib.load().dtraj_debug_umma_error())
+    """Non-zero if a kernel flagged a pipeline time-out or an fp16 overflow that nobody has collected yet: the
+    library-wide word OR-ed with the word of every live engine (peeked, not cleared)."""
+    v = int(_lib.load().dtraj_debug_umma_error())
+    for eng in list(_live_engines):
+        if getattr(eng, "handle", None):
+            flag = torch.zeros(1, dtype=torch.int32).pin_memory()
+            with torch.cuda.device(eng.device):
+                eng.error_flag_async(flag.data_ptr(), torch.cuda.current_stream().cuda_stream)
+                torch.cuda.current_stream().synchronize()
+            v |= int(flag[0])
+    return v

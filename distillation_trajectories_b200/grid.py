@@ -107,46 +107,62 @@ def stage_chunk(samples, config, guidance_scales, device):
     return ck
 
 
-def run_chunk(teacher_model, student_models, ck, device, precision=None):
+def run_chunk(teacher_model, student_models, ck, device, precision=None, out_traj=None, verify_weights=False):
     """Device side of a chunk: one captured S2 loop per model over all pairs, then the streaming metric
     kernels for every (teacher, student).  Returns device tensors (red [n_students, N, L, 6],
-    w1 [n_students, N, L]) and the number of trajectories generated."""
+    w1 [n_students, N, L]) and the number of trajectories generated.  ``out_traj`` (list): receives one
+    (teacher [N, L, D], student [N, L, D]) pair of views of the samplers' trajectory buffers per student -- valid
+    until the owning sampler runs again (parity checks read the frames behind the reductions through it).
+    ``verify_weights``: content-check the cached packed weights against the live modules first (one synchronisation per
+    model, engine.UNetEngine.for_model); ``sweep`` does it for its first chunk only, so later chunks stay asynchronous."""
     device = torch.device(device)
     prec = precision or te.get_precision("S2")
 
     def gen(model):
         model.eval()
-        eng = te.UNetEngine.for_model(model, ck.x.shape[2], ck.T, prec, device)
+        eng = te.UNetEngine.for_model(model, ck.x.shape[2], ck.T, prec, device, verify=verify_weights)
         return sampling.s2_sample(eng, ck.x, ck.T, ck.ws, ck.bank, ck.z_index, guidance_dev=ck.ws_dev,
                                   groups=getattr(ck, "groups", None))
 
-    # The teacher's and the students' loops are independent until the metrics: the students run on a side stream, so that
+    # The teacher's and the students' loops are independent until the metrics: the students run on side streams, so that
     # their CTAs fill the tails of the teacher's persistent kernels and vice versa (+2.3 % trajectories/s on the bench
-    # workload, identical results; DTRAJ_OVERLAP_MODELS=0 serialises them again).
+    # workload, identical results).  DTRAJ_MODEL_STREAMS = number of side streams the students are dealt over (default 3:
+    # the narrow students of an 11-student sweep leave most SMs idle on their own); 0 serialises everything.
     cur = torch.cuda.current_stream(device)
-    side = _copy_stream(device, "models") if os.environ.get("DTRAJ_OVERLAP_MODELS", "1") != "0" else None
-    if side is not None:
-        side.wait_stream(cur)
+    n_side = int(os.environ.get("DTRAJ_MODEL_STREAMS", "3"))
+    if os.environ.get("DTRAJ_OVERLAP_MODELS", "1") == "0":
+        n_side = 0
+    distinct = [m for m in student_models if m is not teacher_model]
+    sides = [_copy_stream(device, f"models{i}") for i in range(min(n_side, len(distinct)))]
+    for sd in sides:
+        sd.wait_stream(cur)                           # the chunk's uploads were queued on the current stream
     tt = gen(teacher_model)
     t_flat = tt.reshape(tt.shape[0], tt.shape[1], -1)
     n_traj = tt.shape[0]
-    reds, w1s = [], []
-    for sm_model in student_models:
+    flats, k = [], 0
+    for sm_model in student_models:                   # queue every student loop first ...
         if sm_model is teacher_model:
-            s_flat = t_flat
-        else:
-            if side is not None:
-                with torch.cuda.stream(side):
-                    st = gen(sm_model)
-                cur.wait_stream(side)
-            else:
+            flats.append((t_flat, None))
+            continue
+        sd = sides[k % len(sides)] if sides else None
+        k += 1
+        if sd is not None:
+            with torch.cuda.stream(sd):
                 st = gen(sm_model)
-            s_flat = st.reshape(st.shape[0], st.shape[1], -1)
-            n_traj += st.shape[0]
+        else:
+            st = gen(sm_model)
+        flats.append((st.reshape(st.shape[0], st.shape[1], -1), sd))
+        n_traj += st.shape[0]
+    for sd in sides:
+        cur.wait_stream(sd)
+    reds, w1s = [], []
+    for s_flat, sd in flats:                          # ... then the pair metrics behind all of them
         reds.append(tm.pair_reductions(t_flat, s_flat))
         w1s.append(tm.wasserstein_frames(t_flat, s_flat, ck.idx, ck.idx_set))
-    if side is not None:
-        side.wait_stream(cur)                         # the next chunk's student loop must not overtake these metric kernels
+        if out_traj is not None:
+            out_traj.append((t_flat, s_flat))
+    for sd in sides:
+        sd.wait_stream(cur)                           # the next chunk's student loops must not overtake these metric kernels
     return torch.stack(reds), torch.stack(w1s), n_traj
 
 
@@ -154,25 +170,32 @@ class _Readback:
     """Device-to-host copy of a chunk's reductions on a side stream, so that waiting for chunk i's numbers
     does not wait for chunk i+1's kernels (already queued on the compute stream)."""
 
-    def __init__(self, red, w1, device):
+    def __init__(self, red, w1, device, engines=()):
         self.stream = _copy_stream(device)
         ready = torch.cuda.Event()
         ready.record(torch.cuda.current_stream(device))
         self.red_h = torch.empty(red.shape, dtype=red.dtype, pin_memory=True)
         self.w1_h = torch.empty(w1.shape, dtype=w1.dtype, pin_memory=True)
-        self.flag_h = torch.zeros(1, dtype=torch.int32, pin_memory=True)   # device error word, read without a device-wide sync
+        self.engines = list(engines)
+        self.flag_h = torch.zeros(1 + len(self.engines), dtype=torch.int32, pin_memory=True)   # device error words (library-wide, then
+                                                                                                 # one per engine), read without a device-wide sync
         self.keep = (red, w1)                       # keep the device tensors alive until the copy is done
         with torch.cuda.stream(self.stream):
             self.stream.wait_event(ready)
             self.red_h.copy_(red, non_blocking=True)
             self.w1_h.copy_(w1, non_blocking=True)
             _lib.check(_lib.load().dtraj_error_flag_async(self.flag_h.data_ptr(), self.stream.cuda_stream))
+            for i, eng in enumerate(self.engines):
+                eng.error_flag_async(self.flag_h.data_ptr() + 4 * (i + 1), self.stream.cuda_stream)
             self.done = torch.cuda.Event()
             self.done.record(self.stream)
 
     def wait(self):
         self.done.synchronize()
         self.keep = None
+        for i, eng in enumerate(self.engines):        # the engine (model) whose kernels flagged the error is named in the message
+            if int(self.flag_h[i + 1]) != 0:
+                eng.check_errors()
         if int(self.flag_h[0]) != 0:
             te.check_device_errors()                  # raises (pipeline time-out / fp16 overflow) and clears the flag
         return self.red_h.numpy(), self.w1_h.numpy()
@@ -235,8 +258,10 @@ def sweep(teacher_model, students, config, guidance_scales, num_samples, device=
     for i in range(len(pieces)):
         ck = nxt
         t0 = time.perf_counter()
-        red, w1, nt = run_chunk(teacher_model, models, ck, device, precision)      # queued, not waited for
-        rb = _Readback(red, w1, device)
+        red, w1, nt = run_chunk(teacher_model, models, ck, device, precision, verify_weights=(i == 0))   # queued, not waited for
+        engines = [ent[1] for m in [teacher_model] + models for ent in m.__dict__.get("_dtraj_engines", {}).values()
+                   if getattr(ent[1], "handle", None)]
+        rb = _Readback(red, w1, device, engines)
         t1 = time.perf_counter()
         nxt = stage_chunk(pieces[i + 1], config, guidance_scales, device) if i + 1 < len(pieces) else None
         t2 = time.perf_counter()

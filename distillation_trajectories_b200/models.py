@@ -12,7 +12,7 @@ import torch
 import torch.nn as nn
 
 from ._lib import DtrajError, VAR_COND0, VAR_COND1, VAR_NONE
-from .engine import UNetEngine, get_precision
+from .engine import UNetEngine, check_device_errors, get_precision
 
 
 class SinusoidalPositionEmbeddings(nn.Module):
@@ -87,7 +87,9 @@ class DiffusionUNet(nn.Module):
             if not bool(((c == 0) | (c == 1)).all()):
                 raise DtrajError("DiffusionUNet.forward: cond must be 0/1 flags")
             variants = torch.where(c > 0.5, VAR_COND1, VAR_COND0).to(torch.int32)
-        return eng.forward(x, t0 if shared else tv, variants)
+        eps = eng.forward(x, t0 if shared else tv, variants)
+        check_device_errors(eng.device)          # an fp16 overflow / pipeline time-out must not leave as a plain tensor
+        return eps
 
 
 class SimpleUNet(DiffusionUNet):

@@ -10,7 +10,7 @@ optimizers stay out of scope.
 import torch
 
 from .. import sampling
-from ..engine import UNetEngine, get_precision
+from ..engine import UNetEngine, check_device_errors, get_precision
 from .._lib import DtrajError, RULE_S1, VAR_COND1, VAR_NONE
 
 linear_beta_schedule = sampling.linear_beta_schedule
@@ -97,6 +97,7 @@ def p_sample(model, x, t, t_index, diffusion_params, guidance_scale=1.0):
         _lib.check(eng.lib.dtraj_step_fused(RULE_S1, kk.ctypes.data_as(C.c_void_p), _lib.ptr(eps[:B]), _lib.ptr(eps[B:]),
                                             _lib.ptr(w), _lib.ptr(xx), D, _lib.ptr(z), D, _lib.ptr(out), D, B, D,
                                             _lib.stream_ptr()))
+    check_device_errors(eng.device)
     return out
 
 
@@ -123,4 +124,5 @@ def p_sample_loop(model, shape, sample_steps, diffusion_params, device=None, con
     final = traj[:, -1].clone().to(device)
     if track_trajectory:
         return final, sampling.frames_to_cpu_list(traj)
+    check_device_errors(eng.device)
     return final

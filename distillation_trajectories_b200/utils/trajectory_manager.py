@@ -42,7 +42,9 @@ class TrajectoryManager:
         ndev = sampling.noise_device(self.device)
         noise = torch.stack([torch.randn(x.shape, device=ndev) for _ in range(n_upd)]) if n_upd else None
         traj = sampling.s3_sample(eng, x, ts, cfg.teacher_steps, noise)
-        return [(traj[:, k].clone(), t) for k, t in enumerate(ts)]
+        frames = [(traj[:, k].clone(), t) for k, t in enumerate(ts)]
+        check_device_errors(self.device)         # frames leave the library here (pickled or handed to the caller)
+        return frames
 
     def _pair(self, seed, sample):
         cfg = self.config

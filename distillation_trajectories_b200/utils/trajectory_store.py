@@ -62,17 +62,49 @@ def list_pickles(directory, size_factor):
     return sorted(out)
 
 
+def _mmap_member(path, zf, name):
+    """Memory-map one STORED (uncompressed) ``.npy`` member of an ``.npz`` archive; None if it cannot be mapped.
+    (``np.load(path, mmap_mode="r")`` silently ignores mmap_mode for archives and reads every member into memory.)"""
+    import struct
+    import zipfile
+    try:
+        info = zf.getinfo(name + ".npy")
+    except KeyError:
+        return None
+    if info.compress_type != zipfile.ZIP_STORED:
+        return None
+    with open(path, "rb") as f:
+        f.seek(info.header_offset)
+        hdr = f.read(30)                                     # local file header: sizes of its name / extra fields
+        if hdr[:4] != b"PK\x03\x04":
+            return None
+        n_name, n_extra = struct.unpack("<HH", hdr[26:30])
+        f.seek(info.header_offset + 30 + n_name + n_extra)
+        major, _ = np.lib.format.read_magic(f)
+        shape, fortran, dtype = (np.lib.format.read_array_header_1_0 if major == 1 else np.lib.format.read_array_header_2_0)(f)
+        if fortran or dtype.hasobject:
+            return None
+        return np.memmap(path, dtype=dtype, mode="r", offset=f.tell(), shape=shape)
+
+
 def read_pack(path, mmap=True):
-    """dict of arrays; the two big ones are memory-mapped when the file is an uncompressed npz."""
-    z = np.load(path, mmap_mode="r" if mmap else None)
-    return {k: z[k] for k in ("teacher", "student", "teacher_t", "student_t", "samples")}
+    """dict of arrays; ``teacher`` / ``student`` are memory-mapped straight out of the (uncompressed) archive, so
+    reading a few samples of a large pack touches only their pages."""
+    import zipfile
+    out = {}
+    with zipfile.ZipFile(path) as zf, np.load(path) as z:
+        for k in ("teacher", "student", "teacher_t", "student_t", "samples"):
+            a = _mmap_member(path, zf, k) if mmap and k in ("teacher", "student") else None
+            out[k] = a if a is not None else z[k]
+    return out
 
 
 def stored_samples(directory, size_factor):
     """All sample indices present in either format."""
     have = {i for i, _ in list_pickles(directory, size_factor)}
     for p in list_packs(directory, size_factor):
-        have.update(int(s) for s in np.load(p)["samples"])
+        with np.load(p) as z:
+            have.update(int(s) for s in z["samples"])
     return have
 
 

@@ -13,8 +13,9 @@
  *   - pointers marked "dev" are CUDA device pointers owned by the caller (torch tensors'
  *     data_ptr()); "host" pointers are ordinary memory.  `stream` is a cudaStream_t
  *     passed as void* (0 = legacy default stream).
- *   - activations are fp32.  Images and trajectories use the reference layout
- *     [N, C, H, W] / [N, L, C, H, W]; internal feature maps are NHWC in the workspace.
+ *   - images, eps maps and trajectories are fp32 in the reference layout [N, C, H, W] /
+ *     [N, L, C, H, W].  Internal feature maps live in the caller-owned workspace, NHWC:
+ *     fp16 in DTRAJ_PREC_F16 (the default of the sweeps), fp32 in the other modes.
  *   - a handle is used by one host thread at a time; one process drives one GPU.
  */
 #ifndef DTRAJ_H
@@ -196,6 +197,11 @@ int64_t dtraj_sampler_launches(const dtraj_sampler* s);
  */
 int dtraj_sampler_profile(dtraj_sampler* s, void* stream, double* class_ms5, int64_t* class_launches5,
                           double* conv_flops2);
+/* the two flop counts of dtraj_sampler_profile without running anything */
+int dtraj_sampler_flops(const dtraj_sampler* s, double* conv_flops2);
+/* Per-launch form (tools/profile_layers.py): runs the loop once, un-captured, and writes one line
+ * "name <TAB> grid <TAB> device microseconds <TAB> algorithmic flops" per launch of sampler step `step` into `buf`. */
+int dtraj_sampler_profile_text(dtraj_sampler* s, void* stream, int32_t step, char* buf, int64_t buf_len);
 
 /* ------------------------------------------------------------------ trajectory metrics */
 
@@ -241,14 +247,18 @@ int dtraj_project(const float* frames, int64_t n_frames, int32_t D, const float*
                   const float* offset, int32_t K, float* out, void* stream);
 
 /* ------------------------------------------------------------------ device-side error state
- * Kernels never trap: a tcgen05 pipeline role whose mbarrier wait times out, or an
- * activation that leaves the fp16 range in DTRAJ_PREC_F16, sets a sticky device flag.
- * dtraj_check_errors() reads and clears it (it synchronises the device: call it where the
- * results are read back anyway).  Returns 0, DTRAJ_ECUDA (pipeline time-out: results are
- * invalid) or DTRAJ_ERANGE (fp16 overflow: rerun with DTRAJ_PREC_TF32). */
+ * Kernels never trap: a tcgen05 pipeline role whose mbarrier wait times out (bit 0), or an
+ * activation that leaves the fp16 range in DTRAJ_PREC_F16 (bit 1), sets a sticky device word.
+ * Every dtraj_unet handle owns its own word, so two models running on two streams can tell whose
+ * launch failed.  dtraj_unet_check_errors() reads and clears the handle's word (it synchronises
+ * the device: call it where results leave the library).  Returns 0, DTRAJ_ECUDA (pipeline
+ * time-out: results are invalid) or DTRAJ_ERANGE (fp16 overflow: rerun with DTRAJ_PREC_TF32). */
+int dtraj_unet_check_errors(dtraj_unet* unet);
+/* Non-blocking form for pipelined callers: enqueue a copy of the handle's word into `host_flag` (pinned host memory)
+ * on `stream`; a non-zero word read after the stream has reached that point means "call dtraj_unet_check_errors()". */
+int dtraj_unet_error_flag_async(dtraj_unet* unet, uint32_t* host_flag, void* stream);
+/* The same pair for the library-wide word that launches WITHOUT a handle report to (dtraj_test_conv, dtraj_bench_conv). */
 int dtraj_check_errors(void);
-/* Non-blocking form for pipelined callers: enqueue a copy of the flag word into `host_flag` (pinned host memory) on
- * `stream`; a non-zero word read after the stream has reached that point means "call dtraj_check_errors()". */
 int dtraj_error_flag_async(uint32_t* host_flag, void* stream);
 
 /* ------------------------------------------------------------------ test hooks
@@ -262,6 +272,17 @@ int dtraj_test_conv(int32_t precision, const float* x0, int32_t c0, const float*
                     int64_t n, int32_t H, int32_t W, const float* w_host, const float* bias_host,
                     int32_t cout, int32_t ksize, int32_t flags, const float* resid,
                     float* out, void* stream);
+
+/* ------------------------------------------------------------------ diagnostics (tools/, not used by the package's hot path)
+ * Kernel-only timing of one conv layer shape on zero-filled buffers allocated inside (tools/conv_bench.py): `iters`
+ * launches between one event pair, average milliseconds in *ms_out.  flags: bit0 relu, bit2 residual input, plus the
+ * CONV_POOL / CONV_NOSTORE / CONV_RESX / CONV_FINAL tail bits of csrc/conv_simt.cuh.  `debug` must be 0. */
+int dtraj_bench_conv(int32_t precision, int32_t c0, int32_t c1, int32_t cout, int64_t n, int32_t H, int32_t ksize,
+                     int32_t flags, int32_t iters, int32_t debug, float* ms_out);
+/* Peek at the library-wide error word without clearing it (tests assert it stays 0). */
+unsigned int dtraj_debug_umma_error(void);
+/* (csrc/probe.cuh -- the tcgen05 descriptor-view and permuted-TMA hardware probes behind profiles/r01_*_probe.txt -- is
+ * compiled only with -DDTRAJ_PROBES and exports dtraj_probe_umma_view / dtraj_probe_tma_permuted; the product build has neither.) */
 
 #ifdef __cplusplus
 }

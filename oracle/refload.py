@@ -1,9 +1,11 @@
-"""Import the UNMODIFIED reference from /root/reference (build container only).
+"""Import the UNMODIFIED reference: from /root/reference (build container) or from the byte-for-byte
+copies ``oracle/sync_ref.py`` stages under the git-ignored ``oracle/_ref/`` (they travel to the GPU box).
 
-TEST INFRASTRUCTURE (see oracle/__init__.py).  Used by ``oracle/make_golden.py`` and
+TEST / BASELINE INFRASTRUCTURE (see oracle/__init__.py).  Used by ``oracle/make_golden.py`` and
 ``tests/test_oracle_vs_reference.py`` to pin the oracle restatement against the real
-reference code.  /root/reference does not exist on the GPU box, so nothing that runs
-there may call this; ``available()`` says whether it can be used.
+reference code, and by ``bench.py --impl reference`` / its ``cpu_baseline`` leg to TIME the
+reference itself on the host cores.  ``available()`` says whether either tree can be used;
+``DTRAJ_REFERENCE_ROOT`` overrides the choice.
 
 The only imports the reference needs that this image lacks are plotting packages
 (SURVEY.md 8c); they are replaced by inert stub modules.  ``analysis/__init__.py``
@@ -15,7 +17,20 @@ import os
 import sys
 import types
 
-REF_ROOT = os.environ.get("DTRAJ_REFERENCE_ROOT", "/root/reference")
+_STAGED = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
+
+
+def _pick_root():
+    env = os.environ.get("DTRAJ_REFERENCE_ROOT")
+    if env:
+        return env
+    for cand in ("/root/reference", _STAGED):
+        if os.path.isfile(os.path.join(cand, "models.py")):
+            return cand
+    return "/root/reference"
+
+
+REF_ROOT = _pick_root()
 
 
 def available():

@@ -23,6 +23,14 @@ def test_library_exports_header_symbols():
     assert sorted(_lib.SIGNATURES) == names, "ctypes signature table out of sync with the header"
 
 
+def test_library_exports_nothing_the_header_does_not_declare():
+    """every dtraj_* symbol of the shared object is part of the documented C ABI (no hidden test / probe exports)"""
+    import subprocess
+    out = subprocess.run(["nm", "-D", "--defined-only", _lib.LIB_PATH], capture_output=True, text=True, check=True).stdout
+    exported = sorted({ln.split()[-1] for ln in out.splitlines() if ln.split() and ln.split()[-1].startswith("dtraj_")})
+    assert exported == _declared()
+
+
 def test_version_and_error_string_without_gpu():
     lib = _lib.load()
     assert lib.dtraj_version() == 100

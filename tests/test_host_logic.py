@@ -183,3 +183,127 @@ def test_shard_samples_blocks_are_contiguous_and_balanced():
         assert max(sizes) - min(sizes) <= 1
         for p in parts:
             assert p == list(range(p[0], p[0] + len(p))) if p else True
+
+
+# ------------------------------------------------------------------ round-2 host logic
+def test_weights_checksum_sees_data_writes_that_versions_miss():
+    """ADVICE r1: in-place writes through ``.data`` (the EMA idiom) bump neither tensor versions nor data pointers;
+    the content checksum of engine.for_model(verify=True) must change, the storage fingerprint must catch ``p.data = new``."""
+    from distillation_trajectories_b200 import engine
+    from helpers import make_model
+    m = make_model(Cfg(1, 16, 4), 0.05, 3)
+    fp0, cs0 = engine._weights_fingerprint(m), engine._weights_checksum(m)
+    assert engine._weights_checksum(m) == cs0                       # deterministic
+    p = m.enc2.conv1.weight
+    p.data.mul_(0.999).add_(1e-3)                                    # EMA-style update: version stays 0
+    assert engine._weights_fingerprint(m) == fp0 and engine._weights_checksum(m) != cs0
+    cs1 = engine._weights_checksum(m)
+    p.data = p.data.clone()                                          # same values, new storage
+    assert engine._weights_fingerprint(m) != fp0 and engine._weights_checksum(m) == cs1
+    m.dec1.norm2.running_var.data.add_(0.5)                          # buffers count too
+    assert engine._weights_checksum(m) != cs1
+
+
+def test_s3_repeated_zero_timesteps_are_frame_copies_not_errors(monkeypatch):
+    """ADVICE r1: steps > sample_steps gives stride 0 and the index list [0, ..., 0, S-1] (utils/trajectory_manager.py:88-96);
+    the reference stores one frame per entry and never updates at t == 0 -- the drop-in must not raise."""
+    assert sampling.s3_timestep_indices(4, 6) == osmp.s3_timestep_indices(4, 6) == [0, 0, 0, 0, 0, 0, 3]
+    calls = []
+
+    def fake_sampler(engine, key, factory):
+        calls.append(key)
+
+        class S:
+            n_updates = 1
+            z_index = torch.zeros(1, 2, dtype=torch.int32)
+            z_bank = torch.zeros(2, 256)
+            traj = torch.arange(2 * 2 * 256, dtype=torch.float32).reshape(2, 2, 1, 16, 16)
+
+            def run(self):
+                return self.traj
+        return S()
+
+    class Eng:
+        device = torch.device("cpu")
+    monkeypatch.setattr(sampling, "cached_sampler", fake_sampler)
+    out = sampling.s3_sample(Eng(), torch.zeros(2, 1, 16, 16), [3, 0, 0, 0, 0, 0, 0], 6, torch.zeros(1, 2, 1, 16, 16))
+    assert out.shape == (2, 7, 1, 16, 16) and calls[0][2] == (3,)                    # one update, six copies of its result
+    for k in range(2, 7):
+        assert torch.equal(out[:, k], out[:, 1])
+    with pytest.raises(ValueError):
+        sampling.s3_sample(Eng(), torch.zeros(2, 1, 16, 16), [3, 0, 2, 0], 6, torch.zeros(2, 2, 1, 16, 16))
+
+
+def test_oracle_matches_reference_batch_metrics_fixture():
+    """E2 pin on the CPU side: the oracle's per-pair metrics reproduce every list the unmodified reference's
+    compute_trajectory_metrics_batch returned (tests/golden/batch_metrics.npz, oracle/make_golden_batch.py)."""
+    g = load_golden("batch_metrics")
+    lists = {"wasserstein_distances": "mean_wasserstein", "endpoint_distances": "endpoint_distance",
+             "teacher_path_lengths": "teacher_path_length", "student_path_lengths": "student_path_length",
+             "teacher_efficiency": "teacher_efficiency", "student_efficiency": "student_efficiency"}
+    same = ["path_length_similarity", "efficiency_similarity", "mean_velocity_similarity", "mean_directional_consistency",
+            "mean_position_difference", "distribution_similarity"]
+    for name in ("b16", "b32"):
+        n = int(g[f"{name}/meta"][4])
+        np.random.seed(7)
+        per = []
+        for i in range(n):
+            t = [(torch.from_numpy(a), int(ts)) for a, ts in zip(g[f"{name}/teacher"][i], g[f"{name}/teacher_t"])]
+            s = [(torch.from_numpy(a), int(ts)) for a, ts in zip(g[f"{name}/student"][i], g[f"{name}/student_t"])]
+            per.append(om.trajectory_metrics(t, s))
+        for dst, src in list(lists.items()) + [(k, k) for k in same]:
+            np.testing.assert_allclose([m[src] for m in per], g[f"{name}/m/{dst}"], rtol=1e-6, atol=1e-9, err_msg=f"{name}/{dst}")
+            np.testing.assert_allclose(np.mean([m[src] for m in per]), g[f"{name}/m/{dst}_avg"], rtol=1e-6, atol=1e-9)
+        np.testing.assert_allclose([m["wasserstein_distances"] for m in per], g[f"{name}/m/wasserstein_distances_per_timestep"],
+                                   rtol=1e-6, atol=1e-9)
+
+
+def test_pack_reader_memory_maps_the_big_arrays(tmp_path):
+    """np.load(mmap_mode=) is ignored for .npz archives; read_pack maps the stored members itself."""
+    from distillation_trajectories_b200.utils import trajectory_store as store
+    T = np.random.RandomState(0).randn(5, 4, 1, 16, 16).astype(np.float32)
+    S = np.random.RandomState(1).randn(5, 3, 1, 16, 16).astype(np.float32)
+    p = store.write_pack(str(tmp_path), 0.3, [2, 3, 4, 5, 6], T, S, [3, 2, 1, 0], [3, 1, 0])
+    r = store.read_pack(p)
+    assert isinstance(r["teacher"], np.memmap) and isinstance(r["student"], np.memmap)
+    assert np.array_equal(r["teacher"], T) and np.array_equal(r["student"], S) and list(r["samples"]) == [2, 3, 4, 5, 6]
+    assert np.array_equal(store.read_pack(p, mmap=False)["teacher"], T)
+    assert store.stored_samples(str(tmp_path), 0.3) == {2, 3, 4, 5, 6}
+
+
+def test_staged_reference_is_byte_identical_and_complete():
+    """oracle/_ref (what bench.py --impl reference times on the GPU box) holds unmodified copies of the reference files."""
+    import hashlib
+    import os
+    from oracle import sync_ref
+    if not os.path.isfile(os.path.join(sync_ref.SRC, "models.py")):
+        pytest.skip("reference tree not present")
+    assert sync_ref.sync() == sync_ref.FILES and sync_ref.staged()
+    for rel in sync_ref.FILES:
+        a = hashlib.sha256(open(os.path.join(sync_ref.SRC, rel), "rb").read()).hexdigest()
+        b = hashlib.sha256(open(os.path.join(sync_ref.DST, rel), "rb").read()).hexdigest()
+        assert a == b, rel
+    tracked = os.popen(f"git -C {os.path.dirname(sync_ref.DST)} ls-files _ref").read().strip()
+    assert tracked == "", "oracle/_ref must stay out of the git history"
+
+
+def test_model_aliases_match_the_reference_constructors():
+    """M4 (models.py:227-242): SimpleUNet / StudentUNet create the same parameters as the reference's aliases."""
+    from oracle import refload
+    if not refload.available():
+        pytest.skip("reference tree not present")
+    import contextlib
+    import io
+    from distillation_trajectories_b200 import models as ours
+    ref = refload.load()
+    cfg = refload.RefConfig(1, 16, 8)
+    for mk_ref, mk_ours in ((lambda: ref.models.SimpleUNet(cfg), lambda: ours.SimpleUNet(cfg)),
+                            (lambda: ref.models.StudentUNet(cfg, 0.3, "tiny"), lambda: ours.StudentUNet(cfg, 0.3, "tiny"))):
+        with contextlib.redirect_stdout(io.StringIO()):
+            torch.manual_seed(4)
+            a = mk_ref()
+            torch.manual_seed(4)
+            b = mk_ours()
+        sa, sb = a.state_dict(), b.state_dict()
+        assert list(sa) == list(sb) and all(torch.equal(sa[k], sb[k]) for k in sa)
+        assert a.dims == b.dims and a.time_emb_dim == b.time_emb_dim

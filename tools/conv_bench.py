@@ -1,7 +1,7 @@
 """GPU: kernel-only timing of the conv layer shapes of the bench workload (teacher + student, 3840 rows).
     python tools/conv_bench.py [rows] [precision]
-Prints per layer: ms, TFLOP/s (real flops), and timing with the debug knobs (no B loads / no A loads / no
-epilogue traffic) that show which stream paces the kernel."""
+Prints per layer: ms and TFLOP/s (real flops).  (Round 1 also timed operand knock-outs -- no weight loads / no pixel
+loads / no epilogue traffic, profiles/r01f_conv_knockout.txt; those debug paths were removed from the kernels in round 2.)"""
 import ctypes as C
 import os
 import sys
@@ -12,7 +12,7 @@ from distillation_trajectories_b200 import _lib
 lib = _lib.load()
 rows = int(sys.argv[1]) if len(sys.argv) > 1 else 3840
 prec = _lib.PRECISIONS[sys.argv[2]] if len(sys.argv) > 2 else _lib.PREC_TF32
-dbgs = [int(a) for a in sys.argv[3].split(",")] if len(sys.argv) > 3 else [0, 1, 2, 3, 4, 7]
+dbgs = [0]
 
 # (name, c0, c1, cout, H, ksize, flags)  flags: 1 relu, 4 residual
 def layers(b, m, H):

@@ -8,7 +8,8 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 from distillation_trajectories_b200 import _lib
 
-lib = _lib.load()
+from distillation_trajectories_b200 import build as _build
+lib = C.CDLL(_build.build(probes=True))      # the probes live in libdtraj_probes.so (-DDTRAJ_PROBES), built on the CPU box before gpurun
 lib.dtraj_probe_tma_permuted.restype = C.c_int
 lib.dtraj_probe_tma_permuted.argtypes = [C.c_int32, C.c_int32, C.c_void_p]
 for n_img, img0 in ((4, 0), (4, 2), (3, 2)):

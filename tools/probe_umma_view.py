@@ -5,7 +5,8 @@ import ctypes as C, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 from distillation_trajectories_b200 import _lib
-lib = _lib.load()
+from distillation_trajectories_b200 import build as _build
+lib = C.CDLL(_build.build(probes=True))      # the probes live in libdtraj_probes.so (-DDTRAJ_PROBES), built on the CPU box before gpurun
 lib.dtraj_probe_umma_view.restype = C.c_int
 lib.dtraj_probe_umma_view.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]
 for sbo in (1024, 1280, 1792):
