@@ -60,6 +60,7 @@ SIGNATURES = {
     "dtraj_metrics_pairs": (C.c_int, [_P, _P, _I64, _I32, _I32, _P, _P]),
     "dtraj_wasserstein": (C.c_int, [_P, _P, _I64, _I32, _I32, _P, _P, _I32, _P, _P]),
     "dtraj_unet_forward_rows": (C.c_int, [_P, _P, _I64, _P, _P, _P, _I64, _P]),
+    "dtraj_numpy_choice_sets": (C.c_int, [_P, _I32, _I32, _I32, _I32, _P, _P]),
     "dtraj_project": (C.c_int, [_P, _I64, _I32, _P, _P, _I32, _P, _P]),
     "dtraj_sampler_flops": (C.c_int, [_P, C.POINTER(C.c_double)]),
     "dtraj_sampler_profile_text": (C.c_int, [_P, _P, _I32, C.c_char_p, _I64]),

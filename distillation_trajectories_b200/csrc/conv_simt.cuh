@@ -29,6 +29,7 @@ struct ConvLayer {
     int coutp;
     const float* tbias;        // + variant*tb_var_stride + c  (already offset to t and block)
     int tb_var_stride;
+    int tb_rows;               // 1: row_variant indexes the WHOLE [T][3] table (a timestep per row, dtraj_unet_forward_rows)
     const int32_t* row_variant;  // per image; null = variant 0
     const float* resid;        // [M, coutp] or null
     float* out;                // [M, coutp]

@@ -43,7 +43,12 @@ struct UmmaConv {
     int acc_stages;            // 2 when two accumulator sets fit in 512 columns, else 1
     int corr_col;              // offset of the correction accumulator inside a set (3 passes), else 0
     int res_col;               // offset of the residual-conv accumulator inside a set (CONV_RESACC), else 0
-    int r_nch0, r_nch;         // 32-channel chunks of the residual conv's first source / of both sources
+    int nch0, nch;             // K chunks (one 128-byte K block per pixel: 32 fp32 / 64 fp16 channels) of source 0 / of both sources
+    uint32_t half_mask;        // fp16 mode: bit c set = chunk c holds only 32 real channels (a source padded to an odd multiple of
+                               // 32: TMA zero-fills the rest of the box, the weights are zero there, and only 2 of the 4 K = 16
+                               // MMAs are issued)
+    int r_nch0, r_nch;         // the same counts for the residual conv's sources (CONV_RESACC)
+    uint32_t r_half_mask;
     int n_tiles;               // 128-row output tiles
     int n_split;               // column split of a tile when there are fewer tiles than SMs (power of two)
     int ncols;                 // coutp / n_split: columns per work item (multiple of 32)
@@ -260,6 +265,12 @@ k_conv_umma_t(const __grid_constant__ UmmaMaps maps, const UmmaConv p) {
     const uint32_t hfull0 = tmem_slot + 16u;                   // [4] halo buffer loaded   (TMA -> issuer)
     const uint32_t hempty0 = hfull0 + 32u;                     // [4] halo buffer consumed (issuer -> TMA)
     const uint32_t fin_base = hempty0 + 32u;                   // CONV_FINAL partial sums [4 quarters][32 lanes][4]
+    // Per-channel epilogue constants, staged ONCE per CTA: rows of coutp floats [bias | residual-conv bias | time bias x 3 variants |
+    // final-1x1 weights x finC].  Read from global memory at their point of use they were the epilogue's bottleneck: with 227 KB of
+    // shared memory the L1 keeps ~28 KB, every chunk's ~20 dependent LDGs went to an L2 busy streaming operands at 5 TB/s, and the
+    // epilogue warps of the 256-wide residual layers were busy 78 % of the kernel (ncu source view, profiles/r02_conv_epilogue.txt).
+    const uint32_t cst_base = fin_base + ((p.L.flags & CONV_FINAL) ? 2048u : 0u);
+    float* const cst = reinterpret_cast<float*>(smem_raw + (cst_base - ptx::smem_u32(smem_raw)));
     volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(
         smem_raw + (tmem_slot - ptx::smem_u32(smem_raw)));
 
@@ -268,7 +279,7 @@ k_conv_umma_t(const __grid_constant__ UmmaMaps maps, const UmmaConv p) {
     const int crank = kPair ? (int)ptx::cluster_ctarank() : 0;
     const uint16_t cmask = kPair ? 3 : 1;
     const int work0 = (int)blockIdx.x - crank;   // first work item of this CTA's cluster; all its CTAs loop alike
-    const int nch0 = p.L.c0p / kCh, nch = nch0 + p.L.c1p / kCh;
+    const int nch0 = p.nch0, nch = p.nch;
     const int iters_per_pass = p.L.ntaps * nch;
 
     if (warp == 0) {
@@ -298,11 +309,25 @@ k_conv_umma_t(const __grid_constant__ UmmaMaps maps, const UmmaConv p) {
             asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
         }
     }
+    {   // (weights and tables only: nothing here was written by the preceding kernel, so it may run before pdl_wait)
+        const int coutp_ = p.L.coutp, fl_ = p.L.flags;
+        for (int i = threadIdx.x; i < coutp_; i += blockDim.x) {
+            cst[i] = p.L.bias[i];
+            if (fl_ & CONV_RESACC) cst[coutp_ + i] = p.L.rbias[i];
+            if ((fl_ & CONV_TBIAS) && !p.L.tb_rows)
+                for (int v = 0; v < 3; ++v) cst[(2 + v) * coutp_ + i] = p.L.tbias[(size_t)v * p.L.tb_var_stride + i];
+        }
+        if (fl_ & CONV_FINAL)
+            for (int i = threadIdx.x; i < p.L.finC * coutp_; i += blockDim.x) cst[5 * coutp_ + i] = p.L.finw[i];
+    }
     ptx::tc_fence_before();
     __syncthreads();
     if constexpr (kPair) ptx::cluster_sync_all(); // the peer's barriers exist before anything arrives on them
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
+    const float* const bias_s = cst;                           // generic pointers into shared memory
+    const float* const rbias_s = cst + p.L.coutp;
+    const float* const finw_s = cst + 5 * p.L.coutp;
     pdl_launch_dependents();                   // the next kernel of the stream / graph may start its prologue
     pdl_wait();                                // ... and this one touches activations only after its predecessor is complete
     auto arrive_acc_empty = [&](int acc) {     // "accumulator drained": to this CTA's issuer, or to the pair leader's
@@ -428,9 +453,10 @@ k_conv_umma_t(const __grid_constant__ UmmaMaps maps, const UmmaConv p) {
                 const uint64_t hdesc0 = ((uint64_t)1 << 16) | ((uint64_t)(1280 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
                 int hb = 0;
                 uint32_t hph = 0;
-                auto mma4 = [&](uint32_t d_tmem, uint64_t ad, uint64_t bd, uint32_t& accum) {
+                auto mma4 = [&](uint32_t d_tmem, uint64_t ad, uint64_t bd, uint32_t& accum, int nk) {
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
+                        if (k >= nk) break;
                         if constexpr (!kPair) ptx::mma_f16(d_tmem, ad + 2u * k, bd + 2u * k, idesc, accum);
                         else ptx::mma_f16_2sm(d_tmem, ad + 2u * k, bd + 2u * k, idesc, accum);
                         accum = 1u;
@@ -454,11 +480,12 @@ k_conv_umma_t(const __grid_constant__ UmmaMaps maps, const UmmaConv p) {
                         ptx::tc_fence_after();
                         const uint32_t hbuf = halo_base + (uint32_t)hb * kHaloBytes;
                         int dy = 0, dx = 0;
+                        const int nk = ((p.half_mask >> chunk) & 1u) ? 2 : 4;
                         for (int tap = 0; tap < 9 && ok; ++tap) {
                             ok = ptx::mbar_wait(errw, full_bar(s), ph);
                             ptx::tc_fence_after();
                             const uint32_t a_addr = hbuf + (uint32_t)(dy * 20 + dx) * 128u;
-                            mma4(d_set, hdesc0 | (uint64_t)((a_addr >> 4) & 0x3fffu), umma_desc_sw128(base + s * stage_bytes), accum);
+                            mma4(d_set, hdesc0 | (uint64_t)((a_addr >> 4) & 0x3fffu), umma_desc_sw128(base + s * stage_bytes), accum, nk);
                             free_stage();
                             if (++dx == 3) { dx = 0; ++dy; }
                         }
@@ -470,7 +497,8 @@ k_conv_umma_t(const __grid_constant__ UmmaMaps maps, const UmmaConv p) {
                             ok = ptx::mbar_wait(errw, hfull0 + 8u * hb, hph);
                             ok = ok && ptx::mbar_wait(errw, full_bar(s), ph);
                             ptx::tc_fence_after();
-                            mma4(d_set + (uint32_t)p.res_col, umma_desc_sw128(halo_base + (uint32_t)hb * kHaloBytes), umma_desc_sw128(base + s * stage_bytes), accum_r);
+                            mma4(d_set + (uint32_t)p.res_col, umma_desc_sw128(halo_base + (uint32_t)hb * kHaloBytes), umma_desc_sw128(base + s * stage_bytes), accum_r,
+                                 ((p.r_half_mask >> rc) & 1u) ? 2 : 4);
                             free_stage();
                             free_halo();
                         }
@@ -487,14 +515,18 @@ k_conv_umma_t(const __grid_constant__ UmmaMaps maps, const UmmaConv p) {
                 // accumulator with round-toward-zero; adding 2^-11-sized terms to a full-size accumulator for 2/3 of
                 // the K loop costs ~K/16 ulps of systematic shrink (measured 6e-5 at K = 4608), a separate
                 // accumulator keeps that at the single-pass level.
-                auto run_stages = [&](uint32_t d_tmem, uint32_t accum, int n_kblocks) {
+                auto run_stages = [&](uint32_t d_tmem, uint32_t accum, int n_kblocks, int n_chunks, uint32_t hmask) {
+                    int chunk = 0;
                     for (int it = 0; it < n_kblocks && ok; it += p.kbs) {
                         ok = ptx::mbar_wait(errw, full_bar(s), ph);
                         ptx::tc_fence_after();
                         const uint64_t md = desc0 + (uint64_t)(s * stage16), nd = md + n_off16;
                         for (int j = 0; j < p.kbs; ++j) {
+                            const int nk = ((hmask >> chunk) & 1u) ? 2 : 4;
+                            if (++chunk == n_chunks) chunk = 0;
 #pragma unroll
                             for (int k = 0; k < 4; ++k) {   // 4 x (K = 8 tf32 / 16 fp16 = 32 bytes) inside the 128-byte swizzle atom
+                                if (k >= nk) break;
                                 const uint64_t mdk = md + (uint64_t)(j * m_step16 + 2 * k), ndk = nd + (uint64_t)(j * n_step16 + 2 * k);
                                 if constexpr (kF16) {
                                     if constexpr (!kPair) ptx::mma_f16(d_tmem, mdk, ndk, idesc, accum);
@@ -515,8 +547,8 @@ k_conv_umma_t(const __grid_constant__ UmmaMaps maps, const UmmaConv p) {
                 const uint32_t d_set = tmem_base + (uint32_t)(acc * p.acc_cols);
                 // passes 1 and 2 of 3xTF32 share the correction accumulator
                 for (int pass = 0; pass < p.npass && ok; ++pass)
-                    run_stages(d_set + (pass ? (uint32_t)p.corr_col : 0u), pass == 2 ? 1u : 0u, iters_per_pass);
-                if (p.L.flags & CONV_RESACC) run_stages(d_set + (uint32_t)p.res_col, 0u, p.r_nch);
+                    run_stages(d_set + (pass ? (uint32_t)p.corr_col : 0u), pass == 2 ? 1u : 0u, iters_per_pass, nch, p.half_mask);
+                if (p.L.flags & CONV_RESACC) run_stages(d_set + (uint32_t)p.res_col, 0u, p.r_nch, p.r_nch, p.r_half_mask);
                 if constexpr (kPair) ptx::tc_commit_2sm(acc_full0 + 8u * acc, cmask);   // accumulator complete, in both CTAs
                 else ptx::tc_commit(acc_full0 + 8u * acc);
                 if (++acc == p.acc_stages) { acc = 0; acc_ph ^= 1u; }
@@ -586,7 +618,10 @@ k_conv_umma_t(const __grid_constant__ UmmaMaps maps, const UmmaConv p) {
                 if (!valid) img = 0;
             }
             const float* tb = nullptr;
-            if (fl & CONV_TBIAS) tb = p.L.tbias + (size_t)(p.L.row_variant ? p.L.row_variant[img] : 0) * p.L.tb_var_stride;
+            if (fl & CONV_TBIAS) {
+                const int var = p.L.row_variant ? p.L.row_variant[img] : 0;
+                tb = p.L.tb_rows ? p.L.tbias + (size_t)var * p.L.tb_var_stride : cst + (2 + var) * coutp;   // per-row timesteps: the whole table stays in global memory
+            }
             float xv[4] = {0.f, 0.f, 0.f, 0.f}, fe[4] = {0.f, 0.f, 0.f, 0.f};
             if ((fl & CONV_RESX) && valid) {
                 const int HWm = (1 << p.log2_hw);
@@ -603,31 +638,27 @@ k_conv_umma_t(const __grid_constant__ UmmaMaps maps, const UmmaConv p) {
                 __syncwarp();
                 if (lane == 0) arrive_acc_empty(acc);
             }
-            for (int c = h, k = 0; c < nchunk; c += 2, ++k) {
-                const int b = k % kEpiBufs;
-                uint32_t raw[32];
+            // One 32-column chunk, first half: TMEM -> registers -> bias / ReLU / time bias / residuals -> 16 packed half2 words.
+            // `b`: ring buffer holding the TMA-loaded residual chunk (CONV_RESID).
+            auto compute_chunk = [&](int c, int b, uint32_t (&pk)[16]) {
+                uint32_t raw[32], rres[32];
                 ptx::tmem_ld32(t_acc + (uint32_t)(32 * c), raw);
+                if (fl & CONV_RESACC) ptx::tmem_ld32(t_acc + (uint32_t)(p.res_col + 32 * c), rres);
                 ptx::tmem_ld_wait();
-                uint32_t rres[32];
-                if (fl & CONV_RESACC) {
-                    ptx::tmem_ld32(t_acc + (uint32_t)(p.res_col + 32 * c), rres);
-                    ptx::tmem_ld_wait();
-                }
                 if (c == c_last) {
                     ptx::tc_fence_before();
                     __syncwarp();
                     if (lane == 0) arrive_acc_empty(acc);
                 }
                 if (has_res) { ptx::mbar_wait(errw, rbar + 8u * b, (res_par >> b) & 1u); res_par ^= 1u << b; }
-                uint8_t* bufp = smem_raw + (buf0 + 4096u * b - ptx::smem_u32(smem_raw));
-                uint8_t* rowp = bufp + lane * 64;
+                const uint8_t* rowp = smem_raw + (buf0 + 4096u * b - ptx::smem_u32(smem_raw)) + lane * 64;
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     const int col = n0 + 32 * c + 8 * j;
                     float v[8];
                     {
-                        const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.L.bias + col));
-                        const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.L.bias + col + 4));
+                        const float4 b0 = *reinterpret_cast<const float4*>(bias_s + col);
+                        const float4 b1 = *reinterpret_cast<const float4*>(bias_s + col + 4);
                         v[0] = __uint_as_float(raw[8 * j]) + b0.x; v[1] = __uint_as_float(raw[8 * j + 1]) + b0.y;
                         v[2] = __uint_as_float(raw[8 * j + 2]) + b0.z; v[3] = __uint_as_float(raw[8 * j + 3]) + b0.w;
                         v[4] = __uint_as_float(raw[8 * j + 4]) + b1.x; v[5] = __uint_as_float(raw[8 * j + 5]) + b1.y;
@@ -638,8 +669,8 @@ k_conv_umma_t(const __grid_constant__ UmmaMaps maps, const UmmaConv p) {
                         for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], 0.f);
                     }
                     if (tb) {
-                        const float4 t0 = __ldg(reinterpret_cast<const float4*>(tb + col));
-                        const float4 t1 = __ldg(reinterpret_cast<const float4*>(tb + col + 4));
+                        const float4 t0 = *reinterpret_cast<const float4*>(tb + col);
+                        const float4 t1 = *reinterpret_cast<const float4*>(tb + col + 4);
                         v[0] += t0.x; v[1] += t0.y; v[2] += t0.z; v[3] += t0.w;
                         v[4] += t1.x; v[5] += t1.y; v[6] += t1.z; v[7] += t1.w;
                     }
@@ -657,27 +688,26 @@ k_conv_umma_t(const __grid_constant__ UmmaMaps maps, const UmmaConv p) {
                             v[4 * hh] += r4.x; v[4 * hh + 1] += r4.y; v[4 * hh + 2] += r4.z; v[4 * hh + 3] += r4.w;
                         }
                     }
-                    if (fl & CONV_RESACC) {
-                        const float4 r0 = __ldg(reinterpret_cast<const float4*>(p.L.rbias + col));
-                        const float4 r1 = __ldg(reinterpret_cast<const float4*>(p.L.rbias + col + 4));
+                    if (fl & CONV_RESACC) {   // residual_conv(x) + its bias, accumulated by this kernel's extra MMAs
+                        const float4 r0 = *reinterpret_cast<const float4*>(rbias_s + col);
+                        const float4 r1 = *reinterpret_cast<const float4*>(rbias_s + col + 4);
                         v[0] += __uint_as_float(rres[8 * j]) + r0.x; v[1] += __uint_as_float(rres[8 * j + 1]) + r0.y;
                         v[2] += __uint_as_float(rres[8 * j + 2]) + r0.z; v[3] += __uint_as_float(rres[8 * j + 3]) + r0.w;
                         v[4] += __uint_as_float(rres[8 * j + 4]) + r1.x; v[5] += __uint_as_float(rres[8 * j + 5]) + r1.y;
                         v[6] += __uint_as_float(rres[8 * j + 6]) + r1.z; v[7] += __uint_as_float(rres[8 * j + 7]) + r1.w;
                     }
-                    uint4* cell = reinterpret_cast<uint4*>(rowp + (((uint32_t)j ^ swz) << 4));
                     if (has_res) {
-                        const uint4 rr = *cell;
+                        const uint4 rr = *reinterpret_cast<const uint4*>(rowp + (((uint32_t)j ^ swz) << 4));
                         const __half2* rh = reinterpret_cast<const __half2*>(&rr);
 #pragma unroll
                         for (int i = 0; i < 4; ++i) { const float2 f = __half22float2(rh[i]); v[2 * i] += f.x; v[2 * i + 1] += f.y; }
                     }
-                    uint4 pk;
-                    __half2* ph2 = reinterpret_cast<__half2*>(&pk);
+                    __half2 ph2[4];
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
                         amax = fmaxf(amax, fmaxf(fabsf(v[2 * i]), fabsf(v[2 * i + 1])));
                         ph2[i] = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+                        pk[4 * j + i] = *reinterpret_cast<const uint32_t*>(&ph2[i]);
                     }
                     if (fl & CONV_FINAL) {
                         float vr[8];
@@ -686,13 +716,22 @@ k_conv_umma_t(const __grid_constant__ UmmaMaps maps, const UmmaConv p) {
 #pragma unroll
                         for (int o = 0; o < 4; ++o) {
                             if (o >= p.L.finC) break;
-                            const float4 w0 = __ldg(reinterpret_cast<const float4*>(p.L.finw + (size_t)o * coutp + col));
-                            const float4 w1 = __ldg(reinterpret_cast<const float4*>(p.L.finw + (size_t)o * coutp + col + 4));
+                            const float4 w0 = *reinterpret_cast<const float4*>(finw_s + (size_t)o * coutp + col);
+                            const float4 w1 = *reinterpret_cast<const float4*>(finw_s + (size_t)o * coutp + col + 4);
                             fe[o] = fmaf(vr[0], w0.x, fmaf(vr[1], w0.y, fmaf(vr[2], w0.z, fmaf(vr[3], w0.w, fe[o]))));
                             fe[o] = fmaf(vr[4], w1.x, fmaf(vr[5], w1.y, fmaf(vr[6], w1.z, fmaf(vr[7], w1.w, fe[o]))));
                         }
                     }
-                    if (do_store || do_pool) *cell = pk;
+                }
+            };
+            // ... second half: packed words -> swizzled ring buffer -> fused 2x2 max-pool -> TMA store (+ ring upkeep)
+            auto emit_chunk = [&](int c, int k, int b, const uint32_t (&pk)[16]) {
+                uint8_t* bufp = smem_raw + (buf0 + 4096u * b - ptx::smem_u32(smem_raw));
+                uint8_t* rowp = bufp + lane * 64;
+                if (do_store || do_pool) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        *reinterpret_cast<uint4*>(rowp + (((uint32_t)j ^ swz) << 4)) = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
                 }
                 if (do_store) ptx::fence_proxy_async();
                 __syncwarp();
@@ -729,6 +768,8 @@ k_conv_umma_t(const __grid_constant__ UmmaMaps maps, const UmmaConv p) {
                     else ptx::tma_store_2d(&maps.out, buf0 + 4096u * b, n0 + 32 * c, row);
                     ptx::bulk_commit();
                 }
+                // ring upkeep (depth B = kEpiBufs): my next chunk reuses buffer (k + 1) % B, last read by the store of my chunk
+                // k + 1 - B -- allow B - 1 younger stores to stay in flight, then refill (residual) / rewrite it
                 if (c + 2 < nchunk && k + 1 >= kEpiBufs && (has_res || do_store)) {
                     if (lane == 0) {
                         if (do_store) { if (kEpiBufs == 2) ptx::bulk_wait_read<1>(); else ptx::bulk_wait_read<0>(); }
@@ -741,6 +782,11 @@ k_conv_umma_t(const __grid_constant__ UmmaMaps maps, const UmmaConv p) {
                     }
                     __syncwarp();
                 }
+            };
+            for (int c = h, k = 0; c < nchunk; c += 2, ++k) {
+                uint32_t pk[16];
+                compute_chunk(c, k % kEpiBufs, pk);
+                emit_chunk(c, k, k % kEpiBufs, pk);
             }
             if (fl & CONV_FINAL) {
                 float4* part = reinterpret_cast<float4*>(smem_raw + (fin_base - ptx::smem_u32(smem_raw))) + q * 32 + lane;
@@ -793,7 +839,10 @@ k_conv_umma_t(const __grid_constant__ UmmaMaps maps, const UmmaConv p) {
             const bool valid = m < p.L.M;
             const int img = valid ? (int)(m >> p.log2_hw) : 0;
             const float* tb = nullptr;
-            if (fl & CONV_TBIAS) tb = p.L.tbias + (size_t)(p.L.row_variant ? p.L.row_variant[img] : 0) * p.L.tb_var_stride;
+            if (fl & CONV_TBIAS) {
+                const int var = p.L.row_variant ? p.L.row_variant[img] : 0;
+                tb = p.L.tb_rows ? p.L.tbias + (size_t)var * p.L.tb_var_stride : cst + (2 + var) * coutp;   // per-row timesteps: the whole table stays in global memory
+            }
             float xv[4] = {0.f, 0.f, 0.f, 0.f}, fe[4] = {0.f, 0.f, 0.f, 0.f};
             if ((fl & CONV_RESX) && valid) {
                 const int HWm = (1 << p.log2_hw);
@@ -841,14 +890,14 @@ k_conv_umma_t(const __grid_constant__ UmmaMaps maps, const UmmaConv p) {
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                     const int col = n0 + 32 * c + 4 * j;
-                    const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.L.bias + col));
+                    const float4 b4 = *reinterpret_cast<const float4*>(bias_s + col);
                     float4 v = make_float4(__uint_as_float(raw[4 * j]) + b4.x, __uint_as_float(raw[4 * j + 1]) + b4.y,
                                            __uint_as_float(raw[4 * j + 2]) + b4.z, __uint_as_float(raw[4 * j + 3]) + b4.w);
                     if (fl & CONV_RELU) {
                         v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
                     }
                     if (tb) {
-                        const float4 t4 = __ldg(reinterpret_cast<const float4*>(tb + col));
+                        const float4 t4 = *reinterpret_cast<const float4*>(tb + col);
                         v.x += t4.x; v.y += t4.y; v.z += t4.z; v.w += t4.w;
                     }
                     if (fl & CONV_RESX) {
@@ -863,7 +912,7 @@ k_conv_umma_t(const __grid_constant__ UmmaMaps maps, const UmmaConv p) {
                         v.x += r4.x; v.y += r4.y; v.z += r4.z; v.w += r4.w;
                     }
                     if (fl & CONV_RESACC) {   // residual_conv(x) + its bias, accumulated by this kernel's extra MMAs
-                        const float4 rb4 = __ldg(reinterpret_cast<const float4*>(p.L.rbias + col));
+                        const float4 rb4 = *reinterpret_cast<const float4*>(rbias_s + col);
                         v.x += __uint_as_float(rres[4 * j]) + rb4.x; v.y += __uint_as_float(rres[4 * j + 1]) + rb4.y;
                         v.z += __uint_as_float(rres[4 * j + 2]) + rb4.z; v.w += __uint_as_float(rres[4 * j + 3]) + rb4.w;
                     }
@@ -877,7 +926,7 @@ k_conv_umma_t(const __grid_constant__ UmmaMaps maps, const UmmaConv p) {
 #pragma unroll
                         for (int o = 0; o < 4; ++o) {
                             if (o >= p.L.finC) break;
-                            const float4 w4 = __ldg(reinterpret_cast<const float4*>(p.L.finw + (size_t)o * coutp + col));
+                            const float4 w4 = *reinterpret_cast<const float4*>(finw_s + (size_t)o * coutp + col);
                             fe[o] = fmaf(v.x, w4.x, fmaf(v.y, w4.y, fmaf(v.z, w4.z, fmaf(v.w, w4.w, fe[o]))));
                         }
                     }
@@ -1060,13 +1109,25 @@ inline int build_umma_launch(UmmaLaunch* U, const ConvLayer& L, int npass, const
     if (L.W > 32 || L.H != L.W || (HW & (HW - 1)) != 0)
         return fail(DTRAJ_EINVAL, "umma conv: unsupported spatial size %dx%d", L.H, L.W);
     const int f16 = L.f16 ? 1 : 0, kch = f16 ? 64 : 32;     // channels per 128-byte K block
-    if (L.coutp % 32 || L.coutp > 256 || L.c0p % kch || L.c1p % kch) return fail(DTRAJ_EINVAL, "umma conv: bad channel padding");
+    // channel counts are padded to 32 in every mode; in fp16 mode a K block carries 64 channels, so a source padded to an odd
+    // multiple of 32 ends in a half-filled block
+    if (L.coutp % 32 || L.coutp > 256 || L.c0p % 32 || L.c1p % 32 || L.c0p > 512 || L.c1p > 512) return fail(DTRAJ_EINVAL, "umma conv: bad channel padding");
     if (f16 && (npass != 1 || L.act_mode == ACT_SPLIT)) return fail(DTRAJ_EINVAL, "umma conv: fp16 mode is single-pass");
     UmmaConv& c = U->conv;
     c.L = L;
     c.f16 = f16;
     c.npass = npass;
-    const int nkb_all = L.ntaps * (L.c0p + L.c1p) / kch;       // K blocks (128 bytes of channels per row) of the whole K loop
+    auto chunks_of = [&](int cp) { return (cp + kch - 1) / kch; };
+    auto halves_of = [&](int c0p, int c1p) {
+        uint32_t m = 0;
+        if (c0p % kch) m |= 1u << (chunks_of(c0p) - 1);
+        if (c1p % kch) m |= 1u << (chunks_of(c0p) + chunks_of(c1p) - 1);
+        return m;
+    };
+    c.nch0 = chunks_of(L.c0p);
+    c.nch = c.nch0 + chunks_of(L.c1p);
+    c.half_mask = halves_of(L.c0p, L.c1p);
+    const int nkb_all = L.ntaps * c.nch;                       // K blocks (128 bytes of channels per row) of the whole K loop
     // a tile = 128 output pixels: box_h image rows of box_n images
     c.box_h = HW >= 128 ? 128 / L.W : L.H;
     c.box_n = HW >= 128 ? 1 : 128 / HW;
@@ -1089,10 +1150,11 @@ inline int build_umma_launch(UmmaLaunch* U, const ConvLayer& L, int npass, const
     c.corr_col = 0;
     if (npass == 3) { c.corr_col = c.acc_cols; c.acc_cols *= 2; }
     c.res_col = 0;
-    c.r_nch0 = L.rc0p / kch;
-    c.r_nch = (L.rc0p + L.rc1p) / kch;
+    c.r_nch0 = chunks_of(L.rc0p);
+    c.r_nch = c.r_nch0 + chunks_of(L.rc1p);
+    c.r_half_mask = halves_of(L.rc0p, L.rc1p);
     if (L.flags & CONV_RESACC) {
-        if (npass != 1 || !rwpk || L.rc0p % kch || L.rc1p % kch || !L.rsrc0 || (L.rc1p && !L.rsrc1))
+        if (npass != 1 || !rwpk || L.rc0p % 32 || L.rc1p % 32 || !L.rsrc0 || (L.rc1p && !L.rsrc1))
             return fail(DTRAJ_EINVAL, "umma conv: fused residual conv needs a single-pass mode and packed residual weights");
         c.res_col = c.acc_cols;
         c.acc_cols *= 2;
@@ -1116,13 +1178,14 @@ inline int build_umma_launch(UmmaLaunch* U, const ConvLayer& L, int npass, const
     // two K blocks per stage halve the single-thread loop overhead per MMA; worth it where an MMA is short
     // (N <= 128: <= 256 cycles per K block) and the stage stays small enough to keep >= 3 stages in flight
     const int n_stage_rows = c.pair ? n_rows / 2 : n_rows;
-    c.kbs = (n_stage_rows <= (c.pair ? 64 : 128) && c.r_nch0 % 2 == 0 && (c.r_nch - c.r_nch0) % 2 == 0 && (L.c0p / kch) % 2 == 0 && (L.c1p / kch) % 2 == 0) ? 2 : 1;
+    c.kbs = (n_stage_rows <= (c.pair ? 64 : 128) && c.r_nch0 % 2 == 0 && (c.r_nch - c.r_nch0) % 2 == 0 && c.nch0 % 2 == 0 && (c.nch - c.nch0) % 2 == 0) ? 2 : 1;
     // halo mode (fp16, 8x8 maps, 3x3, no identity residual): two images per tile, pixels through the halo ring
     c.halo = (f16 && L.H == 8 && L.W == 8 && L.ntaps == 9 && !(L.flags & CONV_RESX) && c.n_split == 1 && L.act_mode != ACT_SPLIT) ? 1 : 0;
     c.n_hb = 0;
     if (c.halo) { c.kbs = 1; c.n_hb = 3; }
     const size_t stage = c.halo ? (size_t)n_stage_rows * 128 : (size_t)c.kbs * (kATileBytes + (size_t)n_stage_rows * 128);
-    const size_t misc = 1024 + 512 + ((L.flags & CONV_FINAL) ? 2048 : 0) + (size_t)c.n_hb * kHaloBytes;
+    const size_t cst_bytes = (size_t)(5 + ((L.flags & CONV_FINAL) ? 4 : 0)) * L.coutp * 4;     // staged per-channel constants
+    const size_t misc = 1024 + 512 + ((L.flags & CONV_FINAL) ? 2048 : 0) + cst_bytes + (size_t)c.n_hb * kHaloBytes;
     auto stages_for = [&](int bufs) { return (int)((227 * 1024 - misc - (size_t)kEpiWarps * bufs * 4096) / stage); };
     c.epi_bufs = 2;
     if (!c.halo && nkb_all >= 16 && stages_for(1) > stages_for(2) && stages_for(2) < 8) c.epi_bufs = 1;

@@ -110,19 +110,26 @@ int bn_fold(const TensorDict& sd, const std::string& conv, const std::string& no
     return 0;
 }
 
-// channel padding unit = channels of one 128-byte K block: 32 fp32 / tf32 values, or 64 halfs (DTRAJ_PREC_F16)
-inline int cpad_of(int precision) { return precision == DTRAJ_PREC_F16 ? 64 : kCPad; }
+// Channel counts of feature maps and weights are padded to 32 in every mode.  A K block (128 bytes per pixel / per output
+// channel) carries 32 fp32 / tf32 channels or 64 halfs (DTRAJ_PREC_F16): there a source padded to an odd multiple of 32 ends in
+// a half-filled block (zero weights; the activation box is zero-filled by TMA beyond the map's channel dimension) of which only
+// two of the four K = 16 MMAs are issued -- so fp16 models execute round_up(C, 32) channels, not round_up(C, 64).
+inline int kblock_of(int precision) { return precision == DTRAJ_PREC_F16 ? 64 : 32; }
 thread_local bool g_pack_overflow = false;   // a folded weight outside the fp16 range (DTRAJ_PREC_F16)
 
 // Pack [cout][c0+c1][k][k] into K-major blocks of one 128-byte row per output channel: [tap][chunk][coutp][32] floats
-// (+ low plane), or [tap][chunk][coutp][64] halfs in DTRAJ_PREC_F16
+// (+ low plane), or [tap][chunk][coutp][64] halfs in DTRAJ_PREC_F16.  c0p / c1p / coutp: the padded channel counts of the
+// feature maps involved (multiples of 32; 0 = round the real count up to 32).
 void pack_conv(Arena* A, size_t* w_off, size_t* b_off, PackedConv* pc, const float* w, int cout, int c0, int c1,
-               int ksize, bool centre_only, const double* scale, const double* shift, int precision) {
-    const int kch = cpad_of(precision);
+               int ksize, bool centre_only, const double* scale, const double* shift, int precision,
+               int c0p = 0, int c1p = 0, int coutp = 0) {
+    const int kch = kblock_of(precision);
     const bool f16 = precision == DTRAJ_PREC_F16;
-    const int c0p = round_up(c0, kch), c1p = c1 ? round_up(c1, kch) : 0, coutp = round_up(cout, kch);
+    if (!c0p) c0p = round_up(c0, kCPad);
+    if (!c1p) c1p = c1 ? round_up(c1, kCPad) : 0;
+    if (!coutp) coutp = round_up(cout, kCPad);
     const int ntaps = (ksize == 3 && !centre_only) ? 9 : 1;
-    const int nch0 = c0p / kch, nch = nch0 + c1p / kch, nkb = ntaps * nch;
+    const int nch0 = (c0p + kch - 1) / kch, nch = nch0 + (c1p + kch - 1) / kch, nkb = ntaps * nch;
     const int npl = precision == DTRAJ_PREC_TF32X3 ? 2 : 1;
     const size_t plane = (size_t)nkb * coutp * 32;          // floats: one 128-byte row per (K block, output channel)
     *w_off = A->alloc(plane * npl);
@@ -186,9 +193,10 @@ extern "C" int dtraj_unet_create(const dtraj_unet_desc* desc, const char* const*
 
     dtraj_unet* u = new dtraj_unet();
     u->d = *desc;
-    const int cpad = cpad_of(desc->precision);
+    const int cpad = kCPad;
     g_pack_overflow = false;
     for (int i = 0; i < 4; ++i) u->dp[i] = round_up(desc->dims[i], cpad);
+    if (desc->precision == DTRAJ_PREC_F16) u->dp[0] = round_up(desc->dims[0], 64);   // the fused enc1 kernel works on whole 64-channel chunks
     for (int l = 0; l < 5; ++l) u->sizes[l] = H >> l;
     u->act_mode = desc->precision == DTRAJ_PREC_FP32 ? ACT_PLAIN : desc->precision == DTRAJ_PREC_TF32X3 ? ACT_SPLIT : ACT_ROUND;
     const int* d = desc->dims;
@@ -197,6 +205,10 @@ extern "C" int dtraj_unet_create(const dtraj_unet_desc* desc, const char* const*
     const int cin1[8] = {0, 0, 0, 0, 0, d[3], d[2], d[1]};
     const int cout[8] = {d[0], d[1], d[2], d[3], d[3], d[2], d[1], d[0]};
     const int lvl[8] = {0, 1, 2, 3, 4, 3, 2, 1};
+    const int* dp = u->dp;
+    const int cin0p[8] = {0, dp[0], dp[1], dp[2], dp[3], dp[3], dp[2], dp[1]};      // padded widths of the maps each block reads / writes
+    const int cin1p[8] = {0, 0, 0, 0, 0, dp[3], dp[2], dp[1]};
+    const int coutp[8] = {dp[0], dp[1], dp[2], dp[3], dp[3], dp[2], dp[1], dp[0]};
 
     Arena A;
     int err = 0;
@@ -236,20 +248,23 @@ extern "C" int dtraj_unet_create(const dtraj_unet_desc* desc, const char* const*
                 A.h[o_fb1 + n] = br[n];
             }
         } else {
-            pack_conv(&A, &off[b].w1, &off[b].b1, &B.conv1, w, B.cout, B.cin0, B.cin1, 3, centre, sc.data(), sh.data(), desc->precision);
+            pack_conv(&A, &off[b].w1, &off[b].b1, &B.conv1, w, B.cout, B.cin0, B.cin1, 3, centre, sc.data(), sh.data(), desc->precision,
+                      cin0p[b], cin1p[b], coutp[b]);
             if (B.has_res) {
                 const float* wr = sd.get(nm + ".residual_conv.weight", (int64_t)B.cout * cin, &err);
                 const float* br = sd.get(nm + ".residual_conv.bias", B.cout, &err);
                 if (err) break;
                 std::vector<double> rb(B.cout);
                 for (int n = 0; n < B.cout; ++n) rb[n] = br[n];
-                pack_conv(&A, &off[b].wr, &off[b].br, &B.res, wr, B.cout, B.cin0, B.cin1, 1, false, nullptr, rb.data(), desc->precision);
+                pack_conv(&A, &off[b].wr, &off[b].br, &B.res, wr, B.cout, B.cin0, B.cin1, 1, false, nullptr, rb.data(), desc->precision,
+                          cin0p[b], cin1p[b], coutp[b]);
             }
         }
         // conv2
         const float* w2 = sd.get(nm + ".conv2.weight", (int64_t)B.cout * B.cout * 9, &err);
         if (err || (err = bn_fold(sd, nm + ".conv2", nm + ".norm2", B.cout, &sc, &sh))) break;
-        pack_conv(&A, &off[b].w2, &off[b].b2, &B.conv2, w2, B.cout, B.cout, 0, 3, centre, sc.data(), sh.data(), desc->precision);
+        pack_conv(&A, &off[b].w2, &off[b].b2, &B.conv2, w2, B.cout, B.cout, 0, 3, centre, sc.data(), sh.data(), desc->precision,
+                  coutp[b], 0, coutp[b]);
         // block time MLP (raw)
         const float* tw = sd.get(nm + ".time_mlp.weight", (int64_t)B.cout * temb, &err);
         const float* tb = sd.get(nm + ".time_mlp.bias", B.cout, &err);
@@ -284,7 +299,7 @@ extern "C" int dtraj_unet_create(const dtraj_unet_desc* desc, const char* const*
 
     // time table layout
     int tbs = 0;
-    for (int b = 0; b < 8; ++b) { u->tb_off[b] = tbs; tbs += round_up(cout[b], cpad); }
+    for (int b = 0; b < 8; ++b) { u->tb_off[b] = tbs; tbs += coutp[b]; }
     u->tb_stride = tbs;
     const size_t o_table = A.alloc((size_t)T * 3 * tbs);
     const size_t o_err = A.alloc(64);                 // (zero-initialised like the rest of the arena)
@@ -365,7 +380,11 @@ struct dtraj_plan {
     // generic conv launches in execution order
     struct ConvOp { ConvLayer L; bool umma; UmmaLaunch U; int tb_block; double flops; bool needs_x; char name[40]; };
     // fused tails (single-pass TF32 mode): which stand-alone kernels the conv epilogues replace
-    bool fuse_resx = false, fuse_final = false, fuse_res = false;
+    bool fuse_resx = false, fuse_final = false;
+    bool fuse_res[8] = {false, false, false, false, false, false, false, false};   // per block: its 1x1 residual conv rides in conv2's launch
+    // execution order of one forward after the enc1 stage: generic convs, stand-alone pools, upsamples
+    struct Op { int kind; int a; };     // kind 0: next conv; 1: pool after encoder level a; 2: upsample of decoder stage a (0..2)
+    std::vector<Op> seq;
     bool fuse_enc1 = false;      // k_enc1_umma replaces k_conv_first + the enc1.conv2 launch
     Enc1Launch enc1;
     Enc1hLaunch enc1h;           // its fp16 form (DTRAJ_PREC_F16): conv2 weights resident in shared memory
@@ -491,11 +510,13 @@ int plan_build(const dtraj_unet* u, int64_t R, void* ws, int64_t ws_bytes, dtraj
     P->fuse_resx = fused;
     P->fuse_final = fused;
     for (int l = 0; l < 4; ++l) P->fuse_pool[l] = fused && S[l] <= 16;
-    // residual 1x1 convs as extra MMAs of the block's conv2 (CONV_RESACC): no r tensor, no extra launch
-    P->fuse_res = fused;
-    const bool fr = P->fuse_res;
+    // Residual 1x1 convs as extra MMAs of the block's conv2 (CONV_RESACC): no r tensor, no extra launch.  (Measured in round 2
+    // with the 1x1 convs of the 256-wide blocks as their own launches + the TMA residual path: conv2 alone gains -- enc2.conv2
+    // 673 -> 454 us at 8880 rows, two accumulator stages instead of one -- but the stand-alone K = 128..512 GEMMs cost more than
+    // that, 3579 vs 3499 us per teacher forward; profiles/r02b_resacc_ab.txt.)
+    for (int b = 1; b < 8; ++b) P->fuse_res[b] = fused && blk(b).has_res;
     auto with_res = [&](Tail t, int b, const dtraj_plan::Buf* s0, const dtraj_plan::Buf* s1) {
-        if (fr && blk(b).has_res) { t.res = &u->blk[b].res; t.rs0 = s0; t.rs1 = s1; }
+        if (P->fuse_res[b]) { t.res = &u->blk[b].res; t.rs0 = s0; t.rs1 = s1; }
         return t;
     };
     const dtraj_plan::Buf* pooled[4] = {&P->p1, &P->p2, &P->p3, &P->p4};
@@ -504,7 +525,7 @@ int plan_build(const dtraj_unet* u, int64_t R, void* ws, int64_t ws_bytes, dtraj
         if (P->fuse_pool[enc]) t.pool_out = pooled[enc]->p;
         return t;
     };
-#define ADD(...) if (!rc) rc = add_conv(P, __VA_ARGS__)
+#define ADD(...) do { if (!rc) { rc = add_conv(P, __VA_ARGS__); P->seq.push_back({0, 0}); } } while (0)
     // enc1: conv1/res by k_conv_first; conv2 here.  x1 itself is never a skip input (models.py:206-216):
     // with the pool fused, only the pooled tile is written.
     P->fuse_enc1 = fused && S[0] % 16 == 0 && u->d.channels <= 4;
@@ -526,24 +547,30 @@ int plan_build(const dtraj_unet* u, int64_t R, void* ws, int64_t ws_bytes, dtraj
         t.nostore = P->fuse_pool[0];
         ADD("enc1.conv2", blk(0).conv2, P->tmp_h, nullptr, S[0], P->tmp_x, t.resx ? nullptr : P->tmp_r.p, t.resx ? CONV_RELU : RR, -1, false, t);
     }
+    if (!P->fuse_enc1) P->seq.push_back({1, 0});
     // enc2 @ level 1
     if (!blk(1).has_res) rc = fail(DTRAJ_EINVAL, "enc2 without residual_conv unsupported");
-    if (!fr) ADD("enc2.res", blk(1).res, P->p1, nullptr, S[1], P->tmp_r, nullptr, 0, -1, true);
-    ADD("enc2.conv1", blk(1).conv1, P->p1, nullptr, S[1], P->tmp_h, nullptr, RT, 1, false);
-    ADD("enc2.conv2", blk(1).conv2, P->tmp_h, nullptr, S[1], P->x2, fr ? nullptr : P->tmp_r.p, fr ? CONV_RELU : RR, -1, false,
-        with_res(tail_for(1), 1, &P->p1, nullptr));
-    // enc3 @ level 2 (identity residual = pooled input)
+    {
+        const bool fr = P->fuse_res[1];
+        if (!fr) ADD("enc2.res", blk(1).res, P->p1, nullptr, S[1], P->tmp_r, nullptr, 0, -1, true);
+        ADD("enc2.conv1", blk(1).conv1, P->p1, nullptr, S[1], P->tmp_h, nullptr, RT, 1, false);
+        ADD("enc2.conv2", blk(1).conv2, P->tmp_h, nullptr, S[1], P->x2, fr ? nullptr : P->tmp_r.p, fr ? CONV_RELU : RR, -1, false,
+            with_res(tail_for(1), 1, &P->p1, nullptr));
+        P->seq.push_back({1, 1});
+    }
+    // enc3, enc4, bottleneck @ levels 2..4 (identity residual = the pooled input, unless the widths differ)
     const dtraj_plan::Buf* pin[3] = {&P->p2, &P->p3, &P->p4};
     const dtraj_plan::Buf* xo[3] = {&P->x3, &P->x4, &P->tmp_x};
     for (int k = 0; k < 3 && !rc; ++k) {
         const int b = 2 + k, lv = 2 + k;
         const float* resid = pin[k]->p;
-        const bool fused_here = fr && blk(b).has_res;
+        const bool fused_here = P->fuse_res[b];
         const std::string bn = kBlockNames[b];
-        if (blk(b).has_res && !fr) { ADD((bn + ".res").c_str(), blk(b).res, *pin[k], nullptr, S[lv], P->tmp_r, nullptr, 0, -1, true); resid = P->tmp_r.p; }
+        if (blk(b).has_res && !fused_here) { ADD((bn + ".res").c_str(), blk(b).res, *pin[k], nullptr, S[lv], P->tmp_r, nullptr, 0, -1, true); resid = P->tmp_r.p; }
         ADD((bn + ".conv1").c_str(), blk(b).conv1, *pin[k], nullptr, S[lv], P->tmp_h, nullptr, RT, b, false);
         ADD((bn + ".conv2").c_str(), blk(b).conv2, P->tmp_h, nullptr, S[lv], *xo[k], fused_here ? nullptr : resid, fused_here ? CONV_RELU : RR, -1, false,
             with_res(k < 2 ? tail_for(2 + k) : Tail(), b, pin[k], nullptr));
+        if (k < 2) P->seq.push_back({1, 2 + k});
     }
     // decoders: [upsampled | skip]
     const dtraj_plan::Buf* up[3] = {&P->u3, &P->u2, &P->u1};
@@ -553,6 +580,8 @@ int plan_build(const dtraj_unet* u, int64_t R, void* ws, int64_t ws_bytes, dtraj
         const int b = 5 + k, lv = 3 - k;
         if (!blk(b).has_res) { rc = fail(DTRAJ_EINVAL, "%s without residual_conv unsupported", kBlockNames[b]); break; }
         const std::string bn = kBlockNames[b];
+        const bool fr = P->fuse_res[b];
+        P->seq.push_back({2, k});
         if (!fr) ADD((bn + ".res").c_str(), blk(b).res, *up[k], skip[k], S[lv], P->tmp_r, nullptr, 0, -1, true);
         ADD((bn + ".conv1").c_str(), blk(b).conv1, *up[k], skip[k], S[lv], P->tmp_h, nullptr, RT, b, false);
         Tail t;
@@ -623,7 +652,7 @@ int plan_forward(dtraj_plan* P, const float* x, int64_t x_stride, const int32_t*
         int rc;
         PROF_BEGIN(prof, KC_CONV, op.name, op.umma ? op.U.grid : 0u, op.flops);
         if (op.umma) {
-            op.U.conv.L.tbias = tb; op.U.conv.L.row_variant = row_variant;
+            op.U.conv.L.tbias = tb; op.U.conv.L.row_variant = row_variant; op.U.conv.L.tb_rows = per_row ? 1 : 0;
             if (op.needs_x) { op.U.conv.L.xraw = x; op.U.conv.L.x_stride = x_stride; op.U.conv.L.row_sample = row_sample; }
             rc = launch_conv_umma(op.U, st);
         } else {
@@ -663,26 +692,14 @@ int plan_forward(dtraj_plan* P, const float* x, int64_t x_stride, const int32_t*
         DTRAJ_LAUNCH_CHECK(); ++nl;
         return 0;
     };
-    if (!P->fuse_enc1) {
-        DTRAJ_TRY(conv());                               // enc1.conv2 -> x1 (tmp_x)
-        DTRAJ_TRY(pool(P->tmp_x, P->p1, S[1], dp[0], 0));
-    }
-    if (!P->fuse_res) DTRAJ_TRY(conv());                  // enc2.residual_conv (else inside conv2)
-    DTRAJ_TRY(conv()); DTRAJ_TRY(conv());                 // enc2 -> x2
-    DTRAJ_TRY(pool(P->x2, P->p2, S[2], dp[1], 1));
-    const dtraj_plan::Buf* xo[3] = {&P->x3, &P->x4, &P->tmp_x};
-    const dtraj_plan::Buf* pn[2] = {&P->p3, &P->p4};
-    for (int k = 0; k < 3; ++k) {                        // enc3, enc4, bottleneck
-        if (u->blk[2 + k].has_res && !P->fuse_res) DTRAJ_TRY(conv());
-        DTRAJ_TRY(conv()); DTRAJ_TRY(conv());
-        if (k < 2) DTRAJ_TRY(pool(*xo[k], *pn[k], S[3 + k], dp[2 + k], 2 + k));
-    }
+    const dtraj_plan::Buf* pool_in[4] = {&P->tmp_x, &P->x2, &P->x3, &P->x4};
+    const dtraj_plan::Buf* pool_out[4] = {&P->p1, &P->p2, &P->p3, &P->p4};
     const dtraj_plan::Buf* up[3] = {&P->u3, &P->u2, &P->u1};
     const int upc[3] = {dp[3], dp[2], dp[1]};
-    for (int k = 0; k < 3; ++k) {                        // dec3, dec2, dec1
-        DTRAJ_TRY(upsample(P->tmp_x, *up[k], S[4 - k], upc[k]));
-        if (!P->fuse_res) DTRAJ_TRY(conv());
-        DTRAJ_TRY(conv()); DTRAJ_TRY(conv());
+    for (const dtraj_plan::Op& op : P->seq) {
+        if (op.kind == 0) DTRAJ_TRY(conv());
+        else if (op.kind == 1) DTRAJ_TRY(pool(*pool_in[op.a], *pool_out[op.a], S[op.a + 1], dp[op.a], op.a));
+        else DTRAJ_TRY(upsample(P->tmp_x, *up[op.a], S[4 - op.a], upc[op.a]));
     }
     if (!P->fuse_final) {   // final 1x1 at half resolution (else: dec1.conv2's epilogue)
         const int64_t npix = R * S[1] * S[1];
@@ -869,10 +886,10 @@ extern "C" int dtraj_sampler_create(dtraj_unet* u, const dtraj_sampler_desc* d, 
         cudaStreamDestroy(cs);
         if (rc) { dtraj_sampler_destroy(s); return rc; }
     } else {
-        // dry count of launches
-        int extra = 3 + (s->plan->fuse_final ? 0 : 1) + (s->plan->fuse_enc1 ? -1 : 0);     // upsamples + final
-        for (int l = 0; l < 4; ++l) extra += s->plan->fuse_pool[l] ? 0 : 1;
-        s->launches = (int64_t)d->n_updates * (2 + (int64_t)s->plan->convs.size() + extra) + (d->copy_last ? 1 : 0);
+        // dry count of launches: enc1 stage + the plan's ops (fused pools launch nothing) + final 1x1 + fused step
+        int64_t per = 1 + (s->plan->fuse_final ? 0 : 1) + 1;
+        for (const dtraj_plan::Op& op : s->plan->seq) per += (op.kind == 1 && s->plan->fuse_pool[op.a]) ? 0 : 1;
+        s->launches = (int64_t)d->n_updates * per + (d->copy_last ? 1 : 0);
     }
     *out = s;
     return 0;
@@ -968,6 +985,12 @@ extern "C" int dtraj_wasserstein(const float* teacher, const float* student, int
     if (N == 0) return 0;
     if (!teacher || !student || !out || N < 0 || L < 1) return fail(DTRAJ_EINVAL, "wasserstein: bad argument");
     return launch_wasserstein(teacher, student, N, L, D, idx, idx_set, K, out, (cudaStream_t)stream);
+}
+
+extern "C" int dtraj_numpy_choice_sets(const uint32_t* seeds, int32_t n_seeds, int32_t L, int32_t D, int32_t K, int32_t* out, void* stream) {
+    if (n_seeds == 0) return 0;
+    if (!seeds || !out) return fail(DTRAJ_EINVAL, "numpy_choice_sets: null argument");
+    return launch_numpy_choice(seeds, n_seeds, L, D, K, out, (cudaStream_t)stream);
 }
 
 extern "C" int dtraj_project(const float* frames, int64_t n_frames, int32_t D, const float* comps, const float* offset, int32_t K,
@@ -1077,7 +1100,7 @@ extern "C" unsigned int dtraj_debug_umma_error(void) {
 extern "C" int dtraj_bench_conv(int32_t precision, int32_t c0, int32_t c1, int32_t cout, int64_t n, int32_t H, int32_t ksize,
                                 int32_t flags, int32_t iters, int32_t debug, float* ms_out) {
     if (debug) return fail(DTRAJ_EINVAL, "bench_conv: the operand knock-out experiments (profiles/r01f_conv_knockout.txt) were removed from the kernels");
-    const int cpad = cpad_of(precision);
+    const int cpad = kCPad;
     const int c0p = round_up(c0, cpad), c1p = c1 ? round_up(c1, cpad) : 0, coutp = round_up(cout, cpad);
     const int64_t M = n * H * H;
     std::vector<float> w((size_t)cout * (c0 + c1) * ksize * ksize, 0.01f);

@@ -323,4 +323,91 @@ inline int launch_wasserstein(const float* T, const float* S, int64_t N, int L, 
     return 0;
 }
 
+// ---------------------------------------------------------------- Wasserstein subsample indices on the device
+// compute_trajectory_metrics subsamples every frame larger than 1000 elements with
+//     np.random.choice(D, 1000, replace=False)                        (analysis/metrics/trajectory_metrics.py:301-306)
+// from the GLOBAL numpy RNG, which compare_trajectories' callers left seeded at seed + 1 (analysis/trajectory_engine.py:91-93).
+// That is numpy's legacy RandomState (third-party, numpy==1.26.4 pinned by the reference; the legacy stream is frozen
+// across versions): MT19937 seeded by init_genrand(seed); choice(replace=False) = permutation(D)[:K]; permutation =
+// Fisher-Yates `for i = D-1 .. 1: j = random_interval(i); swap(x[i], x[j])` with random_interval(max) = draw 32-bit
+// words, mask to the smallest 2^k - 1 >= max, reject values > max.  The kernel below reproduces that stream bit for bit
+// (integer work: tests/test_gpu_metrics.py compares it with numpy itself): one thread per seed walks its L consecutive
+// permutations; MT state and permutation live in shared memory, interleaved over the block's threads (bank = thread).
+constexpr int kChoiceThreads = 16;
+
+__global__ void __launch_bounds__(kChoiceThreads) k_numpy_choice(const uint32_t* __restrict__ seeds, int n_seeds, int L, int D, int K,
+                                                                 int32_t* __restrict__ out) {
+    extern __shared__ __align__(16) uint8_t ch_smem[];
+    uint32_t* mt = reinterpret_cast<uint32_t*>(ch_smem);                                   // [624][16]
+    uint16_t* perm = reinterpret_cast<uint16_t*>(ch_smem + 624 * kChoiceThreads * 4);      // [D][16]
+    const int t = threadIdx.x;
+    const int sidx = blockIdx.x * kChoiceThreads + t;
+    const bool live = sidx < n_seeds;
+    uint32_t* my = mt + t;
+    uint16_t* pm = perm + t;
+    int pos = 624;
+    if (live) {
+        uint32_t sd = seeds[sidx];
+        for (int i = 0; i < 624; ++i) { my[i * kChoiceThreads] = sd; sd = 1812433253u * (sd ^ (sd >> 30)) + (uint32_t)i + 1u; }
+    }
+    auto next32 = [&]() -> uint32_t {
+        if (pos == 624) {
+            int kk = 0;
+            for (; kk < 624 - 397; ++kk) {
+                const uint32_t y = (my[kk * kChoiceThreads] & 0x80000000u) | (my[(kk + 1) * kChoiceThreads] & 0x7fffffffu);
+                my[kk * kChoiceThreads] = my[(kk + 397) * kChoiceThreads] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+            }
+            for (; kk < 623; ++kk) {
+                const uint32_t y = (my[kk * kChoiceThreads] & 0x80000000u) | (my[(kk + 1) * kChoiceThreads] & 0x7fffffffu);
+                my[kk * kChoiceThreads] = my[(kk - 227) * kChoiceThreads] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+            }
+            const uint32_t y = (my[623 * kChoiceThreads] & 0x80000000u) | (my[0] & 0x7fffffffu);
+            my[623 * kChoiceThreads] = my[396 * kChoiceThreads] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+            pos = 0;
+        }
+        uint32_t y = my[(pos++) * kChoiceThreads];
+        y ^= y >> 11;
+        y ^= (y << 7) & 0x9d2c5680u;
+        y ^= (y << 15) & 0xefc60000u;
+        y ^= y >> 18;
+        return y;
+    };
+    for (int f = 0; f < L; ++f) {
+        if (live) {
+            for (int i = 0; i < D; ++i) pm[i * kChoiceThreads] = (uint16_t)i;
+            for (int i = D - 1; i >= 1; --i) {
+                const uint32_t mask = 0xffffffffu >> __clz((uint32_t)i);
+                uint32_t j;
+                do { j = next32() & mask; } while (j > (uint32_t)i);
+                const uint16_t a = pm[i * kChoiceThreads], b = pm[j * kChoiceThreads];
+                pm[i * kChoiceThreads] = b;
+                pm[j * kChoiceThreads] = a;
+            }
+        }
+        __syncwarp(0xffffu);
+        // coalesced write-out: the block's threads share the rows of each seed
+        for (int s = 0; s < kChoiceThreads; ++s) {
+            const int so = blockIdx.x * kChoiceThreads + s;
+            if (so >= n_seeds) break;
+            int32_t* dst = out + ((size_t)so * L + f) * K;
+            for (int k = t; k < K; k += kChoiceThreads) dst[k] = (int32_t)perm[k * kChoiceThreads + s];
+        }
+        __syncwarp(0xffffu);
+    }
+}
+
+inline int launch_numpy_choice(const uint32_t* seeds, int n_seeds, int L, int D, int K, int32_t* out, cudaStream_t st) {
+    if (n_seeds < 0 || L < 1 || D < 2 || D > 4096 || K < 1 || K > D) return fail(DTRAJ_EINVAL, "numpy_choice: bad argument (2 <= D <= 4096, 1 <= K <= D)");
+    if (n_seeds == 0) return 0;
+    const size_t smem = (size_t)624 * kChoiceThreads * 4 + (size_t)D * kChoiceThreads * 2;
+    static bool attr_set = false;
+    if (!attr_set) {
+        DTRAJ_CUDA(cudaFuncSetAttribute(k_numpy_choice, cudaFuncAttributeMaxDynamicSharedMemorySize, 624 * kChoiceThreads * 4 + 4096 * kChoiceThreads * 2));
+        attr_set = true;
+    }
+    k_numpy_choice<<<(unsigned)((n_seeds + kChoiceThreads - 1) / kChoiceThreads), kChoiceThreads, smem, st>>>(seeds, n_seeds, L, D, K, out);
+    DTRAJ_LAUNCH_CHECK();
+    return 0;
+}
+
 }  // namespace dtraj

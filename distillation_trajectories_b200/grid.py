@@ -87,7 +87,8 @@ def stage_chunk(samples, config, guidance_scales, device):
     ts = np.arange(T - 1, 0, -1)
     zi = (np.asarray(ck.seeds)[None, :] + ts[:, None] - first).astype(np.int32) if len(ts) else np.zeros((1, len(ck.seeds)), np.int32)
     L, D = T + 1, C * H * H
-    idx = te.wasserstein_index_sets([42 + s for s in ck.samples], T, L, D)
+    idx = te.wasserstein_index_sets_device([42 + s for s in ck.samples], T, L, D, device) if device.type == "cuda" else \
+        te.wasserstein_index_sets([42 + s for s in ck.samples], T, L, D)
     nbytes = 0
 
     def up(t):
@@ -101,7 +102,7 @@ def stage_chunk(samples, config, guidance_scales, device):
     ck.ws_dev = up(torch.tensor([float(w) if w is not None else 0.0 for w in ck.ws], dtype=torch.float32))
     ck.bank = up(bank)
     ck.z_index = up(torch.from_numpy(zi))
-    ck.idx = None if idx is None else up(torch.from_numpy(idx))
+    ck.idx = None if idx is None else (idx if torch.is_tensor(idx) else up(torch.from_numpy(idx)))
     ck.idx_set = None if idx is None else torch.arange(len(ck.samples), dtype=torch.int32, device=device).repeat_interleave(G)
     ck.h2d_bytes = nbytes
     return ck

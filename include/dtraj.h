@@ -235,6 +235,19 @@ int dtraj_wasserstein(const float* teacher, const float* student,
                       const int32_t* idx, const int32_t* idx_set, int32_t K,
                       float* out, void* stream);
 
+/*
+ * The subsample index sets compute_trajectory_metrics draws for frames larger than 1000 elements
+ * (trajectory_metrics.py:301-306: np.random.choice(D, K, replace=False) per frame, from the global numpy RNG that
+ * compare_trajectories' callers left at seed + 1, analysis/trajectory_engine.py:91-93), generated on the device: numpy's
+ * legacy RandomState stream (MT19937 seeded by init_genrand, Fisher-Yates with masked rejection sampling) reproduced
+ * bit for bit, L consecutive choice() calls per seed.
+ *   seeds  dev uint32 [n_seeds]   (the value passed to np.random.seed)
+ *   out    dev int32  [n_seeds, L, K]  -- directly usable as `idx` of dtraj_wasserstein
+ * 2 <= D <= 4096, 1 <= K <= D.
+ */
+int dtraj_numpy_choice_sets(const uint32_t* seeds, int32_t n_seeds, int32_t L, int32_t D, int32_t K,
+                            int32_t* out, void* stream);
+
 /* ------------------------------------------------------------------ PCA projection
  * Replaces the per-trajectory `pca.transform(process_trajectory(traj))` of the visual analysis
  * (scripts/analysis/analyze_trajectories.py:66-80,100; same in :232-246): frames of any number

@@ -33,7 +33,8 @@ def run_conv(prec, x0, x1, w, b, ksize, relu, resid):
     cout = w.shape[0]
 
     f16 = prec == _lib.PREC_F16
-    pad = 64 if f16 else 32              # channels per 128-byte K block
+    pad = 32                             # channel padding unit of every mode (fp16: a 128-byte K block carries 64 channels, so a
+                                         # source padded to an odd multiple of 32 ends in a half-filled, TMA-zero-filled block)
     dt = torch.float16 if f16 else torch.float32
 
     def nhwc(a, c):
@@ -83,10 +84,14 @@ SHAPES = [
     (1, 256, 256, 128, 16, 3),
     (2, 32, 0, 32, 32, 3),       # 32x32 level 0: 4-row boxes
     (592, 128, 0, 256, 8, 3),    # 296 tiles: CTA pairs (tcgen05.mma.cta_group::2), persistent loop with 2 tiles per pair
-    (300, 64, 64, 128, 8, 3),    # 150 tiles of 128 rows: swapped operands off (K < 1024), single-CTA persistent path
-    (160, 128, 0, 128, 16, 3),   # 160 tiles of 256 pixels: swapped operands (weights as the M operand)
+    (300, 64, 64, 128, 8, 3),    # 150 tiles of 128 rows: single-CTA persistent path
+    (160, 128, 0, 128, 16, 3),   # 320 tiles of half a 16x16 image: CTA pairs on the im2col path
     (3, 64, 0, 32, 16, 1),       # 1x1 residual
     (4, 38, 38, 76, 4, 1),
+    (3, 76, 0, 152, 16, 3),      # sf 0.6 widths: 96 -> 160 padded channels (fp16: half-filled last K block, N = 160)
+    (3, 152, 152, 76, 8, 3),     # ... two half-filled sources (160 + 160), N = 96, halo mode in fp16
+    (300, 204, 0, 204, 8, 3),    # sf 0.8: 224 channels, CTA pairs with 112 weight rows per CTA
+    (2, 16, 0, 32, 32, 3),       # tiny students: one half-filled K block per tap, N = 32
 ]
 
 

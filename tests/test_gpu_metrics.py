@@ -94,6 +94,31 @@ def test_wasserstein_vs_oracle(D, K):
             np.testing.assert_allclose(got[n, i], want, rtol=1e-5, atol=1e-7)
 
 
+@pytest.mark.parametrize("D,K,L", [(3072, 1000, 51), (1024, 1000, 3), (4096, 4096, 2), (2, 1, 5), (1500, 7, 4)])
+def test_device_index_sets_reproduce_numpy_legacy_stream(D, K, L):
+    """dtraj_numpy_choice_sets == np.random.RandomState(seed).choice(D, K, replace=False) called L times (the subsample
+    draws of trajectory_metrics.py:301-306): bit-exact, including seeds at the ends of the 32-bit range and a seed count
+    that is not a multiple of the kernel's block."""
+    import ctypes as C
+    from distillation_trajectories_b200 import _lib
+    seeds = [0, 1, 43, 44, 2 ** 31 - 1, 2 ** 31, 2 ** 32 - 1, 123456789] + list(range(1000, 1011))
+    sd = torch.tensor(seeds, dtype=torch.int64).to(torch.int32).cuda()
+    out = torch.full((len(seeds), L, K), -1, dtype=torch.int32, device="cuda")
+    _lib.check(_lib.load().dtraj_numpy_choice_sets(_lib.ptr(sd), len(seeds), L, D, K, _lib.ptr(out), _lib.stream_ptr()))
+    got = out.cpu().numpy()
+    for i, s in enumerate(seeds):
+        rs = np.random.RandomState(s)
+        want = np.stack([rs.choice(D, K, replace=False) for _ in range(L)])
+        np.testing.assert_array_equal(got[i], want, err_msg=f"seed {s}")
+    # the wrapper the sweeps use (seed + 1 as compare_trajectories' callers leave the RNG) agrees with the host loop
+    a = te.wasserstein_index_sets_device([42, 43, 44], 50, L, D, "cuda")
+    b = te.wasserstein_index_sets([42, 43, 44], 50, L, D)
+    if K == min(1000, D) and K < D:
+        np.testing.assert_array_equal(a.cpu().numpy(), b)
+    else:
+        assert (a is None) == (b is None)
+
+
 @pytest.mark.parametrize("name", ["tiny16", "tiny32"])
 def test_compare_trajectories_fixture(name):
     """analysis/trajectory_engine.py:117-180 end to end (fp32 convolutions so that the metric scalars
