@@ -15,6 +15,11 @@
 //     (zero rows where the halo leaves the image: conv2's zero padding).  The first form of this kernel computed conv1
 //     with CUDA-core FMAs in "generator" warps: 115 instructions per 8 outputs made it issue-bound (572 us against
 //     ~170 us of conv2 MMAs for the teacher); the tensor-core form leaves ~25;
+//   * the raw pixels conv1 needs -- a [C][20][12] fp32 patch per tile -- are copied by warp 0 with cp.async (zero-filled outside the
+//     image = conv1's padding; a TMA box cannot be used: its innermost start x0 - 2 is not 16-byte aligned) into a small ring a few
+//     tiles ahead, completion on an mbarrier, so the gather is 9C shared-memory loads without bounds checks
+//     (round 1 gathered with 9C predicated global loads per halo pixel held in registers a tile ahead: at C = 3 that made the
+//     mid warps the bottleneck, 64 ns per tile against 43 at C = 1, and spilled);
 //   * each conv2 tap is a descriptor VIEW of the halo tile (start shifted by (dy*10 + dx) rows, 8-row groups 1280 bytes
 //     apart; profiles/r01_umma_view_probe.txt): nothing is copied, no im2col re-reads;
 //   * epilogue: bias, ReLU, 1x1 residual recomputed from x (fp32 FMAs), fp16 rounding, 2x2 max-pool, 16-byte stores.
@@ -27,7 +32,11 @@ namespace dtraj {
 
 constexpr int kE1Mid = 8;                        // mid warps (two per TMEM lane quarter)
 constexpr int kE1hThreads = 64 + 32 * kE1Epi + 32 * kE1Mid;
-constexpr int kA1SliceBytes = 256 * 32;          // 256 rows x 16 halfs
+constexpr int kA1Rows = 192;                     // rows of an A1 operand slice kept in shared memory: 180 halo pixels, rounded up to 64.  The
+                                                 // second M = 128 half of conv1's MMA reads rows 128..255 -- 64 rows past the slice, into
+                                                 // whatever follows inside the CTA's allocation -- and D1 rows >= 180 are never looked at
+constexpr int kA1SliceBytes = kA1Rows * 32;      // x 16 halfs
+constexpr int kE1PatchH = 20, kE1PatchW = 12;    // conv1's receptive field of the 18 x 10 halo
 
 struct Enc1hParams {
     int C, H, W, coutp;
@@ -40,6 +49,7 @@ struct Enc1hParams {
     int w_rows;                  // output channels this CTA holds: coutp, or coutp / 2 in pair mode
     int n_slices;                // K slices (16 values) of conv1's GEMM: ceil(9C / 16)
     const float* x; int64_t x_stride; const int32_t* row_sample; const int32_t* row_variant;
+    int n_patch;                 // raw-input patch ring depth: 4, or 2 where 4 would cost a halo buffer
     const float* w3; const float* b3;          // conv1, BN folded, fp32: [9*C][coutp] (k = tap * C + cin); [coutp]
     const float* tbias; int tb_var_stride;     // relu(time_mlp(temb)) rows of enc1 for this t, 3 variants
     int tb_rows;                 // 1: row_variant indexes the whole [T][3] table (per-row timesteps): read the bias from global memory
@@ -80,6 +90,10 @@ k_enc1_f16(const __grid_constant__ Enc1Maps maps, const Enc1hParams p) {
     const uint32_t acc_full0 = bar0 + 128u, acc_empty0 = bar0 + 144u, wbar = bar0 + 160u;
     const uint32_t a1_full0 = bar0 + 168u, d1_full0 = bar0 + 184u, d1_empty0 = bar0 + 200u;   // each [2]
     const uint32_t tmem_slot = bar0 + 216u;
+    auto patch_full = [&](int b) { return bar0 + 232u + 8u * b; };
+    auto patch_empty = [&](int b) { return bar0 + 264u + 8u * b; };
+    const uint32_t patch_bytes = ((uint32_t)(C * kE1PatchH * kE1PatchW * 4) + 127u) & ~127u;
+    const uint32_t patch0 = (bar0 + 296u + 127u) & ~127u;
     const uint32_t tmem_cols = (uint32_t)((2 + 2 * p.n_d1) * p.acc_cols) <= 256u ? 256u : 512u;
     volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gbase + (tmem_slot - base));
     float* cst = reinterpret_cast<float*>(gbase + (cst0 - base));
@@ -112,6 +126,7 @@ k_enc1_f16(const __grid_constant__ Enc1Maps maps, const Enc1hParams p) {
                 ptx::mbar_init(d1_full0 + 8u * i, 1);
                 ptx::mbar_init(d1_empty0 + 8u * i, nrep);
             }
+            for (int i = 0; i < p.n_patch; ++i) { ptx::mbar_init(patch_full(i), 32); ptx::mbar_init(patch_empty(i), 1); }
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
         __syncwarp();
@@ -134,8 +149,8 @@ k_enc1_f16(const __grid_constant__ Enc1Maps maps, const Enc1hParams p) {
     for (int i = threadIdx.x; i < p.n_d1 * p.n_slices * (kA1SliceBytes / 16); i += blockDim.x)
         reinterpret_cast<uint4*>(gbase + (a1_0 - base))[i] = make_uint4(0u, 0u, 0u, 0u);
     __syncthreads();
-    for (int i = threadIdx.x; i < p.n_d1 * 2 * 256; i += blockDim.x) {    // the bias slots of every A1 row hold 1.0
-        const int bb = i >> 9, r = (i >> 1) & 255, k = kBiasK + (i & 1);
+    for (int i = threadIdx.x; i < p.n_d1 * 2 * kA1Rows; i += blockDim.x) {    // the bias slots of every A1 row hold 1.0
+        const int bb = i / (2 * kA1Rows), r = (i >> 1) % kA1Rows, k = kBiasK + (i & 1);
         *reinterpret_cast<__half*>(gbase + (a1_0 - base) + bb * a1_buf + (k >> 4) * kA1SliceBytes + k16_off(r, (k >> 3) & 1) + (k & 7) * 2) = __float2half_rn(1.f);
     }
     for (int i = threadIdx.x; i < p.n_slices * p.w_rows * 16; i += blockDim.x) {
@@ -173,6 +188,35 @@ k_enc1_f16(const __grid_constant__ Enc1Maps maps, const Enc1hParams p) {
                 const int row = b * coutp + crank * p.w_rows;
                 if constexpr (kPair) ptx::tma_load_2d_2sm(wres0 + b * wblk_bytes, &maps.w, fb, 0, row);
                 else ptx::tma_load_2d(wres0 + b * wblk_bytes, &maps.w, fb, 0, row);
+            }
+        }
+        __syncwarp();
+        // ---- then (all 32 lanes) the raw-input patches of this CTA's tiles, a few tiles ahead of the mid warps: 4-byte cp.async
+        // per element with zero fill outside the image, one cp.async.mbarrier.arrive per lane and patch
+        {
+            int pb = 0;
+            uint32_t pph = 0;
+            bool ok = true;
+            const int HW = p.H * p.W, n_el = C * kE1PatchH * kE1PatchW;
+            for (int wk = work0; wk < p.n_tiles && ok; wk += gridDim.x) {
+                const int tile = wk + crank;
+                int img, y0, x0;
+                tile_geom(tile, img, y0, x0);
+                const bool real = tile < p.n_tiles;                 // (a pair's padding tile gets an all-zero patch)
+                const int smp = real ? (p.row_sample ? __ldg(p.row_sample + img) : img) : 0;
+                const float* xs = p.x + (size_t)smp * p.x_stride;
+                ok = ptx::mbar_wait(errw, patch_empty(pb), pph ^ 1u);
+                const uint32_t dst0 = patch0 + (uint32_t)pb * patch_bytes;
+                for (int e = lane; e < n_el; e += 32) {
+                    const int ci = e / (kE1PatchH * kE1PatchW), rem = e - ci * (kE1PatchH * kE1PatchW);
+                    const int r = rem / kE1PatchW, cc = rem - r * kE1PatchW;
+                    const int sy = y0 - 2 + r, sx = x0 - 2 + cc;
+                    const bool in = real && sy >= 0 && sy < p.H && sx >= 0 && sx < p.W;
+                    const float* src = in ? xs + (size_t)ci * HW + sy * p.W + sx : p.x;
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst0 + 4u * (uint32_t)e), "l"(src), "r"(in ? 4u : 0u) : "memory");
+                }
+                asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(patch_full(pb)) : "memory");
+                if (++pb == p.n_patch) { pb = 0; pph ^= 1u; }
             }
         }
     } else if (warp == 1) {
@@ -262,41 +306,28 @@ k_enc1_f16(const __grid_constant__ Enc1Maps maps, const Enc1hParams p) {
         const int px0 = 32 * q + lane, px1 = 128 + 32 * q + lane;
         const bool has1 = 128 + 32 * q < kE1HaloRows;               // warp-uniform: quarters 0 and 1 own rows of region 1
         const int ry0 = px0 / 10, rx0 = px0 - ry0 * 10, ry1 = px1 / 10, rx1 = px1 - ry1 * 10;
-        float xr[2][kC][9];                                         // prefetched conv1 inputs of this thread's A1 rows: [row][cin][tap]
-        // per-image indices are fetched TWO tiles ahead and the pixels ONE tile ahead, so no load is waited for in the loop
-        int smp_n = 0, var_n = 0;                                   // indices of the tile fetched last (two tiles ahead of the pixels)
+        // the time-bias variant of a tile's image is fetched two tiles ahead, so that load is never waited for in the loop
+        int var_n = 0;
         auto fetch_idx = [&](int wk) {
             const int tile = wk + crank;
             const int img = tile >> p.lg_tpi;
-            const bool real = wk < p.n_tiles && tile < p.n_tiles;
-            smp_n = real ? (p.row_sample ? __ldg(p.row_sample + img) : img) : 0;
-            var_n = (real && p.row_variant) ? __ldg(p.row_variant + img) : 0;
+            var_n = (wk < p.n_tiles && tile < p.n_tiles && p.row_variant) ? __ldg(p.row_variant + img) : 0;
         };
-        auto prefetch = [&](int wk, int smp) {
-            const int tile = wk + crank;
-            int img, y0, x0;
-            tile_geom(tile, img, y0, x0);
-            const float* xs = p.x + (size_t)smp * p.x_stride;
-#pragma unroll
-            for (int rr = 0; rr < 2; ++rr) {
-                if (!a_has[rr]) continue;                           // (warp-uniform for rr = 0; the second row ends inside one warp)
-                const bool real = tile < p.n_tiles;
-                const int yy = y0 - 1 + a_ry[rr], xx = x0 - 1 + a_rx[rr];
-#pragma unroll
-                for (int ci = 0; ci < kC; ++ci)
-#pragma unroll
-                    for (int t9 = 0; t9 < 9; ++t9) {
-                        const int sy = yy - 1 + t9 / 3, sx = xx - 1 + t9 % 3;
-                        xr[rr][ci][t9] = (real && sy >= 0 && sy < p.H && sx >= 0 && sx < p.W) ? __ldg(xs + (size_t)ci * HW + sy * p.W + sx) : 0.f;
-                    }
-            }
-        };
-        // xr -> this thread's A1 row: per K slice two 16-byte stores (taps, the two bias slots = 1.0, zero padding)
-        auto store_a1 = [&](int buf) {
+        // this thread's A1 rows of tile-iteration `pit`, gathered from that tile's raw patch [C][20][12] (origin = two pixels up and
+        // left of the tile; TMA zero-filled it outside the image): per K slice two 16-byte stores (taps, the two bias slots = 1.0,
+        // zero padding).  The patch is released (patch_empty) by thread 0 after the named barrier that follows every call.
+        auto gather_a1 = [&](int buf, int pit) {
+            const int pbuf = pit & (p.n_patch - 1);
+            ptx::mbar_wait(errw, patch_full(pbuf), (uint32_t)((pit / p.n_patch) & 1));
+            const float* patch = reinterpret_cast<const float*>(gbase + (patch0 - base) + (uint32_t)pbuf * patch_bytes);
             uint8_t* const a1b = a1p + (uint32_t)buf * a1_buf;
 #pragma unroll
             for (int rr = 0; rr < 2; ++rr) {
-                if (!a_has[rr]) continue;
+                if (!a_has[rr]) continue;                           // (warp-uniform for rr = 0; the second row ends inside one warp)
+                const float* pp = patch + a_ry[rr] * kE1PatchW + a_rx[rr];
+                float xv[9 * kC];
+#pragma unroll
+                for (int k = 0; k < 9 * kC; ++k) xv[k] = pp[(k % kC) * (kE1PatchH * kE1PatchW) + ((k / kC) / 3) * kE1PatchW + (k / kC) % 3];
 #pragma unroll
                 for (int sl = 0; sl < (9 * kC + 2 + 15) / 16; ++sl)
 #pragma unroll
@@ -305,7 +336,7 @@ k_enc1_f16(const __grid_constant__ Enc1Maps maps, const Enc1hParams p) {
 #pragma unroll
                         for (int e = 0; e < 8; ++e) {
                             const int k = 16 * sl + 8 * kc + e;
-                            v[e] = k < 9 * kC ? xr[rr][k % kC][k / kC] : ((k == kBiasK || k == kBiasK + 1) ? 1.f : 0.f);
+                            v[e] = k < 9 * kC ? xv[k] : ((k == kBiasK || k == kBiasK + 1) ? 1.f : 0.f);
                         }
                         uint4 o;
                         __half2* oh = reinterpret_cast<__half2*>(&o);
@@ -324,9 +355,9 @@ k_enc1_f16(const __grid_constant__ Enc1Maps maps, const Enc1hParams p) {
             if constexpr (kPair) asm volatile("fence.acq_rel.cluster;" ::: "memory");
         };
         // Software pipeline with lead Ld = n_d1 (buffers of A1 and of D1).  At the top of iteration `it`: A1(it .. it+Ld-1) are
-        // published (their conv1 issued or done), xr = pixels of tile it + Ld, vq[k] = variant of tile it + k (k <= Ld),
-        // (smp_n, var_n) = indices of tile it + Ld + 1.  With Ld = 2 the conv1 round trip (publish -> issue -> MMA -> commit)
-        // of tile it + 2 runs under the conversion of tile it + 1, so the mid warps never wait for it.
+        // published (their conv1 issued or done), the patch of tile it + Ld is loaded or in flight, vq[k] = variant of tile
+        // it + k (k <= Ld), var_n = variant of tile it + Ld + 1.  With Ld = 2 the conv1 round trip (publish -> issue -> MMA ->
+        // commit) of tile it + 2 runs under the conversion of tile it + 1, so the mid warps never wait for it.
         const int G = (int)gridDim.x, Ld = p.n_d1;
         int hb = 0, it = 0, vq[3] = {0, 0, 0};
         uint32_t hph = 0;
@@ -334,17 +365,15 @@ k_enc1_f16(const __grid_constant__ Enc1Maps maps, const Enc1hParams p) {
             fetch_idx(work0);
             for (int j = 0; j < Ld; ++j) {                         // A1(0 .. Ld-1)
                 const bool ex = work0 + j * G < p.n_tiles;          // (CTA-uniform)
-                if (ex) prefetch(work0 + j * G, smp_n);
                 vq[j] = var_n;
                 fetch_idx(work0 + (j + 1) * G);
                 if (ex) {
-                    store_a1(j);
+                    gather_a1(j, j);
                     ptx::fence_proxy_async();
                     asm volatile("bar.sync 9, 256;" ::: "memory");
-                    if (mt == 0) { release_fence(); arrive_one(a1_full0 + 8u * j); }
+                    if (mt == 0) { ptx::mbar_arrive(patch_empty(j & (p.n_patch - 1))); release_fence(); arrive_one(a1_full0 + 8u * j); }
                 }
             }
-            if (work0 + Ld * G < p.n_tiles) prefetch(work0 + Ld * G, smp_n);
             vq[Ld] = var_n;
             fetch_idx(work0 + (Ld + 1) * G);
         }
@@ -357,10 +386,7 @@ k_enc1_f16(const __grid_constant__ Enc1Maps maps, const Enc1hParams p) {
             ptx::mbar_wait(errw, d1_full0 + 8u * b, (uint32_t)((it >> (Ld - 1)) & 1));    // conv1(it) done: D1 readable, A1 buffer b free
             ptx::tc_fence_after();
             const bool next = wk + Ld * G < p.n_tiles;
-            if (next) {
-                store_a1(b);                                        // A1(it + Ld); published together with the first halo chunk below
-                if (wk + (Ld + 1) * G < p.n_tiles) prefetch(wk + (Ld + 1) * G, smp_n);   // loads stay in flight under the conversion
-            }
+            if (next) gather_a1(b, it + Ld);                        // A1(it + Ld); published together with the first halo chunk below
             const int var0 = vq[0];
             const float* tb = p.tb_rows ? p.tbias + (size_t)var0 * p.tb_var_stride : tbs + var0 * coutp;
             vq[0] = vq[1];
@@ -401,6 +427,7 @@ k_enc1_f16(const __grid_constant__ Enc1Maps maps, const Enc1hParams p) {
                 ptx::fence_proxy_async();                           // generic-proxy writes -> visible to the tensor core
                 asm volatile("bar.sync 9, 256;" ::: "memory");
                 if (mt == 0) {                                      // one release fence, then relaxed arrivals
+                    if (c == 0 && next) ptx::mbar_arrive(patch_empty((it + Ld) & (p.n_patch - 1)));   // every gatherer is past the barrier
                     release_fence();
                     if (c == 0 && next) arrive_one(a1_full0 + 8u * b);
                     arrive_one(hfull(hb));
@@ -559,20 +586,27 @@ inline int build_enc1h_launch(Enc1hLaunch* E, int C, int H, int coutp, int cout_
     p.acc_cols = 32;
     while (p.acc_cols < coutp) p.acc_cols *= 2;
     p.n_d1 = 6 * p.acc_cols <= 512 ? 2 : 1;
-    auto fixed_for = [&](int pair) {
+    auto fixed_for = [&](int pair, int n_patch) {
         const size_t wr = (size_t)coutp / (pair ? 2 : 1);
         return (size_t)1024 + (size_t)9 * p.n_chunks * wr * 128 + kE1Epi * 2048 + (size_t)p.n_d1 * p.n_slices * kA1SliceBytes +
-               (((size_t)p.n_slices * wr * 32 + 1023) & ~(size_t)1023) + (size_t)(6 + C) * coutp * 4 + 16 + 256;
+               (((size_t)p.n_slices * wr * 32 + 1023) & ~(size_t)1023) + (size_t)(6 + C) * coutp * 4 + 16 + 296 + 128 +
+               (size_t)n_patch * (((size_t)C * kE1PatchH * kE1PatchW * 4 + 127) & ~(size_t)127);
     };
     // pairs halve the resident weights per CTA; without them the weights must still fit next to one halo buffer
     E->pair = p.n_tiles >= 2 * kNumSMs ? 1 : 0;
-    if (!E->pair && fixed_for(0) + kE1HaloBytes > 227 * 1024) E->pair = 1;     // n_tiles >= 2 always (two tiles per 16-row band)
+    if (!E->pair && fixed_for(0, 2) + kE1HaloBytes > 227 * 1024) E->pair = 1;     // n_tiles >= 2 always (two tiles per 16-row band)
     p.w_rows = coutp / (E->pair ? 2 : 1);
-    const size_t fixed = fixed_for(E->pair);
-    if (fixed + kE1HaloBytes > 227 * 1024) return fail(DTRAJ_EINVAL, "enc1(f16): shared memory does not fit (coutp=%d C=%d)", coutp, C);
-    int nh = (int)((227 * 1024 - fixed) / kE1HaloBytes);
-    if (nh > 2 * p.n_chunks) nh = 2 * p.n_chunks;
-    if (nh > 8) nh = 8;
+    auto halo_bufs = [&](int n_patch) {
+        const size_t f = fixed_for(E->pair, n_patch);
+        if (f + kE1HaloBytes > 227 * 1024) return 0;
+        int nh = (int)((227 * 1024 - f) / kE1HaloBytes);
+        if (nh > 2 * p.n_chunks) nh = 2 * p.n_chunks;
+        return nh > 8 ? 8 : nh;
+    };
+    p.n_patch = halo_bufs(4) == halo_bufs(2) ? 4 : 2;
+    const size_t fixed = fixed_for(E->pair, p.n_patch);
+    const int nh = halo_bufs(p.n_patch);
+    if (nh < 1) return fail(DTRAJ_EINVAL, "enc1(f16): shared memory does not fit (coutp=%d C=%d)", coutp, C);
     p.n_hbuf = nh;
     E->smem = fixed + (size_t)nh * kE1HaloBytes;
     E->grid = (unsigned)(p.n_tiles < kNumSMs ? p.n_tiles : kNumSMs);
