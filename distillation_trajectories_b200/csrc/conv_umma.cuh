@@ -64,8 +64,10 @@ struct UmmaConv {
     int log2_hw;               // H*W is a power of two: image index of output row m is m >> log2_hw
     int log2_wh;               // log2(W / 2) (CONV_POOL)
     int f16;                   // 1: DTRAJ_PREC_F16 -- fp16 feature maps / weights (64 channels per 128-byte K block), kind::f16 MMAs
-    int halo;                  // 1: HALO mode (fp16, 8x8 maps, 3x3): a tile is two images whose halos [10 rows][2 images][10 pixels]
-                               //    arrive by ONE TMA box per 64-channel chunk; the nine taps are descriptor views of it
+    int halo;                  // HALO mode (fp16, 3x3): a tile's pixels arrive ONCE per 64-channel chunk as a halo box, the nine taps are
+                               //    descriptor views of it.  1: 8x8 maps, a tile = two images, halos [10 rows][2 images][10 pixels] through
+                               //    the permuted dimensions {c, x, image, y};  2: 16x16 maps, a tile = the left or right half (16 rows x 8
+                               //    columns) of one image, halo [18 rows][10 pixels] through the standard dimensions {c, x, y, image}
     int n_hb;                  // halo ring depth
 };
 
@@ -363,21 +365,25 @@ k_conv_umma_t(const __grid_constant__ UmmaMaps maps, const UmmaConv p) {
                     if (++s == p.stages) { s = 0; ph ^= 1u; }
                     return true;
                 };
-                auto pixel_box = [&](const CUtensorMap* am, int c0, int xy0, int img0, uint32_t bytes) -> bool {
+                // `tile`: this CTA's tile; xy0 = -1: the halo box of a 3x3 tap set, 0: the un-shifted 128 pixels (residual conv)
+                auto pixel_box = [&](const CUtensorMap* am, int c0, int xy0, int tile, uint32_t bytes) -> bool {
                     if (!ptx::mbar_wait(errw, hempty0 + 8u * hb, hph ^ 1u)) return false;
                     uint32_t fb = hfull0 + 8u * hb;
                     if constexpr (kPair) fb = ptx::map_to_cta(fb, 0);
                     if (!kPair || crank == 0) ptx::mbar_expect_tx(hfull0 + 8u * hb, bytes * (kPair ? 2u : 1u));
-                    if constexpr (kPair) ptx::tma_load_4d_2sm(halo_base + hb * kHaloBytes, am, fb, c0, xy0, img0, xy0);
-                    else ptx::tma_load_4d(halo_base + hb * kHaloBytes, am, fb, c0, xy0, img0, xy0);
+                    // mode 1: dims {c, x, image, y}, two images from 2 * tile;  mode 2: dims {c, x, y, image}, columns from (tile & 1) * 8
+                    const int k1 = p.halo == 1 ? xy0 : (tile & 1) * 8 + xy0, k2 = p.halo == 1 ? 2 * tile : xy0, k3 = p.halo == 1 ? xy0 : tile >> 1;
+                    if constexpr (kPair) ptx::tma_load_4d_2sm(halo_base + hb * kHaloBytes, am, fb, c0, k1, k2, k3);
+                    else ptx::tma_load_4d(halo_base + hb * kHaloBytes, am, fb, c0, k1, k2, k3);
                     if (++hb == p.n_hb) { hb = 0; hph ^= 1u; }
                     return true;
                 };
+                const uint32_t halo_tx = p.halo == 1 ? kHaloTx : 180u * 128u;
                 for (int wk = work0; wk < p.n_work && ok; wk += gridDim.x) {
-                    const int img0 = 2 * (wk + crank);             // a tile = two images (a padding tile loads zeros)
+                    const int img0 = wk + crank;                   // this CTA's tile (a padding tile loads zeros)
                     for (int chunk = 0; chunk < nch && ok; ++chunk) {
                         const bool second = chunk >= nch0;
-                        ok = pixel_box(second ? &maps.a[1] : &maps.a[0], (second ? chunk - nch0 : chunk) * kCh, -1, img0, kHaloTx);
+                        ok = pixel_box(second ? &maps.a[1] : &maps.a[0], (second ? chunk - nch0 : chunk) * kCh, -1, img0, halo_tx);
                         for (int tap = 0; tap < 9 && ok; ++tap) ok = weight_stage(&maps.b, (tap * nch + chunk) * coutp + crank * w_half);
                     }
                     if (p.L.flags & CONV_RESACC)                   // 1x1 residual conv: the un-shifted 128 pixels of the block input
@@ -453,6 +459,7 @@ k_conv_umma_t(const __grid_constant__ UmmaMaps maps, const UmmaConv p) {
                 const uint64_t hdesc0 = ((uint64_t)1 << 16) | ((uint64_t)(1280 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
                 int hb = 0;
                 uint32_t hph = 0;
+                const int tap_rows = p.halo == 1 ? 20 : 10;         // halo rows (of 128 B) one image row down
                 auto mma4 = [&](uint32_t d_tmem, uint64_t ad, uint64_t bd, uint32_t& accum, int nk) {
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
@@ -484,7 +491,7 @@ k_conv_umma_t(const __grid_constant__ UmmaMaps maps, const UmmaConv p) {
                         for (int tap = 0; tap < 9 && ok; ++tap) {
                             ok = ptx::mbar_wait(errw, full_bar(s), ph);
                             ptx::tc_fence_after();
-                            const uint32_t a_addr = hbuf + (uint32_t)(dy * 20 + dx) * 128u;
+                            const uint32_t a_addr = hbuf + (uint32_t)(dy * tap_rows + dx) * 128u;
                             mma4(d_set, hdesc0 | (uint64_t)((a_addr >> 4) & 0x3fffu), umma_desc_sw128(base + s * stage_bytes), accum, nk);
                             free_stage();
                             if (++dx == 3) { dx = 0; ++dy; }
@@ -596,12 +603,15 @@ k_conv_umma_t(const __grid_constant__ UmmaMaps maps, const UmmaConv p) {
             const int tile = work / p.n_split, n0 = (work % p.n_split) * ncols;
             const int64_t m_warp = (int64_t)tile * 128 + q * 32;
             const int row = (int)m_warp;
+            const int hx0 = p.halo == 2 ? (tile & 1) * 8 : 0;       // halo mode 2: first column of the tile's half image
+            // coordinates of this warp's 32-row box in the 4-d output / residual maps (halo modes)
+            const int hk1 = p.halo == 1 ? 0 : hx0, hk2 = p.halo == 1 ? 2 * tile : 4 * q, hk3 = p.halo == 1 ? 2 * q : (tile >> 1);
             if (lane == 0) {
                 ptx::bulk_wait_read<0>();
                 if (has_res)
                     for (int k = 0; k < kEpiBufs && h + 2 * k < nchunk; ++k) {
                         ptx::mbar_expect_tx(rbar + 8u * k, 2048u);
-                        if (p.halo) ptx::tma_load_4d(buf0 + 4096u * k, &maps.res, rbar + 8u * k, n0 + 32 * (h + 2 * k), 0, 2 * tile, 2 * q);
+                        if (p.halo) ptx::tma_load_4d(buf0 + 4096u * k, &maps.res, rbar + 8u * k, n0 + 32 * (h + 2 * k), hk1, hk2, hk3);
                         else ptx::tma_load_2d(buf0 + 4096u * k, &maps.res, rbar + 8u * k, n0 + 32 * (h + 2 * k), row);
                     }
             }
@@ -610,11 +620,17 @@ k_conv_umma_t(const __grid_constant__ UmmaMaps maps, const UmmaConv p) {
             int64_t m = m_warp + lane;
             bool valid = m < p.L.M;
             int img = valid ? (int)(m >> p.log2_hw) : 0;
-            if (p.halo) {
+            if (p.halo == 1) {
                 const int r = q * 32 + lane;
                 img = 2 * tile + ((r >> 3) & 1);
                 valid = (int64_t)img * 64 < p.L.M;
                 m = (int64_t)img * 64 + (r >> 4) * 8 + (r & 7);
+                if (!valid) img = 0;
+            } else if (p.halo == 2) {                                // rows ordered (y, x): y = r >> 3 of 16, x = x0 + (r & 7)
+                const int r = q * 32 + lane;
+                img = tile >> 1;
+                valid = (int64_t)img * 256 < p.L.M;
+                m = (int64_t)img * 256 + (r >> 3) * 16 + hx0 + (r & 7);
                 if (!valid) img = 0;
             }
             const float* tb = nullptr;
@@ -741,11 +757,16 @@ k_conv_umma_t(const __grid_constant__ UmmaMaps maps, const UmmaConv p) {
                     int r00 = 2 * t * W + 2 * x2, rdn = W;               // window rows r00, r00 + 1, r00 + rdn, r00 + rdn + 1 of the warp's buffer
                     int64_t prow = (m_warp >> 2) + pr;                   // pooled pixel (row of the [M/4, coutp] output)
                     bool pvalid = m_warp + r00 < p.L.M;
-                    if (p.halo) {                                        // warp rows = (y in {2q, 2q+1}, image, x): lane -> (image, window column)
+                    if (p.halo == 1) {                                   // warp rows = (y in {2q, 2q+1}, image, x): lane -> (image, window column)
                         const int im2 = pr >> 2, wx = pr & 3;
                         r00 = im2 * 8 + 2 * wx; rdn = 16;
                         prow = ((int64_t)(2 * tile + im2) * 4 + q) * 4 + wx;
                         pvalid = (int64_t)(2 * tile + im2) * 64 < p.L.M;
+                    } else if (p.halo == 2) {                            // warp rows = (y in 4q .. 4q+3, x in x0 .. x0+7): 2 x 4 windows
+                        const int wy = pr >> 2, wx = pr & 3;
+                        r00 = wy * 16 + 2 * wx; rdn = 8;
+                        prow = ((int64_t)(tile >> 1) * 8 + 2 * q + wy) * 8 + (hx0 >> 1) + wx;
+                        pvalid = (int64_t)(tile >> 1) * 256 < p.L.M;
                     }
                     if (pvalid) {
                         const uint32_t jj = (uint32_t)(lane & 3);
@@ -764,7 +785,7 @@ k_conv_umma_t(const __grid_constant__ UmmaMaps maps, const UmmaConv p) {
                     __syncwarp();
                 }
                 if (lane == 0 && do_store) {
-                    if (p.halo) ptx::tma_store_4d(&maps.out, buf0 + 4096u * b, n0 + 32 * c, 0, 2 * tile, 2 * q);   // box {32 ch, 8 x, 2 images, 2 rows}
+                    if (p.halo) ptx::tma_store_4d(&maps.out, buf0 + 4096u * b, n0 + 32 * c, hk1, hk2, hk3);   // box {32 ch, 8 x, 2 images, 2 rows} / {32 ch, 8 x, 4 rows, 1 image}
                     else ptx::tma_store_2d(&maps.out, buf0 + 4096u * b, n0 + 32 * c, row);
                     ptx::bulk_commit();
                 }
@@ -776,7 +797,7 @@ k_conv_umma_t(const __grid_constant__ UmmaMaps maps, const UmmaConv p) {
                         if (has_res) {
                             const int nb = (k + 1) % kEpiBufs;
                             ptx::mbar_expect_tx(rbar + 8u * nb, 2048u);
-                            if (p.halo) ptx::tma_load_4d(buf0 + 4096u * nb, &maps.res, rbar + 8u * nb, n0 + 32 * (c + 2), 0, 2 * tile, 2 * q);
+                            if (p.halo) ptx::tma_load_4d(buf0 + 4096u * nb, &maps.res, rbar + 8u * nb, n0 + 32 * (c + 2), hk1, hk2, hk3);
                             else ptx::tma_load_2d(buf0 + 4096u * nb, &maps.res, rbar + 8u * nb, n0 + 32 * (c + 2), row);
                         }
                     }
@@ -1180,7 +1201,8 @@ inline int build_umma_launch(UmmaLaunch* U, const ConvLayer& L, int npass, const
     const int n_stage_rows = c.pair ? n_rows / 2 : n_rows;
     c.kbs = (n_stage_rows <= (c.pair ? 64 : 128) && c.r_nch0 % 2 == 0 && (c.r_nch - c.r_nch0) % 2 == 0 && c.nch0 % 2 == 0 && (c.nch - c.nch0) % 2 == 0) ? 2 : 1;
     // halo mode (fp16, 8x8 maps, 3x3, no identity residual): two images per tile, pixels through the halo ring
-    c.halo = (f16 && L.H == 8 && L.W == 8 && L.ntaps == 9 && !(L.flags & CONV_RESX) && c.n_split == 1 && L.act_mode != ACT_SPLIT) ? 1 : 0;
+    c.halo = (f16 && L.ntaps == 9 && !(L.flags & CONV_RESX) && c.n_split == 1 && L.act_mode != ACT_SPLIT)
+                 ? (L.H == 8 && L.W == 8 ? 1 : (L.H == 16 && L.W == 16 ? 2 : 0)) : 0;
     c.n_hb = 0;
     if (c.halo) { c.kbs = 1; c.n_hb = 3; }
     const size_t stage = c.halo ? (size_t)n_stage_rows * 128 : (size_t)c.kbs * (kATileBytes + (size_t)n_stage_rows * 128);
@@ -1210,6 +1232,30 @@ inline int build_umma_launch(UmmaLaunch* U, const ConvLayer& L, int npass, const
         DTRAJ_TRY(make_w_map(&U->maps.rb, rwpk, rw_rows, c.ncols / (c.pair ? 2 : 1), f16));
     }
     if (L.M >= (int64_t)1 << 31) return fail(DTRAJ_EINVAL, "umma conv: M too large for 32-bit TMA coordinates");
+    if (c.halo == 2) {  // 16x16 maps: standard dimensions {c, x, y, image}; halo box 10 x 18, residual-conv box 8 x 16, output / residual box 8 x 4
+        auto map4 = [&](CUtensorMap* m, const float* base, int cp, int bc, int bx, int by, bool sw64) -> int {
+            PFN_encodeTiled enc = get_encode_tiled();
+            if (!enc) return fail(DTRAJ_ECUDA, "cuTensorMapEncodeTiled not available");
+            cuuint64_t dims[4] = {(cuuint64_t)cp, 16, 16, (cuuint64_t)n_img};
+            cuuint64_t strides[3] = {(cuuint64_t)cp * 2, (cuuint64_t)16 * cp * 2, (cuuint64_t)256 * cp * 2};
+            cuuint32_t box[4] = {(cuuint32_t)bc, (cuuint32_t)bx, (cuuint32_t)by, 1};
+            cuuint32_t es[4] = {1, 1, 1, 1};
+            CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, (void*)base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                             sw64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r != CUDA_SUCCESS) return fail(DTRAJ_ECUDA, "cuTensorMapEncodeTiled(16x16 halo map cp=%d n=%lld) -> %d", cp, (long long)n_img, (int)r);
+            return 0;
+        };
+        DTRAJ_TRY(map4(&U->maps.a[0], L.src0, L.c0p, 64, 10, 18, false));
+        if (L.c1p) DTRAJ_TRY(map4(&U->maps.a[1], L.src1, L.c1p, 64, 10, 18, false));
+        if (L.flags & CONV_RESACC) {
+            DTRAJ_TRY(map4(&U->maps.ra[0], L.rsrc0, L.rc0p, 64, 8, 16, false));
+            if (L.rc1p) DTRAJ_TRY(map4(&U->maps.ra[1], L.rsrc1, L.rc1p, 64, 8, 16, false));
+        }
+        if (!(L.flags & CONV_NOSTORE)) DTRAJ_TRY(map4(&U->maps.out, L.out, L.coutp, 32, 8, 4, true));
+        if (L.flags & CONV_RESID) DTRAJ_TRY(map4(&U->maps.res, L.resid, L.coutp, 32, 8, 4, true));
+        return 0;
+    }
     if (c.halo) {      // every pixel-side map goes through the permuted dimensions {c, x, image, y}
         DTRAJ_TRY(make_perm8_map(&U->maps.a[0], L.src0, L.c0p, n_img, 64, 10, 10, false));
         if (L.c1p) DTRAJ_TRY(make_perm8_map(&U->maps.a[1], L.src1, L.c1p, n_img, 64, 10, 10, false));
