@@ -675,7 +675,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--quick", action="store_true", help="headline line only: no parity / by_precision / by_config legs")
     ap.add_argument("--ref-seeds", type=int, default=1, help="--impl reference: seeds per step (x 8 scales x 2 models)")
-    ap.add_argument("--config3-seeds", type=int, default=512, help="seeds per chunk of the configs[2] leg (0 = skip)")
+    ap.add_argument("--config3-seeds", type=int, default=1024, help="seeds per chunk of the configs[2] leg (0 = skip)")
     ap.add_argument("--config4-seeds", type=int, default=9472, help="TOTAL seeds of the configs[3]-shaped strong-scaling slice (0 = skip)")
     args = ap.parse_args()
     if args.quick:
