@@ -33,6 +33,14 @@ namespace dtraj {
 // that two models running on two streams can tell whose launch failed; launches without a handle (dtraj_test_conv,
 // dtraj_bench_conv) report to this library-wide word.
 __device__ unsigned int g_umma_error = 0;
+#ifdef DTRAJ_PROBES
+// Probe build only (tools/timeline.py): SM-clock stamps of CTA 0's issuer and two of its epilogue warps over its first 16 tiles of a
+// 256-column CONV_RESACC layer at 8x8 -- [pooled layer | other][tile][issuer | epilogue warp 2 | epilogue warp 6][event].
+__device__ long long g_timeline[2][16][3][16];
+#define DTRAJ_TL(who, ev) do { if (tl_on && tl_tile < 16) g_timeline[tl_slot][tl_tile][who][ev] = clock64(); } while (0)
+#else
+#define DTRAJ_TL(who, ev) do { } while (0)
+#endif
 
 struct UmmaConv {
     ConvLayer L;               // epilogue parameters + shapes (wpk unused here)
@@ -270,7 +278,7 @@ k_conv_umma_t(const __grid_constant__ UmmaMaps maps, const UmmaConv p) {
     // Per-channel epilogue constants, staged ONCE per CTA: rows of coutp floats [bias | residual-conv bias | time bias x 3 variants |
     // final-1x1 weights x finC].  Read from global memory at their point of use they were the epilogue's bottleneck: with 227 KB of
     // shared memory the L1 keeps ~28 KB, every chunk's ~20 dependent LDGs went to an L2 busy streaming operands at 5 TB/s, and the
-    // epilogue warps of the 256-wide residual layers were busy 78 % of the kernel (ncu source view, profiles/r02_conv_epilogue.txt).
+    // epilogue warps of the 256-wide residual layers were busy 78 % of the kernel (ncu source view, profiles/r02b_resacc_ab.txt).
     const uint32_t cst_base = fin_base + ((p.L.flags & CONV_FINAL) ? 2048u : 0u);
     float* const cst = reinterpret_cast<float*>(smem_raw + (cst_base - ptx::smem_u32(smem_raw)));
     volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(
@@ -278,6 +286,11 @@ k_conv_umma_t(const __grid_constant__ UmmaMaps maps, const UmmaConv p) {
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     unsigned int* const errw = p.L.err ? p.L.err : &g_umma_error;
+#ifdef DTRAJ_PROBES
+    const bool tl_on = blockIdx.x == 0 && (threadIdx.x & 31) == 0 && (p.L.flags & CONV_RESACC) && p.L.coutp == 256 && p.L.W == 8;
+    const int tl_slot = (p.L.flags & CONV_POOL) ? 0 : 1;
+    int tl_tile = 0;
+#endif
     const int crank = kPair ? (int)ptx::cluster_ctarank() : 0;
     const uint16_t cmask = kPair ? 3 : 1;
     const int work0 = (int)blockIdx.x - crank;   // first work item of this CTA's cluster; all its CTAs loop alike
@@ -478,8 +491,10 @@ k_conv_umma_t(const __grid_constant__ UmmaMaps maps, const UmmaConv p) {
                     if (++hb == p.n_hb) { hb = 0; hph ^= 1u; }
                 };
                 for (int wk = work0; wk < p.n_work && ok; wk += gridDim.x) {
+                    DTRAJ_TL(0, 0);
                     ok = ptx::mbar_wait(errw, acc_empty0 + 8u * acc, acc_ph ^ 1u);
                     ptx::tc_fence_after();
+                    DTRAJ_TL(0, 1);
                     const uint32_t d_set = tmem_base + (uint32_t)(acc * p.acc_cols);
                     uint32_t accum = 0u;
                     for (int chunk = 0; chunk < nch && ok; ++chunk) {
@@ -511,6 +526,10 @@ k_conv_umma_t(const __grid_constant__ UmmaMaps maps, const UmmaConv p) {
                         }
                     }
                     if constexpr (kPair) ptx::tc_commit_2sm(acc_full0 + 8u * acc, cmask); else ptx::tc_commit(acc_full0 + 8u * acc);
+                    DTRAJ_TL(0, 2);
+#ifdef DTRAJ_PROBES
+                    ++tl_tile;
+#endif
                     if (++acc == p.acc_stages) { acc = 0; acc_ph ^= 1u; }
                 }
                 ok = false;                                        // (skip the im2col loop below)
@@ -606,6 +625,12 @@ k_conv_umma_t(const __grid_constant__ UmmaMaps maps, const UmmaConv p) {
             const int hx0 = p.halo == 2 ? (tile & 1) * 8 : 0;       // halo mode 2: first column of the tile's half image
             // coordinates of this warp's 32-row box in the 4-d output / residual maps (halo modes)
             const int hk1 = p.halo == 1 ? 0 : hx0, hk2 = p.halo == 1 ? 2 * tile : 4 * q, hk3 = p.halo == 1 ? 2 * q : (tile >> 1);
+#ifdef DTRAJ_PROBES
+            const int tl_who = 1 + h;
+            const bool tl_outer = tl_on;
+            const bool tl_on = tl_outer && q == 2;       // (shadows the kernel-wide flag: warps 2 and 6 only)
+#endif
+            DTRAJ_TL(tl_who, 0);
             if (lane == 0) {
                 ptx::bulk_wait_read<0>();
                 if (has_res)
@@ -647,6 +672,7 @@ k_conv_umma_t(const __grid_constant__ UmmaMaps maps, const UmmaConv p) {
             }
             ptx::mbar_wait(errw, acc_full0 + 8u * acc, acc_ph);
             ptx::tc_fence_after();
+            DTRAJ_TL(tl_who, 1);
             const uint32_t t_acc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.acc_cols);
             const int c_last = nchunk - 1 - ((nchunk - 1 - h) & 1);
             if (c_last < h) {
@@ -661,6 +687,7 @@ k_conv_umma_t(const __grid_constant__ UmmaMaps maps, const UmmaConv p) {
                 ptx::tmem_ld32(t_acc + (uint32_t)(32 * c), raw);
                 if (fl & CONV_RESACC) ptx::tmem_ld32(t_acc + (uint32_t)(p.res_col + 32 * c), rres);
                 ptx::tmem_ld_wait();
+                DTRAJ_TL(tl_who, 2 + 3 * (((c - h) >> 1) & 3));
                 if (c == c_last) {
                     ptx::tc_fence_before();
                     __syncwarp();
@@ -807,8 +834,13 @@ k_conv_umma_t(const __grid_constant__ UmmaMaps maps, const UmmaConv p) {
             for (int c = h, k = 0; c < nchunk; c += 2, ++k) {
                 uint32_t pk[16];
                 compute_chunk(c, k % kEpiBufs, pk);
+                DTRAJ_TL(tl_who, 3 + 3 * (k & 3));
                 emit_chunk(c, k, k % kEpiBufs, pk);
+                DTRAJ_TL(tl_who, 4 + 3 * (k & 3));
             }
+#ifdef DTRAJ_PROBES
+            ++tl_tile;
+#endif
             if (fl & CONV_FINAL) {
                 float4* part = reinterpret_cast<float4*>(smem_raw + (fin_base - ptx::smem_u32(smem_raw))) + q * 32 + lane;
                 if (h == 1) *part = make_float4(fe[0], fe[1], fe[2], fe[3]);

@@ -1087,6 +1087,13 @@ extern "C" int dtraj_probe_tma_permuted(int32_t n_img, int32_t img0, float* out_
     return 0;
 }
 
+// tools/timeline.py: copy out (and clear) the SM-clock stamps k_conv_umma_t leaves in a probe build
+extern "C" int dtraj_probe_timeline(long long* host_out, int64_t n) {
+    if (n != (int64_t)(sizeof(g_timeline) / sizeof(long long))) return fail(DTRAJ_EINVAL, "probe_timeline: expected %zu values", sizeof(g_timeline) / sizeof(long long));
+    DTRAJ_CUDA(cudaDeviceSynchronize());
+    DTRAJ_CUDA(cudaMemcpyFromSymbol(host_out, g_timeline, sizeof(g_timeline)));
+    return 0;
+}
 #endif  // DTRAJ_PROBES
 
 extern "C" unsigned int dtraj_debug_umma_error(void) {

@@ -65,7 +65,8 @@ def test_sweep_three_students_default_precision_vs_oracle(C, H, T):
     teacher = make_model(cfg, 1.0 if H == 16 else 0.5, 31, device="cuda")
     students = {sf: make_model(cfg, sf, 1000 + int(sf * 100), device="cuda") for sf in (0.05, 0.3, 0.5)}
     scales, n_seeds = [1.0, 3.0, 7.5], 3
-    res = grid.sweep(teacher, students, cfg, scales, n_seeds, reduce=False, max_pairs=2 * len(scales))   # two chunks
+    chunk_seeds = 2                                      # max_pairs below: the sweep runs seeds {0, 1} and {2} as two chunks
+    res = grid.sweep(teacher, students, cfg, scales, n_seeds, reduce=False, max_pairs=chunk_seeds * len(scales))
     assert umma_error_flag() == 0
     ft = oracle_fn(teacher)
     x, seeds, ws = [], [], []
@@ -75,14 +76,24 @@ def test_sweep_three_students_default_precision_vs_oracle(C, H, T):
         for gs in scales:
             x.append(noise); seeds.append(42 + s); ws.append(gs)
     x = torch.cat(x)
-    groups = [i for i in range(n_seeds) for _ in scales]
-    t_gpu = te.generate_trajectories_batched(teacher, x, seeds, ws, T, "cuda", groups=groups).cpu().numpy().copy()
+
+    def regenerate(model):
+        """the sweep's own frames: same chunking, hence the same launch shapes (kernel forms -- column split, split-K -- are
+        chosen per launch shape and sum in different orders), and the samplers are deterministic"""
+        out = []
+        for c0 in range(0, n_seeds, chunk_seeds):
+            sl = slice(c0 * len(scales), min(n_seeds, c0 + chunk_seeds) * len(scales))
+            groups = [i // len(scales) for i in range(sl.stop - sl.start)]
+            out.append(te.generate_trajectories_batched(model, x[sl], seeds[sl], ws[sl], T, "cuda", groups=groups).cpu().numpy().copy())
+        return np.concatenate(out)
+
+    t_gpu = regenerate(teacher)
     t_ref = [torch.stack(osmp.s2_generate_trajectory(ft, x[p:p + 1], T, seed=seeds[p], guidance_scale=ws[p]))[:, 0].numpy()
              for p in range(len(seeds))]
     assert_close(t_gpu, np.stack(t_ref), RTOL, ATOL, "teacher frames of the sweep")
     for sf, model in students.items():
         fs = oracle_fn(model)
-        s_gpu = te.generate_trajectories_batched(model, x, seeds, ws, T, "cuda", groups=groups).cpu().numpy().copy()
+        s_gpu = regenerate(model)
         s_ref = [torch.stack(osmp.s2_generate_trajectory(fs, x[p:p + 1], T, seed=seeds[p], guidance_scale=ws[p]))[:, 0].numpy()
                  for p in range(len(seeds))]
         assert_close(s_gpu, np.stack(s_ref), RTOL, ATOL, f"student {sf} frames of the sweep")
