@@ -21,6 +21,7 @@
 // (the two cross terms into a separate accumulator), where x_lo = x - trunc_tf32(x) is kept in a
 // second plane by every producer of an activation (ACT_SPLIT) and the weights are split on the host.
 #pragma once
+#include <type_traits>
 #include <cstdlib>
 #include <cuda_fp16.h>
 #include "common.cuh"
@@ -65,6 +66,7 @@ struct UmmaConv {
                                //    stages only ITS half of the weight tile, the leader CTA issues for both
     int kbs;                   // 32-channel K blocks per pipeline stage (2 when both sources have an even number of them)
     int epi_bufs;              // epilogue ring depth per warp (1 when the freed 32 KB buy another operand stage)
+    int epi_kind;              // fp16 epilogue: 1..4 = one of the flag sets compiled as straight-line code (epi_kind_of), 0 = generic
     int box_h, box_n;          // A box = {32, W, box_h, box_n}
     int tiles_per_img;         // >= 1
     int b_lo_row;              // row offset of the low-plane weights inside the B tensor map
@@ -178,6 +180,14 @@ __device__ __forceinline__ uint32_t map_to_cta(uint32_t addr, uint32_t rank) {
 }
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// The same arrival WITHOUT release semantics, for barriers that hand over TMEM only ("accumulator drained": the tcgen05.ld results are
+// in registers after tcgen05.wait::ld, and tcgen05.fence::before_thread_sync / ::after_thread_sync order the tensor-memory accesses
+// around the barrier).  The .release.cluster form compiles to MEMBAR.ALL.GPU + ERRBAR in front of the arrive and waited there for the
+// warp's global pool stores: 9 % of the epilogue's stall samples and ~1500 cycles between a tile's last TMEM load and the issuer
+// seeing the accumulator free (profiles/r02i_timeline.txt, r02i_epilogue_stalls.txt).
+__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 __device__ __forceinline__ uint32_t cluster_ctarank() {
     uint32_t r;
@@ -347,7 +357,7 @@ k_conv_umma_t(const __grid_constant__ UmmaMaps maps, const UmmaConv p) {
     pdl_wait();                                // ... and this one touches activations only after its predecessor is complete
     auto arrive_acc_empty = [&](int acc) {     // "accumulator drained": to this CTA's issuer, or to the pair leader's
         if constexpr (!kPair) ptx::mbar_arrive(acc_empty0 + 8u * acc);
-        else ptx::mbar_arrive_cluster(ptx::map_to_cta(acc_empty0 + 8u * acc, 0));
+        else ptx::mbar_arrive_cluster_relaxed(ptx::map_to_cta(acc_empty0 + 8u * acc, 0));
     };
 
     if (warp == 0) {
@@ -609,6 +619,7 @@ k_conv_umma_t(const __grid_constant__ UmmaMaps maps, const UmmaConv p) {
         const bool has_res = (fl & CONV_RESID) != 0;
         const bool do_store = !(fl & CONV_NOSTORE);
         const bool do_pool = (fl & CONV_POOL) != 0;
+        const int epi_kind = (p.epi_kind == 1 && p.L.tb_rows) ? 0 : p.epi_kind;   // (per-row timesteps: the time-bias table stays in global memory)
         const uint32_t buf0 = ring_base + (uint32_t)ew * kEpiBufs * 4096u;
         const uint32_t rbar = res_bar0 + 8u * (ew * kEpiBufsMax);
         const uint32_t swz = (uint32_t)((lane >> 1) & 3);
@@ -659,9 +670,11 @@ k_conv_umma_t(const __grid_constant__ UmmaMaps maps, const UmmaConv p) {
                 if (!valid) img = 0;
             }
             const float* tb = nullptr;
+            const float* tb_s = cst;                                 // (kind 1: the time-bias row in shared memory)
             if (fl & CONV_TBIAS) {
                 const int var = p.L.row_variant ? p.L.row_variant[img] : 0;
-                tb = p.L.tb_rows ? p.L.tbias + (size_t)var * p.L.tb_var_stride : cst + (2 + var) * coutp;   // per-row timesteps: the whole table stays in global memory
+                tb_s = cst + (2 + var) * coutp;
+                tb = p.L.tb_rows ? p.L.tbias + (size_t)var * p.L.tb_var_stride : tb_s;   // per-row timesteps: the whole table stays in global memory
             }
             float xv[4] = {0.f, 0.f, 0.f, 0.f}, fe[4] = {0.f, 0.f, 0.f, 0.f};
             if ((fl & CONV_RESX) && valid) {
@@ -682,10 +695,23 @@ k_conv_umma_t(const __grid_constant__ UmmaMaps maps, const UmmaConv p) {
             }
             // One 32-column chunk, first half: TMEM -> registers -> bias / ReLU / time bias / residuals -> 16 packed half2 words.
             // `b`: ring buffer holding the TMA-loaded residual chunk (CONV_RESID).
-            auto compute_chunk = [&](int c, int b, uint32_t (&pk)[16]) {
+            // `kind_c` (std::integral_constant): 0 = every tail tested at run time; 1..4 = the forward plan's common flag sets with the
+            // tests folded at compile time.  The run-time form splits the 32-value arithmetic into ~20 basic blocks the compiler cannot
+            // schedule across (each LDS -> FADD -> FMNMX -> ... chain waits out its own latencies: 1400 cycles for ~250 instructions,
+            // profiles/r02i_timeline.txt); as straight-line code the loads hoist and the chains interleave.
+            auto compute_chunk = [&](auto kind_c, int c, int b, uint32_t (&pk)[16]) {
+                constexpr int KIND = decltype(kind_c)::value;
+                constexpr bool SPEC = KIND != 0;
+                const bool f_relu = SPEC ? true : (fl & CONV_RELU) != 0;
+                const bool f_tb = SPEC ? KIND == 1 : tb != nullptr;
+                const bool f_resx = SPEC ? false : (fl & CONV_RESX) != 0;
+                const bool f_resacc = SPEC ? (KIND == 2 || KIND == 4) : (fl & CONV_RESACC) != 0;
+                const bool f_resid = SPEC ? KIND == 3 : has_res;
+                const bool f_final = SPEC ? KIND == 4 : (fl & CONV_FINAL) != 0;
+                const float* const tbp = SPEC ? tb_s : tb;
                 uint32_t raw[32], rres[32];
                 ptx::tmem_ld32(t_acc + (uint32_t)(32 * c), raw);
-                if (fl & CONV_RESACC) ptx::tmem_ld32(t_acc + (uint32_t)(p.res_col + 32 * c), rres);
+                if (f_resacc) ptx::tmem_ld32(t_acc + (uint32_t)(p.res_col + 32 * c), rres);
                 ptx::tmem_ld_wait();
                 DTRAJ_TL(tl_who, 2 + 3 * (((c - h) >> 1) & 3));
                 if (c == c_last) {
@@ -693,7 +719,7 @@ k_conv_umma_t(const __grid_constant__ UmmaMaps maps, const UmmaConv p) {
                     __syncwarp();
                     if (lane == 0) arrive_acc_empty(acc);
                 }
-                if (has_res) { ptx::mbar_wait(errw, rbar + 8u * b, (res_par >> b) & 1u); res_par ^= 1u << b; }
+                if (f_resid) { ptx::mbar_wait(errw, rbar + 8u * b, (res_par >> b) & 1u); res_par ^= 1u << b; }
                 const uint8_t* rowp = smem_raw + (buf0 + 4096u * b - ptx::smem_u32(smem_raw)) + lane * 64;
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
@@ -707,17 +733,17 @@ k_conv_umma_t(const __grid_constant__ UmmaMaps maps, const UmmaConv p) {
                         v[4] = __uint_as_float(raw[8 * j + 4]) + b1.x; v[5] = __uint_as_float(raw[8 * j + 5]) + b1.y;
                         v[6] = __uint_as_float(raw[8 * j + 6]) + b1.z; v[7] = __uint_as_float(raw[8 * j + 7]) + b1.w;
                     }
-                    if (fl & CONV_RELU) {
+                    if (f_relu) {
 #pragma unroll
                         for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], 0.f);
                     }
-                    if (tb) {
-                        const float4 t0 = *reinterpret_cast<const float4*>(tb + col);
-                        const float4 t1 = *reinterpret_cast<const float4*>(tb + col + 4);
+                    if (f_tb) {
+                        const float4 t0 = *reinterpret_cast<const float4*>(tbp + col);
+                        const float4 t1 = *reinterpret_cast<const float4*>(tbp + col + 4);
                         v[0] += t0.x; v[1] += t0.y; v[2] += t0.z; v[3] += t0.w;
                         v[4] += t1.x; v[5] += t1.y; v[6] += t1.z; v[7] += t1.w;
                     }
-                    if (fl & CONV_RESX) {
+                    if (f_resx) {
 #pragma unroll
                         for (int hh = 0; hh < 2; ++hh) {
                             float4 r4 = __ldg(reinterpret_cast<const float4*>(p.L.rb1 + col + 4 * hh));
@@ -731,7 +757,7 @@ k_conv_umma_t(const __grid_constant__ UmmaMaps maps, const UmmaConv p) {
                             v[4 * hh] += r4.x; v[4 * hh + 1] += r4.y; v[4 * hh + 2] += r4.z; v[4 * hh + 3] += r4.w;
                         }
                     }
-                    if (fl & CONV_RESACC) {   // residual_conv(x) + its bias, accumulated by this kernel's extra MMAs
+                    if (f_resacc) {   // residual_conv(x) + its bias, accumulated by this kernel's extra MMAs
                         const float4 r0 = *reinterpret_cast<const float4*>(rbias_s + col);
                         const float4 r1 = *reinterpret_cast<const float4*>(rbias_s + col + 4);
                         v[0] += __uint_as_float(rres[8 * j]) + r0.x; v[1] += __uint_as_float(rres[8 * j + 1]) + r0.y;
@@ -739,7 +765,7 @@ k_conv_umma_t(const __grid_constant__ UmmaMaps maps, const UmmaConv p) {
                         v[4] += __uint_as_float(rres[8 * j + 4]) + r1.x; v[5] += __uint_as_float(rres[8 * j + 5]) + r1.y;
                         v[6] += __uint_as_float(rres[8 * j + 6]) + r1.z; v[7] += __uint_as_float(rres[8 * j + 7]) + r1.w;
                     }
-                    if (has_res) {
+                    if (f_resid) {
                         const uint4 rr = *reinterpret_cast<const uint4*>(rowp + (((uint32_t)j ^ swz) << 4));
                         const __half2* rh = reinterpret_cast<const __half2*>(&rr);
 #pragma unroll
@@ -752,7 +778,7 @@ k_conv_umma_t(const __grid_constant__ UmmaMaps maps, const UmmaConv p) {
                         ph2[i] = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
                         pk[4 * j + i] = *reinterpret_cast<const uint32_t*>(&ph2[i]);
                     }
-                    if (fl & CONV_FINAL) {
+                    if (f_final) {
                         float vr[8];
 #pragma unroll
                         for (int i = 0; i < 4; ++i) { const float2 f = __half22float2(ph2[i]); vr[2 * i] = f.x; vr[2 * i + 1] = f.y; }
@@ -822,7 +848,7 @@ k_conv_umma_t(const __grid_constant__ UmmaMaps maps, const UmmaConv p) {
                     if (lane == 0) {
                         if (do_store) { if (kEpiBufs == 2) ptx::bulk_wait_read<1>(); else ptx::bulk_wait_read<0>(); }
                         if (has_res) {
-                            const int nb = (k + 1) % kEpiBufs;
+                            const int nb = (k + 1) & (kEpiBufs - 1);          // (depth 1 or 2)
                             ptx::mbar_expect_tx(rbar + 8u * nb, 2048u);
                             if (p.halo) ptx::tma_load_4d(buf0 + 4096u * nb, &maps.res, rbar + 8u * nb, n0 + 32 * (c + 2), hk1, hk2, hk3);
                             else ptx::tma_load_2d(buf0 + 4096u * nb, &maps.res, rbar + 8u * nb, n0 + 32 * (c + 2), row);
@@ -831,12 +857,40 @@ k_conv_umma_t(const __grid_constant__ UmmaMaps maps, const UmmaConv p) {
                     __syncwarp();
                 }
             };
-            for (int c = h, k = 0; c < nchunk; c += 2, ++k) {
-                uint32_t pk[16];
-                compute_chunk(c, k % kEpiBufs, pk);
-                DTRAJ_TL(tl_who, 3 + 3 * (k & 3));
-                emit_chunk(c, k, k % kEpiBufs, pk);
-                DTRAJ_TL(tl_who, 4 + 3 * (k & 3));
+            auto run_chunks = [&](auto kind_c) {
+                if constexpr (decltype(kind_c)::value == 2) {
+                    // ONE accumulator set (main + residual accumulators of a 256-column tile fill TMEM): the issuer cannot start the next
+                    // tile before the last tcgen05.ld of this one, so all chunks leave TMEM first -- as packed halfs, 16 registers per
+                    // chunk -- and the ring buffer / pool / TMA-store halves (~950 cycles each) run under the next tile's K loop
+                    if (p.acc_stages == 1 && nchunk <= 8) {
+                        uint32_t pk4[4][16];
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            if (h + 2 * k < nchunk) compute_chunk(kind_c, h + 2 * k, k & (kEpiBufs - 1), pk4[k]);
+                            DTRAJ_TL(tl_who, 3 + 3 * k);
+                        }
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            if (h + 2 * k < nchunk) emit_chunk(h + 2 * k, k, k & (kEpiBufs - 1), pk4[k]);
+                            DTRAJ_TL(tl_who, 4 + 3 * k);
+                        }
+                        return;
+                    }
+                }
+                for (int c = h, k = 0; c < nchunk; c += 2, ++k) {
+                    uint32_t pk[16];
+                    compute_chunk(kind_c, c, k & (kEpiBufs - 1), pk);
+                    DTRAJ_TL(tl_who, 3 + 3 * (k & 3));
+                    emit_chunk(c, k, k & (kEpiBufs - 1), pk);
+                    DTRAJ_TL(tl_who, 4 + 3 * (k & 3));
+                }
+            };
+            switch (epi_kind) {
+                case 1: run_chunks(std::integral_constant<int, 1>{}); break;
+                case 2: run_chunks(std::integral_constant<int, 2>{}); break;
+                case 3: run_chunks(std::integral_constant<int, 3>{}); break;
+                case 4: run_chunks(std::integral_constant<int, 4>{}); break;
+                default: run_chunks(std::integral_constant<int, 0>{}); break;
             }
 #ifdef DTRAJ_PROBES
             ++tl_tile;
@@ -913,7 +967,7 @@ k_conv_umma_t(const __grid_constant__ UmmaMaps maps, const UmmaConv p) {
                 if (lane == 0) arrive_acc_empty(acc);
             }
             for (int c = h, k = 0; c < nchunk; c += 2, ++k) {
-                const int b = k % kEpiBufs;
+                const int b = k & (kEpiBufs - 1);
                 uint32_t raw[32];
                 ptx::tmem_ld32(t_acc + (uint32_t)(32 * c), raw);
                 if (p.npass == 3) {
@@ -1022,7 +1076,7 @@ k_conv_umma_t(const __grid_constant__ UmmaMaps maps, const UmmaConv p) {
                     if (lane == 0) {
                         if (do_store) { if (kEpiBufs == 2) ptx::bulk_wait_read<1>(); else ptx::bulk_wait_read<0>(); }
                         if (has_res) {
-                            const int nb = (k + 1) % kEpiBufs;
+                            const int nb = (k + 1) & (kEpiBufs - 1);          // (depth 1 or 2)
                             ptx::mbar_expect_tx(rbar + 8u * nb, 4096u);
                             ptx::tma_load_2d(buf0 + 4096u * nb, &maps.res, rbar + 8u * nb, n0 + 32 * (c + 2), row);
                         }
@@ -1147,6 +1201,18 @@ inline cudaError_t umma_set_smem_attr() {
     return e;
 }
 
+// fp16 epilogue: the flag sets of the forward plan's layers that k_conv_umma_t compiles as straight-line code (CONV_POOL / CONV_NOSTORE
+// only steer the stores and go with any of them)
+inline int epi_kind_of(int flags) {
+    switch (flags & ~(CONV_POOL | CONV_NOSTORE)) {
+        case CONV_RELU | CONV_TBIAS: return 1;                 // conv1 of a block
+        case CONV_RELU | CONV_RESACC: return 2;                // conv2 + fused 1x1 residual conv
+        case CONV_RELU | CONV_RESID: return 3;                 // conv2 + identity residual
+        case CONV_RELU | CONV_RESACC | CONV_FINAL: return 4;   // dec1.conv2 + residual conv + final 1x1
+        default: return 0;
+    }
+}
+
 struct UmmaLaunch {            // everything a launch needs, built once per (layer, batch)
     UmmaMaps maps;
     UmmaConv conv;
@@ -1242,6 +1308,7 @@ inline int build_umma_launch(UmmaLaunch* U, const ConvLayer& L, int npass, const
     const size_t misc = 1024 + 512 + ((L.flags & CONV_FINAL) ? 2048 : 0) + cst_bytes + (size_t)c.n_hb * kHaloBytes;
     auto stages_for = [&](int bufs) { return (int)((227 * 1024 - misc - (size_t)kEpiWarps * bufs * 4096) / stage); };
     c.epi_bufs = 2;
+    c.epi_kind = f16 ? epi_kind_of(L.flags) : 0;
     if (!c.halo && nkb_all >= 16 && stages_for(1) > stages_for(2) && stages_for(2) < 8) c.epi_bufs = 1;
     int stages = stages_for(c.epi_bufs);
     if (stages < 2) return fail(DTRAJ_EINVAL, "umma conv: operand ring does not fit");

@@ -449,7 +449,7 @@ k_enc1_f16(const __grid_constant__ Enc1Maps maps, const Enc1hParams p) {
         float amax = 0.f;
         auto arrive_acc_empty = [&]() {
             if constexpr (!kPair) ptx::mbar_arrive(acc_empty0 + 8u * acc);
-            else ptx::mbar_arrive_cluster(ptx::map_to_cta(acc_empty0 + 8u * acc, 0));
+            else ptx::mbar_arrive_cluster_relaxed(ptx::map_to_cta(acc_empty0 + 8u * acc, 0));
         };
         float xn[4] = {0.f, 0.f, 0.f, 0.f};                        // this thread's pixel of x for the NEXT tile
         int smp_n = 0;                                              // sample index of the next tile, fetched two tiles ahead

@@ -279,7 +279,7 @@ k_enc1_umma(const __grid_constant__ Enc1Maps maps, const Enc1Params p) {
         uint32_t acc_ph = 0;
         auto arrive_acc_empty = [&]() {
             if constexpr (!kPair) ptx::mbar_arrive(acc_empty0 + 8u * acc);
-            else ptx::mbar_arrive_cluster(ptx::map_to_cta(acc_empty0 + 8u * acc, 0));
+            else ptx::mbar_arrive_cluster_relaxed(ptx::map_to_cta(acc_empty0 + 8u * acc, 0));
         };
         for (int wk = work0; wk < p.n_tiles; wk += gridDim.x) {
             const int tile = wk + crank;
