@@ -31,7 +31,8 @@
 namespace dtraj {
 
 constexpr int kE1Mid = 8;                        // mid warps (two per TMEM lane quarter)
-constexpr int kE1hThreads = 64 + 32 * kE1Epi + 32 * kE1Mid;
+constexpr int kE1hThreads = 64 + 32 * kE1Epi + 32 * kE1Mid + 32;      // + the signal warp
+constexpr int kE1SigBar = 11;                    // named barriers 11 .. 14: mid warps (bar.arrive) -> signal warp (bar.sync), one per halo buffer in flight
 constexpr int kA1Rows = 192;                     // rows of an A1 operand slice kept in shared memory: 180 halo pixels, rounded up to 64.  The
                                                  // second M = 128 half of conv1's MMA reads rows 128..255 -- 64 rows past the slice, into
                                                  // whatever follows inside the CTA's allocation -- and D1 rows >= 180 are never looked at
@@ -109,6 +110,12 @@ k_enc1_f16(const __grid_constant__ Enc1Maps maps, const Enc1hParams p) {
     const uint16_t cmask = kPair ? 3 : 1;
     const int work0 = (int)blockIdx.x - crank;
     const uint32_t nrep = kPair ? 2u : 1u;                                 // CTAs reporting to the (leader's) barriers
+#ifdef DTRAJ_PROBES
+    // probe build (tools/timeline.py): slot 1 of g_timeline = this kernel's CTA 0: [tile][issuer | first mid warp | epilogue warp 2][event]
+    const bool tl_on = blockIdx.x == 0 && (threadIdx.x & 31) == 0;
+    const int tl_slot = 1;
+    int tl_tile = 0;
+#endif
 
     if (warp == 0) {
         if (ptx::elect_one()) {
@@ -124,7 +131,7 @@ k_enc1_f16(const __grid_constant__ Enc1Maps maps, const Enc1hParams p) {
             for (int i = 0; i < 2; ++i) {
                 ptx::mbar_init(a1_full0 + 8u * i, nrep);
                 ptx::mbar_init(d1_full0 + 8u * i, 1);
-                ptx::mbar_init(d1_empty0 + 8u * i, nrep);
+                ptx::mbar_init(d1_empty0 + 8u * i, kE1Mid * nrep);        // every mid warp reports its last D1 load
             }
             for (int i = 0; i < p.n_patch; ++i) { ptx::mbar_init(patch_full(i), 32); ptx::mbar_init(patch_empty(i), 1); }
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -253,8 +260,10 @@ k_enc1_f16(const __grid_constant__ Enc1Maps maps, const Enc1hParams p) {
             if (n_my > 0) issue_conv1(0);
             if (p.n_d1 == 2 && n_my > 1) issue_conv1(1);
             for (int wk = work0; wk < p.n_tiles && ok; wk += gridDim.x, ++it) {
+                DTRAJ_TL(0, 0);
                 ok = ptx::mbar_wait(errw, acc_empty0 + 8u * acc, acc_ph ^ 1u);
                 ptx::tc_fence_after();
+                DTRAJ_TL(0, 1);
                 const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.acc_cols);
                 uint32_t accum = 0u;
                 for (int c = 0; c < p.n_chunks && ok; ++c) {
@@ -263,6 +272,7 @@ k_enc1_f16(const __grid_constant__ Enc1Maps maps, const Enc1hParams p) {
                     if (p.n_d1 == 1 && c == p.n_chunks - 1 && it + 1 < n_my) issue_conv1(it + 1);
                     ok = ok && ptx::mbar_wait(errw, hfull(hb), hph);      // this chunk's halo tile is in shared memory (both CTAs)
                     ptx::tc_fence_after();
+                    DTRAJ_TL(0, 2 + 2 * (c & 1));
                     const uint32_t hbuf = halo0 + (uint32_t)hb * kE1HaloBytes;
                     int dy = 0, dx = 0;
                     for (int t = 0; t < 9; ++t) {
@@ -278,12 +288,46 @@ k_enc1_f16(const __grid_constant__ Enc1Maps maps, const Enc1hParams p) {
                         if (++dx == 3) { dx = 0; ++dy; }
                     }
                     if constexpr (kPair) ptx::tc_commit_2sm(hempty(hb), cmask); else ptx::tc_commit(hempty(hb));
+                    DTRAJ_TL(0, 3 + 2 * (c & 1));
                     if (++hb == p.n_hbuf) { hb = 0; hph ^= 1u; }
                 }
                 if constexpr (kPair) ptx::tc_commit_2sm(acc_full0 + 8u * acc, cmask); else ptx::tc_commit(acc_full0 + 8u * acc);
                 if (++acc == 2) { acc = 0; acc_ph ^= 1u; }
                 // two D1 buffers: tile it's buffer is free once its conversion is done; refill it for tile it + 2
                 if (p.n_d1 == 2 && it + 2 < n_my) issue_conv1(it + 2);
+                DTRAJ_TL(0, 6);
+#ifdef DTRAJ_PROBES
+                ++tl_tile;
+#endif
+            }
+        }
+    } else if (warp == 2 + kE1Epi + kE1Mid) {
+        // ------------------------------------------------------------ signal warp: publishes what the mid warps wrote
+        // Round 1 published a halo chunk with fence.acq_rel.cluster + relaxed arrivals from a mid thread: MEMBAR.ALL.GPU + CCTL.IVALL,
+        // 1500 - 2800 cycles, between every two chunks of all eight mid warps (they met at a barrier per chunk) -- the mid warps were
+        // the kernel's bottleneck at 3000 cycles per chunk, 1350 of them work, the issuer waiting for halo tiles 60 % of the time
+        // (profiles/r02i_timeline.txt).  Now the mid warps only bar.arrive and go on; this warp waits for all 256 of them and arrives
+        // on the leader's barriers with CTA-scope release: every writer has already made its shared-memory stores visible to the
+        // tensor core's proxy (fence.proxy.async) before the named barrier, so the arrival only has to follow that barrier.
+        auto arrive_one = [&](uint32_t bar) {
+            if constexpr (!kPair) ptx::mbar_arrive(bar);
+            else asm volatile("mbarrier.arrive.release.cta.shared::cluster.b64 _, [%0];" ::"r"(ptx::map_to_cta(bar, 0)) : "memory");
+        };
+        const int G = (int)gridDim.x, Ld = p.n_d1;
+        int hb = 0, it = 0;
+        unsigned cnt = 0;
+        for (int wk = work0; wk < p.n_tiles; wk += G, ++it) {
+            const int b = it & (Ld - 1);
+            const bool next = wk + Ld * G < p.n_tiles;
+            for (int c = 0; c < p.n_chunks; ++c, ++cnt) {
+                asm volatile("bar.sync %0, %1;" ::"r"(kE1SigBar + (int)(cnt & 3u)), "r"(32 * kE1Mid + 32) : "memory");
+                if (lane == 0) {
+                    if (c == 0 && next) ptx::mbar_arrive(patch_empty((it + Ld) & (p.n_patch - 1)));   // every gatherer has arrived
+                    if (c == 0 && next) arrive_one(a1_full0 + 8u * b);
+                    arrive_one(hfull(hb));
+                }
+                __syncwarp();
+                if (++hb == p.n_hbuf) hb = 0;
             }
         }
     } else if (warp >= 2 + kE1Epi) {
@@ -349,10 +393,7 @@ k_enc1_f16(const __grid_constant__ Enc1Maps maps, const Enc1hParams p) {
         // the CTA's single arrival on (the leader's) barrier `bar`, after the role's warps met at a named barrier
         auto arrive_one = [&](uint32_t bar) {
             if constexpr (!kPair) ptx::mbar_arrive(bar);
-            else asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(ptx::map_to_cta(bar, 0)) : "memory");
-        };
-        auto release_fence = [&]() {
-            if constexpr (kPair) asm volatile("fence.acq_rel.cluster;" ::: "memory");
+            else asm volatile("mbarrier.arrive.release.cta.shared::cluster.b64 _, [%0];" ::"r"(ptx::map_to_cta(bar, 0)) : "memory");
         };
         // Software pipeline with lead Ld = n_d1 (buffers of A1 and of D1).  At the top of iteration `it`: A1(it .. it+Ld-1) are
         // published (their conv1 issued or done), the patch of tile it + Ld is loaded or in flight, vq[k] = variant of tile
@@ -361,6 +402,7 @@ k_enc1_f16(const __grid_constant__ Enc1Maps maps, const Enc1hParams p) {
         const int G = (int)gridDim.x, Ld = p.n_d1;
         int hb = 0, it = 0, vq[3] = {0, 0, 0};
         uint32_t hph = 0;
+        unsigned cnt = 0;                                           // chunks handed to the signal warp
         if (work0 < p.n_tiles) {
             fetch_idx(work0);
             for (int j = 0; j < Ld; ++j) {                         // A1(0 .. Ld-1)
@@ -371,7 +413,7 @@ k_enc1_f16(const __grid_constant__ Enc1Maps maps, const Enc1hParams p) {
                     gather_a1(j, j);
                     ptx::fence_proxy_async();
                     asm volatile("bar.sync 9, 256;" ::: "memory");
-                    if (mt == 0) { ptx::mbar_arrive(patch_empty(j & (p.n_patch - 1))); release_fence(); arrive_one(a1_full0 + 8u * j); }
+                    if (mt == 0) { ptx::mbar_arrive(patch_empty(j & (p.n_patch - 1))); arrive_one(a1_full0 + 8u * j); }
                 }
             }
             vq[Ld] = var_n;
@@ -383,10 +425,17 @@ k_enc1_f16(const __grid_constant__ Enc1Maps maps, const Enc1hParams p) {
             tile_geom(tile, img, y0, x0);
             const bool real = tile < p.n_tiles;
             const int b = it & (Ld - 1);
+#ifdef DTRAJ_PROBES
+            const bool tl_outer = tl_on;
+            const bool tl_on = tl_outer && mt == 0;
+#endif
+            DTRAJ_TL(1, 0);
             ptx::mbar_wait(errw, d1_full0 + 8u * b, (uint32_t)((it >> (Ld - 1)) & 1));    // conv1(it) done: D1 readable, A1 buffer b free
             ptx::tc_fence_after();
+            DTRAJ_TL(1, 1);
             const bool next = wk + Ld * G < p.n_tiles;
-            if (next) gather_a1(b, it + Ld);                        // A1(it + Ld); published together with the first halo chunk below
+            if (next) gather_a1(b, it + Ld);
+            DTRAJ_TL(1, 2);                        // A1(it + Ld); published together with the first halo chunk below
             const int var0 = vq[0];
             const float* tb = p.tb_rows ? p.tbias + (size_t)var0 * p.tb_var_stride : tbs + var0 * coutp;
             vq[0] = vq[1];
@@ -404,37 +453,54 @@ k_enc1_f16(const __grid_constant__ Enc1Maps maps, const Enc1hParams p) {
                 if (has1) ptx::tmem_ld32(t_d1 + (uint32_t)(p.acc_cols + col0), r1);
                 ptx::tmem_ld_wait();
                 ptx::tc_fence_before();
-                ptx::mbar_wait(errw, hempty(hb), hph ^ 1u);               // the conv2 MMAs that read this buffer have retired
-                uint8_t* hbuf = gbase + (halo0 - base) + (size_t)hb * kE1HaloBytes;
-                // h = relu(D1) + time bias (conv1's folded bias is inside D1), rounded to fp16; zero rows outside the image
-                auto emit = [&](const uint32_t* raw, int px, bool inside) {
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        uint4 o = make_uint4(0u, 0u, 0u, 0u);
-                        if (inside) {
-                            const float4 ta = *reinterpret_cast<const float4*>(tb + col0 + 8 * j), tc = *reinterpret_cast<const float4*>(tb + col0 + 8 * j + 4);
-                            __half2* oh = reinterpret_cast<__half2*>(&o);
-                            oh[0] = __floats2half2_rn(fmaxf(__uint_as_float(raw[8 * j]), 0.f) + ta.x, fmaxf(__uint_as_float(raw[8 * j + 1]), 0.f) + ta.y);
-                            oh[1] = __floats2half2_rn(fmaxf(__uint_as_float(raw[8 * j + 2]), 0.f) + ta.z, fmaxf(__uint_as_float(raw[8 * j + 3]), 0.f) + ta.w);
-                            oh[2] = __floats2half2_rn(fmaxf(__uint_as_float(raw[8 * j + 4]), 0.f) + tc.x, fmaxf(__uint_as_float(raw[8 * j + 5]), 0.f) + tc.y);
-                            oh[3] = __floats2half2_rn(fmaxf(__uint_as_float(raw[8 * j + 6]), 0.f) + tc.z, fmaxf(__uint_as_float(raw[8 * j + 7]), 0.f) + tc.w);
-                        }
-                        *reinterpret_cast<uint4*>(hbuf + px * 128 + (((uint32_t)(4 * h + j) ^ (uint32_t)(px & 7)) << 4)) = o;
-                    }
-                };
-                emit(r0, px0, in0);
-                if (has1 && px1 < kE1HaloRows) emit(r1, px1, in1);
-                ptx::fence_proxy_async();                           // generic-proxy writes -> visible to the tensor core
-                asm volatile("bar.sync 9, 256;" ::: "memory");
-                if (mt == 0) {                                      // one release fence, then relaxed arrivals
-                    if (c == 0 && next) ptx::mbar_arrive(patch_empty((it + Ld) & (p.n_patch - 1)));   // every gatherer is past the barrier
-                    release_fence();
-                    if (c == 0 && next) arrive_one(a1_full0 + 8u * b);
-                    arrive_one(hfull(hb));
-                    if (c == p.n_chunks - 1) arrive_one(d1_empty0 + 8u * b);      // this D1 buffer may be overwritten
+                // D1 is in registers: with the tile's last chunk this warp is done with the buffer.  Reported HERE, not with the chunk's
+                // publication ~2000 cycles later: with one D1 buffer (coutp = 128) the next tile's conv1 -- and through it the whole next
+                // tile of the mid warps -- hangs on this arrival (profiles/r02i_timeline.txt: they idled 2500 of 6600 cycles per tile)
+                if (c == p.n_chunks - 1) {
+                    __syncwarp();
+                    if (lane == 0) arrive_one(d1_empty0 + 8u * b);
                 }
+                DTRAJ_TL(1, 3 + 4 * (c & 1));
+                ptx::mbar_wait(errw, hempty(hb), hph ^ 1u);               // the conv2 MMAs that read this buffer have retired
+                DTRAJ_TL(1, 4 + 4 * (c & 1));
+                uint8_t* hbuf = gbase + (halo0 - base) + (size_t)hb * kE1HaloBytes;
+                // h = relu(D1) + time bias (conv1's folded bias is inside D1), rounded to fp16; zero rows outside the image.
+                // Both rows of a thread in ONE branch-free pass: they share the time-bias loads, and the two independent chains fill
+                // each other's latencies (as two predicated passes the quarters that own two rows took 1800 cycles per chunk and set
+                // the pace of all mid warps, profiles/r02i_timeline.txt)
+                const bool st1 = has1 && px1 < kE1HaloRows;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float4 ta = *reinterpret_cast<const float4*>(tb + col0 + 8 * j), tc = *reinterpret_cast<const float4*>(tb + col0 + 8 * j + 4);
+                    const float t8[8] = {ta.x, ta.y, ta.z, ta.w, tc.x, tc.y, tc.z, tc.w};
+                    uint4 o0, o1;
+                    __half2* h0 = reinterpret_cast<__half2*>(&o0);
+                    __half2* h1 = reinterpret_cast<__half2*>(&o1);
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        h0[e] = __floats2half2_rn(fmaxf(__uint_as_float(r0[8 * j + 2 * e]), 0.f) + t8[2 * e], fmaxf(__uint_as_float(r0[8 * j + 2 * e + 1]), 0.f) + t8[2 * e + 1]);
+                        if (has1) h1[e] = __floats2half2_rn(fmaxf(__uint_as_float(r1[8 * j + 2 * e]), 0.f) + t8[2 * e], fmaxf(__uint_as_float(r1[8 * j + 2 * e + 1]), 0.f) + t8[2 * e + 1]);
+                    }
+                    if (!in0) o0 = make_uint4(0u, 0u, 0u, 0u);
+                    *reinterpret_cast<uint4*>(hbuf + px0 * 128 + (((uint32_t)(4 * h + j) ^ (uint32_t)(px0 & 7)) << 4)) = o0;
+                    if (has1) {
+                        if (!in1) o1 = make_uint4(0u, 0u, 0u, 0u);
+                        if (st1) *reinterpret_cast<uint4*>(hbuf + px1 * 128 + (((uint32_t)(4 * h + j) ^ (uint32_t)(px1 & 7)) << 4)) = o1;
+                    }
+                }
+                DTRAJ_TL(1, 5 + 4 * (c & 1));
+                ptx::fence_proxy_async();                           // generic-proxy writes -> visible to the tensor core
+                // hand the chunk (with c == 0: also A1 of tile it + Ld and its consumed patch) to the signal warp and go on.  At most
+                // n_hbuf <= 4 chunks are in flight (hempty above), one named barrier each
+                asm volatile("bar.arrive %0, %1;" ::"r"(kE1SigBar + (int)(cnt & 3u)), "r"(32 * kE1Mid + 32) : "memory");
+                ++cnt;
+                DTRAJ_TL(1, 6 + 4 * (c & 1));
                 if (++hb == p.n_hbuf) { hb = 0; hph ^= 1u; }
             }
+            DTRAJ_TL(1, 11);
+#ifdef DTRAJ_PROBES
+            ++tl_tile;
+#endif
         }
     } else {
         // ------------------------------------------------------------ epilogue (warps 2..5): thread = output pixel
@@ -483,13 +549,20 @@ k_enc1_f16(const __grid_constant__ Enc1Maps maps, const Enc1hParams p) {
                 prefetch(wk + (int)gridDim.x, smp_n);
                 fetch_idx(wk + 2 * (int)gridDim.x);
             }
+#ifdef DTRAJ_PROBES
+            const bool tl_outer = tl_on;
+            const bool tl_on = tl_outer && ew == 0;
+#endif
+            DTRAJ_TL(2, 0);
             ptx::mbar_wait(errw, acc_full0 + 8u * acc, acc_ph);
             ptx::tc_fence_after();
+            DTRAJ_TL(2, 1);
             const uint32_t t_acc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.acc_cols);
             for (int c = 0; c < nchunk; ++c) {
                 uint32_t raw[32];
                 ptx::tmem_ld32(t_acc + (uint32_t)(32 * c), raw);
                 ptx::tmem_ld_wait();
+                DTRAJ_TL(2, 2 + 3 * (c & 3));
                 if (c == nchunk - 1) {
                     ptx::tc_fence_before();
                     asm volatile("bar.sync 10, 128;" ::: "memory");
@@ -524,6 +597,7 @@ k_enc1_f16(const __grid_constant__ Enc1Maps maps, const Enc1hParams p) {
                     }
                     *reinterpret_cast<uint4*>(rowp + (((uint32_t)j ^ swz) << 4)) = pk;
                 }
+                DTRAJ_TL(2, 3 + 3 * (c & 3));
                 __syncwarp();
                 if (real) {
                     // the warp's 4 x 8 pixel patch holds 2 x 4 complete 2x2 windows: lane -> (window, 16-byte cell)
@@ -544,7 +618,11 @@ k_enc1_f16(const __grid_constant__ Enc1Maps maps, const Enc1hParams p) {
                     *reinterpret_cast<uint4*>(p.pool_out + (((size_t)img * (p.H >> 1) + py) * Wh + pxx) * coutp + 32 * c + 8 * (int)jj) = o4;
                 }
                 __syncwarp();
+                DTRAJ_TL(2, 4 + 3 * (c & 3));
             }
+#ifdef DTRAJ_PROBES
+            ++tl_tile;
+#endif
             if (++acc == 2) { acc = 0; acc_ph ^= 1u; }
         }
         if (!(amax <= 65504.f)) atomicOr(errw, 2u);
@@ -601,7 +679,7 @@ inline int build_enc1h_launch(Enc1hLaunch* E, int C, int H, int coutp, int cout_
         if (f + kE1HaloBytes > 227 * 1024) return 0;
         int nh = (int)((227 * 1024 - f) / kE1HaloBytes);
         if (nh > 2 * p.n_chunks) nh = 2 * p.n_chunks;
-        return nh > 8 ? 8 : nh;
+        return nh > 4 ? 4 : nh;                   // (one named barrier per buffer in flight: kE1SigBar .. kE1SigBar + 3)
     };
     p.n_patch = halo_bufs(4) == halo_bufs(2) ? 4 : 2;
     const size_t fixed = fixed_for(E->pair, p.n_patch);

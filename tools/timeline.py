@@ -31,16 +31,24 @@ tl = np.zeros((2, 16, 3, 16), dtype=np.int64)
 lib.dtraj_probe_timeline.restype = C.c_int
 lib.dtraj_probe_timeline.argtypes = [C.c_void_p, C.c_int64]
 _lib.check(lib.dtraj_probe_timeline(tl.ctypes.data, tl.size))
-names = ["enc2.conv2 +res +pool", "dec2.conv2 +res"]
-for s in range(2):
-    print(f"== {names[s]}: CTA 0, cycles relative to the issuer's first stamp of tile 2")
-    t0 = tl[s, 2, 0, 0]
-    for t in range(2, 8):
-        iss = tl[s, t, 0, :3] - t0
-        print(f"tile {t}: issuer  start {iss[0]:7d}  acc drained {iss[1]:7d}  committed {iss[2]:7d}   (K loop issue {iss[2] - iss[1]} cycles)")
-        for w in (1, 2):
-            e = tl[s, t, w] - t0
-            chunks = "  ".join(f"[ld {e[2 + 3 * k]:7d} cmp {e[3 + 3 * k]:7d} emit {e[4 + 3 * k]:7d}]" for k in range(4))
-            print(f"        warp {2 + 4 * (w - 1)}: start {e[0]:7d}  acc ready {e[1]:7d}  {chunks}")
-    per_tile = (tl[s, 7, 0, 0] - tl[s, 2, 0, 0]) / 5
-    print(f"   tile period {per_tile:.0f} cycles")
+print("== enc2.conv2 +res +pool (k_conv_umma_t): CTA 0, cycles relative to the issuer's first stamp of tile 2")
+t0 = tl[0, 2, 0, 0]
+for t in range(2, 8):
+    iss = tl[0, t, 0, :3] - t0
+    print(f"tile {t}: issuer  start {iss[0]:7d}  acc drained {iss[1]:7d}  committed {iss[2]:7d}   (K loop issue {iss[2] - iss[1]} cycles)")
+    for w in (1, 2):
+        e = tl[0, t, w] - t0
+        chunks = "  ".join(f"[ld {e[2 + 3 * k]:7d} cmp {e[3 + 3 * k]:7d} emit {e[4 + 3 * k]:7d}]" for k in range(4))
+        print(f"        warp {2 + 4 * (w - 1)}: start {e[0]:7d}  acc ready {e[1]:7d}  {chunks}")
+print(f"   tile period {(tl[0, 7, 0, 0] - tl[0, 2, 0, 0]) / 5:.0f} cycles")
+print("== enc1 fused (k_enc1_f16): CTA 0, cycles relative to the issuer's first stamp of tile 4")
+t0 = tl[1, 4, 0, 0]
+for t in range(4, 10):
+    i_ = tl[1, t, 0] - t0
+    m_ = tl[1, t, 1] - t0
+    e_ = tl[1, t, 2] - t0
+    print(f"tile {t}: issuer  top {i_[0]:7d}  acc free {i_[1]:7d}  chunk0 [halo ready {i_[2]:7d} issued {i_[3]:7d}]  chunk1 [halo ready {i_[4]:7d} issued {i_[5]:7d}]  end {i_[6]:7d}")
+    print(f"        mid w0:  top {m_[0]:7d}  D1 ready {m_[1]:7d}  A1 gathered {m_[2]:7d}  " +
+          "  ".join(f"chunk{c} [ld {m_[3 + 4 * c]:7d} buf free {m_[4 + 4 * c]:7d} written {m_[5 + 4 * c]:7d} barrier {m_[6 + 4 * c]:7d}]" for c in range(2)) + f"  end {m_[11]:7d}")
+    print(f"        epi w2:  top {e_[0]:7d}  acc ready {e_[1]:7d}  " + "  ".join(f"[ld {e_[2 + 3 * k]:7d} cmp {e_[3 + 3 * k]:7d} pool {e_[4 + 3 * k]:7d}]" for k in range(4)))
+print(f"   tile period {(tl[1, 9, 0, 0] - tl[1, 4, 0, 0]) / 5:.0f} cycles")
