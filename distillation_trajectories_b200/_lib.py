@@ -8,7 +8,9 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libdtraj.so")
+# DTRAJ_LIB=<path>: load that build of the library instead (A/B timing of two builds inside one GPU job, tools/ab.sh; the driver's
+# "which .so was loaded" record then shows that file)
+LIB_PATH = os.environ.get("DTRAJ_LIB") or os.path.join(_HERE, "csrc", "libdtraj.so")
 
 PREC_FP32, PREC_TF32, PREC_TF32X3, PREC_F16 = 0, 1, 2, 3
 VAR_NONE, VAR_COND0, VAR_COND1 = 0, 1, 2
