@@ -38,6 +38,7 @@ __device__ unsigned int g_umma_error = 0;
 // Probe build only (tools/timeline.py): SM-clock stamps of CTA 0's issuer and two of its epilogue warps over its first 16 tiles of a
 // 256-column CONV_RESACC + CONV_POOL layer at 8x8 -- [this kernel | k_enc1_f16][tile][issuer | epilogue warp 2 | epilogue warp 6][event].
 __device__ long long g_timeline[2][16][3][16];
+__device__ int g_tl_select[4] = {CONV_RESACC | CONV_POOL, CONV_RESACC | CONV_POOL, 256, 8};     // {flag mask, flag value, coutp, W} of the recorded layer
 #define DTRAJ_TL(who, ev) do { if (tl_on && tl_tile < 16) g_timeline[tl_slot][tl_tile][who][ev] = clock64(); } while (0)
 #else
 #define DTRAJ_TL(who, ev) do { } while (0)
@@ -297,7 +298,8 @@ k_conv_umma_t(const __grid_constant__ UmmaMaps maps, const UmmaConv p) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     unsigned int* const errw = p.L.err ? p.L.err : &g_umma_error;
 #ifdef DTRAJ_PROBES
-    const bool tl_on = blockIdx.x == 0 && (threadIdx.x & 31) == 0 && (p.L.flags & CONV_RESACC) && (p.L.flags & CONV_POOL) && p.L.coutp == 256 && p.L.W == 8;
+    const bool tl_on = blockIdx.x == 0 && (threadIdx.x & 31) == 0 && (p.L.flags & g_tl_select[0]) == g_tl_select[1] &&
+                       p.L.coutp == g_tl_select[2] && p.L.W == g_tl_select[3];
     const int tl_slot = 0;        // (slot 1: k_enc1_f16)
     int tl_tile = 0;
 #endif

@@ -1087,6 +1087,12 @@ extern "C" int dtraj_probe_tma_permuted(int32_t n_img, int32_t img0, float* out_
     return 0;
 }
 
+// tools/timeline.py: which layer k_conv_umma_t records: (flags & mask) == value, coutp, W
+extern "C" int dtraj_probe_timeline_select(int mask, int value, int coutp, int W) {
+    const int sel[4] = {mask, value, coutp, W};
+    DTRAJ_CUDA(cudaMemcpyToSymbol(g_tl_select, sel, sizeof(sel)));
+    return 0;
+}
 // tools/timeline.py: copy out (and clear) the SM-clock stamps k_conv_umma_t leaves in a probe build
 extern "C" int dtraj_probe_timeline(long long* host_out, int64_t n) {
     if (n != (int64_t)(sizeof(g_timeline) / sizeof(long long))) return fail(DTRAJ_EINVAL, "probe_timeline: expected %zu values", sizeof(g_timeline) / sizeof(long long));

@@ -21,9 +21,15 @@ import bench
 from distillation_trajectories_b200 import grid
 
 seeds = int(sys.argv[1]) if len(sys.argv) > 1 else 592
+# optional: the conv layer to record, as "<flag mask> <flag value> <coutp> <W>" (csrc/conv_simt.cuh flag bits), and the size factor
+sel = [int(a, 0) for a in sys.argv[2:6]] if len(sys.argv) >= 6 else None
+sf = float(sys.argv[6]) if len(sys.argv) > 6 else 1.0
 dev = torch.device("cuda", 0)
 ck = grid.stage_chunk(list(range(seeds)), bench.Cfg, bench.GUIDANCE, dev)
-m = bench.make_model(bench.Cfg, 1.0, 0, dev)
+m = bench.make_model(bench.Cfg, sf, 0 if sf == 1.0 else 1000 + int(sf * 100), dev)
+if sel:
+    _lib.load().dtraj_probe_timeline_select.argtypes = [C.c_int] * 4
+    _lib.check(_lib.load().dtraj_probe_timeline_select(*sel))
 grid.run_chunk(m, [m], ck, dev, "f16")
 torch.cuda.synchronize()
 lib = _lib.load()
@@ -31,7 +37,7 @@ tl = np.zeros((2, 16, 3, 16), dtype=np.int64)
 lib.dtraj_probe_timeline.restype = C.c_int
 lib.dtraj_probe_timeline.argtypes = [C.c_void_p, C.c_int64]
 _lib.check(lib.dtraj_probe_timeline(tl.ctypes.data, tl.size))
-print("== enc2.conv2 +res +pool (k_conv_umma_t): CTA 0, cycles relative to the issuer's first stamp of tile 2")
+print(f"== k_conv_umma_t layer {sel or 'enc2.conv2 +res +pool'}: CTA 0, cycles relative to the issuer's first stamp of tile 2")
 t0 = tl[0, 2, 0, 0]
 for t in range(2, 8):
     iss = tl[0, t, 0, :3] - t0
