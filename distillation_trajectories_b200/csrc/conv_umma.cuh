@@ -190,6 +190,12 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
 __device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint32_t cluster_addr) {
     asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
+// ... and with CTA-scope release, for barriers that hand over SHARED MEMORY written by this CTA's threads to the pair's tensor core:
+// every writer has executed fence.proxy.async on its stores and been synchronised with the arriving thread (named barrier /
+// __syncwarp), so the remote arrival only has to stay behind that synchronisation -- no MEMBAR.ALL.GPU.
+__device__ __forceinline__ void mbar_arrive_cluster_cta(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cta.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
 __device__ __forceinline__ uint32_t cluster_ctarank() {
     uint32_t r;
     asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));

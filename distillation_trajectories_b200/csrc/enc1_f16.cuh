@@ -311,7 +311,7 @@ k_enc1_f16(const __grid_constant__ Enc1Maps maps, const Enc1hParams p) {
         // tensor core's proxy (fence.proxy.async) before the named barrier, so the arrival only has to follow that barrier.
         auto arrive_one = [&](uint32_t bar) {
             if constexpr (!kPair) ptx::mbar_arrive(bar);
-            else asm volatile("mbarrier.arrive.release.cta.shared::cluster.b64 _, [%0];" ::"r"(ptx::map_to_cta(bar, 0)) : "memory");
+            else ptx::mbar_arrive_cluster_cta(ptx::map_to_cta(bar, 0));
         };
         const int G = (int)gridDim.x, Ld = p.n_d1;
         int hb = 0, it = 0;
@@ -393,7 +393,7 @@ k_enc1_f16(const __grid_constant__ Enc1Maps maps, const Enc1hParams p) {
         // the CTA's single arrival on (the leader's) barrier `bar`, after the role's warps met at a named barrier
         auto arrive_one = [&](uint32_t bar) {
             if constexpr (!kPair) ptx::mbar_arrive(bar);
-            else asm volatile("mbarrier.arrive.release.cta.shared::cluster.b64 _, [%0];" ::"r"(ptx::map_to_cta(bar, 0)) : "memory");
+            else ptx::mbar_arrive_cluster_cta(ptx::map_to_cta(bar, 0));
         };
         // Software pipeline with lead Ld = n_d1 (buffers of A1 and of D1).  At the top of iteration `it`: A1(it .. it+Ld-1) are
         // published (their conv1 issued or done), the patch of tile it + Ld is loaded or in flight, vq[k] = variant of tile

@@ -262,7 +262,7 @@ k_enc1_umma(const __grid_constant__ Enc1Maps maps, const Enc1Params p) {
                 __syncwarp();
                 if (lane == 0) {
                     if constexpr (!kPair) ptx::mbar_arrive(hfull(hb));
-                    else ptx::mbar_arrive_cluster(ptx::map_to_cta(hfull(hb), 0));
+                    else ptx::mbar_arrive_cluster_cta(ptx::map_to_cta(hfull(hb), 0));
                 }
                 if (++hb == p.n_hbuf) { hb = 0; hph ^= 1u; }
             }
