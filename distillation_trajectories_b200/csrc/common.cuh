@@ -106,13 +106,16 @@ __device__ __forceinline__ float4 act_lo4(float4 v) {
 // overlap the tail of the current one -- also inside the captured CUDA graph.  Both instructions are no-ops for a
 // kernel launched without the attribute.  Measured on B200 (bench, fp16 mode, CUDA graph): 132.2 ms per step with the
 // attribute against 132.7 ms without -- the step sits at the board's power cap, so closing launch gaps buys almost
-// nothing; the attribute is therefore OFF unless DTRAJ_PDL=1 is set.
+// nothing for full-size launches.
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
-inline bool use_pdl() {
-    static int v = -1;
-    if (v < 0) v = getenv("DTRAJ_PDL") ? atoi(getenv("DTRAJ_PDL")) : 0;
-    return v != 0;
+// Round 2: small launches are a different case -- a 2-row forward is 19 launches of 1..4 CTAs, ~10 us each of which half is
+// prologue and launch latency (batch-1 trajectory 17.3 -> 16.2 ms with the attribute).  Default now: ON for launches of at most
+// 64 CTAs, off above; DTRAJ_PDL=0 / 1 force it off / on everywhere.
+inline bool use_pdl(unsigned grid) {
+    static int v = -2;
+    if (v == -2) v = getenv("DTRAJ_PDL") ? (atoi(getenv("DTRAJ_PDL")) != 0) : -1;
+    return v == 1 || (v == -1 && grid <= 64u);
 }
 // <<<grid, block, smem, st>>> with optional cluster width and the PDL attribute
 template <typename... KArgs, typename... Args>
@@ -133,7 +136,7 @@ inline cudaError_t launch_ex(void (*kernel)(KArgs...), unsigned grid, unsigned b
         attr[n].val.clusterDim.z = 1;
         ++n;
     }
-    if (pdl && use_pdl()) {
+    if (pdl && use_pdl(grid)) {
         attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         attr[n].val.programmaticStreamSerializationAllowed = 1;
         ++n;

@@ -30,5 +30,5 @@ s1 = timed(lambda: diffusion.p_sample_loop(teacher, (64, 1, 16, 16), 50, params,
 torch.manual_seed(42)
 noise = torch.randn(1, 1, 16, 16)
 b1 = timed(lambda: te.generate_trajectory(teacher, noise, 50, dev, seed=42, guidance_scale=7.5), 20)
-print(f"DTRAJ_PDL={os.environ.get('DTRAJ_PDL', '0')}: S1 batch 64: {s1 * 1e3:.2f} ms per loop = {64 / s1:.0f} trajectories/s;  "
+print(f"DTRAJ_PDL={os.environ.get('DTRAJ_PDL', 'auto')}: S1 batch 64: {s1 * 1e3:.2f} ms per loop = {64 / s1:.0f} trajectories/s;  "
       f"batch-1 S2: {b1 * 1e3:.2f} ms per trajectory")

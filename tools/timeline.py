@@ -24,9 +24,11 @@ seeds = int(sys.argv[1]) if len(sys.argv) > 1 else 592
 # optional: the conv layer to record, as "<flag mask> <flag value> <coutp> <W>" (csrc/conv_simt.cuh flag bits), and the size factor
 sel = [int(a, 0) for a in sys.argv[2:6]] if len(sys.argv) >= 6 else None
 sf = float(sys.argv[6]) if len(sys.argv) > 6 else 1.0
+H = int(sys.argv[7]) if len(sys.argv) > 7 else 16
 dev = torch.device("cuda", 0)
-ck = grid.stage_chunk(list(range(seeds)), bench.Cfg, bench.GUIDANCE, dev)
-m = bench.make_model(bench.Cfg, sf, 0 if sf == 1.0 else 1000 + int(sf * 100), dev)
+cfg = bench.Cfg if H == 16 else bench.Cfg32
+ck = grid.stage_chunk(list(range(seeds)), cfg, bench.GUIDANCE if H == 16 else [7.5], dev)
+m = bench.make_model(cfg, sf, 0 if sf == 1.0 else 1000 + int(sf * 100), dev)
 if sel:
     _lib.load().dtraj_probe_timeline_select.argtypes = [C.c_int] * 4
     _lib.check(_lib.load().dtraj_probe_timeline_select(*sel))
