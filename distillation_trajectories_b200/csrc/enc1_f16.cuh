@@ -204,7 +204,12 @@ k_enc1_f16(const __grid_constant__ Enc1Maps maps, const Enc1hParams p) {
             int pb = 0;
             uint32_t pph = 0;
             bool ok = true;
-            const int HW = p.H * p.W, n_el = C * kE1PatchH * kE1PatchW;
+            // 8-byte copies: a patch row starts at x0 - 2 (even), so its 12 floats are 6 aligned pairs that lie inside or outside the image
+            // together.  30 lanes = 5 rows x 6 pairs per trip, (channel, row) carried incrementally: 4 trips at C = 1, 12 at C = 3
+            // (the first form -- 4-byte copies indexed by two divisions -- took ~4800 cycles per C = 3 patch in this one warp and
+            // was the kernel's pace on 3-channel models, profiles/r02i_timeline.txt)
+            const int HW = p.H * p.W, n_rows = C * kE1PatchH;
+            const int l_row = lane / 6, l_pair = lane - 6 * l_row;           // lanes 30, 31 idle
             for (int wk = work0; wk < p.n_tiles && ok; wk += gridDim.x) {
                 const int tile = wk + crank;
                 int img, y0, x0;
@@ -214,13 +219,17 @@ k_enc1_f16(const __grid_constant__ Enc1Maps maps, const Enc1hParams p) {
                 const float* xs = p.x + (size_t)smp * p.x_stride;
                 ok = ptx::mbar_wait(errw, patch_empty(pb), pph ^ 1u);
                 const uint32_t dst0 = patch0 + (uint32_t)pb * patch_bytes;
-                for (int e = lane; e < n_el; e += 32) {
-                    const int ci = e / (kE1PatchH * kE1PatchW), rem = e - ci * (kE1PatchH * kE1PatchW);
-                    const int r = rem / kE1PatchW, cc = rem - r * kE1PatchW;
-                    const int sy = y0 - 2 + r, sx = x0 - 2 + cc;
-                    const bool in = real && sy >= 0 && sy < p.H && sx >= 0 && sx < p.W;
+                const int sx = x0 - 2 + 2 * l_pair;
+                const bool in_x = real && lane < 30 && sx >= 0 && sx < p.W;
+                int ci = 0, r = l_row;                              // this lane's (channel, patch row) of the current trip
+                for (int rp = l_row; rp < n_rows; rp += 5) {
+                    const int sy = y0 - 2 + r;
+                    const bool in = in_x && sy >= 0 && sy < p.H;
                     const float* src = in ? xs + (size_t)ci * HW + sy * p.W + sx : p.x;
-                    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst0 + 4u * (uint32_t)e), "l"(src), "r"(in ? 4u : 0u) : "memory");
+                    if (lane < 30)
+                        asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst0 + 4u * (uint32_t)(rp * kE1PatchW + 2 * l_pair)), "l"(src), "r"(in ? 8u : 0u) : "memory");
+                    r += 5;
+                    if (r >= kE1PatchH) { r -= kE1PatchH; ++ci; }
                 }
                 asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(patch_full(pb)) : "memory");
                 if (++pb == p.n_patch) { pb = 0; pph ^= 1u; }
@@ -363,6 +372,9 @@ k_enc1_f16(const __grid_constant__ Enc1Maps maps, const Enc1hParams p) {
         auto gather_a1 = [&](int buf, int pit) {
             const int pbuf = pit & (p.n_patch - 1);
             ptx::mbar_wait(errw, patch_full(pbuf), (uint32_t)((pit / p.n_patch) & 1));
+#ifdef DTRAJ_PROBES
+            if (tl_on && mt == 0 && tl_tile < 16) g_timeline[1][tl_tile][1][12] = clock64();
+#endif
             const float* patch = reinterpret_cast<const float*>(gbase + (patch0 - base) + (uint32_t)pbuf * patch_bytes);
             uint8_t* const a1b = a1p + (uint32_t)buf * a1_buf;
 #pragma unroll

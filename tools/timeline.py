@@ -56,7 +56,7 @@ for t in range(4, 10):
     m_ = tl[1, t, 1] - t0
     e_ = tl[1, t, 2] - t0
     print(f"tile {t}: issuer  top {i_[0]:7d}  acc free {i_[1]:7d}  chunk0 [halo ready {i_[2]:7d} issued {i_[3]:7d}]  chunk1 [halo ready {i_[4]:7d} issued {i_[5]:7d}]  end {i_[6]:7d}")
-    print(f"        mid w0:  top {m_[0]:7d}  D1 ready {m_[1]:7d}  A1 gathered {m_[2]:7d}  " +
+    print(f"        mid w0:  top {m_[0]:7d}  D1 ready {m_[1]:7d}  patch ready {m_[12]:7d}  A1 gathered {m_[2]:7d}  " +
           "  ".join(f"chunk{c} [ld {m_[3 + 4 * c]:7d} buf free {m_[4 + 4 * c]:7d} written {m_[5 + 4 * c]:7d} barrier {m_[6 + 4 * c]:7d}]" for c in range(2)) + f"  end {m_[11]:7d}")
     print(f"        epi w2:  top {e_[0]:7d}  acc ready {e_[1]:7d}  " + "  ".join(f"[ld {e_[2 + 3 * k]:7d} cmp {e_[3 + 3 * k]:7d} pool {e_[4 + 3 * k]:7d}]" for k in range(4)))
 print(f"   tile period {(tl[1, 9, 0, 0] - tl[1, 4, 0, 0]) / 5:.0f} cycles")
