@@ -67,6 +67,9 @@ struct UmmaConv {
                                //    stages only ITS half of the weight tile, the leader CTA issues for both
     int kbs;                   // 32-channel K blocks per pipeline stage (2 when both sources have an even number of them)
     int epi_bufs;              // epilogue ring depth per warp (1 when the freed 32 KB buy another operand stage)
+    int posm;                  // position-major tiles (fp16, maps of <= 4x4): a tile = ONE output position of 128 images, K loop over
+                               //    the taps that fall inside the map only; nblk_img = tiles per position
+    int nblk_img;
     int epi_kind;              // fp16 epilogue: 1..4 = one of the flag sets compiled as straight-line code (epi_kind_of), 0 = generic
     int box_h, box_n;          // A box = {32, W, box_h, box_n}
     int tiles_per_img;         // >= 1
@@ -426,6 +429,47 @@ k_conv_umma_t(const __grid_constant__ UmmaMaps maps, const UmmaConv p) {
                 }
                 ok = false;                                        // (skip the im2col loop below)
             }
+            if (p.posm) {
+                // ---- position-major tiles: rows = 128 images at one output position (px, py); a tap (dy, dx) that leaves the map is
+                // all zeros for every row of the tile and is skipped -- 4 of 9 taps remain on a 2x2 map, 6.25 on average on 4x4, 1 on 1x1
+                for (int wk = work0; wk < p.n_work && ok; wk += gridDim.x) {
+                    const int work = wk + crank;
+                    const int tile = work / p.n_split, n0 = (work % p.n_split) * ncols;
+                    const int pos = tile / p.nblk_img, img0 = (tile - pos * p.nblk_img) * 128;
+                    const int py = pos / p.L.W, px = pos - py * p.L.W;
+                    auto stage1 = [&](const CUtensorMap* am, const CUtensorMap* wm, int c0, int x, int y, int b_row) -> bool {
+                        if (!ptx::mbar_wait(errw, empty_bar(s), ph ^ 1u)) return false;
+                        const uint32_t st0 = base + s * stage_bytes;
+                        uint32_t fb = full_bar(s);
+                        if constexpr (kPair) fb = ptx::map_to_cta(fb, 0);
+                        if (!kPair || crank == 0) ptx::mbar_expect_tx(full_bar(s), tx_bytes);
+                        if constexpr (!kPair) {
+                            ptx::tma_load_4d(st0, am, fb, c0, x, y, img0);
+                            ptx::tma_load_2d(st0 + w_base_off, wm, fb, 0, b_row);
+                        } else {
+                            ptx::tma_load_4d_2sm(st0, am, fb, c0, x, y, img0);
+                            ptx::tma_load_2d_2sm(st0 + w_base_off, wm, fb, 0, b_row);
+                        }
+                        if (++s == p.stages) { s = 0; ph ^= 1u; }
+                        return true;
+                    };
+                    for (int tap = 0; tap < 9 && ok; ++tap) {
+                        const int y = py + tap / 3 - 1, x = px + tap % 3 - 1;
+                        if (y < 0 || y >= p.L.H || x < 0 || x >= p.L.W) continue;
+                        for (int chunk = 0; chunk < nch && ok; ++chunk) {
+                            const bool second = chunk >= nch0;
+                            ok = stage1(second ? &maps.a[1] : &maps.a[0], &maps.b, (second ? chunk - nch0 : chunk) * kCh, x, y,
+                                        (tap * nch + chunk) * coutp + n0 + crank * w_half);
+                        }
+                    }
+                    if (p.L.flags & CONV_RESACC)
+                        for (int rc = 0; rc < p.r_nch && ok; ++rc) {
+                            const bool second = rc >= p.r_nch0;
+                            ok = stage1(second ? &maps.ra[1] : &maps.ra[0], &maps.rb, (second ? rc - p.r_nch0 : rc) * kCh, px, py, rc * coutp + n0 + crank * w_half);
+                        }
+                }
+                ok = false;                                        // (skip the im2col loop below)
+            }
             for (int wk = work0; wk < p.n_work && ok; wk += gridDim.x) {
                 const int work = wk + crank;                   // may be a padding item past n_work: loads hit OOB zeros
                 const int tile = work / p.n_split, n0 = (work % p.n_split) * ncols;
@@ -589,9 +633,15 @@ k_conv_umma_t(const __grid_constant__ UmmaMaps maps, const UmmaConv p) {
                     }
                 };
                 const uint32_t d_set = tmem_base + (uint32_t)(acc * p.acc_cols);
+                int n_kb = iters_per_pass;
+                if (p.posm) {                                   // taps inside the map at this tile's position (pair: the same for both tiles)
+                    const int pos = (wk / p.n_split) / p.nblk_img, py = pos / p.L.W, px = pos - py * p.L.W;
+                    const int ny = 1 + (py > 0) + (py < p.L.H - 1), nx = 1 + (px > 0) + (px < p.L.W - 1);
+                    n_kb = ny * nx * nch;
+                }
                 // passes 1 and 2 of 3xTF32 share the correction accumulator
                 for (int pass = 0; pass < p.npass && ok; ++pass)
-                    run_stages(d_set + (pass ? (uint32_t)p.corr_col : 0u), pass == 2 ? 1u : 0u, iters_per_pass, nch, p.half_mask);
+                    run_stages(d_set + (pass ? (uint32_t)p.corr_col : 0u), pass == 2 ? 1u : 0u, n_kb, nch, p.half_mask);
                 if (p.L.flags & CONV_RESACC) run_stages(d_set + (uint32_t)p.res_col, 0u, p.r_nch, p.r_nch, p.r_half_mask);
                 if constexpr (kPair) ptx::tc_commit_2sm(acc_full0 + 8u * acc, cmask);   // accumulator complete, in both CTAs
                 else ptx::tc_commit(acc_full0 + 8u * acc);
@@ -643,7 +693,14 @@ k_conv_umma_t(const __grid_constant__ UmmaMaps maps, const UmmaConv p) {
             const int row = (int)m_warp;
             const int hx0 = p.halo == 2 ? (tile & 1) * 8 : 0;       // halo mode 2: first column of the tile's half image
             // coordinates of this warp's 32-row box in the 4-d output / residual maps (halo modes)
-            const int hk1 = p.halo == 1 ? 0 : hx0, hk2 = p.halo == 1 ? 2 * tile : 4 * q, hk3 = p.halo == 1 ? 2 * q : (tile >> 1);
+            int hk1 = p.halo == 1 ? 0 : hx0, hk2 = p.halo == 1 ? 2 * tile : 4 * q, hk3 = p.halo == 1 ? 2 * q : (tile >> 1);
+            int pm_pos = 0, pm_img0 = 0;
+            if (p.posm) {                                           // box {32 ch, 1, 1, 32 images} at (x, y, first image of the warp)
+                pm_pos = tile / p.nblk_img;
+                pm_img0 = (tile - pm_pos * p.nblk_img) * 128 + 32 * q;
+                hk2 = pm_pos / p.L.W; hk1 = pm_pos - hk2 * p.L.W; hk3 = pm_img0;
+            }
+            const bool st4 = p.halo != 0 || p.posm != 0;           // stores / residual loads through a 4-d map
 #ifdef DTRAJ_PROBES
             const int tl_who = 1 + h;
             const bool tl_outer = tl_on;
@@ -655,7 +712,7 @@ k_conv_umma_t(const __grid_constant__ UmmaMaps maps, const UmmaConv p) {
                 if (has_res)
                     for (int k = 0; k < kEpiBufs && h + 2 * k < nchunk; ++k) {
                         ptx::mbar_expect_tx(rbar + 8u * k, 2048u);
-                        if (p.halo) ptx::tma_load_4d(buf0 + 4096u * k, &maps.res, rbar + 8u * k, n0 + 32 * (h + 2 * k), hk1, hk2, hk3);
+                        if (st4) ptx::tma_load_4d(buf0 + 4096u * k, &maps.res, rbar + 8u * k, n0 + 32 * (h + 2 * k), hk1, hk2, hk3);
                         else ptx::tma_load_2d(buf0 + 4096u * k, &maps.res, rbar + 8u * k, n0 + 32 * (h + 2 * k), row);
                     }
             }
@@ -675,6 +732,11 @@ k_conv_umma_t(const __grid_constant__ UmmaMaps maps, const UmmaConv p) {
                 img = tile >> 1;
                 valid = (int64_t)img * 256 < p.L.M;
                 m = (int64_t)img * 256 + (r >> 3) * 16 + hx0 + (r & 7);
+                if (!valid) img = 0;
+            } else if (p.posm) {                                     // rows = images at one position
+                img = pm_img0 + lane;
+                m = ((int64_t)img << p.log2_hw) + pm_pos;
+                valid = m < p.L.M;
                 if (!valid) img = 0;
             }
             const float* tb = nullptr;
@@ -846,7 +908,7 @@ k_conv_umma_t(const __grid_constant__ UmmaMaps maps, const UmmaConv p) {
                     __syncwarp();
                 }
                 if (lane == 0 && do_store) {
-                    if (p.halo) ptx::tma_store_4d(&maps.out, buf0 + 4096u * b, n0 + 32 * c, hk1, hk2, hk3);   // box {32 ch, 8 x, 2 images, 2 rows} / {32 ch, 8 x, 4 rows, 1 image}
+                    if (st4) ptx::tma_store_4d(&maps.out, buf0 + 4096u * b, n0 + 32 * c, hk1, hk2, hk3);   // box {32 ch, 8 x, 2 images, 2 rows} / {32 ch, 8 x, 4 rows, 1 image}
                     else ptx::tma_store_2d(&maps.out, buf0 + 4096u * b, n0 + 32 * c, row);
                     ptx::bulk_commit();
                 }
@@ -858,7 +920,7 @@ k_conv_umma_t(const __grid_constant__ UmmaMaps maps, const UmmaConv p) {
                         if (has_res) {
                             const int nb = (k + 1) & (kEpiBufs - 1);          // (depth 1 or 2)
                             ptx::mbar_expect_tx(rbar + 8u * nb, 2048u);
-                            if (p.halo) ptx::tma_load_4d(buf0 + 4096u * nb, &maps.res, rbar + 8u * nb, n0 + 32 * (c + 2), hk1, hk2, hk3);
+                            if (st4) ptx::tma_load_4d(buf0 + 4096u * nb, &maps.res, rbar + 8u * nb, n0 + 32 * (c + 2), hk1, hk2, hk3);
                             else ptx::tma_load_2d(buf0 + 4096u * nb, &maps.res, rbar + 8u * nb, n0 + 32 * (c + 2), row);
                         }
                     }
@@ -1260,6 +1322,18 @@ inline int build_umma_launch(UmmaLaunch* U, const ConvLayer& L, int npass, const
     c.box_n = HW >= 128 ? 1 : 128 / HW;
     c.tiles_per_img = HW >= 128 ? HW / 128 : 1;
     c.n_tiles = (int)((L.M + 127) / 128);
+    // Maps of at most 4x4 (fp16): POSITION-MAJOR tiles.  With [image][y][x] rows a 128-row tile mixes positions, so every one of the
+    // nine taps is loaded and multiplied although most of them fall into the zero padding (2x2: 5 of 9, 4x4: 2.75 of 9 on average,
+    // 1x1: 8 of 9) -- and these layers are bound by the weight tiles they pull through L2 (8.7 TB/s on enc4 of the teacher at 8880
+    // rows).  A tile of 128 images at ONE position skips the taps outside the map for all its rows at once.  No fused pool there
+    // (a 2x2 window spans four tiles): the forward plan keeps the stand-alone pool kernel at these levels.
+    c.posm = (f16 && L.ntaps == 9 && L.H <= 4 && L.act_mode != ACT_SPLIT && !(L.flags & (CONV_POOL | CONV_RESX | CONV_FINAL))) ? 1 : 0;
+    const int64_t n_img_all = L.M / HW;
+    if (c.posm) {
+        c.nblk_img = (int)((n_img_all + 127) / 128);
+        if (c.nblk_img >= 2 * kNumSMs / HW && (c.nblk_img & 1)) ++c.nblk_img;    // pairs: both tiles of a pair at the same position
+        c.n_tiles = HW * c.nblk_img;
+    }
     // fewer tiles than SMs (deep levels, small batches): split a tile's columns over up to 4 CTAs
     c.n_split = 1;
     if (!(L.flags & CONV_FINAL))
@@ -1271,7 +1345,7 @@ inline int build_umma_launch(UmmaLaunch* U, const ConvLayer& L, int npass, const
     // CTA pairs (tcgen05.mma.cta_group::2): each CTA stages its own 128 pixels and HALF of the weight tile, so a K
     // block costs 16 + N/4 KB of its shared memory instead of 16 + N/2 KB -- more K blocks in flight in the
     // latency-bound operand ring.  Wide, long layers with at least two waves of tiles only (profiles/r01c_conv_layers.txt).
-    c.pair = (c.n_split == 1 && L.coutp >= 64 && nkb_all >= 16 && c.n_work >= 2 * kNumSMs) ? 1 : 0;
+    c.pair = (c.n_split == 1 && L.coutp >= 64 && nkb_all >= 16 && c.n_work >= 2 * kNumSMs && (!c.posm || (c.nblk_img & 1) == 0)) ? 1 : 0;
     c.acc_cols = 32;
     while (c.acc_cols < n_rows) c.acc_cols *= 2;
     c.corr_col = 0;
@@ -1309,6 +1383,7 @@ inline int build_umma_launch(UmmaLaunch* U, const ConvLayer& L, int npass, const
     // halo mode (fp16, 8x8 maps, 3x3, no identity residual): two images per tile, pixels through the halo ring
     c.halo = (f16 && L.ntaps == 9 && !(L.flags & CONV_RESX) && c.n_split == 1 && L.act_mode != ACT_SPLIT)
                  ? (L.H == 8 && L.W == 8 ? 1 : (L.H == 16 && L.W == 16 ? 2 : 0)) : 0;
+    if (c.posm) c.kbs = 1;
     c.n_hb = 0;
     if (c.halo) { c.kbs = 1; c.n_hb = 3; }
     const size_t stage = c.halo ? (size_t)n_stage_rows * 128 : (size_t)c.kbs * (kATileBytes + (size_t)n_stage_rows * 128);
@@ -1339,6 +1414,30 @@ inline int build_umma_launch(UmmaLaunch* U, const ConvLayer& L, int npass, const
         DTRAJ_TRY(make_w_map(&U->maps.rb, rwpk, rw_rows, c.ncols / (c.pair ? 2 : 1), f16));
     }
     if (L.M >= (int64_t)1 << 31) return fail(DTRAJ_EINVAL, "umma conv: M too large for 32-bit TMA coordinates");
+    if (c.posm) {       // position-major tiles: dimensions {c, x, y, image}; operand box = one position of 128 images, output / residual box of 32
+        auto mapp = [&](CUtensorMap* m, const float* base, int cp, int bc, int bn, bool sw64) -> int {
+            PFN_encodeTiled enc = get_encode_tiled();
+            if (!enc) return fail(DTRAJ_ECUDA, "cuTensorMapEncodeTiled not available");
+            cuuint64_t dims[4] = {(cuuint64_t)cp, (cuuint64_t)L.W, (cuuint64_t)L.H, (cuuint64_t)n_img};
+            cuuint64_t strides[3] = {(cuuint64_t)cp * 2, (cuuint64_t)L.W * cp * 2, (cuuint64_t)HW * cp * 2};
+            cuuint32_t box[4] = {(cuuint32_t)bc, 1, 1, (cuuint32_t)bn};
+            cuuint32_t es[4] = {1, 1, 1, 1};
+            CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, (void*)base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                             sw64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r != CUDA_SUCCESS) return fail(DTRAJ_ECUDA, "cuTensorMapEncodeTiled(position-major map cp=%d n=%lld) -> %d", cp, (long long)n_img, (int)r);
+            return 0;
+        };
+        DTRAJ_TRY(mapp(&U->maps.a[0], L.src0, L.c0p, 64, 128, false));
+        if (L.c1p) DTRAJ_TRY(mapp(&U->maps.a[1], L.src1, L.c1p, 64, 128, false));
+        if (L.flags & CONV_RESACC) {
+            DTRAJ_TRY(mapp(&U->maps.ra[0], L.rsrc0, L.rc0p, 64, 128, false));
+            if (L.rc1p) DTRAJ_TRY(mapp(&U->maps.ra[1], L.rsrc1, L.rc1p, 64, 128, false));
+        }
+        if (!(L.flags & CONV_NOSTORE)) DTRAJ_TRY(mapp(&U->maps.out, L.out, L.coutp, 32, 32, true));
+        if (L.flags & CONV_RESID) DTRAJ_TRY(mapp(&U->maps.res, L.resid, L.coutp, 32, 32, true));
+        return 0;
+    }
     if (c.halo == 2) {  // 16x16 maps: standard dimensions {c, x, y, image}; halo box 10 x 18, residual-conv box 8 x 16, output / residual box 8 x 4
         auto map4 = [&](CUtensorMap* m, const float* base, int cp, int bc, int bx, int by, bool sw64) -> int {
             PFN_encodeTiled enc = get_encode_tiled();

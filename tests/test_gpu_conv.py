@@ -92,6 +92,8 @@ SHAPES = [
     (3, 152, 152, 76, 8, 3),     # ... two half-filled sources (160 + 160), N = 96, halo mode in fp16
     (300, 204, 0, 204, 8, 3),    # sf 0.8: 224 channels, CTA pairs with 112 weight rows per CTA
     (2, 16, 0, 32, 32, 3),       # tiny students: one half-filled K block per tap, N = 32
+    (2400, 64, 64, 64, 4, 3),    # fp16: position-major tiles (one output position of 128 images, taps outside the map skipped), CTA pairs
+    (9500, 32, 0, 64, 2, 3),     # ... 2x2 maps: 4 of 9 taps per tile, 75 image blocks per position padded to 76 for the pairs
 ]
 
 
