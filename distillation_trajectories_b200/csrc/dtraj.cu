@@ -487,6 +487,11 @@ int add_conv(dtraj_plan* P, const char* name, const PackedConv& pc, const dtraj_
     op.umma = u->d.precision != DTRAJ_PREC_FP32;
     if (op.umma) DTRAJ_TRY(build_umma_launch(&op.U, L, u->d.precision == DTRAJ_PREC_TF32X3 ? 3 : 1, pc.w, pc.rows,
                                              tail.res ? tail.res->w : nullptr, tail.res ? tail.res->rows : 0));
+    if (op.umma && op.U.conv.posm) {    // position-major tiles skip the taps outside the map: ((3H - 2) / H)^2 of 9 are executed on average
+        const double t_eff = ((3.0 * L.H - 2.0) / L.H) * ((3.0 * L.W - 2.0) / L.W);
+        op.flops = 2.0 * (double)L.M * pc.cout * (double)(pc.c0 + pc.c1) * t_eff +
+                   (tail.res ? 2.0 * (double)L.M * tail.res->cout * (double)(tail.res->c0 + tail.res->c1) : 0.0);
+    }
     P->convs.push_back(op);
     return 0;
 }
