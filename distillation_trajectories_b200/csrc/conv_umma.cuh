@@ -453,13 +453,16 @@ k_conv_umma_t(const __grid_constant__ UmmaMaps maps, const UmmaConv p) {
                         if (++s == p.stages) { s = 0; ph ^= 1u; }
                         return true;
                     };
-                    for (int tap = 0; tap < 9 && ok; ++tap) {
-                        const int y = py + tap / 3 - 1, x = px + tap % 3 - 1;
-                        if (y < 0 || y >= p.L.H || x < 0 || x >= p.L.W) continue;
-                        for (int chunk = 0; chunk < nch && ok; ++chunk) {
-                            const bool second = chunk >= nch0;
-                            ok = stage1(second ? &maps.a[1] : &maps.a[0], &maps.b, (second ? chunk - nch0 : chunk) * kCh, x, y,
-                                        (tap * nch + chunk) * coutp + n0 + crank * w_half);
+                    for (int pass = 0; pass < p.npass && ok; ++pass) {       // 3xTF32: hi x hi, hi x lo weights, lo x hi
+                        const int am = pass == 2 ? 2 : 0, b_pass = (pass == 1 ? p.b_lo_row : 0) + n0 + crank * w_half;
+                        for (int tap = 0; tap < 9 && ok; ++tap) {
+                            const int y = py + tap / 3 - 1, x = px + tap % 3 - 1;
+                            if (y < 0 || y >= p.L.H || x < 0 || x >= p.L.W) continue;
+                            for (int chunk = 0; chunk < nch && ok; ++chunk) {
+                                const bool second = chunk >= nch0;
+                                ok = stage1(&maps.a[am + (second ? 1 : 0)], &maps.b, (second ? chunk - nch0 : chunk) * kCh, x, y,
+                                            (tap * nch + chunk) * coutp + b_pass);
+                            }
                         }
                     }
                     if (p.L.flags & CONV_RESACC)
@@ -1002,19 +1005,32 @@ k_conv_umma_t(const __grid_constant__ UmmaMaps maps, const UmmaConv p) {
             const int work = wk + crank;
             const int tile = work / p.n_split, n0 = (work % p.n_split) * ncols;
             const int64_t m_warp = (int64_t)tile * 128 + q * 32;
-            const int row = (int)m_warp;        // TMA coordinates are 32-bit; M < 2^31 is checked on the host
+            const int row = (int)m_warp;
+            int pm_pos = 0, pm_img0 = 0, pk1 = 0, pk2 = 0;           // position-major tiles: box {32 ch, 1, 1, 32 images} at (x, y, first image of the warp)
+            if (p.posm) {
+                pm_pos = tile / p.nblk_img;
+                pm_img0 = (tile - pm_pos * p.nblk_img) * 128 + 32 * q;
+                pk2 = pm_pos / p.L.W; pk1 = pm_pos - pk2 * p.L.W;
+            }        // TMA coordinates are 32-bit; M < 2^31 is checked on the host
             if (lane == 0) {
                 ptx::bulk_wait_read<0>();       // the previous tile's stores have left the ring
                 if (has_res)
                     for (int k = 0; k < kEpiBufs && h + 2 * k < nchunk; ++k) {
                         ptx::mbar_expect_tx(rbar + 8u * k, 4096u);
-                        ptx::tma_load_2d(buf0 + 4096u * k, &maps.res, rbar + 8u * k, n0 + 32 * (h + 2 * k), row);
+                        if (p.posm) ptx::tma_load_4d(buf0 + 4096u * k, &maps.res, rbar + 8u * k, n0 + 32 * (h + 2 * k), pk1, pk2, pm_img0);
+                        else ptx::tma_load_2d(buf0 + 4096u * k, &maps.res, rbar + 8u * k, n0 + 32 * (h + 2 * k), row);
                     }
             }
             __syncwarp();
-            const int64_t m = m_warp + lane;
-            const bool valid = m < p.L.M;
-            const int img = valid ? (int)(m >> p.log2_hw) : 0;
+            int64_t m = m_warp + lane;
+            bool valid = m < p.L.M;
+            int img = valid ? (int)(m >> p.log2_hw) : 0;
+            if (p.posm) {                                            // rows = images at one position (see the fp16 branch)
+                img = pm_img0 + lane;
+                m = ((int64_t)img << p.log2_hw) + pm_pos;
+                valid = m < p.L.M;
+                if (!valid) img = 0;
+            }
             const float* tb = nullptr;
             if (fl & CONV_TBIAS) {
                 const int var = p.L.row_variant ? p.L.row_variant[img] : 0;
@@ -1129,7 +1145,11 @@ k_conv_umma_t(const __grid_constant__ UmmaMaps maps, const UmmaConv p) {
                     }
                     __syncwarp();
                 }
-                if (lane == 0 && do_store) { ptx::tma_store_2d(&maps.out, buf0 + 4096u * b, n0 + 32 * c, row); ptx::bulk_commit(); }
+                if (lane == 0 && do_store) {
+                    if (p.posm) ptx::tma_store_4d(&maps.out, buf0 + 4096u * b, n0 + 32 * c, pk1, pk2, pm_img0);
+                    else ptx::tma_store_2d(&maps.out, buf0 + 4096u * b, n0 + 32 * c, row);
+                    ptx::bulk_commit();
+                }
                 if (split && do_store) {
                     // low plane: reuse the same buffer once the high-plane store has read it
                     if (lane == 0) ptx::bulk_wait_read<0>();
@@ -1138,7 +1158,11 @@ k_conv_umma_t(const __grid_constant__ UmmaMaps maps, const UmmaConv p) {
                     for (int j = 0; j < 8; ++j) *reinterpret_cast<float4*>(rowp + (((uint32_t)j ^ swz) << 4)) = act_lo4(keep[j]);
                     ptx::fence_proxy_async();
                     __syncwarp();
-                    if (lane == 0) { ptx::tma_store_2d(&maps.out_lo, buf0 + 4096u * b, n0 + 32 * c, row); ptx::bulk_commit(); }
+                    if (lane == 0) {
+                        if (p.posm) ptx::tma_store_4d(&maps.out_lo, buf0 + 4096u * b, n0 + 32 * c, pk1, pk2, pm_img0);
+                        else ptx::tma_store_2d(&maps.out_lo, buf0 + 4096u * b, n0 + 32 * c, row);
+                        ptx::bulk_commit();
+                    }
                 }
                 // ring upkeep (depth B = kEpiBufs): my next chunk reuses buffer (k + 1) % B, last read by the store of
                 // my chunk k + 1 - B -- allow B - 1 younger stores to stay in flight, then refill / rewrite it
@@ -1148,7 +1172,8 @@ k_conv_umma_t(const __grid_constant__ UmmaMaps maps, const UmmaConv p) {
                         if (has_res) {
                             const int nb = (k + 1) & (kEpiBufs - 1);          // (depth 1 or 2)
                             ptx::mbar_expect_tx(rbar + 8u * nb, 4096u);
-                            ptx::tma_load_2d(buf0 + 4096u * nb, &maps.res, rbar + 8u * nb, n0 + 32 * (c + 2), row);
+                            if (p.posm) ptx::tma_load_4d(buf0 + 4096u * nb, &maps.res, rbar + 8u * nb, n0 + 32 * (c + 2), pk1, pk2, pm_img0);
+                            else ptx::tma_load_2d(buf0 + 4096u * nb, &maps.res, rbar + 8u * nb, n0 + 32 * (c + 2), row);
                         }
                     }
                     __syncwarp();
@@ -1322,12 +1347,12 @@ inline int build_umma_launch(UmmaLaunch* U, const ConvLayer& L, int npass, const
     c.box_n = HW >= 128 ? 1 : 128 / HW;
     c.tiles_per_img = HW >= 128 ? HW / 128 : 1;
     c.n_tiles = (int)((L.M + 127) / 128);
-    // Maps of at most 4x4 (fp16): POSITION-MAJOR tiles.  With [image][y][x] rows a 128-row tile mixes positions, so every one of the
+    // Maps of at most 4x4: POSITION-MAJOR tiles.  With [image][y][x] rows a 128-row tile mixes positions, so every one of the
     // nine taps is loaded and multiplied although most of them fall into the zero padding (2x2: 5 of 9, 4x4: 2.75 of 9 on average,
     // 1x1: 8 of 9) -- and these layers are bound by the weight tiles they pull through L2 (8.7 TB/s on enc4 of the teacher at 8880
     // rows).  A tile of 128 images at ONE position skips the taps outside the map for all its rows at once.  No fused pool there
     // (a 2x2 window spans four tiles): the forward plan keeps the stand-alone pool kernel at these levels.
-    c.posm = (f16 && L.ntaps == 9 && L.H <= 4 && L.act_mode != ACT_SPLIT && !(L.flags & (CONV_POOL | CONV_RESX | CONV_FINAL))) ? 1 : 0;
+    c.posm = (L.ntaps == 9 && L.H <= 4 && !(L.flags & (CONV_POOL | CONV_RESX | CONV_FINAL))) ? 1 : 0;
     const int64_t n_img_all = L.M / HW;
     if (c.posm) {
         c.nblk_img = (int)((n_img_all + 127) / 128);
@@ -1415,27 +1440,34 @@ inline int build_umma_launch(UmmaLaunch* U, const ConvLayer& L, int npass, const
     }
     if (L.M >= (int64_t)1 << 31) return fail(DTRAJ_EINVAL, "umma conv: M too large for 32-bit TMA coordinates");
     if (c.posm) {       // position-major tiles: dimensions {c, x, y, image}; operand box = one position of 128 images, output / residual box of 32
+        const cuuint64_t esz = f16 ? 2 : 4;                    // operand box = 128 bytes of channels per pixel, epilogue box = 32 channels
         auto mapp = [&](CUtensorMap* m, const float* base, int cp, int bc, int bn, bool sw64) -> int {
             PFN_encodeTiled enc = get_encode_tiled();
             if (!enc) return fail(DTRAJ_ECUDA, "cuTensorMapEncodeTiled not available");
             cuuint64_t dims[4] = {(cuuint64_t)cp, (cuuint64_t)L.W, (cuuint64_t)L.H, (cuuint64_t)n_img};
-            cuuint64_t strides[3] = {(cuuint64_t)cp * 2, (cuuint64_t)L.W * cp * 2, (cuuint64_t)HW * cp * 2};
+            cuuint64_t strides[3] = {(cuuint64_t)cp * esz, (cuuint64_t)L.W * cp * esz, (cuuint64_t)HW * cp * esz};
             cuuint32_t box[4] = {(cuuint32_t)bc, 1, 1, (cuuint32_t)bn};
             cuuint32_t es[4] = {1, 1, 1, 1};
-            CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, (void*)base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CUresult r = enc(m, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                              sw64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
             if (r != CUDA_SUCCESS) return fail(DTRAJ_ECUDA, "cuTensorMapEncodeTiled(position-major map cp=%d n=%lld) -> %d", cp, (long long)n_img, (int)r);
             return 0;
         };
-        DTRAJ_TRY(mapp(&U->maps.a[0], L.src0, L.c0p, 64, 128, false));
-        if (L.c1p) DTRAJ_TRY(mapp(&U->maps.a[1], L.src1, L.c1p, 64, 128, false));
-        if (L.flags & CONV_RESACC) {
-            DTRAJ_TRY(mapp(&U->maps.ra[0], L.rsrc0, L.rc0p, 64, 128, false));
-            if (L.rc1p) DTRAJ_TRY(mapp(&U->maps.ra[1], L.rsrc1, L.rc1p, 64, 128, false));
+        DTRAJ_TRY(mapp(&U->maps.a[0], L.src0, L.c0p, kch, 128, false));
+        if (L.c1p) DTRAJ_TRY(mapp(&U->maps.a[1], L.src1, L.c1p, kch, 128, false));
+        if (npass == 3) {
+            DTRAJ_TRY(mapp(&U->maps.a[2], L.src0_lo, L.c0p, kch, 128, false));
+            if (L.c1p) DTRAJ_TRY(mapp(&U->maps.a[3], L.src1_lo, L.c1p, kch, 128, false));
         }
-        if (!(L.flags & CONV_NOSTORE)) DTRAJ_TRY(mapp(&U->maps.out, L.out, L.coutp, 32, 32, true));
-        if (L.flags & CONV_RESID) DTRAJ_TRY(mapp(&U->maps.res, L.resid, L.coutp, 32, 32, true));
+        if (L.flags & CONV_RESACC) {
+            DTRAJ_TRY(mapp(&U->maps.ra[0], L.rsrc0, L.rc0p, kch, 128, false));
+            if (L.rc1p) DTRAJ_TRY(mapp(&U->maps.ra[1], L.rsrc1, L.rc1p, kch, 128, false));
+        }
+        // (fp16 rows of 32 channels are 64 bytes: 64-byte swizzle; fp32 rows 128 bytes: 128-byte swizzle)
+        if (!(L.flags & CONV_NOSTORE)) DTRAJ_TRY(mapp(&U->maps.out, L.out, L.coutp, 32, 32, f16 != 0));
+        if (L.act_mode == ACT_SPLIT) DTRAJ_TRY(mapp(&U->maps.out_lo, L.out + L.lo_off, L.coutp, 32, 32, false));
+        if (L.flags & CONV_RESID) DTRAJ_TRY(mapp(&U->maps.res, L.resid, L.coutp, 32, 32, f16 != 0));
         return 0;
     }
     if (c.halo == 2) {  // 16x16 maps: standard dimensions {c, x, y, image}; halo box 10 x 18, residual-conv box 8 x 16, output / residual box 8 x 4
