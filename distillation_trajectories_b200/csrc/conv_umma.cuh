@@ -1315,6 +1315,16 @@ struct UmmaLaunch {            // everything a launch needs, built once per (lay
     size_t smem;
 };
 
+// Position-major tiles (UmmaConv::posm) pay on 1x1 / 2x2 maps always (every tile skips the same taps) and on 4x4 maps only when the
+// launch has more tiles than SMs: the four centre positions still run all nine taps, so a single wave is as long as before
+// (measured at 128 rows in 3xTF32: enc3.conv1 58 -> 62 us with them, enc4.conv1 58 -> 35 us).  The forward plan asks the same
+// question to decide where the 2x2 pool can stay fused into the producing conv.
+inline bool umma_posm_applies(int H, int64_t n_img) {
+    if (H > 4) return false;
+    if (H <= 2) return true;
+    return (int64_t)H * H * ((n_img + 127) / 128) > kNumSMs;
+}
+
 // `w_rows` = rows of the packed weight matrix (hi planes then, for 3 passes, lo planes)
 inline int build_umma_launch(UmmaLaunch* U, const ConvLayer& L, int npass, const float* wpk, int64_t w_rows,
                              const float* rwpk = nullptr, int64_t rw_rows = 0) {
@@ -1352,7 +1362,7 @@ inline int build_umma_launch(UmmaLaunch* U, const ConvLayer& L, int npass, const
     // 1x1: 8 of 9) -- and these layers are bound by the weight tiles they pull through L2 (8.7 TB/s on enc4 of the teacher at 8880
     // rows).  A tile of 128 images at ONE position skips the taps outside the map for all its rows at once.  No fused pool there
     // (a 2x2 window spans four tiles): the forward plan keeps the stand-alone pool kernel at these levels.
-    c.posm = (L.ntaps == 9 && L.H <= 4 && !(L.flags & (CONV_POOL | CONV_RESX | CONV_FINAL))) ? 1 : 0;
+    c.posm = (L.ntaps == 9 && umma_posm_applies(L.H, L.M / HW) && !(L.flags & (CONV_POOL | CONV_RESX | CONV_FINAL))) ? 1 : 0;
     const int64_t n_img_all = L.M / HW;
     if (c.posm) {
         c.nblk_img = (int)((n_img_all + 127) / 128);

@@ -516,7 +516,7 @@ int plan_build(const dtraj_unet* u, int64_t R, void* ws, int64_t ws_bytes, dtraj
     P->fuse_final = fused;
     // (maps of at most 4x4 run position-major tiles -- csrc/conv_umma.cuh -- whose rows are images, so a 2x2 pool window is not
     //  inside one tile: those levels keep the stand-alone pool kernel)
-    for (int l = 0; l < 4; ++l) P->fuse_pool[l] = fused && S[l] <= 16 && S[l] > 4;
+    for (int l = 0; l < 4; ++l) P->fuse_pool[l] = fused && S[l] <= 16 && !umma_posm_applies(S[l], P->R);
     // Residual 1x1 convs as extra MMAs of the block's conv2 (CONV_RESACC): no r tensor, no extra launch.  (Measured in round 2
     // with the 1x1 convs of the 256-wide blocks as their own launches + the TMA residual path: conv2 alone gains -- enc2.conv2
     // 673 -> 454 us at 8880 rows, two accumulator stages instead of one -- but the stand-alone K = 128..512 GEMMs cost more than
