@@ -295,7 +295,9 @@ int dtraj_bench_conv(int32_t precision, int32_t c0, int32_t c1, int32_t cout, in
 /* Peek at the library-wide error word without clearing it (tests assert it stays 0). */
 unsigned int dtraj_debug_umma_error(void);
 /* (csrc/probe.cuh -- the tcgen05 descriptor-view and permuted-TMA hardware probes behind profiles/r01_*_probe.txt -- is
- * compiled only with -DDTRAJ_PROBES and exports dtraj_probe_umma_view / dtraj_probe_tma_permuted; the product build has neither.) */
+ * compiled only with -DDTRAJ_PROBES and exports dtraj_probe_umma_view / dtraj_probe_tma_permuted; the same build flag
+ * turns on the SM-clock stamps read by dtraj_probe_timeline / dtraj_probe_timeline_select (tools/timeline.py).  The product build has
+ * none of them.) */
 
 #ifdef __cplusplus
 }
