@@ -276,11 +276,13 @@ k_enc1_f16(const __grid_constant__ Enc1Maps maps, const Enc1hParams p) {
                 const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.acc_cols);
                 uint32_t accum = 0u;
                 for (int c = 0; c < p.n_chunks && ok; ++c) {
-                    // one D1 buffer: the next tile's conv1 goes in front of this tile's last chunk, so that its conversion
-                    // overlaps that chunk's MMAs
-                    if (p.n_d1 == 1 && c == p.n_chunks - 1 && it + 1 < n_my) issue_conv1(it + 1);
                     ok = ok && ptx::mbar_wait(errw, hfull(hb), hph);      // this chunk's halo tile is in shared memory (both CTAs)
                     ptx::tc_fence_after();
+                    // one D1 buffer: the next tile's conv1 goes in front of THIS tile's first chunk.  A1(it + 1) is published together
+                    // with that chunk and the mid warps release D1(it) a few hundred cycles later (their last tcgen05.ld), so the issuer
+                    // waits briefly here -- but D1(it + 1) is then ready one chunk of MMAs (~2500 cycles) earlier than behind chunk 0, and
+                    // that wait was on the critical cycle D1 -> gather -> conversion -> chunk-0 MMAs -> conv1 (profiles/r02i_timeline.txt)
+                    if (p.n_d1 == 1 && c == 0 && it + 1 < n_my) issue_conv1(it + 1);
                     DTRAJ_TL(0, 2 + 2 * (c & 1));
                     const uint32_t hbuf = halo0 + (uint32_t)hb * kE1HaloBytes;
                     int dy = 0, dx = 0;
