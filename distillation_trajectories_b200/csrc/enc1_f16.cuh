@@ -125,7 +125,7 @@ k_enc1_f16(const __grid_constant__ Enc1Maps maps, const Enc1hParams p) {
             for (int b = 0; b < p.n_hbuf; ++b) { ptx::mbar_init(hfull(b), nrep); ptx::mbar_init(hempty(b), 1); }
             for (int i = 0; i < 2; ++i) {
                 ptx::mbar_init(acc_full0 + 8u * i, 1);
-                ptx::mbar_init(acc_empty0 + 8u * i, nrep);
+                ptx::mbar_init(acc_empty0 + 8u * i, kE1Epi * nrep);       // every epilogue warp reports its last accumulator load
             }
             ptx::mbar_init(wbar, 1);
             for (int i = 0; i < 2; ++i) {
@@ -572,28 +572,44 @@ k_enc1_f16(const __grid_constant__ Enc1Maps maps, const Enc1hParams p) {
             ptx::tc_fence_after();
             DTRAJ_TL(2, 1);
             const uint32_t t_acc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.acc_cols);
+            // One warp per scheduler does all of this, and since the mid warps stopped being the kernel's pace the epilogue is (5600 of
+            // 6200 cycles per tile, profiles/r02i_timeline.txt): the next chunk's TMEM load is issued before this chunk's pool + store,
+            // the per-channel constants of the next 8 columns are loaded ahead of the math, and "accumulator drained" is a relaxed
+            // arrival per warp instead of a named barrier + one arrival
+            uint32_t raw[32];
+            ptx::tmem_ld32(t_acc, raw);
             for (int c = 0; c < nchunk; ++c) {
-                uint32_t raw[32];
-                ptx::tmem_ld32(t_acc + (uint32_t)(32 * c), raw);
                 ptx::tmem_ld_wait();
                 DTRAJ_TL(2, 2 + 3 * (c & 3));
                 if (c == nchunk - 1) {
                     ptx::tc_fence_before();
-                    asm volatile("bar.sync 10, 128;" ::: "memory");
-                    if (ew == 0 && lane == 0) arrive_acc_empty();
+                    __syncwarp();
+                    if (lane == 0) arrive_acc_empty();
                 }
                 uint8_t* rowp = bufp + lane * 64;
+                float4 cb[2][2], cr[2][2], cw[2][kC][2];            // [parity of j][...][half]: bias2 | rb1 | rw1 of 8 columns
+                auto load_consts = [&](int j, int par) {
+                    const int col = 32 * c + 8 * j;
+#pragma unroll
+                    for (int hh = 0; hh < 2; ++hh) {
+                        cb[par][hh] = *reinterpret_cast<const float4*>(bias2s + col + 4 * hh);
+                        cr[par][hh] = *reinterpret_cast<const float4*>(rb1s + col + 4 * hh);
+#pragma unroll
+                        for (int ci = 0; ci < kC; ++ci) cw[par][ci][hh] = *reinterpret_cast<const float4*>(rw1s + (size_t)ci * coutp + col + 4 * hh);
+                    }
+                };
+                load_consts(0, 0);
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    const int col = 32 * c + 8 * j;
+                    if (j < 3) load_consts(j + 1, (j + 1) & 1);
                     float v[8];
 #pragma unroll
                     for (int hh = 0; hh < 2; ++hh) {
-                        const float4 b4 = *reinterpret_cast<const float4*>(bias2s + col + 4 * hh);
-                        float4 r4 = *reinterpret_cast<const float4*>(rb1s + col + 4 * hh);
+                        const float4 b4 = cb[j & 1][hh];
+                        float4 r4 = cr[j & 1][hh];
 #pragma unroll
                         for (int ci = 0; ci < kC; ++ci) {
-                            const float4 w4 = *reinterpret_cast<const float4*>(rw1s + (size_t)ci * coutp + col + 4 * hh);
+                            const float4 w4 = cw[j & 1][ci][hh];
                             r4.x = fmaf(xv[ci], w4.x, r4.x); r4.y = fmaf(xv[ci], w4.y, r4.y);
                             r4.z = fmaf(xv[ci], w4.z, r4.z); r4.w = fmaf(xv[ci], w4.w, r4.w);
                         }
@@ -611,6 +627,7 @@ k_enc1_f16(const __grid_constant__ Enc1Maps maps, const Enc1hParams p) {
                     }
                     *reinterpret_cast<uint4*>(rowp + (((uint32_t)j ^ swz) << 4)) = pk;
                 }
+                if (c + 1 < nchunk) ptx::tmem_ld32(t_acc + (uint32_t)(32 * (c + 1)), raw);     // in flight under the pool + store below
                 DTRAJ_TL(2, 3 + 3 * (c & 3));
                 __syncwarp();
                 if (real) {
