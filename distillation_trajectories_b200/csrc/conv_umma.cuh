@@ -1430,7 +1430,7 @@ inline int build_umma_launch(UmmaLaunch* U, const ConvLayer& L, int npass, const
     if (!c.halo && nkb_all >= 16 && stages_for(1) > stages_for(2) && stages_for(2) < 8) c.epi_bufs = 1;
     int stages = stages_for(c.epi_bufs);
     if (stages < 2) return fail(DTRAJ_EINVAL, "umma conv: operand ring does not fit");
-    if (stages > 8) stages = 8;
+    if (stages > 16) stages = 16;
     c.stages = stages;
     U->smem = misc + (size_t)kEpiWarps * c.epi_bufs * 4096 + stages * stage;
     U->grid = (unsigned)(c.n_work < kNumSMs ? c.n_work : kNumSMs);
