@@ -307,3 +307,32 @@ def test_model_aliases_match_the_reference_constructors():
         sa, sb = a.state_dict(), b.state_dict()
         assert list(sa) == list(sb) and all(torch.equal(sa[k], sb[k]) for k in sa)
         assert a.dims == b.dims and a.time_emb_dim == b.time_emb_dim
+
+
+def test_bench_flop_counts_match_the_survey_and_the_reference_layers():
+    """bench.conv_flops_per_forward: the standard 2 x MACs of the eight blocks' convs (0.404 of 0.423 GFLOP per row at 16x16,
+    1.62 of 1.69 at 32x32 for the 3x3 convs) -- checked against a count taken from the model's own Conv2d modules -- and the executed
+    count of the position-major tiles (taps outside a <= 4x4 map skipped)."""
+    import contextlib
+    import io
+    import bench
+    from distillation_trajectories_b200 import models as ours
+    for cfg, H, C in ((bench.Cfg, 16, 1), (bench.Cfg32, 32, 3)):
+        with contextlib.redirect_stdout(io.StringIO()):
+            m = ours.DiffusionUNet(cfg, 1.0)
+        # every Conv2d of the eight blocks at its level's map size (models.py:138-157, 205-217)
+        sizes = {"enc1": H, "enc2": H // 2, "enc3": H // 4, "enc4": H // 8, "bottleneck": H // 16, "dec3": H // 8, "dec2": H // 4, "dec1": H // 2}
+        want = 0.0
+        for name, mod in m.named_modules():
+            if isinstance(mod, torch.nn.Conv2d) and name.split(".")[0] in sizes:
+                h = sizes[name.split(".")[0]]
+                want += 2.0 * h * h * mod.in_channels * mod.out_channels * mod.kernel_size[0] * mod.kernel_size[1]
+        got = bench.conv_flops_per_forward(m.dims, C, H, False)
+        assert abs(got - want) <= 1e-9 * want, (H, got, want)
+        ex = bench.conv_flops_per_forward(m.dims, C, H, True)
+        assert 0.85 * got < ex < got
+    assert abs(bench.conv_flops_per_forward([128, 256, 256, 256], 1, 16, False) / 1e9 - 0.4219) < 1e-3
+    # a 2x2 map meets 4 of the 9 taps, a 4x4 map 6.25 on average, a 1x1 map the centre tap only
+    d = [8, 8, 8, 8]
+    blocks_32 = bench.conv_flops_per_forward(d, 8, 32, True)
+    assert blocks_32 < bench.conv_flops_per_forward(d, 8, 32, False)
