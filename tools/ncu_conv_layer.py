@@ -3,6 +3,8 @@ import ctypes as C, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from distillation_trajectories_b200 import _lib
 lib = _lib.load()
+if len(sys.argv) < 7:
+    sys.exit(__doc__)
 c0, c1, cout, H, k, fl = (int(a) for a in sys.argv[1:7])
 rows = int(sys.argv[7]) if len(sys.argv) > 7 else 3840
 ms = C.c_float()
