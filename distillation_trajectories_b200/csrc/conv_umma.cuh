@@ -1421,6 +1421,18 @@ inline int build_umma_launch(UmmaLaunch* U, const ConvLayer& L, int npass, const
     if (c.posm) c.kbs = 1;
     c.n_hb = 0;
     if (c.halo) { c.kbs = 1; c.n_hb = 3; }
+    // Halo layers with a fused residual conv: its K blocks bring an un-shifted 16 KB pixel box EACH through the halo ring, so where they
+    // outnumber the main chunks (dec1.conv2: 2 halo boxes + 8 residual boxes per tile at the teacher's widths) three slots make that
+    // phase latency-bound (3 boxes per ~1.5 us TMA round trip): a fourth slot, paid for by a single-buffered epilogue ring
+    // (profiles/r02q_ring_ab.txt: teacher dec1.conv2 259 -> 241 us, sf 0.5 115 -> 108 us; enc2.conv2 with the single-buffered
+    // epilogue ring alone 550 -> 530 us).
+    const bool halo_res = c.halo && (L.flags & CONV_RESACC);
+    if (halo_res && c.r_nch > c.nch) c.n_hb = 4;
+    // ... and a conv1 whose whole K loop is two halo boxes of 16 KB weight stages (enc2.conv1 at N = 256) does better with two halo
+    // slots and a single-buffered epilogue ring, i.e. three more weight stages (teacher enc2.conv1 244 -> 227 us; the same
+    // trade loses on the 8-chunk dec1.conv1 and on 8 KB stages, same file)
+    const bool halo_short = c.halo && !(L.flags & CONV_RESACC) && c.nch <= 2 && n_stage_rows * 128 >= 16384;
+    if (halo_short) c.n_hb = 2;
     const size_t stage = c.halo ? (size_t)n_stage_rows * 128 : (size_t)c.kbs * (kATileBytes + (size_t)n_stage_rows * 128);
     const size_t cst_bytes = (size_t)(5 + ((L.flags & CONV_FINAL) ? 4 : 0)) * L.coutp * 4;     // staged per-channel constants
     const size_t misc = 1024 + 512 + ((L.flags & CONV_FINAL) ? 2048 : 0) + cst_bytes + (size_t)c.n_hb * kHaloBytes;
@@ -1428,6 +1440,7 @@ inline int build_umma_launch(UmmaLaunch* U, const ConvLayer& L, int npass, const
     c.epi_bufs = 2;
     c.epi_kind = f16 ? epi_kind_of(L.flags) : 0;
     if (!c.halo && nkb_all >= 16 && stages_for(1) > stages_for(2) && stages_for(2) < 8) c.epi_bufs = 1;
+    if ((halo_res || halo_short) && stages_for(2) < 16) c.epi_bufs = 1;
     int stages = stages_for(c.epi_bufs);
     if (stages < 2) return fail(DTRAJ_EINVAL, "umma conv: operand ring does not fit");
     if (stages > 16) stages = 16;
