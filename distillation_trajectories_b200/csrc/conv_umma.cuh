@@ -1433,6 +1433,7 @@ inline int build_umma_launch(UmmaLaunch* U, const ConvLayer& L, int npass, const
     // trade loses on the 8-chunk dec1.conv1 and on 8 KB stages, same file)
     const bool halo_short = c.halo && !(L.flags & CONV_RESACC) && c.nch <= 2 && n_stage_rows * 128 >= 16384;
     if (halo_short) c.n_hb = 2;
+    if (c.n_hb > 4) return fail(DTRAJ_EINVAL, "umma conv: the kernel has four halo-ring barriers");
     const size_t stage = c.halo ? (size_t)n_stage_rows * 128 : (size_t)c.kbs * (kATileBytes + (size_t)n_stage_rows * 128);
     const size_t cst_bytes = (size_t)(5 + ((L.flags & CONV_FINAL) ? 4 : 0)) * L.coutp * 4;     // staged per-channel constants
     const size_t misc = 1024 + 512 + ((L.flags & CONV_FINAL) ? 2048 : 0) + cst_bytes + (size_t)c.n_hb * kHaloBytes;
