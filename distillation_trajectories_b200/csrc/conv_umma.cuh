@@ -274,7 +274,7 @@ __global__ void __launch_bounds__(kUmmaThreads, 1)
 k_conv_umma_t(const __grid_constant__ UmmaMaps maps, const UmmaConv p) {
     constexpr int kCh = kF16 ? 64 : 32;      // channels of one 128-byte K block
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    // carve: [stages x (A 16 KB | B coutp*128 B)] [epilogue ring 4 warps x kEpiBufs x 4 KB] [barriers]
+    // carve: [stages x (A 16 KB | B coutp*128 B)] [epilogue ring kEpiWarps x kEpiBufs x 4 KB (2 KB in fp16 mode)] [barriers]
     const uint32_t base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
     const int coutp = p.L.coutp;
     const int ncols = p.ncols;                                 // columns this CTA computes per work item (coutp / n_split)
@@ -285,7 +285,9 @@ k_conv_umma_t(const __grid_constant__ UmmaMaps maps, const UmmaConv p) {
     const uint32_t halo_base = base + p.stages * stage_bytes;
     const uint32_t ring_base = halo_base + (p.halo ? (uint32_t)p.n_hb * kHaloBytes : 0u);
     const int kEpiBufs = p.epi_bufs;
-    const uint32_t bar_base = ring_base + (uint32_t)(kEpiWarps * kEpiBufs * 4096);
+    // (an epilogue buffer is [32 rows][32 columns]: 4 KB of floats, 2 KB of halfs -- the fp16 kernels give the other half to the operand ring)
+    constexpr uint32_t kEpiBufBytes = kF16 ? 2048u : 4096u;
+    const uint32_t bar_base = ring_base + (uint32_t)(kEpiWarps * kEpiBufs) * kEpiBufBytes;
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
     auto empty_bar = [&](int s) { return bar_base + 8u * (p.stages + s); };
     const uint32_t acc_full0 = bar_base + 16u * p.stages;      // [2] accumulator ready   (issuer -> epilogue)
@@ -681,7 +683,7 @@ k_conv_umma_t(const __grid_constant__ UmmaMaps maps, const UmmaConv p) {
         const bool do_store = !(fl & CONV_NOSTORE);
         const bool do_pool = (fl & CONV_POOL) != 0;
         const int epi_kind = (p.epi_kind == 1 && p.L.tb_rows) ? 0 : p.epi_kind;   // (per-row timesteps: the time-bias table stays in global memory)
-        const uint32_t buf0 = ring_base + (uint32_t)ew * kEpiBufs * 4096u;
+        const uint32_t buf0 = ring_base + (uint32_t)ew * kEpiBufs * kEpiBufBytes;
         const uint32_t rbar = res_bar0 + 8u * (ew * kEpiBufsMax);
         const uint32_t swz = (uint32_t)((lane >> 1) & 3);
         __half* const pool_h = reinterpret_cast<__half*>(p.L.pool_out);
@@ -715,8 +717,8 @@ k_conv_umma_t(const __grid_constant__ UmmaMaps maps, const UmmaConv p) {
                 if (has_res)
                     for (int k = 0; k < kEpiBufs && h + 2 * k < nchunk; ++k) {
                         ptx::mbar_expect_tx(rbar + 8u * k, 2048u);
-                        if (st4) ptx::tma_load_4d(buf0 + 4096u * k, &maps.res, rbar + 8u * k, n0 + 32 * (h + 2 * k), hk1, hk2, hk3);
-                        else ptx::tma_load_2d(buf0 + 4096u * k, &maps.res, rbar + 8u * k, n0 + 32 * (h + 2 * k), row);
+                        if (st4) ptx::tma_load_4d(buf0 + kEpiBufBytes * k, &maps.res, rbar + 8u * k, n0 + 32 * (h + 2 * k), hk1, hk2, hk3);
+                        else ptx::tma_load_2d(buf0 + kEpiBufBytes * k, &maps.res, rbar + 8u * k, n0 + 32 * (h + 2 * k), row);
                     }
             }
             __syncwarp();
@@ -793,7 +795,7 @@ k_conv_umma_t(const __grid_constant__ UmmaMaps maps, const UmmaConv p) {
                     if (lane == 0) arrive_acc_empty(acc);
                 }
                 if (f_resid) { ptx::mbar_wait(errw, rbar + 8u * b, (res_par >> b) & 1u); res_par ^= 1u << b; }
-                const uint8_t* rowp = smem_raw + (buf0 + 4096u * b - ptx::smem_u32(smem_raw)) + lane * 64;
+                const uint8_t* rowp = smem_raw + (buf0 + kEpiBufBytes * b - ptx::smem_u32(smem_raw)) + lane * 64;
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     const int col = n0 + 32 * c + 8 * j;
@@ -868,7 +870,7 @@ k_conv_umma_t(const __grid_constant__ UmmaMaps maps, const UmmaConv p) {
             };
             // ... second half: packed words -> swizzled ring buffer -> fused 2x2 max-pool -> TMA store (+ ring upkeep)
             auto emit_chunk = [&](int c, int k, int b, const uint32_t (&pk)[16]) {
-                uint8_t* bufp = smem_raw + (buf0 + 4096u * b - ptx::smem_u32(smem_raw));
+                uint8_t* bufp = smem_raw + (buf0 + kEpiBufBytes * b - ptx::smem_u32(smem_raw));
                 uint8_t* rowp = bufp + lane * 64;
                 if (do_store || do_pool) {
 #pragma unroll
@@ -911,8 +913,8 @@ k_conv_umma_t(const __grid_constant__ UmmaMaps maps, const UmmaConv p) {
                     __syncwarp();
                 }
                 if (lane == 0 && do_store) {
-                    if (st4) ptx::tma_store_4d(&maps.out, buf0 + 4096u * b, n0 + 32 * c, hk1, hk2, hk3);   // box {32 ch, 8 x, 2 images, 2 rows} / {32 ch, 8 x, 4 rows, 1 image}
-                    else ptx::tma_store_2d(&maps.out, buf0 + 4096u * b, n0 + 32 * c, row);
+                    if (st4) ptx::tma_store_4d(&maps.out, buf0 + kEpiBufBytes * b, n0 + 32 * c, hk1, hk2, hk3);   // box {32 ch, 8 x, 2 images, 2 rows} / {32 ch, 8 x, 4 rows, 1 image}
+                    else ptx::tma_store_2d(&maps.out, buf0 + kEpiBufBytes * b, n0 + 32 * c, row);
                     ptx::bulk_commit();
                 }
                 // ring upkeep (depth B = kEpiBufs): my next chunk reuses buffer (k + 1) % B, last read by the store of my chunk
@@ -923,8 +925,8 @@ k_conv_umma_t(const __grid_constant__ UmmaMaps maps, const UmmaConv p) {
                         if (has_res) {
                             const int nb = (k + 1) & (kEpiBufs - 1);          // (depth 1 or 2)
                             ptx::mbar_expect_tx(rbar + 8u * nb, 2048u);
-                            if (st4) ptx::tma_load_4d(buf0 + 4096u * nb, &maps.res, rbar + 8u * nb, n0 + 32 * (c + 2), hk1, hk2, hk3);
-                            else ptx::tma_load_2d(buf0 + 4096u * nb, &maps.res, rbar + 8u * nb, n0 + 32 * (c + 2), row);
+                            if (st4) ptx::tma_load_4d(buf0 + kEpiBufBytes * nb, &maps.res, rbar + 8u * nb, n0 + 32 * (c + 2), hk1, hk2, hk3);
+                            else ptx::tma_load_2d(buf0 + kEpiBufBytes * nb, &maps.res, rbar + 8u * nb, n0 + 32 * (c + 2), row);
                         }
                     }
                     __syncwarp();
@@ -1437,7 +1439,8 @@ inline int build_umma_launch(UmmaLaunch* U, const ConvLayer& L, int npass, const
     const size_t stage = c.halo ? (size_t)n_stage_rows * 128 : (size_t)c.kbs * (kATileBytes + (size_t)n_stage_rows * 128);
     const size_t cst_bytes = (size_t)(5 + ((L.flags & CONV_FINAL) ? 4 : 0)) * L.coutp * 4;     // staged per-channel constants
     const size_t misc = 1024 + 512 + ((L.flags & CONV_FINAL) ? 2048 : 0) + cst_bytes + (size_t)c.n_hb * kHaloBytes;
-    auto stages_for = [&](int bufs) { return (int)((227 * 1024 - misc - (size_t)kEpiWarps * bufs * 4096) / stage); };
+    const size_t epi_buf_bytes = f16 ? 2048 : 4096;            // [32 rows][32 columns] of halfs / floats
+    auto stages_for = [&](int bufs) { return (int)((227 * 1024 - misc - (size_t)kEpiWarps * bufs * epi_buf_bytes) / stage); };
     c.epi_bufs = 2;
     c.epi_kind = f16 ? epi_kind_of(L.flags) : 0;
     if (!c.halo && nkb_all >= 16 && stages_for(1) > stages_for(2) && stages_for(2) < 8) c.epi_bufs = 1;
@@ -1445,8 +1448,9 @@ inline int build_umma_launch(UmmaLaunch* U, const ConvLayer& L, int npass, const
     int stages = stages_for(c.epi_bufs);
     if (stages < 2) return fail(DTRAJ_EINVAL, "umma conv: operand ring does not fit");
     if (stages > 16) stages = 16;
+    if (c.halo && !halo_res && stages > 12) stages = 12;      // (dec1.conv1: 484 us with 10-12 weight stages, 495 with 14, 510 with 8, 550 with 6)
     c.stages = stages;
-    U->smem = misc + (size_t)kEpiWarps * c.epi_bufs * 4096 + stages * stage;
+    U->smem = misc + (size_t)kEpiWarps * c.epi_bufs * epi_buf_bytes + stages * stage;
     U->grid = (unsigned)(c.n_work < kNumSMs ? c.n_work : kNumSMs);
     if (c.pair) U->grid = (U->grid + 1) / 2 * 2;
     const int64_t n_img = L.M / HW;
