@@ -553,6 +553,14 @@ def run_ours(args, emit=print):
                        "consistency + MSE reductions)", "bound": "hbm", "achieved": m5_bytes / (m5_ms / 1e3) / 1e9, "peak": hbm,
              "unit": "GB/s", "frac": m5_bytes / (m5_ms / 1e3) / 1e9 / hbm, "traffic": None,
              "note": f"{m5_bytes / 1e9:.1f} GB per launch, every element read once; metric-kernel GB/s of BASELINE.json's metric"}]
+    if os.path.exists(tp):          # per-launch DRAM bytes of the side kernels from the committed ncu passes (profiles/traffic.json)
+        tj = json.load(open(tp))
+        side[0]["traffic"] = tj.get("k_step_dram_bytes_per_launch")
+        if args.seeds == 592:
+            side[1]["traffic"] = tj.get("k_metrics_pairs_workload_dram_bytes_per_launch")
+        side[2]["traffic"] = tj.get("k_metrics_pairs_config4_chunk_dram_bytes_per_launch")
+        for sd in side:
+            sd["traffic_source"] = tj.get("side_kernels_source")
     by_config["configs[4] chunk"] = {"workload": "metric-kernel bandwidth on a [8192, 50, 3, 32, 32] x 2 chunk of the synthetic pair",
                                      "value": side[2]["achieved"], "unit": "GB/s", "frac_of_hbm_peak": side[2]["frac"]}
 
