@@ -281,7 +281,7 @@ k_conv_umma_t(const __grid_constant__ UmmaMaps maps, const UmmaConv p) {
     const int n_rows = ncols;                                  // rows of the N operand tile (UMMA N)
     const uint32_t b_bytes = (uint32_t)(kPair ? n_rows / 2 : n_rows) * 128u;   // N-operand bytes staged in THIS CTA
     // halo mode: a stage holds ONE weight tile (a tap of a chunk); the pixels live in the halo ring behind the stages
-    const uint32_t stage_bytes = p.halo ? b_bytes : (uint32_t)p.kbs * (kATileBytes + b_bytes);   // kbs x [M tile 16 KB] then kbs x [N tile]
+    const uint32_t stage_bytes = p.halo ? (uint32_t)p.kbs * b_bytes : (uint32_t)p.kbs * (kATileBytes + b_bytes);   // kbs x [M tile 16 KB] then kbs x [N tile]; halo mode: kbs weight tiles (taps)
     const uint32_t halo_base = base + p.stages * stage_bytes;
     const uint32_t ring_base = halo_base + (p.halo ? (uint32_t)p.n_hb * kHaloBytes : 0u);
     const int kEpiBufs = p.epi_bufs;
@@ -391,6 +391,9 @@ k_conv_umma_t(const __grid_constant__ UmmaMaps maps, const UmmaConv p) {
                 // {c, x, image, y} (out-of-bounds rows / columns zero-filled = the conv's padding), then the nine weight tiles
                 int hb = 0;
                 uint32_t hph = 0;
+                // one stage = `n` weight tiles (taps b_row, b_row + row_step, ...) behind ONE barrier round trip: this thread's
+                // instruction stream, not the memory system, paces the N <= 128 layers (an issuer that sends one of the four MMAs
+                // of a K block is only 17 % faster on dec1.conv1, 7 % on the sf 0.5 student's: profiles/r02q_ring_ab.txt)
                 auto weight_stage = [&](const CUtensorMap* wm, int b_row) -> bool {
                     if (!ptx::mbar_wait(errw, empty_bar(s), ph ^ 1u)) return false;
                     uint32_t fb = full_bar(s);
@@ -398,6 +401,24 @@ k_conv_umma_t(const __grid_constant__ UmmaMaps maps, const UmmaConv p) {
                     if (!kPair || crank == 0) ptx::mbar_expect_tx(full_bar(s), b_bytes * (kPair ? 2u : 1u));
                     if constexpr (kPair) ptx::tma_load_2d_2sm(base + s * stage_bytes, wm, fb, 0, b_row);
                     else ptx::tma_load_2d(base + s * stage_bytes, wm, fb, 0, b_row);
+                    if (++s == p.stages) { s = 0; ph ^= 1u; }
+                    return true;
+                };
+                // kb = 3 or 9 taps' weight tiles (rows b_row, + row_step, ...) behind ONE barrier round trip: the instruction streams of this
+                // thread and of the issuer, not the memory system, pace the N <= 128 layers (an issuer that sends one of the four MMAs of
+                // a K block is only 17 % faster on dec1.conv1, 7 % on the sf 0.5 student's: profiles/r02q_ring_ab.txt)
+                auto weight_stage_n = [&](auto KB, const CUtensorMap* wm, int b_row, int row_step) -> bool {
+                    constexpr int kb = decltype(KB)::value;
+                    if (!ptx::mbar_wait(errw, empty_bar(s), ph ^ 1u)) return false;
+                    uint32_t fb = full_bar(s);
+                    if constexpr (kPair) fb = ptx::map_to_cta(fb, 0);
+                    if (!kPair || crank == 0) ptx::mbar_expect_tx(full_bar(s), (uint32_t)kb * b_bytes * (kPair ? 2u : 1u));
+                    const uint32_t dst = base + s * stage_bytes;
+#pragma unroll
+                    for (int j = 0; j < kb; ++j) {
+                        if constexpr (kPair) ptx::tma_load_2d_2sm(dst + (uint32_t)j * b_bytes, wm, fb, 0, b_row + j * row_step);
+                        else ptx::tma_load_2d(dst + (uint32_t)j * b_bytes, wm, fb, 0, b_row + j * row_step);
+                    }
                     if (++s == p.stages) { s = 0; ph ^= 1u; }
                     return true;
                 };
@@ -420,7 +441,9 @@ k_conv_umma_t(const __grid_constant__ UmmaMaps maps, const UmmaConv p) {
                     for (int chunk = 0; chunk < nch && ok; ++chunk) {
                         const bool second = chunk >= nch0;
                         ok = pixel_box(second ? &maps.a[1] : &maps.a[0], (second ? chunk - nch0 : chunk) * kCh, -1, img0, halo_tx);
-                        for (int tap = 0; tap < 9 && ok; ++tap) ok = weight_stage(&maps.b, (tap * nch + chunk) * coutp + crank * w_half);
+                        if (p.kbs == 9) ok = weight_stage_n(std::integral_constant<int, 9>{}, &maps.b, chunk * coutp + crank * w_half, nch * coutp);
+                        else if (p.kbs == 3) for (int tap = 0; tap < 9 && ok; tap += 3) ok = weight_stage_n(std::integral_constant<int, 3>{}, &maps.b, (tap * nch + chunk) * coutp + crank * w_half, nch * coutp);
+                        else for (int tap = 0; tap < 9 && ok; ++tap) ok = weight_stage(&maps.b, (tap * nch + chunk) * coutp + crank * w_half);
                     }
                     if (p.L.flags & CONV_RESACC)                   // 1x1 residual conv: the un-shifted 128 pixels of the block input
                         for (int rc = 0; rc < p.r_nch && ok; ++rc) {
@@ -439,18 +462,22 @@ k_conv_umma_t(const __grid_constant__ UmmaMaps maps, const UmmaConv p) {
                     const int tile = work / p.n_split, n0 = (work % p.n_split) * ncols;
                     const int pos = tile / p.nblk_img, img0 = (tile - pos * p.nblk_img) * 128;
                     const int py = pos / p.L.W, px = pos - py * p.L.W;
+                    // one stage = kbs (1 or 2) K blocks of ONE source at one tap: consecutive 64-channel chunks, their weight tiles
+                    // coutp rows apart -- laid out [kbs pixel tiles][kbs weight tiles] as the generic issuer loop expects
                     auto stage1 = [&](const CUtensorMap* am, const CUtensorMap* wm, int c0, int x, int y, int b_row) -> bool {
                         if (!ptx::mbar_wait(errw, empty_bar(s), ph ^ 1u)) return false;
                         const uint32_t st0 = base + s * stage_bytes;
                         uint32_t fb = full_bar(s);
                         if constexpr (kPair) fb = ptx::map_to_cta(fb, 0);
                         if (!kPair || crank == 0) ptx::mbar_expect_tx(full_bar(s), tx_bytes);
-                        if constexpr (!kPair) {
-                            ptx::tma_load_4d(st0, am, fb, c0, x, y, img0);
-                            ptx::tma_load_2d(st0 + w_base_off, wm, fb, 0, b_row);
-                        } else {
-                            ptx::tma_load_4d_2sm(st0, am, fb, c0, x, y, img0);
-                            ptx::tma_load_2d_2sm(st0 + w_base_off, wm, fb, 0, b_row);
+                        for (int j = 0; j < p.kbs; ++j) {
+                            if constexpr (!kPair) {
+                                ptx::tma_load_4d(st0 + (uint32_t)j * kATileBytes, am, fb, c0 + j * kCh, x, y, img0);
+                                ptx::tma_load_2d(st0 + w_base_off + (uint32_t)j * b_bytes, wm, fb, 0, b_row + j * coutp);
+                            } else {
+                                ptx::tma_load_4d_2sm(st0 + (uint32_t)j * kATileBytes, am, fb, c0 + j * kCh, x, y, img0);
+                                ptx::tma_load_2d_2sm(st0 + w_base_off + (uint32_t)j * b_bytes, wm, fb, 0, b_row + j * coutp);
+                            }
                         }
                         if (++s == p.stages) { s = 0; ph ^= 1u; }
                         return true;
@@ -460,7 +487,7 @@ k_conv_umma_t(const __grid_constant__ UmmaMaps maps, const UmmaConv p) {
                         for (int tap = 0; tap < 9 && ok; ++tap) {
                             const int y = py + tap / 3 - 1, x = px + tap % 3 - 1;
                             if (y < 0 || y >= p.L.H || x < 0 || x >= p.L.W) continue;
-                            for (int chunk = 0; chunk < nch && ok; ++chunk) {
+                            for (int chunk = 0; chunk < nch && ok; chunk += p.kbs) {
                                 const bool second = chunk >= nch0;
                                 ok = stage1(&maps.a[am + (second ? 1 : 0)], &maps.b, (second ? chunk - nch0 : chunk) * kCh, x, y,
                                             (tap * nch + chunk) * coutp + b_pass);
@@ -468,7 +495,7 @@ k_conv_umma_t(const __grid_constant__ UmmaMaps maps, const UmmaConv p) {
                         }
                     }
                     if (p.L.flags & CONV_RESACC)
-                        for (int rc = 0; rc < p.r_nch && ok; ++rc) {
+                        for (int rc = 0; rc < p.r_nch && ok; rc += p.kbs) {
                             const bool second = rc >= p.r_nch0;
                             ok = stage1(second ? &maps.ra[1] : &maps.ra[0], &maps.rb, (second ? rc - p.r_nch0 : rc) * kCh, px, py, rc * coutp + n0 + crank * w_half);
                         }
@@ -570,6 +597,25 @@ k_conv_umma_t(const __grid_constant__ UmmaMaps maps, const UmmaConv p) {
                         const uint32_t hbuf = halo_base + (uint32_t)hb * kHaloBytes;
                         int dy = 0, dx = 0;
                         const int nk = ((p.half_mask >> chunk) & 1u) ? 2 : 4;
+                        if (p.kbs > 1) {                                  // a stage holds the weight tiles of 3 taps (one tap row) or of all 9
+                            const uint64_t ha = hdesc0 | (uint64_t)((hbuf >> 4) & 0x3fffu);
+                            const uint32_t w16 = b_bytes >> 4;                // (descriptor addresses count 16 bytes)
+                            auto run_taps = [&](auto KB) {
+                                constexpr int kb = decltype(KB)::value;
+                                for (int g = 0; g < 9 / kb && ok; ++g) {
+                                    ok = ptx::mbar_wait(errw, full_bar(s), ph);
+                                    ptx::tc_fence_after();
+                                    const uint64_t wd = umma_desc_sw128(base + s * stage_bytes);
+                                    const uint64_t hr = ha + (uint64_t)(uint32_t)(g * tap_rows * 8);     // kb = 3: g is the tap row
+#pragma unroll
+                                    for (int j = 0; j < kb; ++j)
+                                        mma4(d_set, hr + (uint64_t)(uint32_t)((j / 3) * tap_rows * 8 + (j % 3) * 8), wd + (uint64_t)(w16 * (uint32_t)j), accum, nk);
+                                    free_stage();
+                                }
+                            };
+                            if (p.kbs == 9) run_taps(std::integral_constant<int, 9>{});
+                            else run_taps(std::integral_constant<int, 3>{});
+                        } else
                         for (int tap = 0; tap < 9 && ok; ++tap) {
                             ok = ptx::mbar_wait(errw, full_bar(s), ph);
                             ptx::tc_fence_after();
@@ -1420,9 +1466,11 @@ inline int build_umma_launch(UmmaLaunch* U, const ConvLayer& L, int npass, const
     // halo mode (fp16, 8x8 maps, 3x3, no identity residual): two images per tile, pixels through the halo ring
     c.halo = (f16 && L.ntaps == 9 && !(L.flags & CONV_RESX) && c.n_split == 1 && L.act_mode != ACT_SPLIT)
                  ? (L.H == 8 && L.W == 8 ? 1 : (L.H == 16 && L.W == 16 ? 2 : 0)) : 0;
-    if (c.posm) c.kbs = 1;
+    if (c.posm && (c.half_mask || c.r_half_mask || c.n_split > 1)) c.kbs = 1;   // (position-major tiles: two K blocks per stage where every chunk is a full one)
     c.n_hb = 0;
-    if (c.halo) { c.kbs = 1; c.n_hb = 3; }
+    // (halo mode: kbs = weight tiles (taps) per stage -- all nine where a tile is at most 4 KB, three where it is 8 KB, i.e. where four
+    //  MMAs are shorter than the barrier round trip of the two single-thread loops)
+    if (c.halo) { c.kbs = n_stage_rows * 128 <= 4096 ? 9 : n_stage_rows * 128 <= 8192 ? 3 : 1; c.n_hb = 3; }
     // Halo layers with a fused residual conv: its K blocks bring an un-shifted 16 KB pixel box EACH through the halo ring, so where they
     // outnumber the main chunks (dec1.conv2: 2 halo boxes + 8 residual boxes per tile at the teacher's widths) three slots make that
     // phase latency-bound (3 boxes per ~1.5 us TMA round trip): a fourth slot, paid for by a single-buffered epilogue ring
@@ -1436,7 +1484,7 @@ inline int build_umma_launch(UmmaLaunch* U, const ConvLayer& L, int npass, const
     const bool halo_short = c.halo && !(L.flags & CONV_RESACC) && c.nch <= 2 && n_stage_rows * 128 >= 16384;
     if (halo_short) c.n_hb = 2;
     if (c.n_hb > 4) return fail(DTRAJ_EINVAL, "umma conv: the kernel has four halo-ring barriers");
-    const size_t stage = c.halo ? (size_t)n_stage_rows * 128 : (size_t)c.kbs * (kATileBytes + (size_t)n_stage_rows * 128);
+    const size_t stage = c.halo ? (size_t)c.kbs * n_stage_rows * 128 : (size_t)c.kbs * (kATileBytes + (size_t)n_stage_rows * 128);
     const size_t cst_bytes = (size_t)(5 + ((L.flags & CONV_FINAL) ? 4 : 0)) * L.coutp * 4;     // staged per-channel constants
     const size_t misc = 1024 + 512 + ((L.flags & CONV_FINAL) ? 2048 : 0) + cst_bytes + (size_t)c.n_hb * kHaloBytes;
     const size_t epi_buf_bytes = f16 ? 2048 : 4096;            // [32 rows][32 columns] of halfs / floats
