@@ -65,7 +65,7 @@ struct UmmaConv {
     int n_work;                // n_tiles * n_split work items; CTA b handles b, b + gridDim.x, ...
     int pair;                  // 1: CTA pairs run tcgen05.mma.cta_group::2 -- M = 256 (two 128-row tiles, one per CTA), each CTA
                                //    stages only ITS half of the weight tile, the leader CTA issues for both
-    int kbs;                   // 32-channel K blocks per pipeline stage (2 when both sources have an even number of them)
+    int kbs;                   // K blocks per pipeline stage (2 when both sources have an even number of them); halo mode: weight tiles (taps) per stage, 1 / 3 / 9
     int epi_bufs;              // epilogue ring depth per warp (1 when the freed 32 KB buy another operand stage)
     int posm;                  // position-major tiles (fp16, maps of <= 4x4): a tile = ONE output position of 128 images, K loop over
                                //    the taps that fall inside the map only; nblk_img = tiles per position
