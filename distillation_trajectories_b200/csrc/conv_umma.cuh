@@ -445,12 +445,22 @@ k_conv_umma_t(const __grid_constant__ UmmaMaps maps, const UmmaConv p) {
                         else if (p.kbs == 3) for (int tap = 0; tap < 9 && ok; tap += 3) ok = weight_stage_n(std::integral_constant<int, 3>{}, &maps.b, (tap * nch + chunk) * coutp + crank * w_half, nch * coutp);
                         else for (int tap = 0; tap < 9 && ok; ++tap) ok = weight_stage(&maps.b, (tap * nch + chunk) * coutp + crank * w_half);
                     }
-                    if (p.L.flags & CONV_RESACC)                   // 1x1 residual conv: the un-shifted 128 pixels of the block input
-                        for (int rc = 0; rc < p.r_nch && ok; ++rc) {
-                            const bool second = rc >= p.r_nch0;
-                            ok = pixel_box(second ? &maps.ra[1] : &maps.ra[0], (second ? rc - p.r_nch0 : rc) * kCh, 0, img0, (uint32_t)kATileBytes);
-                            if (ok) ok = weight_stage(&maps.rb, rc * coutp + crank * w_half);
+                    if (p.L.flags & CONV_RESACC) {                 // 1x1 residual conv: the un-shifted 128 pixels of the block input
+                        // (its weight tiles also share a stage -- up to 3, or 4 where a stage has room for 9 -- one pixel box per K block)
+                        const int rk = p.kbs >= 9 ? 4 : p.kbs >= 3 ? 3 : 1;
+                        for (int rc = 0; rc < p.r_nch && ok;) {
+                            const int n = p.r_nch - rc < rk ? p.r_nch - rc : rk;
+                            const int b_row = rc * coutp + crank * w_half;
+                            if (n == 4) ok = weight_stage_n(std::integral_constant<int, 4>{}, &maps.rb, b_row, coutp);
+                            else if (n == 3) ok = weight_stage_n(std::integral_constant<int, 3>{}, &maps.rb, b_row, coutp);
+                            else if (n == 2) ok = weight_stage_n(std::integral_constant<int, 2>{}, &maps.rb, b_row, coutp);
+                            else ok = weight_stage(&maps.rb, b_row);
+                            for (int j = 0; j < n && ok; ++j, ++rc) {
+                                const bool second = rc >= p.r_nch0;
+                                ok = pixel_box(second ? &maps.ra[1] : &maps.ra[0], (second ? rc - p.r_nch0 : rc) * kCh, 0, img0, (uint32_t)kATileBytes);
+                            }
                         }
+                    }
                 }
                 ok = false;                                        // (skip the im2col loop below)
             }
@@ -628,14 +638,19 @@ k_conv_umma_t(const __grid_constant__ UmmaMaps maps, const UmmaConv p) {
                     }
                     if (p.L.flags & CONV_RESACC) {
                         uint32_t accum_r = 0u;
-                        for (int rc = 0; rc < p.r_nch && ok; ++rc) {
-                            ok = ptx::mbar_wait(errw, hfull0 + 8u * hb, hph);
-                            ok = ok && ptx::mbar_wait(errw, full_bar(s), ph);
-                            ptx::tc_fence_after();
-                            mma4(d_set + (uint32_t)p.res_col, umma_desc_sw128(halo_base + (uint32_t)hb * kHaloBytes), umma_desc_sw128(base + s * stage_bytes), accum_r,
-                                 ((p.r_half_mask >> rc) & 1u) ? 2 : 4);
+                        const int rk = p.kbs >= 9 ? 4 : p.kbs >= 3 ? 3 : 1;     // residual weight tiles per stage (as the producer packs them)
+                        for (int rc = 0; rc < p.r_nch && ok;) {
+                            const int n = p.r_nch - rc < rk ? p.r_nch - rc : rk;
+                            ok = ptx::mbar_wait(errw, full_bar(s), ph);
+                            const uint64_t wd = umma_desc_sw128(base + s * stage_bytes);
+                            for (int j = 0; j < n && ok; ++j, ++rc) {
+                                ok = ptx::mbar_wait(errw, hfull0 + 8u * hb, hph);
+                                ptx::tc_fence_after();
+                                mma4(d_set + (uint32_t)p.res_col, umma_desc_sw128(halo_base + (uint32_t)hb * kHaloBytes), wd + (uint64_t)((b_bytes >> 4) * (uint32_t)j), accum_r,
+                                     ((p.r_half_mask >> rc) & 1u) ? 2 : 4);
+                                free_halo();
+                            }
                             free_stage();
-                            free_halo();
                         }
                     }
                     if constexpr (kPair) ptx::tc_commit_2sm(acc_full0 + 8u * acc, cmask); else ptx::tc_commit(acc_full0 + 8u * acc);
